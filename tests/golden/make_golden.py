@@ -1,0 +1,171 @@
+"""Generate the golden vectors under tests/golden/ by running the UPSTREAM reference.
+
+Run in the authoring container (the reference tree is at /root/reference there):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or fixtures of its own, so these files are the
+pin for the oracle restatement (oracle/p2c_oracle.py) and, through it, for the CUDA path.  Inputs
+are regenerated deterministically from seeds by point2cyl_b200.synthetic / oracle.init_state_dict,
+so only the reference OUTPUTS are stored.  The training script's inline base/barrel loss
+(train_Point2Cyl_without_sketch.py:283-313) is not an importable function; its source lines are
+read from the reference file and exec'd here so that the golden is the reference's own code.
+"""
+import os
+import sys
+import textwrap
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle import p2c_oracle as orc  # noqa: E402
+from point2cyl_b200 import synthetic  # noqa: E402
+
+
+def np32(t):
+    return t.detach().cpu().numpy().copy()  # copy: state_dict tensors are live views
+
+
+def pointops_case(ref, name, xyz, npoint, radius, nsample, seed):
+    """FPS / ball query / gather / 3-NN interpolation known answers."""
+    B, N, _ = xyz.shape
+    torch.manual_seed(seed)
+    start = torch.randint(0, N, (B,), dtype=torch.long)
+    torch.manual_seed(seed)
+    fps_idx = ref.util.farthest_point_sample(xyz, npoint)
+    assert torch.equal(fps_idx[:, 0], start)
+    new_xyz = ref.util.index_points(xyz, fps_idx)
+    grp = ref.util.query_ball_point(radius, nsample, xyz, new_xyz)
+    d = ref.util.square_distance(new_xyz, xyz)
+    # three-NN interpolation exactly as PointNetFeaturePropagation.forward does it (:301-308)
+    g = torch.Generator().manual_seed(seed + 1)
+    feats2 = torch.randn(B, npoint, 16, generator=g)
+    dists, idx = ref.util.square_distance(xyz, new_xyz).sort(dim=-1)
+    dists, idx = dists[:, :, :3], idx[:, :, :3]
+    recip = 1.0 / (dists + 1e-8)
+    w = recip / torch.sum(recip, dim=2, keepdim=True)
+    interp = torch.sum(ref.util.index_points(feats2, idx) * w.view(B, N, 3, 1), dim=2)
+    np.savez_compressed(
+        os.path.join(HERE, name),
+        start=np32(start), fps_idx=np32(fps_idx).astype(np.int32), group_idx=np32(grp).astype(np.int32),
+        sqdist_row0=np32(d[:, 0, :]), nn_idx=np32(idx).astype(np.int32), nn_w=np32(w), interp=np32(interp),
+        meta=np.array([B, N, npoint, nsample, seed], dtype=np.int64), radius=np.float64(radius))
+    print("wrote", name)
+
+
+def backbone_case(ref, name, B, N, K, seed):
+    data = synthetic.s_cyl(B, N, K, seed)
+    sd = orc.init_state_dict(output_sizes=(3, 2 * K), seed=seed)
+    net = ref.net.backbone(output_sizes=[3, 2 * K])
+    net.load_state_dict(sd, strict=True)
+    out = {}
+    real_dropout = ref.net.F.dropout
+    ref.net.F.dropout = lambda x, p=0.5, **kw: x  # identity on both sides
+    try:
+        for mode in ("train", "eval"):
+            net.load_state_dict(sd, strict=True)
+            net.train(mode == "train")
+            torch.manual_seed(seed)
+            s1 = torch.randint(0, N, (B,), dtype=torch.long)
+            s2 = torch.randint(0, 512, (B,), dtype=torch.long)
+            torch.manual_seed(seed)
+            with torch.no_grad():
+                X, W = net(data["pcs"])
+            out[f"{mode}_X"] = np32(X)
+            out[f"{mode}_W"] = np32(W)
+            out[f"{mode}_s1"] = np32(s1)
+            out[f"{mode}_s2"] = np32(s2)
+            if mode == "train":
+                new = net.state_dict()
+                for k in ("sa1.mlp_bns.0.running_mean", "sa1.mlp_bns.0.running_var",
+                          "sa3.mlp_bns.2.running_var", "fp1.mlp_bns.2.running_mean", "bn1.running_var",
+                          "bn1.num_batches_tracked"):
+                    out["stat_" + k] = np32(new[k])
+    finally:
+        ref.net.F.dropout = real_dropout
+    out["meta"] = np.array([B, N, K, seed], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name)
+
+
+def _inline_bb_loss_source():
+    """Source lines of the inline bb loss, dedented, from the reference training script."""
+    path = os.path.join(ref_shim.REF_ROOT, "train_Point2Cyl_without_sketch.py")
+    with open(path) as f:
+        lines = f.readlines()
+    block = lines[285:307]  # 1-based 286..307: from 'cur_batch_size' to the double mean
+    src = textwrap.dedent("".join(l.replace("\t", "    ") for l in block))
+    assert "W_sorted, label = torch.sort" in src and "cross_entropy" in src, src
+    return src
+
+
+def loss_case(ref, name, B, N, K, seed, norm_eig):
+    data = synthetic.s_cyl(B, N, K, seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    X_raw = data["normals"] + 0.3 * torch.randn(B, N, 3, generator=g)
+    # logits correlated with the gt labels so that matching is non-trivial but well separated
+    W_raw = torch.randn(B, N, 2 * K, generator=g)
+    perm = torch.stack([torch.randperm(K, generator=g) for _ in range(B)])
+    col = torch.gather(perm, 1, data["inst"]) * 2 + data["bb"]
+    W_raw.scatter_add_(2, col[:, :, None], torch.full((B, N, 1), 2.5))
+    pcs, gt_normals = data["pcs"], data["normals"]
+    gt_extrusion_instances, gt_bb_labels = data["inst"], data["bb"]
+
+    X = F.normalize(X_raw, p=2, dim=2, eps=1e-12)
+    W_2K = torch.softmax(W_raw, dim=2)
+    W_barrel, W_barrel_bb = W_2K[:, :, ::2], W_raw[:, :, ::2]
+    W_base, W_base_bb = W_2K[:, :, 1::2], W_raw[:, :, 1::2]
+    W = W_barrel + W_base
+    total, l_n, l_seg, matching_indices, mask = ref.losses.compute_all_losses(
+        pcs, W, gt_extrusion_instances, X, gt_normals, 1.0, 1.0, return_match_indices=True)
+    ns = dict(torch=torch, F=F, W=W, matching_indices=matching_indices, mask=mask, K=K, NUM_POINT=N,
+              batch_size=B, sampled_pcs=pcs, W_barrel_bb=W_barrel_bb, W_base_bb=W_base_bb,
+              gt_bb_labels=gt_bb_labels)
+    exec(_inline_bb_loss_source(), ns)
+    l_bb = ns["total_bb_loss"]
+    mask_gt = ref.losses.get_mask_gt(gt_extrusion_instances, K)
+    gi = matching_indices.unsqueeze(1).expand(B, N, K)
+    E_AX = ref.data_utils.estimate_extrusion_axis(
+        X, torch.gather(W_barrel, 2, gi), torch.gather(W_base, 2, gi), gt_bb_labels,
+        gt_extrusion_instances, normalize=norm_eig)
+    ext = ref.losses.compute_normal_loss(E_AX, data["axes"], angle_diff=False, collapse=False)
+    l_ax = torch.mean(ref.losses.reduce_mean_masked_instance(ext, mask_gt))
+    centers = ref.data_utils.estimate_extrusion_centers(torch.gather(W, 2, gi), pcs)
+    cd = torch.square(centers - data["centers"]).sum(dim=-1)
+    l_c = torch.mean(ref.losses.reduce_mean_masked_instance(cd, mask_gt))
+    hard = ref.losses.hard_W_encoding(W, to_null_mask=True)
+    np.savez_compressed(
+        os.path.join(HERE, name),
+        X_raw=np32(X_raw), W_raw=np32(W_raw), total=np32(total), normal=np32(l_n), miou=np32(l_seg),
+        bb=np32(l_bb), axis=np32(l_ax), center=np32(l_c), matching_indices=np32(matching_indices),
+        mask=np32(ns["mask"] > 0), E_AX=np32(E_AX), centers=np32(centers),
+        hard_argmax=np32(hard.argmax(-1)).astype(np.int8), hard_rowsum=np32(hard.sum(-1)).astype(np.int8),
+        seg_iou=np32(ref.losses.compute_segmentation_iou(W, gt_extrusion_instances, matching_indices,
+                                                         (ns["mask"] > 0).float())),
+        normal_diff=np32(ref.losses.compute_normal_difference(X, gt_normals)),
+        meta=np.array([B, N, K, seed, int(norm_eig)], dtype=np.int64))
+    print("wrote", name)
+
+
+def main():
+    assert ref_shim.available(), "reference tree not present"
+    torch.set_num_threads(8)
+    ref = ref_shim.load()
+    cyl = synthetic.s_cyl(2, 1024, 4, seed=0)["pcs"]
+    pointops_case(ref, "pointops_cyl_n1024.npz", cyl, npoint=128, radius=0.2, nsample=32, seed=0)
+    uni = synthetic.s_uniform(2, 2048, seed=1)
+    pointops_case(ref, "pointops_uniform_n2048.npz", uni, npoint=256, radius=0.2, nsample=64, seed=1)
+    backbone_case(ref, "backbone_b2_n1024_k4.npz", 2, 1024, 4, seed=0)
+    backbone_case(ref, "backbone_b1_n1024_k4.npz", 1, 1024, 4, seed=3)   # BASELINE.json config 1
+    loss_case(ref, "loss_b2_n1024_k4.npz", 2, 1024, 4, seed=0, norm_eig=False)
+    loss_case(ref, "loss_b3_n2048_k8_normeig.npz", 3, 2048, 8, seed=5, norm_eig=True)
+
+
+if __name__ == "__main__":
+    main()

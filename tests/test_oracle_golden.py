@@ -1,0 +1,135 @@
+"""Pins the oracle restatement (oracle/p2c_oracle.py) to the golden vectors produced by the upstream
+reference (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import p2c_oracle as orc
+from point2cyl_b200 import synthetic
+
+FLOAT_TOL = 1e-6
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64)
+    b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+POINTOPS = [("pointops_cyl_n1024.npz", "cyl"), ("pointops_uniform_n2048.npz", "uniform")]
+
+
+def pointops_inputs(g, kind):
+    B, N, npoint, nsample, seed = (int(v) for v in g["meta"])
+    xyz = synthetic.s_cyl(B, N, 4, seed)["pcs"] if kind == "cyl" else synthetic.s_uniform(B, N, seed)
+    return xyz, npoint, float(g["radius"]), nsample, seed
+
+
+@pytest.mark.parametrize("name,kind", POINTOPS)
+def test_fps_and_ball_query_bit_exact(golden_dir, name, kind):
+    g = load(golden_dir, name)
+    xyz, npoint, radius, nsample, seed = pointops_inputs(g, kind)
+    start = torch.from_numpy(g["start"])
+    fps = orc.farthest_point_sample(xyz, npoint, start)
+    assert np.array_equal(fps.numpy(), g["fps_idx"].astype(np.int64))
+    new_xyz = orc.gather_points(xyz, fps)
+    grp = orc.query_ball_point(radius, nsample, xyz, new_xyz)
+    assert np.array_equal(grp.numpy(), g["group_idx"].astype(np.int64))
+    d = orc.square_distance(new_xyz, xyz)
+    assert np.array_equal(d[:, 0, :].numpy(), g["sqdist_row0"])
+
+
+@pytest.mark.parametrize("name,kind", POINTOPS)
+def test_fma_recipe_matches_matmul(golden_dir, name, kind):
+    """The dot-product recipe the CUDA kernels implement == what torch.matmul produced in the goldens."""
+    g = load(golden_dir, name)
+    xyz, npoint, radius, nsample, seed = pointops_inputs(g, kind)
+    fps = torch.from_numpy(g["fps_idx"].astype(np.int64))
+    new_xyz = orc.gather_points(xyz, fps)
+    d = orc.square_distance_fma_emulated(new_xyz[:, :1], xyz)
+    assert np.array_equal(d[:, 0, :].numpy(), g["sqdist_row0"])
+
+
+@pytest.mark.parametrize("name,kind", POINTOPS)
+def test_three_nn_interp(golden_dir, name, kind):
+    g = load(golden_dir, name)
+    xyz, npoint, radius, nsample, seed = pointops_inputs(g, kind)
+    B = xyz.shape[0]
+    fps = torch.from_numpy(g["fps_idx"].astype(np.int64))
+    new_xyz = orc.gather_points(xyz, fps)
+    feats2 = torch.randn(B, npoint, 16, generator=torch.Generator().manual_seed(seed + 1))
+    interp, idx, w = orc.three_nn_interpolate(xyz, new_xyz, feats2)
+    assert np.array_equal(idx.numpy(), g["nn_idx"].astype(np.int64))
+    assert np.array_equal(w.numpy(), g["nn_w"])
+    assert rel_err(interp, g["interp"]) <= FLOAT_TOL
+
+
+@pytest.mark.parametrize("name", ["backbone_b2_n1024_k4.npz", "backbone_b1_n1024_k4.npz"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_backbone(golden_dir, name, mode):
+    g = load(golden_dir, name)
+    B, N, K, seed = (int(v) for v in g["meta"])
+    data = synthetic.s_cyl(B, N, K, seed)
+    sd = orc.init_state_dict(output_sizes=(3, 2 * K), seed=seed)
+    starts = (torch.from_numpy(g[f"{mode}_s1"]), torch.from_numpy(g[f"{mode}_s2"]))
+    new_stats = {}
+    with torch.no_grad():
+        X, W = orc.backbone_forward(sd, data["pcs"], training=(mode == "train"), fps_start=starts,
+                                    new_stats=new_stats)
+    assert rel_err(X, g[f"{mode}_X"]) <= FLOAT_TOL
+    assert rel_err(W, g[f"{mode}_W"]) <= FLOAT_TOL
+    if mode == "train":
+        for k in g.files:
+            if k.startswith("stat_") and "num_batches" not in k:
+                assert rel_err(new_stats[k[5:]], g[k]) <= FLOAT_TOL, k
+
+
+LOSS = ["loss_b2_n1024_k4.npz", "loss_b3_n2048_k8_normeig.npz"]
+
+
+def loss_inputs(g):
+    B, N, K, seed, norm_eig = (int(v) for v in g["meta"])
+    data = synthetic.s_cyl(B, N, K, seed)
+    return data, torch.from_numpy(g["X_raw"]), torch.from_numpy(g["W_raw"]), bool(norm_eig)
+
+
+@pytest.mark.parametrize("name", LOSS)
+@pytest.mark.parametrize("dense", [True, False])
+def test_loss_block(golden_dir, name, dense):
+    g = load(golden_dir, name)
+    data, X_raw, W_raw, norm_eig = loss_inputs(g)
+    if dense and X_raw.shape[1] > 1024:
+        pytest.skip("dense (B,N,N) route only on the small case")
+    out = orc.loss_block(data["pcs"], X_raw, W_raw, data["normals"], data["inst"], data["bb"],
+                         data["axes"], data["centers"], norm_eig=norm_eig, dense_axis=dense)
+    assert np.array_equal(out["matching_indices"].numpy(), g["matching_indices"])
+    assert np.array_equal(out["mask"].numpy(), g["mask"])
+    for k in ("normal", "miou", "bb", "center"):
+        assert rel_err(out[k], g[k]) <= 2e-6, k
+    # axes: sign-free comparison; the fp32 dense route and the f64 scatter route agree to ~1e-5
+    dots = (out["E_AX"] * torch.from_numpy(g["E_AX"])).sum(-1).abs()
+    m = torch.from_numpy(g["mask"])
+    assert float((1 - dots[m]).max()) <= 1e-5
+    assert rel_err(out["axis"], g["axis"]) <= 1e-4
+    assert rel_err(out["centers"], g["centers"]) <= 2e-6
+
+
+@pytest.mark.parametrize("name", LOSS)
+def test_eval_helpers(golden_dir, name):
+    g = load(golden_dir, name)
+    data, X_raw, W_raw, _ = loss_inputs(g)
+    X, Wb, Wc, W = orc.postnet_split(X_raw, W_raw)
+    hard = orc.hard_W_encoding(W, to_null_mask=True)
+    assert np.array_equal(hard.argmax(-1).numpy().astype(np.int8), g["hard_argmax"])
+    assert np.array_equal(hard.sum(-1).numpy().astype(np.int8), g["hard_rowsum"])
+    match = torch.from_numpy(g["matching_indices"])
+    iou = orc.compute_segmentation_iou(W, data["inst"], match, torch.from_numpy(g["mask"]).float())
+    assert rel_err(iou, g["seg_iou"]) <= 2e-6
+    nd = orc.compute_normal_difference(X, data["normals"])
+    assert rel_err(nd, g["normal_diff"]) <= 2e-6
