@@ -1,0 +1,155 @@
+/*
+ * point2cyl.h — C-ABI of libp2c.so: the sm_100a kernels behind Point2Cyl's forward+loss hot path.
+ *
+ * The reference (mikacuy/point2cyl) has no FFI of its own: its plug point is Python module names
+ * (SURVEY.md section 8b).  This library is what the Python drop-in modules under
+ * point2cyl_b200/dropin/ bind with ctypes; each entry point names the reference code it replaces
+ * (paths relative to the upstream repo root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host;
+ *   - no allocation, no ownership transfer: outputs and scratch are allocated by the caller;
+ *   - no exceptions cross the boundary: 0 = ok, >0 = cudaError_t, <0 = argument check (P2C_E*);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - no global state besides one-time cudaFuncSetAttribute per device; re-entrant per device, so
+ *     one process per GPU is safe;
+ *   - clouds are point-major float32: xyz (B,N,3), features (rows, C) with an explicit row stride
+ *     `ld` in elements; indices are int64 like the reference's torch.long.
+ */
+#ifndef POINT2CYL_H
+#define POINT2CYL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2C_EINVAL (-1)      /* bad size / null pointer */
+#define P2C_EUNSUPPORTED (-2) /* shape outside what this build's kernels cover */
+#define P2C_EALIGN (-3)      /* pointer / stride alignment */
+
+/* build checks */
+int p2c_version(void);           /* 100 * major + minor */
+const char* p2c_arch(void);      /* "sm_100a" */
+
+/* Farthest point sampling — replaces farthest_point_sample, models/pointnet_util.py:63-84, fused
+ * with the gather of the sampled centres (index_points, :43-60, as used at :124).
+ * start[b] is the first centroid (the reference draws it on the CPU generator, :75).
+ * Bit-exact contract: dist = (dx*dx + dy*dy) + dz*dz with every op rounded (no FMA contraction),
+ * running distance init 1e10, strict '<' update, first arg-max. */
+int p2c_fps(const float* xyz, const int64_t* start, int B, int N, int npoint,
+            int64_t* out_idx /* (B,npoint) */, float* out_xyz /* (B,npoint,3) */, void* stream);
+
+/* Ball query — replaces query_ball_point, models/pointnet_util.py:87-107 (and the (B,S,N)
+ * square_distance :19-40 it thresholds).  First nsample indices, ascending, with
+ * !(d > r2), d = ((-2*dot) + |q|^2) + |p|^2, dot = fma(q2,p2, fma(q1,p1, q0*p0)); padded with the
+ * first hit; a query with no hit yields N everywhere (the reference's own out-of-range value).
+ * r2 = (float)(radius*radius) computed by the caller in double then rounded (:102). */
+int p2c_ball_query(const float* xyz /* (B,N,3) */, const float* new_xyz /* (B,S,3) */, int B, int N,
+                   int S, float r2, int nsample, int64_t* out_idx /* (B,S,nsample) */, void* stream);
+
+/* Grouping gather — replaces index_points + centring + concat in sample_and_group,
+ * models/pointnet_util.py:130-139, and sample_and_group_all :146-163 (idx == NULL: every point in
+ * order, one group per cloud, centre 0).  out row r = (b,s,j): [xyz[b,idx]-new_xyz[b,s] (3),
+ * feats[b,idx] (D)], zero padded to ldo.  feats may be NULL (D = 0). */
+int p2c_group(const float* xyz, const float* feats, int64_t ldf, const float* new_xyz,
+              const int64_t* idx, int B, int N, int S, int nsample, int D, float* out, int64_t ldo,
+              void* stream);
+
+/* One 1x1-conv layer of a per-point MLP — replaces Conv2d/Conv1d (kernel 1) at
+ * models/pointnet_util.py:200-203, :317-319 and models/pointnet_extrusion.py:58-65, with the
+ * previous layer's BatchNorm+ReLU (and the head's dropout mask) folded into the operand load and
+ * this layer's BatchNorm statistics and the nsample max-pool (:205) folded into the epilogue.
+ *   A[m,k] = X[m,k]                                   (in_scale == NULL)
+ *          = max(X[m,k]*in_scale[k]+in_shift[k], 0)   (otherwise)      [* in_mask[m,k] if given]
+ *   Y[m,n] = sum_k A[m,k] * W[n,k] + bias[n]
+ *   stats[n] += sum_m Y[m,n];  stats[N+n] += sum_m Y[m,n]^2          (stats != NULL, float64)
+ *   pool_group G > 0: Ymax/Ymin[m/G, n] = max/min over the G consecutive rows of a group.
+ * Y may be NULL when only the pooled output is wanted.  precision: P2C_PREC_*. */
+#define P2C_PREC_FP32 0      /* SIMT fp32 FMA */
+#define P2C_PREC_3XTF32 1    /* tcgen05 kind::tf32, error-compensated split (fp32-faithful) */
+#define P2C_PREC_BF16 2      /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate */
+int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
+               const float* in_scale, const float* in_shift, const float* in_mask, int64_t ldmask,
+               float* Y, int64_t ldy, int M, int N, int K, double* stats, int pool_group,
+               float* Ymax, float* Ymin, int precision, void* stream);
+
+/* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
+ * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
+ * training != 0: mean/var from stats (count rows), running stats updated in place with `momentum`;
+ * training == 0: running stats.  Writes scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
+int p2c_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta,
+                    float eps, float momentum, int training, float* running_mean,
+                    float* running_var, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, int C, void* stream);
+
+/* out[m,c] = max(Y[m,c]*scale[c]+shift[c], 0) — the BN+ReLU application where a layer's output
+ * has to exist in memory (module outputs). */
+int p2c_bn_relu_apply(const float* Y, int64_t ldy, const float* scale, const float* shift,
+                      float* out, int64_t ldo, int64_t M, int C, void* stream);
+
+/* Pooled BN+ReLU: out[g,c] = max(v*scale[c]+shift[c], 0) with v = scale[c] >= 0 ? Ymax : Ymin —
+ * equals max over the group of relu(bn(y)) (models/pointnet_util.py:203-205) by monotonicity.
+ * Also emits nothing else; arg-max routing for backward is recomputed there. */
+int p2c_pool_bn_relu(const float* Ymax, const float* Ymin, const float* scale, const float* shift,
+                     float* out, int64_t ldo, int64_t G, int C, void* stream);
+
+/* 3-NN inverse-distance interpolation — replaces PointNetFeaturePropagation's
+ * square_distance + sort + gather + weighted sum, models/pointnet_util.py:301-308.
+ * Distances in the reference's expanded form (may be slightly negative), w = 1/(d+1e-8) normalised.
+ * out row (b,n) gets D floats at out + row*ldo.  idx_out (B,N,3) int64 / w_out (B,N,3) optional. */
+int p2c_three_nn_interp(const float* xyz1 /* (B,N,3) */, const float* xyz2 /* (B,S,3) */,
+                        const float* feats2 /* (B*S, D) */, int64_t ldf, int B, int N, int S, int D,
+                        float* out, int64_t ldo, int64_t* idx_out, float* w_out, void* stream);
+
+/* Loss pass 1 — one sweep over the points that produces every per-cloud sufficient statistic of
+ * train_Point2Cyl_without_sketch.py:246-353: unit normals (:247), softmax over 2K and the
+ * barrel/base split (:254-265), normal loss sum (losses.py:130), the Hungarian cost ingredients
+ * (losses.py:38-41), centre sums (data_utils.py:253-266) and the 3x3 scatter matrices of
+ * estimate_extrusion_axis (data_utils.py:155-163) for every predicted column.
+ * stats: (B, P2C_SEG_STRIDE(K)) float32, layout in point2cyl_b200/csrc/segfit.cu. */
+int p2c_segfit_stats_stride(int K);
+int p2c_segfit_stats(const float* X_raw, int64_t ldx, const float* W_raw, int64_t ldw,
+                     const float* pcs, const float* gt_normals, const int64_t* inst,
+                     const int64_t* bb, int B, int N, int K, float* partial /* scratch */,
+                     int64_t partial_elems /* >= B*ceil(N/1024)*stride */, float* stats, void* stream);
+
+/* Hungarian cost (losses.py:39-42): cost (B,K,K) = D / max(cnt_g + colsum_k - D, 1e-10), n_gt (B). */
+int p2c_segfit_cost(const float* stats, int B, int K, float* cost, int32_t* n_gt, void* stream);
+
+/* Loss pass 2 — the base/barrel loss of train_Point2Cyl_without_sketch.py:283-313 given the match,
+ * summed per cloud (the sort at :292 cancels out of the sum). bb_sum: (B). */
+int p2c_bb_loss(const float* W_raw, int64_t ldw, const int64_t* bb, const int64_t* match,
+                const int32_t* n_gt, int B, int N, int K, float* partial /* scratch */,
+                int64_t partial_elems /* >= B*ceil(N/1024) */, float* bb_sum, void* stream);
+
+/* Loss finalisation — per (cloud, gt slot): relaxed IoU (losses.py:95-101), centre
+ * (data_utils.py:253-266), axis = eigenvector of the smallest eigenvalue of the matched 3x3
+ * scatter (data_utils.py:162-172; cyclic Jacobi, one warp per segment), then the masked means of
+ * losses.py:83-88 / train_...:330-352.  out_losses: 6 floats {total, normal, miou, bb, axis, center}. */
+int p2c_loss_finalize(const float* stats, const float* bb_sum, const int64_t* match,
+                      const int32_t* n_gt, const float* gt_axes, const float* gt_centers, int B,
+                      int N, int K, int norm_eig, const float* weights /* host, 5 */,
+                      float* E_AX /* (B,K,3) */, float* centers /* (B,K,3) */,
+                      float* per_seg /* (B,K,3) {1-iou, axis, centre} */,
+                      float* per_cloud /* (B,5) {miou, normal, bb, axis, centre} */,
+                      float* out_losses /* (6) */, void* stream);
+
+/* Smallest-eigenvalue eigenvector of n symmetric 3x3 matrices (row-major 9 floats each) —
+ * replaces torch.symeig(...)[1][:, :, 0], data_utils.py:170-171. */
+int p2c_eig3x3_smallest(const float* M, int n, float* vec /* (n,3) */, float* eval /* (n,3) */,
+                        void* stream);
+
+/* Function-level helpers of the reference's module API, kept for completeness:
+ * square_distance (models/pointnet_util.py:19-40; same rounding as the ball query) and
+ * index_points (:43-60; out[b,m,:] = points[b, idx[b,m], :], points rows have stride ldp). */
+int p2c_square_distance(const float* src /* (B,S,3) */, const float* dst /* (B,N,3) */, int B, int S,
+                        int N, float* out /* (B,S,N) */, void* stream);
+int p2c_gather_rows(const float* points, int64_t ldp, const int64_t* idx /* (B,Mper) */, int B, int N,
+                    int Mper, int C, float* out /* (B,Mper,C) */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINT2CYL_H */

@@ -1,0 +1,138 @@
+// Farthest point sampling, one CTA per cloud (replaces models/pointnet_util.py:63-84).
+//
+// The npoint rounds are strictly sequential (each arg-max feeds the next centroid), so the kernel
+// is latency bound, not bandwidth bound: the cloud is read from HBM exactly once (12*N bytes),
+// lives in shared memory as SoA, and each thread keeps its PPT points plus their running distance
+// in registers.  One round = PPT distance updates per thread, a two-instruction warp arg-max
+// (redux.sync max on the float bits, redux.sync min on the candidate indices), one __syncthreads
+// and a second redux pair over the per-warp winners (double-buffered slots, so one barrier per
+// round is enough).  Tie-break and rounding follow the reference bit for bit:
+//   dist = (dx*dx + dy*dy) + dz*dz, every op rounded (intrinsics: never contracted to FMA);
+//   running = dist < running ? dist : running (init 1e10); farthest = FIRST index of the max.
+#include "common.cuh"
+
+namespace {
+
+template <int PPT, bool XYZ_IN_REGS>
+__global__ void __launch_bounds__(1024, 1)
+fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int N, int npoint,
+           int64_t* __restrict__ out_idx, float* __restrict__ out_xyz) {
+  extern __shared__ float s_xyz[];  // xs[N] ys[N] zs[N]
+  __shared__ unsigned s_val[2][32];
+  __shared__ unsigned s_idx[2][32];
+  const int T = blockDim.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nwarps = T >> 5;
+  const int b = blockIdx.x;
+  float* xs = s_xyz;
+  float* ys = s_xyz + N;
+  float* zs = s_xyz + 2 * N;
+
+  const float* p = xyz + (size_t)b * N * 3;
+  for (int i = tid; i < 3 * N; i += T) {
+    float v = __ldg(p + i);
+    int pt = i / 3;
+    int c = i - pt * 3;
+    s_xyz[c * N + pt] = v;
+  }
+  __syncthreads();
+
+  float px[XYZ_IN_REGS ? PPT : 1], py[XYZ_IN_REGS ? PPT : 1], pz[XYZ_IN_REGS ? PPT : 1];
+  float run[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    int i = j * T + tid;
+    bool ok = i < N;
+    // padded slots hold running distance 0: they can only tie, and ties go to the lowest index
+    run[j] = ok ? 1e10f : 0.0f;
+    if (XYZ_IN_REGS) {
+      px[j] = ok ? xs[i] : 0.0f;
+      py[j] = ok ? ys[i] : 0.0f;
+      pz[j] = ok ? zs[i] : 0.0f;
+    }
+  }
+
+  int far = (int)start[b];
+  int buf = 0;
+  int64_t* oidx = out_idx + (size_t)b * npoint;
+  float* oxyz = out_xyz + (size_t)b * npoint * 3;
+
+  for (int it = 0; it < npoint; ++it) {
+    const float cx = xs[far], cy = ys[far], cz = zs[far];
+    if (tid == 0) {
+      oidx[it] = far;
+      oxyz[it * 3 + 0] = cx;
+      oxyz[it * 3 + 1] = cy;
+      oxyz[it * 3 + 2] = cz;
+    }
+    float best = 0.0f;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      float x, y, z;
+      if (XYZ_IN_REGS) {
+        x = px[j]; y = py[j]; z = pz[j];
+      } else {
+        int i = j * T + tid;
+        i = i < N ? i : N - 1;
+        x = xs[i]; y = ys[i]; z = zs[i];
+      }
+      float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy), dz = __fsub_rn(z, cz);
+      float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (!XYZ_IN_REGS) d = (j * T + tid < N) ? d : 0.0f;
+      run[j] = fminf(run[j], d);
+      best = fmaxf(best, run[j]);
+    }
+    // distances are >= +0, so their bit patterns order like unsigned integers
+    const unsigned vb = __float_as_uint(best);
+    const unsigned wmax = __reduce_max_sync(P2C_FULL_MASK, vb);
+    unsigned mine = 0xffffffffu;
+    if (vb == wmax) {
+#pragma unroll
+      for (int j = PPT - 1; j >= 0; --j)
+        if (__float_as_uint(run[j]) == wmax) mine = (unsigned)(j * T + tid);
+    }
+    const unsigned widx = __reduce_min_sync(P2C_FULL_MASK, mine);
+    if (lane == 0) {
+      s_val[buf][warp] = wmax;
+      s_idx[buf][warp] = widx;
+    }
+    __syncthreads();
+    const unsigned v = lane < nwarps ? s_val[buf][lane] : 0u;
+    const unsigned ix = lane < nwarps ? s_idx[buf][lane] : 0xffffffffu;
+    const unsigned gmax = __reduce_max_sync(P2C_FULL_MASK, v);
+    far = (int)__reduce_min_sync(P2C_FULL_MASK, v == gmax ? ix : 0xffffffffu);
+    buf ^= 1;
+  }
+}
+
+template <int PPT, bool R>
+int launch_fps(const float* xyz, const int64_t* start, int B, int N, int npoint, int64_t* out_idx,
+               float* out_xyz, int T, cudaStream_t st) {
+  size_t smem = (size_t)N * 3 * sizeof(float);
+  auto k = fps_kernel<PPT, R>;
+  if (smem > 48 * 1024) P2C_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<B, T, smem, st>>>(xyz, start, N, npoint, out_idx, out_xyz);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int p2c_fps(const float* xyz, const int64_t* start, int B, int N, int npoint,
+                       int64_t* out_idx, float* out_xyz, void* stream) {
+  if (!xyz || !start || !out_idx || !out_xyz || B <= 0 || N <= 0 || npoint <= 0) return P2C_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto round32 = [](int v) { return (v + 31) / 32 * 32; };
+  if (N <= 1024) {
+    int T = round32((N + 3) / 4);
+    return launch_fps<4, true>(xyz, start, B, N, npoint, out_idx, out_xyz, T, st);
+  }
+  if (N <= 8192) {
+    int T = round32((N + 7) / 8);
+    return launch_fps<8, true>(xyz, start, B, N, npoint, out_idx, out_xyz, T, st);
+  }
+  if (N <= 16384) return launch_fps<16, false>(xyz, start, B, N, npoint, out_idx, out_xyz, 1024, st);
+  return P2C_EUNSUPPORTED;  // larger clouds need the cluster variant
+}

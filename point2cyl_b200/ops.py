@@ -1,0 +1,284 @@
+"""Thin tensor-level wrappers over the C-ABI (one function per kernel entry point).
+
+Layout: clouds (B,N,3) float32 contiguous; feature matrices are 2-D (rows, C) float32 with
+stride(1) == 1 and an arbitrary row stride (so a column slice of a concat buffer is a valid
+operand); indices int64.  Everything runs on torch's current CUDA stream.  No autograd here —
+point2cyl_b200.autograd wraps these for training.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, need_cuda, ptr, stream_ptr
+
+Tensor = torch.Tensor
+
+
+def _rows(t: Tensor) -> Tensor:
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float32:
+        raise _lib.P2CError(f"expected a 2-D float32 matrix with unit column stride, got "
+                            f"{tuple(t.shape)} strides {t.stride()} {t.dtype}")
+    return t
+
+
+def _cloud(t: Tensor) -> Tensor:
+    if t.dim() != 3 or t.shape[2] != 3:
+        raise _lib.P2CError(f"expected (B,N,3), got {tuple(t.shape)}")
+    return t.contiguous().float()
+
+
+def fps(xyz: Tensor, npoint: int, start: Tensor) -> Tuple[Tensor, Tensor]:
+    """(idx (B,npoint) int64, new_xyz (B,npoint,3)).  start: (B,) int64 first centroid per cloud."""
+    need_cuda(xyz)
+    xyz = _cloud(xyz)
+    B, N, _ = xyz.shape
+    start = start.to(device=xyz.device, dtype=torch.long).contiguous()
+    idx = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
+    new_xyz = torch.empty(B, npoint, 3, dtype=torch.float32, device=xyz.device)
+    call("p2c_fps", ptr(xyz), ptr(start), B, N, npoint, ptr(idx), ptr(new_xyz), stream_ptr())
+    return idx, new_xyz
+
+
+def radius_sq_f32(radius: float) -> float:
+    """float32(radius**2): the threshold the reference's `sqrdists > radius ** 2` compares against."""
+    return float(np.float32(float(radius) ** 2))
+
+
+def ball_query(radius: float, nsample: int, xyz: Tensor, new_xyz: Tensor) -> Tensor:
+    need_cuda(xyz, new_xyz)
+    xyz, new_xyz = _cloud(xyz), _cloud(new_xyz)
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
+    call("p2c_ball_query", ptr(xyz), ptr(new_xyz), B, N, S, radius_sq_f32(radius), nsample,
+                                     ptr(out), stream_ptr())
+    return out
+
+
+def pad4(c: int) -> int:
+    return (c + 3) // 4 * 4
+
+
+def group(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: Optional[Tensor],
+          ldo: Optional[int] = None) -> Tensor:
+    """Grouped rows (B*S*nsample, ldo): [xyz[idx]-centre, feats[idx]], zero padded.
+    feats: (B*N, D) rows.  idx None = group-all (one group per cloud, centre 0)."""
+    need_cuda(xyz, feats, new_xyz, idx)
+    xyz = _cloud(xyz)
+    B, N, _ = xyz.shape
+    D = 0 if feats is None else _rows(feats).shape[1]
+    if idx is None:
+        S, ns = 1, N
+    else:
+        idx = idx.contiguous()
+        S, ns = idx.shape[1], idx.shape[2]
+        new_xyz = _cloud(new_xyz)
+    ldo = ldo or pad4(3 + D)
+    out = torch.empty(B * S * ns, ldo, dtype=torch.float32, device=xyz.device)
+    call("p2c_group", ptr(xyz), ptr(feats), 0 if feats is None else feats.stride(0),
+                                ptr(new_xyz) if idx is not None else None, ptr(idx), B, N, S, ns, D,
+                                ptr(out), ldo, stream_ptr())
+    return out
+
+
+def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None,
+           in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
+           in_mask: Optional[Tensor] = None, stats: Optional[Tensor] = None, pool_group: int = 0,
+           out: Optional[Tensor] = None, want_y: bool = True, precision: int = _lib.PREC_FP32):
+    """One MLP layer.  X (M, >=K) rows, W (N, K) (any trailing singleton dims), returns Y (M,N) or,
+    with pool_group, (Y or None, Ymax, Ymin).  stats: float64 (2N,) accumulator (pre-zeroed)."""
+    need_cuda(X, W)
+    X = _rows(X)
+    W2 = W.reshape(W.shape[0], -1)
+    if not W2.is_contiguous():
+        W2 = W2.contiguous()
+    N = W2.shape[0]
+    K = K or W2.shape[1]
+    if W2.shape[1] != K or X.shape[1] < K:
+        raise _lib.P2CError(f"linear: K mismatch X{tuple(X.shape)} W{tuple(W2.shape)} K={K}")
+    M = X.shape[0]
+    Y = None
+    if want_y:
+        Y = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=X.device)
+        _rows(Y)
+    Ymax = Ymin = None
+    if pool_group:
+        Ymax = torch.empty(M // pool_group, N, dtype=torch.float32, device=X.device)
+        Ymin = torch.empty_like(Ymax)
+    if in_mask is not None:
+        _rows(in_mask)
+    call("p2c_linear", 
+        ptr(X), X.stride(0), ptr(W2), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(in_mask),
+        0 if in_mask is None else in_mask.stride(0), ptr(Y), 0 if Y is None else Y.stride(0), M, N, K,
+        ptr(stats), pool_group, ptr(Ymax), ptr(Ymin), precision, stream_ptr())
+    if pool_group:
+        return Y, Ymax, Ymin
+    return Y
+
+
+def bn_finalize(stats: Optional[Tensor], count: int, gamma: Tensor, beta: Tensor, eps: float,
+                momentum: float, training: bool, running_mean: Optional[Tensor],
+                running_var: Optional[Tensor], save: bool = False):
+    """(scale, shift[, mean, invstd]) and in-place running-stat update when training."""
+    C_ = gamma.shape[0]
+    dev = gamma.device
+    scale = torch.empty(C_, dtype=torch.float32, device=dev)
+    shift = torch.empty(C_, dtype=torch.float32, device=dev)
+    mean = torch.empty(C_, dtype=torch.float32, device=dev) if save else None
+    invstd = torch.empty(C_, dtype=torch.float32, device=dev) if save else None
+    call("p2c_bn_finalize", ptr(stats), count, ptr(gamma), ptr(beta), eps, momentum,
+                                      1 if training else 0, ptr(running_mean), ptr(running_var),
+                                      ptr(scale), ptr(shift), ptr(mean), ptr(invstd), C_, stream_ptr())
+    if save:
+        return scale, shift, mean, invstd
+    return scale, shift
+
+
+def bn_relu_apply(Y: Tensor, scale: Tensor, shift: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    Y = _rows(Y)
+    M, C_ = Y.shape
+    if out is None:
+        out = torch.empty(M, C_, dtype=torch.float32, device=Y.device)
+    _rows(out)
+    call("p2c_bn_relu_apply", ptr(Y), Y.stride(0), ptr(scale), ptr(shift), ptr(out),
+                                        out.stride(0), M, C_, stream_ptr())
+    return out
+
+
+def pool_bn_relu(Ymax: Tensor, Ymin: Tensor, scale: Tensor, shift: Tensor,
+                 out: Optional[Tensor] = None) -> Tensor:
+    G, C_ = Ymax.shape
+    if out is None:
+        out = torch.empty(G, C_, dtype=torch.float32, device=Ymax.device)
+    _rows(out)
+    call("p2c_pool_bn_relu", ptr(Ymax), ptr(Ymin), ptr(scale), ptr(shift), ptr(out),
+                                       out.stride(0), G, C_, stream_ptr())
+    return out
+
+
+def three_nn_interp(xyz1: Tensor, xyz2: Tensor, feats2: Tensor, out: Optional[Tensor] = None,
+                    want_idx: bool = False):
+    """feats2 (B*S, D) rows -> out (B*N, D) rows (may be a column slice of a wider buffer)."""
+    need_cuda(xyz1, xyz2, feats2)
+    xyz1, xyz2 = _cloud(xyz1), _cloud(xyz2)
+    feats2 = _rows(feats2)
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    D = feats2.shape[1]
+    if out is None:
+        out = torch.empty(B * N, D, dtype=torch.float32, device=xyz1.device)
+    _rows(out)
+    idx = w = None
+    if want_idx and S > 1:
+        idx = torch.empty(B, N, 3, dtype=torch.long, device=xyz1.device)
+        w = torch.empty(B, N, 3, dtype=torch.float32, device=xyz1.device)
+    call("p2c_three_nn_interp", ptr(xyz1), ptr(xyz2), ptr(feats2), feats2.stride(0), B, N, S, D,
+                                          ptr(out), out.stride(0), ptr(idx), ptr(w), stream_ptr())
+    if want_idx:
+        return out, idx, w
+    return out
+
+
+def segfit_stride(K: int) -> int:
+    return _lib.load().p2c_segfit_stats_stride(K)
+
+
+def segfit_stats(X_raw: Tensor, W_raw: Tensor, pcs: Tensor, gt_normals: Tensor, inst: Tensor,
+                 bb: Tensor, K: int) -> Tensor:
+    """Per-cloud sufficient statistics (B, stride(K)).  X_raw (B,N,>=3 strided rows), W_raw (B,N,2K)."""
+    B, N = inst.shape
+    Xr = _rows(X_raw.reshape(B * N, -1) if X_raw.dim() == 3 and X_raw.is_contiguous() else _as_rows(X_raw))
+    Wr = _rows(W_raw.reshape(B * N, -1) if W_raw.dim() == 3 and W_raw.is_contiguous() else _as_rows(W_raw))
+    pcs, gt_normals = _cloud(pcs), _cloud(gt_normals)
+    inst, bb = inst.contiguous(), bb.contiguous()
+    stride = segfit_stride(K)
+    nchunks = (N + 1023) // 1024
+    partial = torch.empty(B * nchunks * stride, dtype=torch.float32, device=pcs.device)
+    stats = torch.empty(B, stride, dtype=torch.float32, device=pcs.device)
+    call("p2c_segfit_stats", ptr(Xr), Xr.stride(0), ptr(Wr), Wr.stride(0), ptr(pcs),
+                                       ptr(gt_normals), ptr(inst), ptr(bb), B, N, K, ptr(partial),
+                                       partial.numel(), ptr(stats), stream_ptr())
+    return stats
+
+
+def _as_rows(t: Tensor) -> Tensor:
+    """(B,N,C) tensor whose (B,N) dims collapse to one row dim with unit column stride, else copy."""
+    B, N, C_ = t.shape
+    if t.stride(2) == 1 and t.stride(0) == N * t.stride(1):
+        return t.as_strided((B * N, C_), (t.stride(1), 1), t.storage_offset())
+    return t.contiguous().reshape(B * N, C_)
+
+
+def segfit_cost(stats: Tensor, K: int) -> Tuple[Tensor, Tensor]:
+    B = stats.shape[0]
+    cost = torch.empty(B, K, K, dtype=torch.float32, device=stats.device)
+    n_gt = torch.empty(B, dtype=torch.int32, device=stats.device)
+    call("p2c_segfit_cost", ptr(stats), B, K, ptr(cost), ptr(n_gt), stream_ptr())
+    return cost, n_gt
+
+
+def bb_loss_sums(W_raw: Tensor, bb: Tensor, match: Tensor, n_gt: Tensor, K: int) -> Tensor:
+    B, N = bb.shape
+    Wr = _rows(_as_rows(W_raw))
+    nchunks = (N + 1023) // 1024
+    partial = torch.empty(B * nchunks, dtype=torch.float32, device=bb.device)
+    out = torch.empty(B, dtype=torch.float32, device=bb.device)
+    call("p2c_bb_loss", ptr(Wr), Wr.stride(0), ptr(bb.contiguous()), ptr(match.contiguous()),
+                                  ptr(n_gt), B, N, K, ptr(partial), partial.numel(), ptr(out), stream_ptr())
+    return out
+
+
+def loss_finalize(stats: Tensor, bb_sum: Optional[Tensor], match: Tensor, n_gt: Tensor, gt_axes: Tensor,
+                  gt_centers: Tensor, N: int, K: int, norm_eig: bool, weights):
+    B = stats.shape[0]
+    dev = stats.device
+    E_AX = torch.empty(B, K, 3, dtype=torch.float32, device=dev)
+    centers = torch.empty(B, K, 3, dtype=torch.float32, device=dev)
+    per_seg = torch.empty(B, K, 3, dtype=torch.float32, device=dev)
+    per_cloud = torch.empty(B, 5, dtype=torch.float32, device=dev)
+    losses = torch.empty(6, dtype=torch.float32, device=dev)
+    w = (C.c_float * 5)(*[float(v) for v in weights])
+    call("p2c_loss_finalize", ptr(stats), ptr(bb_sum), ptr(match.contiguous()), ptr(n_gt),
+                                        ptr(gt_axes.contiguous().float()), ptr(gt_centers.contiguous().float()),
+                                        B, N, K, 1 if norm_eig else 0, w, ptr(E_AX), ptr(centers),
+                                        ptr(per_seg), ptr(per_cloud), ptr(losses), stream_ptr())
+    return losses, E_AX, centers, per_seg, per_cloud
+
+
+def eig3x3_smallest(M: Tensor) -> Tuple[Tensor, Tensor]:
+    """M (..., 3, 3) symmetric (upper triangle read) -> (vec (...,3), eigenvalues ascending (...,3))."""
+    need_cuda(M)
+    flat = M.reshape(-1, 9).contiguous().float()
+    n = flat.shape[0]
+    vec = torch.empty(n, 3, dtype=torch.float32, device=M.device)
+    ev = torch.empty(n, 3, dtype=torch.float32, device=M.device)
+    call("p2c_eig3x3_smallest", ptr(flat), n, ptr(vec), ptr(ev), stream_ptr())
+    return vec.reshape(*M.shape[:-2], 3), ev.reshape(*M.shape[:-2], 3)
+
+
+def square_distance(src: Tensor, dst: Tensor) -> Tensor:
+    need_cuda(src, dst)
+    src, dst = _cloud(src), _cloud(dst)
+    B, S, _ = src.shape
+    N = dst.shape[1]
+    out = torch.empty(B, S, N, dtype=torch.float32, device=src.device)
+    call("p2c_square_distance", ptr(src), ptr(dst), B, S, N, ptr(out), stream_ptr())
+    return out
+
+
+def gather_rows(points: Tensor, idx: Tensor) -> Tensor:
+    """points (B,N,C), idx (B, ...) int64 -> (B, ..., C)."""
+    need_cuda(points, idx)
+    B, N, C_ = points.shape
+    pts = points if (points.stride(2) == 1 and points.stride(0) == N * points.stride(1)
+                     and points.dtype == torch.float32) else points.contiguous().float()
+    flat = idx.reshape(B, -1).contiguous()
+    Mper = flat.shape[1]
+    out = torch.empty(B, Mper, C_, dtype=torch.float32, device=points.device)
+    call("p2c_gather_rows", ptr(pts), pts.stride(1), ptr(flat), B, N, Mper, C_, ptr(out), stream_ptr())
+    return out.reshape(*idx.shape, C_)

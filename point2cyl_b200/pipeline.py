@@ -1,0 +1,226 @@
+"""Forward + loss of Point2Cyl as a sequence of libp2c kernels (point-major, no permutes).
+
+This is the engine behind the drop-in modules (point2cyl_b200/dropin/): `backbone_forward` is what
+`backbone.forward` runs (models/pointnet_extrusion.py:37-66 in the reference) and `loss_forward`
+is the loss half of a training step (train_Point2Cyl_without_sketch.py:246-353).  Activations are
+2-D row matrices (B*points, C); every BatchNorm+ReLU is folded into the next layer's operand load
+and every layer's statistics / max-pool into its epilogue (see include/point2cyl.h: p2c_linear).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from scipy.optimize import linear_sum_assignment
+
+from . import _lib, ops
+
+Tensor = torch.Tensor
+
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "3xtf32": _lib.PREC_3XTF32, "bf16": _lib.PREC_BF16}
+_default_precision = "fp32"
+
+
+def set_precision(name: str) -> None:
+    """'fp32' (SIMT), '3xtf32' (tcgen05, fp32-faithful) or 'bf16' (tcgen05)."""
+    global _default_precision
+    if name not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+    _default_precision = name
+
+
+def get_precision() -> str:
+    return _default_precision
+
+
+def _bn_momentum(bn) -> float:
+    if bn.momentum is None:  # cumulative moving average
+        return 1.0 / float(int(bn.num_batches_tracked) + 1)
+    return float(bn.momentum)
+
+
+@dataclass
+class Affine:
+    """A pending BatchNorm+ReLU: y = max(x*scale + shift, 0), applied by whoever reads x next."""
+    scale: Tensor
+    shift: Tensor
+
+
+def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0,
+              in_affine: Optional[Affine] = None, in_mask: Optional[Tensor] = None,
+              precision: Optional[str] = None, tag: str = "mlp"):
+    """Runs [conv1x1 -> BN -> ReLU] * L over the rows of X.
+
+    Returns (Y_last_raw, Affine_last) — or, with pool_group, the pooled post-BN/ReLU features
+    (rows/pool_group, C_last).  The BN of layer i is applied inside layer i+1's operand load.
+    """
+    prec = _PRECISIONS[precision or _default_precision]
+    M = X.shape[0]
+    aff = in_affine
+    mask = in_mask
+    last = len(convs) - 1
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        N = conv.weight.shape[0]
+        use_batch_stats = training or (bn.running_mean is None)
+        stats = torch.zeros(2 * N, dtype=torch.float64, device=X.device) if use_batch_stats else None
+        pool = pool_group if i == last else 0
+        _lib.set_tag(f"{tag}.{i}")
+        res = ops.linear(X, conv.weight, conv.bias, K=K,
+                         in_scale=None if aff is None else aff.scale,
+                         in_shift=None if aff is None else aff.shift,
+                         in_mask=mask, stats=stats, pool_group=pool, want_y=(pool == 0), precision=prec)
+        scale, shift = ops.bn_finalize(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn),
+                                       use_batch_stats, bn.running_mean, bn.running_var)
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        aff = Affine(scale, shift)
+        mask = None
+        if pool:
+            _, Ymax, Ymin = res
+            return ops.pool_bn_relu(Ymax, Ymin, scale, shift)
+        X = res
+        K = N
+    return X, aff
+
+
+def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Tensor],
+                    trace: Optional[dict] = None, precision: Optional[str] = None, tag: str = "sa"):
+    """PointNetSetAbstraction in point-major form (models/pointnet_util.py:181-207).
+    xyz (B,N,3), feats (B*N, D) rows or None -> (new_xyz (B,S,3), new_feats (B*S, C))."""
+    B, N, _ = xyz.shape
+    D = 0 if feats is None else feats.shape[1]
+    _lib.set_tag(tag)
+    if sa.group_all:
+        rows = ops.group(xyz, feats, None, None)
+        new_xyz = torch.zeros(B, 1, 3, dtype=torch.float32, device=xyz.device)
+        pool = N
+    else:
+        fps_idx, new_xyz = ops.fps(xyz, sa.npoint, start)
+        gidx = ops.ball_query(sa.radius, sa.nsample, xyz, new_xyz)
+        rows = ops.group(xyz, feats, new_xyz, gidx)
+        pool = sa.nsample
+        if trace is not None:
+            trace["fps_idx"], trace["group_idx"] = fps_idx, gidx
+    out = mlp_stack(rows, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
+                    tag=tag)
+    return new_xyz, out
+
+
+def feature_propagation(fp, xyz1: Tensor, xyz2: Tensor, feats1: Optional[Tensor], feats2: Tensor,
+                        materialize: bool = True, precision: Optional[str] = None, tag: str = "fp"):
+    """PointNetFeaturePropagation in point-major form (models/pointnet_util.py:283-320).
+    feats1 (B*N, D1) or None, feats2 (B*S, D2) -> (B*N, C) post-BN/ReLU rows (materialize=True) or
+    (raw rows, Affine) for a consumer that folds the last BN+ReLU into its own load."""
+    B, N, _ = xyz1.shape
+    D1 = 0 if feats1 is None else feats1.shape[1]
+    D2 = feats2.shape[1]
+    _lib.set_tag(tag)
+    buf = torch.empty(B * N, D1 + D2, dtype=torch.float32, device=xyz1.device)
+    if feats1 is not None:
+        buf[:, :D1].copy_(feats1)           # skip features first (:312)
+    ops.three_nn_interp(xyz1, xyz2, feats2, out=buf[:, D1:])
+    Y, aff = mlp_stack(buf, D1 + D2, fp.mlp_convs, fp.mlp_bns, fp.training, precision=precision, tag=tag)
+    _lib.set_tag(tag)
+    if materialize:
+        return ops.bn_relu_apply(Y, aff.scale, aff.shift)
+    return Y, aff
+
+
+def draw_fps_start(B: int, N: int, device) -> Tensor:
+    """First FPS centroid, drawn exactly like the reference: CPU generator, then moved
+    (models/pointnet_util.py:75)."""
+    return torch.randint(0, N, (B,), dtype=torch.long).to(device)
+
+
+def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = None,
+                     trace: Optional[dict] = None, precision: Optional[str] = None) -> List[Tensor]:
+    """models/pointnet_extrusion.py:37-66.  x (B,N,3[+3]) -> [ (B,N,o_i) ] (views of one buffer)."""
+    _lib.need_cuda(x)
+    B, N, Cx = x.shape
+    x = x.float()
+    xyz = x[:, :, :3].contiguous()
+    feats0 = x[:, :, 3:].reshape(B * N, Cx - 3).contiguous() if Cx > 3 else None
+    dev = x.device
+    s1 = fps_start[0] if fps_start is not None else draw_fps_start(B, N, dev)
+    t1 = {} if trace is not None else None
+    l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, s1, t1, precision, tag="sa1")
+    s2 = fps_start[1] if fps_start is not None else draw_fps_start(B, l1_xyz.shape[1], dev)
+    t2 = {} if trace is not None else None
+    l2_xyz, l2 = set_abstraction(net.sa2, l1_xyz, l1, s2, t2, precision, tag="sa2")
+    l3_xyz, l3 = set_abstraction(net.sa3, l2_xyz, l2, None, None, precision, tag="sa3")
+    l4 = feature_propagation(net.fp3, l2_xyz, l3_xyz, l2, l3, precision=precision, tag="fp3")
+    l5 = feature_propagation(net.fp2, l1_xyz, l2_xyz, l1, l4, precision=precision, tag="fp2")
+    y6, aff6 = feature_propagation(net.fp1, xyz, l1_xyz, feats0, l5, materialize=False, precision=precision,
+                                    tag="fp1")
+    # FC head: fc1 -> bn1 -> ReLU -> dropout(p=.5, always on, :60) -> fc2 heads
+    h, aff_h = mlp_stack(y6, y6.shape[1], [net.fc1], [net.bn1], net.training, in_affine=aff6,
+                         precision=precision, tag="fc1")
+    # Same torch op on the same (B,128,N) shape as the reference so a shared seed gives the same mask.
+    mask_cf = F.dropout(torch.ones(B, h.shape[1], N, dtype=torch.float32, device=dev), p=0.5)
+    mask = mask_cf.permute(0, 2, 1).reshape(B * N, h.shape[1])
+    if not mask.is_contiguous():
+        mask = mask.contiguous()
+    Wcat = torch.cat([fc.weight.reshape(fc.weight.shape[0], -1) for fc in net.fc2], dim=0)
+    bcat = torch.cat([fc.bias for fc in net.fc2], dim=0)
+    prec = _PRECISIONS[precision or _default_precision]
+    _lib.set_tag("fc2")
+    out = ops.linear(h, Wcat, bcat, in_scale=aff_h.scale, in_shift=aff_h.shift, in_mask=mask, precision=prec)
+    if trace is not None:
+        trace.update(sa1=t1, sa2=t2, l1_xyz=l1_xyz, l1=l1, l2_xyz=l2_xyz, l2=l2, l3=l3, l4=l4, l5=l5,
+                     y6=y6, aff6=aff6, h=h, aff_h=aff_h)
+    results, c0 = [], 0
+    out3 = out.reshape(B, N, out.shape[1])
+    for fc in net.fc2:
+        o = fc.weight.shape[0]
+        results.append(out3[:, :, c0:c0 + o])
+        c0 += o
+    return results
+
+
+# ---- loss ----------------------------------------------------------------------------------------
+
+
+def hungarian_from_cost(cost: Tensor, n_gt: Tensor, K: int) -> Tensor:
+    """losses.py:43-45 on the host: one D2H of the (B,K,K) score tensor, scipy per cloud, one H2D."""
+    cost_h = cost.cpu().numpy()
+    n_h = n_gt.cpu().numpy()
+    match = np.zeros((cost_h.shape[0], K), dtype=np.int64)
+    for b in range(cost_h.shape[0]):
+        n = int(n_h[b])
+        if n > 0:
+            _, cols = linear_sum_assignment(-cost_h[b, :n, :])
+            match[b, :n] = cols
+    return torch.from_numpy(match).to(cost.device)
+
+
+def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, gt_inst: Tensor,
+                 gt_bb: Tensor, gt_axes: Tensor, gt_centers: Tensor,
+                 weights=(1.0, 1.0, 1.0, 1.0, 1.0), norm_eig: bool = False) -> Dict[str, Tensor]:
+    """train_Point2Cyl_without_sketch.py:246-353 with all five --pred_* branches on.
+    weights = (seg, normal, bb, extrusion, centre)."""
+    B, N, twoK = W_raw.shape
+    K = twoK // 2
+    _lib.set_tag("loss")
+    stats = ops.segfit_stats(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, K)
+    cost, n_gt = ops.segfit_cost(stats, K)
+    match = hungarian_from_cost(cost, n_gt, K)
+    bb_sum = ops.bb_loss_sums(W_raw, gt_bb, match, n_gt, K)
+    losses, E_AX, centers, per_seg, per_cloud = ops.loss_finalize(
+        stats, bb_sum, match, n_gt, gt_axes, gt_centers, N, K, norm_eig, weights)
+    mask = torch.arange(K, device=pcs.device)[None, :] < n_gt[:, None]
+    return dict(total=losses[0], normal=losses[1], miou=losses[2], bb=losses[3], axis=losses[4],
+                center=losses[5], losses=losses, matching_indices=match, mask=mask, E_AX=E_AX,
+                centers=centers, per_seg=per_seg, per_cloud=per_cloud, n_gt=n_gt, stats=stats)
+
+
+def forward_loss(net, batch: Dict[str, Tensor], fps_start=None, weights=(1.0,) * 5,
+                 norm_eig: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
+    """One forward+loss pass: the unit BASELINE.json's clouds/s metric counts."""
+    X_raw, W_raw = backbone_forward(net, batch["pcs"], fps_start, precision=precision)
+    out = loss_forward(batch["pcs"], X_raw, W_raw, batch["normals"], batch["inst"], batch["bb"],
+                       batch["axes"], batch["centers"], weights, norm_eig)
+    out.update(X_raw=X_raw, W_raw=W_raw)
+    return out

@@ -1,0 +1,285 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the golden vectors.
+
+Bars (BASELINE.json north_star): FPS / ball-query / 3-NN indices bit-exact; floats within 1e-4,
+measured as max|delta| / max|reference| per tensor (TOL below).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import p2c_oracle as orc
+from point2cyl_b200 import ops, pipeline, synthetic
+from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+POINTOPS = [("pointops_cyl_n1024.npz", "cyl"), ("pointops_uniform_n2048.npz", "uniform")]
+
+
+def pointops_inputs(g, kind):
+    B, N, npoint, nsample, seed = (int(v) for v in g["meta"])
+    xyz = synthetic.s_cyl(B, N, 4, seed)["pcs"] if kind == "cyl" else synthetic.s_uniform(B, N, seed)
+    return xyz, npoint, float(g["radius"]), nsample, seed
+
+
+@pytest.mark.parametrize("name,kind", POINTOPS)
+def test_pointops_golden(golden_dir, name, kind):
+    g = load(golden_dir, name)
+    xyz, npoint, radius, nsample, seed = pointops_inputs(g, kind)
+    xg = xyz.to(DEV)
+    idx, new_xyz = ops.fps(xg, npoint, torch.from_numpy(g["start"]).to(DEV))
+    assert np.array_equal(idx.cpu().numpy(), g["fps_idx"].astype(np.int64))
+    assert torch.equal(new_xyz.cpu(), orc.gather_points(xyz, idx.cpu()))
+    grp = ops.ball_query(radius, nsample, xg, new_xyz)
+    assert np.array_equal(grp.cpu().numpy(), g["group_idx"].astype(np.int64))
+    d = ops.square_distance(new_xyz[:, :1].contiguous(), xg)
+    assert np.array_equal(d[:, 0].cpu().numpy(), g["sqdist_row0"])
+    feats2 = torch.randn(xyz.shape[0], npoint, 16, generator=torch.Generator().manual_seed(seed + 1))
+    out, nidx, w = ops.three_nn_interp(xg, new_xyz, feats2.reshape(-1, 16).to(DEV), want_idx=True)
+    assert np.array_equal(nidx.cpu().numpy(), g["nn_idx"].astype(np.int64))
+    assert np.array_equal(w.cpu().numpy(), g["nn_w"])
+    assert rel_err(out.reshape(xyz.shape[0], -1, 16), g["interp"]) <= 1e-6
+
+
+@pytest.mark.parametrize("B,N,npoint,kind", [(4, 8192, 512, "cyl"), (3, 8192, 512, "uniform"),
+                                             (5, 512, 128, "cyl"), (2, 1000, 77, "uniform"),
+                                             (2, 12000, 64, "uniform"), (1, 33, 33, "uniform")])
+def test_fps_vs_oracle(B, N, npoint, kind):
+    xyz = synthetic.s_cyl(B, N, 8, 11)["pcs"] if kind == "cyl" else synthetic.s_uniform(B, N, 12)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(5))
+    ref = orc.farthest_point_sample(xyz, npoint, start)
+    idx, new_xyz = ops.fps(xyz.to(DEV), npoint, start.to(DEV))
+    assert torch.equal(idx.cpu(), ref)
+    assert torch.equal(new_xyz.cpu(), orc.gather_points(xyz, ref))
+
+
+def test_fps_duplicate_points_tie_break():
+    """All-equal distances: torch.max returns the first index; so must the kernel."""
+    xyz = torch.zeros(2, 300, 3)
+    xyz[1, 150:] = 1.0
+    start = torch.tensor([7, 3])
+    ref = orc.farthest_point_sample(xyz, 8, start)
+    idx, _ = ops.fps(xyz.to(DEV), 8, start.to(DEV))
+    assert torch.equal(idx.cpu(), ref)
+
+
+@pytest.mark.parametrize("B,N,S,radius,nsample,kind", [
+    (4, 8192, 512, 0.2, 64, "cyl"), (2, 8192, 512, 0.2, 64, "uniform"), (3, 512, 128, 0.4, 64, "cyl"),
+    (2, 1000, 50, 0.1, 16, "uniform"), (1, 2048, 9, 0.05, 8, "uniform")])
+def test_ball_query_vs_oracle(B, N, S, radius, nsample, kind):
+    xyz = synthetic.s_cyl(B, N, 8, 21)["pcs"] if kind == "cyl" else synthetic.s_uniform(B, N, 22)
+    start = torch.zeros(B, dtype=torch.long)
+    new_xyz = orc.gather_points(xyz, orc.farthest_point_sample(xyz, S, start))
+    ref = orc.query_ball_point(radius, nsample, xyz, new_xyz)
+    got = ops.ball_query(radius, nsample, xyz.to(DEV), new_xyz.to(DEV))
+    assert torch.equal(got.cpu(), ref)
+    # size-independent properties: ascending until the padding starts, padding equals the first hit
+    g = got.cpu()
+    inc = (g[:, :, 1:] > g[:, :, :-1]) | (g[:, :, 1:] == g[:, :, :1])
+    assert bool(inc.all())
+
+
+def test_ball_query_empty_ball_yields_N():
+    xyz = synthetic.s_uniform(1, 256, 3)
+    far = torch.full((1, 2, 3), 10.0)
+    got = ops.ball_query(0.1, 8, xyz.to(DEV), far.to(DEV))
+    assert bool((got == 256).all())  # the reference's own out-of-range marker (pointnet_util.py:102)
+
+
+def test_group_matches_oracle():
+    B, N, S, ns, D = 2, 700, 40, 16, 10
+    xyz = synthetic.s_uniform(B, N, 31)
+    feats = torch.randn(B, N, D, generator=torch.Generator().manual_seed(32))
+    new_xyz, grouped, fps_idx, gidx = orc.sample_and_group(S, 0.3, ns, xyz, feats, torch.zeros(B, dtype=torch.long))
+    rows = ops.group(xyz.to(DEV), feats.reshape(B * N, D).to(DEV), new_xyz.to(DEV), gidx.to(DEV))
+    assert rows.shape == (B * S * ns, 16)
+    assert torch.equal(rows[:, :3 + D].cpu().reshape(B, S, ns, 3 + D), grouped)
+    assert bool((rows[:, 3 + D:] == 0).all())
+    _, allg = orc.sample_and_group_all(xyz, feats)
+    rows = ops.group(xyz.to(DEV), feats.reshape(B * N, D).to(DEV), None, None)
+    assert torch.equal(rows[:, :3 + D].cpu().reshape(B, 1, N, 3 + D), allg)
+
+
+@pytest.mark.parametrize("M,N,K,pool", [(1024, 64, 3, 0), (2048, 128, 131, 64), (512, 256, 259, 128),
+                                        (640, 19, 128, 0), (896, 40, 64, 32), (300, 70, 50, 0)])
+@pytest.mark.parametrize("prologue", [False, True])
+def test_linear_layer(M, N, K, pool, prologue):
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = ops.pad4(K)
+    X = torch.zeros(M, ld)
+    X[:, :K] = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    sc = torch.randn(K, generator=g) if prologue else None
+    sh = torch.randn(K, generator=g) if prologue else None
+    mask = (torch.rand(M, K, generator=g) > 0.5).float() * 2 if prologue else None
+    A = X[:, :K].double()
+    if prologue:
+        A = torch.relu(A * sc.double() + sh.double()) * mask.double()
+    ref = A @ W.double().t() + b.double()
+    stats = torch.zeros(2 * N, dtype=torch.float64, device=DEV)
+    maskg = None
+    if prologue:
+        maskg = torch.zeros(M, ld)
+        maskg[:, :K] = mask
+        maskg = maskg.to(DEV)
+    res = ops.linear(X.to(DEV), W.to(DEV), b.to(DEV), K=K, in_scale=None if sc is None else sc.to(DEV),
+                     in_shift=None if sh is None else sh.to(DEV), in_mask=maskg, stats=stats,
+                     pool_group=pool, want_y=True)
+    Y = res[0] if pool else res
+    assert rel_err(Y, ref) <= 1e-5
+    assert rel_err(stats[:N], ref.sum(0)) <= 1e-5
+    assert rel_err(stats[N:], (ref ** 2).sum(0)) <= 1e-5
+    if pool:
+        assert rel_err(res[1], ref.reshape(M // pool, pool, N).max(1).values) <= 1e-5
+        assert rel_err(res[2], ref.reshape(M // pool, pool, N).min(1).values) <= 1e-5
+
+
+BACKBONE = ["backbone_b2_n1024_k4.npz", "backbone_b1_n1024_k4.npz"]
+
+
+def make_net(K, seed, mode):
+    net = backbone(output_sizes=[3, 2 * K])
+    net.load_state_dict(orc.init_state_dict((3, 2 * K), seed), strict=True)
+    net.train(mode == "train")
+    return net.to(DEV)
+
+
+@pytest.fixture
+def identity_dropout(monkeypatch):
+    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: x)
+
+
+@pytest.mark.parametrize("name", BACKBONE)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_backbone_golden(golden_dir, identity_dropout, name, mode):
+    g = load(golden_dir, name)
+    B, N, K, seed = (int(v) for v in g["meta"])
+    data = synthetic.s_cyl(B, N, K, seed)
+    net = make_net(K, seed, mode)
+    starts = (torch.from_numpy(g[f"{mode}_s1"]).to(DEV), torch.from_numpy(g[f"{mode}_s2"]).to(DEV))
+    with torch.no_grad():
+        X, W = net(data["pcs"].to(DEV), fps_start=starts)
+    assert X.shape == (B, N, 3) and W.shape == (B, N, 2 * K)
+    assert rel_err(X, g[f"{mode}_X"]) <= TOL
+    assert rel_err(W, g[f"{mode}_W"]) <= TOL
+    if mode == "train":
+        sd = net.state_dict()
+        for k in g.files:
+            if k.startswith("stat_"):
+                assert rel_err(sd[k[5:]].float(), g[k].astype(np.float32)) <= TOL, k
+
+
+def test_backbone_seeded_start_matches_reference_order(golden_dir, identity_dropout):
+    """Without explicit starts the drop-in draws them from the CPU generator in the reference's order
+    (sa1 then sa2), so the same torch.manual_seed reproduces the golden run."""
+    g = load(golden_dir, BACKBONE[0])
+    B, N, K, seed = (int(v) for v in g["meta"])
+    net = make_net(K, seed, "eval")
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        X, W = net(synthetic.s_cyl(B, N, K, seed)["pcs"].to(DEV))
+    assert rel_err(W, g["eval_W"]) <= TOL
+
+
+def test_backbone_dropout_mask_path(golden_dir, monkeypatch):
+    """A given multiplicative mask (what F.dropout(ones) returns) is applied like the reference's
+    F.dropout on the (B,128,N) head activations."""
+    B, N, K, seed = 2, 1024, 4, 0
+    data = synthetic.s_cyl(B, N, K, seed)
+    mask = (torch.rand(B, 128, N, generator=torch.Generator().manual_seed(9)) > 0.5).float() * 2.0
+    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: mask.to(x.device))
+    net = make_net(K, seed, "eval")
+    starts = (torch.zeros(B, dtype=torch.long), torch.ones(B, dtype=torch.long))
+    with torch.no_grad():
+        X, W = net(data["pcs"].to(DEV), fps_start=[s.to(DEV) for s in starts])
+        Xr, Wr = orc.backbone_forward(orc.init_state_dict((3, 2 * K), seed), data["pcs"], training=False,
+                                      fps_start=starts, dropout_mask=mask)
+    assert rel_err(X, Xr) <= TOL and rel_err(W, Wr) <= TOL
+
+
+LOSS = ["loss_b2_n1024_k4.npz", "loss_b3_n2048_k8_normeig.npz"]
+
+
+@pytest.mark.parametrize("name", LOSS)
+def test_loss_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    B, N, K, seed, norm_eig = (int(v) for v in g["meta"])
+    data = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, seed).items()}
+    out = pipeline.loss_forward(data["pcs"], torch.from_numpy(g["X_raw"]).to(DEV),
+                                torch.from_numpy(g["W_raw"]).to(DEV), data["normals"], data["inst"],
+                                data["bb"], data["axes"], data["centers"], norm_eig=bool(norm_eig))
+    assert np.array_equal(out["matching_indices"].cpu().numpy(), g["matching_indices"])
+    assert np.array_equal(out["mask"].cpu().numpy(), g["mask"])
+    for k in ("normal", "miou", "bb", "axis", "center"):
+        assert rel_err(out[k], g[k]) <= TOL, k
+    # the golden 'total' is compute_all_losses' (seg + normal); the step adds bb, axis and centre
+    assert rel_err(out["total"], g["total"] + g["bb"] + g["axis"] + g["center"]) <= TOL
+    m = torch.from_numpy(g["mask"])
+    dots = (out["E_AX"].cpu() * torch.from_numpy(g["E_AX"])).sum(-1).abs()
+    assert float((1 - dots[m]).max()) <= TOL
+    assert rel_err(out["centers"].cpu()[m], torch.from_numpy(g["centers"])[m]) <= TOL
+
+
+def test_eig3x3_against_lapack():
+    g = torch.Generator().manual_seed(4)
+    A = torch.randn(500, 3, 3, generator=g)
+    M = A @ A.transpose(1, 2) - 0.5 * torch.eye(3)
+    M[0] = torch.diag(torch.tensor([3.0, 1.0, 2.0]))
+    vec, ev = ops.eig3x3_smallest(M.to(DEV))
+    e_ref, v_ref = torch.linalg.eigh(M.double(), UPLO="U")
+    assert rel_err(ev, e_ref) <= 1e-5
+    assert float((1 - (vec.cpu().double() * v_ref[..., 0]).sum(-1).abs()).max()) <= 1e-6
+
+
+def test_forward_loss_config2_properties():
+    """BASELINE.json config 2 (B=32, N=8192, K=8) at full size: oracle-checked on a slice, and
+    size-independent invariants on the whole batch."""
+    B, N, K = 32, 8192, 8
+    data = synthetic.s_cyl(B, N, K, 1234)
+    dev = {k: v.to(DEV) for k, v in data.items()}
+    net = make_net(K, 0, "train")
+    starts = (torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(1)),
+              torch.randint(0, 512, (B,), generator=torch.Generator().manual_seed(2)))
+    trace = {}
+    with torch.no_grad():
+        X_raw, W_raw = pipeline.backbone_forward(net, dev["pcs"], [s.to(DEV) for s in starts], trace=trace)
+        out = pipeline.loss_forward(dev["pcs"], X_raw, W_raw, dev["normals"], dev["inst"], dev["bb"],
+                                    dev["axes"], dev["centers"])
+    f1 = trace["sa1"]["fps_idx"].cpu()
+    assert f1.shape == (B, 512) and int(f1.min()) >= 0 and int(f1.max()) < N
+    assert all(len(set(r.tolist())) == 512 for r in f1)          # FPS never repeats a point
+    assert torch.equal(f1[:, 0], starts[0])
+    # oracle on the first 3 clouds (FPS + ball query are per-cloud independent)
+    ref_f = orc.farthest_point_sample(data["pcs"][:3], 512, starts[0][:3])
+    assert torch.equal(f1[:3], ref_f)
+    ref_g = orc.query_ball_point(0.2, 64, data["pcs"][:3], orc.gather_points(data["pcs"][:3], ref_f))
+    assert torch.equal(trace["sa1"]["group_idx"][:3].cpu(), ref_g)
+    assert bool(torch.isfinite(out["losses"]).all())
+    m = out["matching_indices"].cpu()
+    ng = out["n_gt"].cpu()
+    for b in range(B):                                           # a match is a partial permutation
+        cols = m[b, :int(ng[b])].tolist()
+        assert len(set(cols)) == len(cols)
+    assert float((out["E_AX"].norm(dim=-1) - 1).abs().max()) <= 1e-5
+    # the loss block against the oracle on the kernel's own network outputs (all 32 clouds)
+    ref = orc.loss_block(data["pcs"], X_raw.cpu(), W_raw.cpu(), data["normals"], data["inst"], data["bb"],
+                         data["axes"], data["centers"])
+    assert torch.equal(m, ref["matching_indices"])
+    for k in ("total", "normal", "miou", "bb", "axis", "center"):
+        assert rel_err(out[k], ref[k]) <= TOL, k
