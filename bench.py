@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — clouds/s of Point2Cyl forward+loss at B=32 x N=8192, K=8 per GPU (BASELINE.json config 2).
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--precision fp32|3xtf32|bf16]
+
+A "step" is one forward+loss pass over one synthetic batch (S-cyl clouds; random-init
+weights of the reference architecture; train-mode BatchNorm; dropout on, as the reference has it).
+One JSON line is printed by rank 0:
+  value      clouds/s over all ranks, inputs resident in HBM, device-timed (CUDA events per step, L2
+             flushed between steps, max over ranks)
+  e2e        same through point2cyl_b200.forward_loss_host: pinned HOST batch -> H2D -> forward+loss
+             -> six loss scalars D2H, all inside the timed region
+  roofline   the dominant kernel, timed live with CUDA events on the launching stream
+  cpu_baseline   the CPU oracle (restated reference algorithm, torch CPU, all host threads) on a
+             bounded sample, rank 0, N=1 only
+  --impl reference   times that CPU path alone (same metric / config / unit)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU, N_POINTS, K_INST = 32, 8192, 8
+METRIC = "point-clouds/sec forward+loss at B=32 N=8192"
+UNIT = "clouds/s"
+CPU_SAMPLE_B = 2  # clouds per CPU-baseline step (B=32 needs ~137 GB on the reference's dense axis fit)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops_sustained"], bf16_burst=p["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_net(device):
+    from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
+    torch.manual_seed(0)
+    net = backbone(output_sizes=[3, 2 * K_INST])  # default nn init = "random-init weights of that architecture"
+    return net.to(device).train()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference algorithm (oracle/, dense axis fit like
+    data_utils.py:118-172), all host threads, bounded sample of the same workload.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import p2c_oracle as orc
+    from point2cyl_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = synthetic.s_cyl(CPU_SAMPLE_B, N_POINTS, K_INST, seed=1234)
+    sd = orc.init_state_dict((3, 2 * K_INST), seed=0)
+    starts = (torch.zeros(CPU_SAMPLE_B, dtype=torch.long), torch.zeros(CPU_SAMPLE_B, dtype=torch.long))
+    mask = torch.nn.functional.dropout(torch.ones(CPU_SAMPLE_B, 128, N_POINTS), p=0.5)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            orc.forward_loss(sd, data, training=True, fps_start=starts, dropout_mask=mask, dense_axis=True)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    v = CPU_SAMPLE_B / sec
+    cores = torch.get_num_threads()
+    sample = f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST} per step, {len(times)} steps, torch CPU no_grad"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * B_PER_GPU / CPU_SAMPLE_B,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args.gpus, "cpu"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def workload_config(n_gpus, precision):
+    return {"workload": f"forward+loss, S-cyl synthetic clouds, B={B_PER_GPU}/GPU x N={N_POINTS}, K={K_INST}, "
+                        "train-mode BN, all five loss terms (BASELINE.json configs[1])",
+            "global_batch": B_PER_GPU * n_gpus, "points": N_POINTS, "K": K_INST, "precision": precision,
+            "parallelism": f"dp{n_gpus} (clouds sharded, no data-path collective)",
+            "l2": "flushed between timed steps (512 MiB write)"}
+
+
+def cpu_baseline_sample():
+    from oracle import p2c_oracle as orc
+    from point2cyl_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = synthetic.s_cyl(CPU_SAMPLE_B, N_POINTS, K_INST, seed=1234)
+    sd = orc.init_state_dict((3, 2 * K_INST), seed=0)
+    starts = (torch.zeros(CPU_SAMPLE_B, dtype=torch.long), torch.zeros(CPU_SAMPLE_B, dtype=torch.long))
+    ts = []
+    with torch.no_grad():
+        for i in range(3):
+            t0 = time.perf_counter()
+            orc.forward_loss(sd, data, training=True, fps_start=starts, dense_axis=True)
+            ts.append(time.perf_counter() - t0)
+    sec = min(ts[1:])
+    return {"value": CPU_SAMPLE_B / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST}, best of 2 after 1 warm-up, torch CPU no_grad, "
+                      "dense (B,N,N) axis fit as the reference"}
+
+
+# algorithmic work per launch for the roofline (SURVEY.md 8d formulas; B clouds)
+def algorithmic_work(name, tag, B):
+    N = N_POINTS
+    mlp = {  # rows, K, N per layer
+        "sa1": (B * 512 * 64, [(3, 64), (64, 64), (64, 128)]),
+        "sa2": (B * 128 * 64, [(131, 128), (128, 128), (128, 256)]),
+        "sa3": (B * 128, [(259, 256), (256, 512), (512, 1024)]),
+        "fp3": (B * 128, [(1280, 256), (256, 256)]),
+        "fp2": (B * 512, [(384, 256), (256, 128)]),
+        "fp1": (B * N, [(128, 128), (128, 128), (128, 128)]),
+        "fc1": (B * N, [(128, 128)]),
+        "fc2": (B * N, [(128, 3 + 2 * K_INST)]),
+    }
+    if name == "p2c_linear":
+        stage, _, li = tag.partition(".")
+        rows, layers = mlp[stage]
+        k, n = layers[int(li) if li else 0]
+        return "tensor", 2.0 * rows * k * n
+    if name == "p2c_fps":
+        return "hbm", B * (12 * N + 8 * 512) if tag == "sa1" else B * (12 * 512 + 8 * 128)
+    if name == "p2c_ball_query":
+        return "hbm", B * (12 * N + 12 * 512 + 8 * 512 * 64) if tag == "sa1" else B * (12 * 512 + 12 * 128 + 8 * 128 * 64)
+    if name == "p2c_three_nn_interp" and tag == "fp1":
+        return "hbm", B * (12 * N + 12 * 512 + 4 * 512 * 128 + 4 * N * 128)
+    return "hbm", None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("P2C_PRECISION", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import point2cyl_b200
+    from point2cyl_b200 import _lib, pipeline, synthetic
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pipeline.set_precision(args.precision)
+    _lib.load()
+
+    net = make_net(dev)
+    host = point2cyl_b200.pin_batch(synthetic.s_cyl(B_PER_GPU, N_POINTS, K_INST, seed=1234 + rank))
+    batch = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """per-step CUDA-event time on the current stream, L2 flushed (untimed) between steps"""
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            ms.append(s.elapsed_time(e))
+        return ms
+
+    def step_resident():
+        with torch.no_grad():
+            return pipeline.forward_loss(net, batch)
+
+    def step_e2e():
+        with torch.no_grad():
+            return point2cyl_b200.forward_loss_host(net, host, device=dev)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        for _ in range(2):
+            step_e2e()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = _lib.launch_count
+    ms = timed(step_resident, args.steps)
+    launches = (_lib.launch_count - l0) // args.steps
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clk = clocks.stop()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = max_over_ranks(sum(ms))
+    total_ms_e2e = max_over_ranks(sum(ms_e2e))
+    clouds = B_PER_GPU * world * args.steps
+    value = clouds / (total_ms / 1e3)
+    e2e = clouds / (total_ms_e2e / 1e3)
+
+    # ---- per-kernel live timing for the roofline (rank 0) --------------------------------------
+    roof, stages = None, None
+    if rank == 0:
+        pk = peaks()
+        agg = {}
+        reps = 3
+        for _ in range(reps):
+            flush.zero_()
+            _lib.profile_start()
+            step_resident()
+            for name, tag, t in _lib.profile_stop():
+                a = agg.setdefault((name, tag), [0.0, 0])
+                a[0] += t
+                a[1] += 1
+        per_kernel = {}
+        for (name, tag), (t, n) in agg.items():
+            d = per_kernel.setdefault(name, {"ms": 0.0, "work": 0.0, "bound": None, "launches": 0})
+            bound, work = algorithmic_work(name, tag, B_PER_GPU)
+            d["ms"] += t / reps
+            d["launches"] += n // reps
+            if work:
+                d["work"] += work
+                d["bound"] = bound
+        top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+        d = per_kernel[top]
+        if d["bound"] == "tensor":
+            ach = d["work"] / (d["ms"] / 1e3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16"], "traffic": None,
+                    "note": f"all {d['launches']} {top} launches of a step: algorithmic MLP FLOPs / summed CUDA-event "
+                            f"time; peak = {pk['src']} sustained bf16 cuBLAS (fp32-faithful path reported against it)"}
+        elif d["work"]:
+            ach = d["work"] / (d["ms"] / 1e3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "note": f"peak = {pk['src']} copy bandwidth"}
+        stages = {k: round(v["ms"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample()
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(world, args.precision),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host),
+                    "d2h_bytes_per_step": 24 + B_PER_GPU * K_INST * K_INST * 4 + B_PER_GPU * 4, "ms_per_step": total_ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "kernel_ms_per_step": stages}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

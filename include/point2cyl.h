@@ -75,6 +75,10 @@ int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                float* Y, int64_t ldy, int M, int N, int K, double* stats, int pool_group,
                float* Ymax, float* Ymin, int precision, void* stream);
 
+/* Which kernel p2c_linear dispatches a (16-byte aligned) layer to: 0 = fp32 SIMT, 1 = tcgen05 3xTF32.
+ * Pure function of the shape; lets tests assert that the tensor-core path really ran. */
+int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision);
+
 /* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
  * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
  * training != 0: mean/var from stats (count rows), running stats updated in place with `momentum`;
