@@ -79,6 +79,10 @@ int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
  * Pure function of the shape; lets tests assert that the tensor-core path really ran. */
 int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision);
 
+/* Tools only (tools/tc_timeline.py): device buffer of 4*512 int64 that CTA 0 of subsequent tensor-core
+ * launches fills with (tag, globaltimer) pairs per warp role; NULL (default) disables the probes. */
+int p2c_debug_set_timeline(void* buf);
+
 /* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
  * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
  * training != 0: mean/var from stats (count rows), running stats updated in place with `momentum`;

@@ -32,6 +32,7 @@ SIGNATURES = {
     "p2c_linear": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, c_f32p, i64, i32, i32, i32,
                    c_f64p, i32, c_f32p, c_f32p, i32, vp],
     "p2c_linear_path": [i64, i32, i32, i32, i32, i32, i32],
+    "p2c_debug_set_timeline": [vp],
     "p2c_bn_finalize": [c_f64p, i64, c_f32p, c_f32p, f32, f32, i32, c_f32p, c_f32p, c_f32p, c_f32p,
                         c_f32p, c_f32p, i32, vp],
     "p2c_bn_relu_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i64, i32, vp],

@@ -2,36 +2,47 @@
 //
 //   Y[m, n] = sum_k f(X[m, k]) * W[n, k] + bias[n]      f = identity | max(x*scale[k]+shift[k], 0)
 //
-// P2C_PREC_3XTF32 (fp32-faithful): every operand is split a = a_hi + a_lo with a_hi exactly
-// representable in tf32 (low 13 mantissa bits cleared) and a_lo = a - a_hi (exact in fp32); the product is
-// accumulated as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in fp32 TMEM accumulators (the dropped a_lo*w_lo
-// term is ~2^-20 relative).  Three kind::tf32 MMAs per k-step.
+// computed TRANSPOSED on the tensor core, D[n, m] = sum_k W[n, k] * f(X)[m, k]:
+//   * the UMMA "A" operand is the weight matrix, resident in TENSOR MEMORY for the whole kernel
+//     (lane = output channel n, column = k; hi | lo halves), so shared memory is free for a deep TMA ring;
+//   * the UMMA "B" operand is the activation tile in shared memory, K-major SWIZZLE_128B - the layout a TMA
+//     box load produces - after the operand transform (folded BatchNorm+ReLU of the previous layer, hi/lo split);
+//   * the accumulator puts one OUTPUT CHANNEL per TMEM lane, i.e. per epilogue thread: bias, the BatchNorm
+//     sum / sum-of-squares and the nsample max/min pool are plain in-register loops over the thread's row of
+//     accumulator columns (no shuffles, no shared-memory staging), and Y[m, n0..n0+127] is one coalesced
+//     512-byte row per store step.
 //
-// Persistent, warp-specialised CTA (384 threads, 1 CTA/SM), one n-tile of BN output channels per CTA:
-//   warp 0      TMA producer: raw fp32 activation k-blocks [128 rows x 32 floats] -> smem ring
-//               (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier complete_tx)
-//   warps 8-11  operand transform (thread = row): smem -> registers, folded BatchNorm+ReLU of the
-//               previous layer, hi/lo split, tcgen05.st into the A-operand TMEM ring
-//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::tf32 with A from TMEM and
-//               W_hi / W_lo from shared memory (K-major, SWIZZLE_128B, resident for the whole kernel);
-//               tcgen05.commit releases A stages and publishes accumulators
-//   warps 4-7   epilogue: tcgen05.ld accumulator -> +bias -> store Y, per-channel sum / sum-of-squares
-//               (lane-transposing butterfly, 31 shuffles per 32 columns) and nsample max/min pool
-//   warp 2      TMEM allocator
-// Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// P2C_PREC_3XTF32 (fp32-faithful): a = a_hi + a_lo with a_hi exactly representable in tf32 (low 13 mantissa bits
+// cleared) and a_lo = a - a_hi (exact); accumulated as w_hi*x_hi + w_lo*x_hi + w_hi*x_lo in fp32 (the dropped
+// w_lo*x_lo term is ~2^-20 relative).  Three kind::tf32 MMAs (M=128, N=128, K=8) per k-step.
 //
-// TMEM map (columns): [0, 2*BN) accumulators, [2*BN, 2*BN + A_STAGES*64) A operand (hi 32 | lo 32).
+// Persistent warp-specialised CTA (384 threads, 1 CTA/SM); CTA (x, y) owns output channels [128y, 128y+128) and
+// row tiles x, x+gridDim.x, ...:
+//   warp 0      TMA producer: raw fp32 k-blocks [128 rows x 32 floats] -> RAW ring (cp.async.bulk.tensor.2d,
+//               SWIZZLE_128B, mbarrier complete_tx)
+//   warps 8-11  operand transform (thread = row): RAW ring -> registers -> BN+ReLU -> hi/lo -> XT ring
+//               (same swizzled layout), fence.proxy.async, mbarrier arrive
+//   warp 1      MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::tf32, A = W from TMEM, B = XT from smem;
+//               tcgen05.commit frees XT stages and publishes accumulators
+//   warps 4-7   epilogue (thread = output channel): tcgen05.ld 32 accumulator columns (= 32 rows of Y) at a time;
+//               Y leaves through per-warp [32 rows x 32 channels] staging tiles and TMA bulk tensor stores
+//   warp 2      TMEM allocator;  warps 8-11 also load W into TMEM in the prologue
+//
+// TMEM columns: [0, 128*ACC) accumulators (ACC = 2 when K <= 128, else 1), then W_hi [KPAD] | W_lo [KPAD].
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int TC_BM = 128;
+constexpr int TC_BM = 128;           // rows of X per tile  (UMMA N)
+constexpr int TC_BN = 128;           // output channels per CTA (UMMA M, TMEM lanes)
 constexpr int TC_BK = 32;            // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_THREADS = 384;
-constexpr int A_STAGES = 2;          // TMEM A-operand ring
-constexpr int RAW_BYTES = TC_BM * TC_BK * 4;
+constexpr int RAW_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int MAX_RAW = 8, MAX_XT = 4;
 
 struct TcArgs {
   const float* W; const float* bias;
@@ -41,8 +52,11 @@ struct TcArgs {
   double* stats;
   int pool_group;
   float* Ymax; float* Ymin;
-  int raw_stages;
+  int raw_stages, xt_stages, acc_bufs;
   int m_tiles;
+  int y_tma;        // Y rows are 16-byte aligned: per-warp TMA stores of [32 rows x 32 channels] boxes
+  long long* dbg;   // optional timeline buffer (tools/tc_timeline.py); NULL in production
+  int dbg_mode;     // tools only (env P2C_TC_DBG): bit0 skip transform math, bit1 skip epilogue body
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -136,110 +150,175 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128 channels, N = 128 rows
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 3) << 17) |
+                              ((uint32_t)(TC_BN >> 4) << 24);
 
-// Lane-transposing reduction: in  v[j] = this lane's (row's) value of column j,
-//                             out v[0] = op over the 32 lanes of column `lane`.
-template <class Op>
-__device__ __forceinline__ void transpose_reduce(float (&v)[32], int lane, Op op) {
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool up = (lane & half) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = up ? v[i] : v[i + half];
-      const float keep = up ? v[i + half] : v[i];
-      v[i] = op(keep, __shfl_xor_sync(P2C_FULL_MASK, send, half));
-    }
+// timeline probe: role r (0 mma, 1 transform, 2 epilogue, 3 producer) of CTA 0 appends (tag, globaltimer)
+__device__ __forceinline__ void dbg_mark(long long* dbg, int role, int& n, int tag) {
+  if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && n < 255) {
+    long long c;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c));
+    dbg[role * 512 + 2 * n] = tag;
+    dbg[role * 512 + 2 * n + 1] = c;
+    ++n;
   }
 }
-struct OpAdd { __device__ float operator()(float a, float b) const { return a + b; } };
-struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
-struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+
+// One 32-row chunk of the epilogue for one output channel.  raw[j] = accumulator of row j.  Everything is
+// fully unrolled over registers; FULL = all 32 rows valid (the common case, no predicates).
+template <bool FULL>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&raw)[32], float bias, int jmax, float* stage,
+                                          float* yp, int64_t ldy, bool do_stats, bool do_pool, float& t1,
+                                          float& t2, float& mx_out, float& mn_out) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + bias;
+  if (stage) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[j * 32] = v[j];           // rows past M are clipped by the TMA store
+  } else if (yp) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (FULL || j < jmax) yp[(size_t)j * ldy] = v[j];
+  }
+  if (do_stats) {
+    float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // short dependency chains
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float y = (FULL || j < jmax) ? v[j] : 0.f;
+      p1[j & 3] += y;
+      p2[j & 3] = fmaf(y, y, p2[j & 3]);
+    }
+    t1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+    t2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+  }
+  if (do_pool) {
+    const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
+    float mx[4] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF}, mn[4] = {POS_INF, POS_INF, POS_INF, POS_INF};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (FULL || j < jmax) { mx[j & 3] = fmaxf(mx[j & 3], v[j]); mn[j & 3] = fminf(mn[j & 3], v[j]); }
+    }
+    mx_out = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    mn_out = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
+  }
+}
 
 struct SmemLayout {
-  uint32_t w_off, raw_off, scale_off, shift_off, pool_off, bar_off, total;
+  uint32_t raw_off, xt_off, ystage_off, scale_off, shift_off, bar_off, total;
 };
-__host__ __device__ inline SmemLayout tc_smem_layout(int BN, int KB, int raw_stages) {
+__host__ __device__ inline SmemLayout tc_smem_layout(int KB, int raw_stages, int xt_stages, int y_stage) {
   SmemLayout L;
   uint32_t o = 0;
-  L.w_off = o;      o += 2u * KB * BN * 128u;              // W_hi | W_lo, [KB][BN rows][128 B]
-  L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES; // 1024-aligned: every term above is
+  L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES;       // [stage][128 rows][128 B]
+  L.xt_off = o;     o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo][128 rows][128 B]
+  L.ystage_off = o; o += y_stage ? 4u * 2u * 4096u : 0u;         // [epilogue warp][buf][32 rows][32 channels]
   L.scale_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.shift_off = o;  o += (uint32_t)KB * TC_BK * 4u;
-  L.pool_off = o;   o += 4u * 2u * BN * 4u;                // [quarter][max|min][BN]
-  L.bar_off = o;    o += 256u;
+  L.bar_off = o;    o += 512u;
   L.total = o;
   return L;
 }
 
-template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const TcArgs a) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms (TMA destination, UMMA descriptors) need 1024-byte aligned shared addresses
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout L = tc_smem_layout(BN, a.KB, a.raw_stages);
-  uint8_t* w_sm = smem + L.w_off;
+  const SmemLayout L = tc_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma);
   uint8_t* raw_sm = smem + L.raw_off;
+  uint8_t* xt_sm = smem + L.xt_off;
+  uint8_t* ystage = smem + L.ystage_off;
   float* s_scale = reinterpret_cast<float*>(smem + L.scale_off);
   float* s_shift = reinterpret_cast<float*>(smem + L.shift_off);
-  float* s_pool = reinterpret_cast<float*>(smem + L.pool_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* raw_full = bars;                 // [raw_stages] (<= 8)
-  uint64_t* raw_empty = bars + 8;            // [raw_stages]
-  uint64_t* a_full = bars + 16;              // [A_STAGES]
-  uint64_t* a_empty = bars + 18;             // [A_STAGES]
-  uint64_t* acc_full = bars + 20;            // [2]
-  uint64_t* acc_empty = bars + 22;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* raw_full = bars;                   // [MAX_RAW]
+  uint64_t* raw_empty = bars + MAX_RAW;        // [MAX_RAW]
+  uint64_t* xt_full = bars + 2 * MAX_RAW;      // [MAX_XT]
+  uint64_t* xt_empty = xt_full + MAX_XT;       // [MAX_XT]
+  uint64_t* acc_full = xt_empty + MAX_XT;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.y * BN;
-  const int KB = a.KB;
-  const int RS = a.raw_stages;
+  const int n0 = blockIdx.y * TC_BN;
+  const int KB = a.KB, KPAD = a.KB * TC_BK;
+  const int RS = a.raw_stages, XS = a.xt_stages, ACC = a.acc_bufs;
+
+  int dbg_k = 200;
+  if (tid == 96) dbg_mark(a.dbg, 3, dbg_k, 9000);          // kernel entry (idle warp 3)
+  auto cta_mark = [&](int slot) {                          // per-CTA entry / prologue / roles-done times
+    if (a.dbg && tid == 96 && blockIdx.y == 0 && blockIdx.x < 256) {
+      long long c;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c));
+      a.dbg[2048 + blockIdx.x * 4 + slot] = c;
+    }
+  };
+  cta_mark(0);
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < XS; ++s) { mbar_init(&xt_full[s], 4); mbar_init(&xt_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  // weights: fp32 -> (hi, lo), K-major SWIZZLE_128B tiles, zero padded in n and k
-  {
-    const int kpad = KB * TC_BK;
-    for (int e = tid; e < BN * kpad; e += TC_THREADS) {
-      const int n = e / kpad, k = e - n * kpad;
-      float w = 0.f;
-      if (n0 + n < a.N && k < a.K) w = __ldg(a.W + (size_t)(n0 + n) * a.K + k);
-      const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-      const float lo = w - hi;
-      const int kb = k >> 5, kk = k & 31;
-      const uint32_t off = (uint32_t)kb * BN * 128u + (uint32_t)n * 128u + ((((uint32_t)kk >> 2) ^ ((uint32_t)n & 7u)) << 4) +
-                           ((uint32_t)kk & 3u) * 4u;
-      *reinterpret_cast<float*>(w_sm + off) = hi;
-      *reinterpret_cast<float*>(w_sm + (uint32_t)KB * BN * 128u + off) = lo;
-    }
-    for (int k = tid; k < kpad; k += TC_THREADS) {
-      const bool ok = a.in_scale != nullptr && k < a.K;
-      s_scale[k] = ok ? __ldg(a.in_scale + k) : (a.in_scale ? 0.f : 1.f);
-      s_shift[k] = ok ? __ldg(a.in_shift + k) : 0.f;
-    }
+  for (int k = tid; k < KPAD; k += TC_THREADS) {
+    const bool ok = a.in_scale != nullptr && k < a.K;
+    s_scale[k] = ok ? __ldg(a.in_scale + k) : 0.f;
+    s_shift[k] = ok ? __ldg(a.in_shift + k) : 0.f;
   }
-  fence_proxy_async();   // generic-proxy smem writes (W tiles) -> visible to the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_acc = tmem_base;                       // + ab*BN
-  const uint32_t tm_a = tmem_base + 2 * BN;                // + as*64 (+32 for lo)
+  const uint32_t tm_acc = tmem_base;                               // + ab*128
+  const uint32_t tm_w = tmem_base + (uint32_t)ACC * TC_BM;         // W_hi at +k, W_lo at +KPAD+k
+
+  // weights -> TMEM (thread = output channel; hi | lo), zero padded in n and k
+  if (warp >= 8) {
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool wvec = (a.K % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
+    for (int kb = 0; kb < KB; ++kb) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k = kb * TC_BK + c * 4;
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < a.N) {
+          const float* wp = a.W + (size_t)n * a.K + k;
+          if (wvec && k + 3 < a.K) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(wp));
+            w[0] = t4.x; w[1] = t4.y; w[2] = t4.z; w[3] = t4.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (k + i < a.K) w[i] = __ldg(wp + i);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t h = __float_as_uint(w[i]) & 0xffffe000u;
+          hi[c * 4 + i] = h;
+          lo[c * 4 + i] = __float_as_uint(w[i] - __uint_as_float(h));
+        }
+      }
+      tmem_st32(tm_w + lane_addr + (uint32_t)(kb * TC_BK), hi);
+      tmem_st32(tm_w + lane_addr + (uint32_t)(KPAD + kb * TC_BK), lo);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 96) dbg_mark(a.dbg, 3, dbg_k, 9001);          // prologue done
+  cta_mark(1);
 
   const int my_tiles = (a.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -247,10 +326,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const TcArgs a) {
     // ===== TMA producer =====
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
+      int dbg_n = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BM;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&raw_empty[s], ph ^ 1);
+          dbg_mark(a.dbg, 3, dbg_n, t * 100 + kb);
           mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
           tma_load_2d(raw_sm + (size_t)s * RAW_BYTES, &tmA, &raw_full[s], kb * TC_BK, m0);
           if (++s == RS) { s = 0; ph ^= 1; }
@@ -260,184 +341,185 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const TcArgs a) {
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BN);
-      const uint32_t w_hi = smem_u32(w_sm);
-      const uint32_t w_lo = w_hi + (uint32_t)KB * BN * 128u;
-      int as = 0; uint32_t aph = 0;
+      int xs = 0; uint32_t xph = 0;
+      int dbg_n = 0;
       for (int t = 0; t < my_tiles; ++t) {
-        const int ab = t & 1;
-        const uint32_t accph = (uint32_t)(t >> 1) & 1u;
+        const int ab = ACC == 2 ? (t & 1) : 0;
+        const uint32_t accph = (ACC == 2 ? (uint32_t)(t >> 1) : (uint32_t)t) & 1u;
         mbar_wait(&acc_empty[ab], accph ^ 1);
         tc_fence_after();
-        const uint32_t d = tm_acc + (uint32_t)ab * BN;
+        dbg_mark(a.dbg, 0, dbg_n, t * 100 + 99);
+        const uint32_t d = tm_acc + (uint32_t)ab * TC_BM;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&a_full[as], aph);
+          mbar_wait(&xt_full[xs], xph);
           tc_fence_after();
-          const uint32_t ahi = tm_a + (uint32_t)as * 64u, alo = ahi + 32u;
+          dbg_mark(a.dbg, 0, dbg_n, t * 100 + kb);
+          const uint32_t x_hi = smem_u32(xt_sm + (size_t)xs * 2 * RAW_BYTES);
+          const uint32_t x_lo = x_hi + RAW_BYTES;
+          const uint32_t w_hi = tm_w + (uint32_t)(kb * TC_BK), w_lo = w_hi + (uint32_t)KPAD;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t bhi = make_kmajor_sw128_desc(w_hi + (uint32_t)kb * BN * 128u + ks * 32u);
-            const uint64_t blo = make_kmajor_sw128_desc(w_lo + (uint32_t)kb * BN * 128u + ks * 32u);
-            umma_tf32_ts(d, ahi + ks * 8u, bhi, idesc, (kb | ks) != 0);
-            umma_tf32_ts(d, alo + ks * 8u, bhi, idesc, 1u);
-            umma_tf32_ts(d, ahi + ks * 8u, blo, idesc, 1u);
+            const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u);
+            const uint64_t blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
+            umma_tf32_ts(d, w_hi + ks * 8u, bhi, TC_IDESC, (kb | ks) != 0);
+            umma_tf32_ts(d, w_lo + ks * 8u, bhi, TC_IDESC, 1u);
+            umma_tf32_ts(d, w_hi + ks * 8u, blo, TC_IDESC, 1u);
           }
-          umma_commit(&a_empty[as]);                 // frees this A stage once the MMAs above retire
+          umma_commit(&xt_empty[xs]);                // frees this XT stage once the MMAs above retire
           if (kb == KB - 1) umma_commit(&acc_full[ab]);
-          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (++xs == XS) { xs = 0; xph ^= 1; }
         }
       }
     }
   } else if (warp >= 8) {
-    // ===== operand transform: raw smem -> BN+ReLU -> hi/lo -> TMEM =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;                    // tile row == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const bool has_affine = a.in_scale != nullptr;
+    // ===== operand transform: RAW ring -> BN+ReLU -> hi/lo -> XT ring =====
+    // thread = (16-byte column chunk cj, 8-row group rg): its four k columns are fixed, so the folded
+    // BatchNorm scale/shift are 8 registers per k-block instead of shared-memory loads per element
+    const int tt = tid - 256;
+    const int cj = tt & 7, rg = tt >> 3;
+    const bool has_affine = a.in_scale != nullptr && !(a.dbg_mode & 1);
     int s = 0; uint32_t ph = 0;
-    int as = 0; uint32_t aph = 0;
+    int xs = 0; uint32_t xph = 0;
+    int dbg_n = 0;
     for (int t = 0; t < my_tiles; ++t) {
       for (int kb = 0; kb < KB; ++kb) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_affine) {
+          sc = *reinterpret_cast<const float4*>(s_scale + kb * TC_BK + cj * 4);
+          sh = *reinterpret_cast<const float4*>(s_shift + kb * TC_BK + cj * 4);
+        }
         mbar_wait(&raw_full[s], ph);
-        const uint8_t* rowp = raw_sm + (size_t)s * RAW_BYTES + (size_t)r * 128;
-        uint32_t hi[32], lo[32];
+        if (tid == 256) dbg_mark(a.dbg, 1, dbg_n, t * 100 + kb);
+        const uint8_t* rawp = raw_sm + (size_t)s * RAW_BYTES;
+        float4 x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x = *reinterpret_cast<const float4*>(rowp + ((c ^ (r & 7)) << 4));
-          float v[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float y = v[i];
-            if (has_affine) {
-              const int k = kb * TC_BK + c * 4 + i;
-              y = fmaxf(fmaf(y, s_scale[k], s_shift[k]), 0.f);
-            }
-            const uint32_t h = __float_as_uint(y) & 0xffffe000u;
-            hi[c * 4 + i] = h;
-            lo[c * 4 + i] = __float_as_uint(y - __uint_as_float(h));
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int r = rg * 8 + i;
+          x[i] = *reinterpret_cast<const float4*>(rawp + (size_t)r * 128 + ((cj ^ (r & 7)) << 4));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[s]);   // raw slot consumed (values are in registers)
         if (++s == RS) { s = 0; ph ^= 1; }
-        mbar_wait(&a_empty[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t ta = tm_a + (uint32_t)as * 64u + lane_addr;
-        tmem_st32(ta, hi);
-        tmem_st32(ta + 32u, lo);
-        tmem_wait_st();
-        tc_fence_before();
+        if (has_affine) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x[i].x = fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f);
+            x[i].y = fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f);
+            x[i].z = fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f);
+            x[i].w = fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f);
+          }
+        }
+        mbar_wait(&xt_empty[xs], xph ^ 1);
+        uint8_t* hip = xt_sm + (size_t)xs * 2 * RAW_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rg * 8 + i;
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u); l.x = x[i].x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u); l.y = x[i].y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u); l.z = x[i].z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u); l.w = x[i].w - h.w;
+          const size_t off = (size_t)r * 128 + ((cj ^ (r & 7)) << 4);
+          *reinterpret_cast<float4*>(hip + off) = h;
+          *reinterpret_cast<float4*>(hip + RAW_BYTES + off) = l;
+        }
+        fence_proxy_async();                         // generic-proxy smem writes -> tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[as]);
-        if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        if (lane == 0) mbar_arrive(&xt_full[xs]);
+        if (tid == 256) dbg_mark(a.dbg, 1, dbg_n, t * 100 + kb + 50);
+        if (++xs == XS) { xs = 0; xph ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
+    // ===== epilogue: thread = output channel n; accumulator columns = rows of Y =====
     const int q = warp & 3;
+    const int ch = q * 32 + lane;                      // channel within the CTA's 128
+    const int n = n0 + ch;
+    const bool n_ok = n < a.N;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    constexpr int NCH = BN / 32;
-    double s1[NCH], s2[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+    const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     const int G = a.pool_group;
+    double s1 = 0.0, s2 = 0.0;
+    float gmx = NEG_INF, gmn = POS_INF;                // running pool over the current group
+    int dbg_n = 0;
+    int ybuf = 0;
+    float* ystg = reinterpret_cast<float*>(ystage + (size_t)q * 8192);   // this warp's two 4 KB staging tiles
+    const bool y_tma = a.Y != nullptr && a.y_tma;
     for (int t = 0; t < my_tiles; ++t) {
-      const int ab = t & 1;
-      const uint32_t accph = (uint32_t)(t >> 1) & 1u;
+      const int ab = ACC == 2 ? (t & 1) : 0;
+      const uint32_t accph = (ACC == 2 ? (uint32_t)(t >> 1) : (uint32_t)t) & 1u;
       const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BM;
-      const int row = m0 + q * 32 + lane;
-      const bool valid = row < a.M;
       mbar_wait(&acc_full[ab], accph);
       tc_fence_after();
+      if (ch == 0) dbg_mark(a.dbg, 2, dbg_n, t * 100 + 99);
+      float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tm_acc + (uint32_t)ab * BN + (uint32_t)c * 32u + lane_addr, raw);
+        tmem_ld32(tm_acc + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
         tmem_wait_ld();
-        float v[32];
-        const int col0 = n0 + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float bj = (a.bias && col0 + j < a.N) ? __ldg(a.bias + col0 + j) : 0.f;
-          v[j] = __uint_as_float(raw[j]) + bj;
+        if (c == 3) {                                  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
-        if (a.Y && valid) {
-          float* yr = a.Y + (size_t)row * a.ldy + col0;
-          if (col0 + 32 <= a.N && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(yr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < a.N) yr[j] = v[j];
+        if (a.dbg_mode & 2) continue;
+        const int mrow = m0 + c * 32;
+        const int jmax = min(32, a.M - mrow);          // rows past M hold garbage (TMA zero fill + affine)
+        if (jmax <= 0) continue;
+        float* st = ystg + ybuf * 1024;
+        if (y_tma) {
+          // the bulk store that read this staging tile two chunks ago must have drained it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        float* yp = (a.Y && !y_tma && n_ok) ? a.Y + (size_t)mrow * a.ldy + n : nullptr;
+        float mx = NEG_INF, mn = POS_INF;
+        if (jmax == 32) epi_chunk<true>(raw, bias, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        else epi_chunk<false>(raw, bias, jmax, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        if (y_tma) {
+          // [32 rows][32 channels] staged (lanes = channels: conflict-free); the TMA engine writes it out:
+          // one bulk tensor store per warp and chunk instead of 32 LSU store instructions
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        }
-        if (a.stats) {
-          float tsum[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tsum[j] = valid ? v[j] : 0.f;
-          transpose_reduce(tsum, lane, OpAdd());
-          s1[c] += (double)tsum[0];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tsum[j] = valid ? v[j] * v[j] : 0.f;
-          transpose_reduce(tsum, lane, OpAdd());
-          s2[c] += (double)tsum[0];
+          ybuf ^= 1;
         }
         if (G) {
-          float tm[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tm[j] = valid ? v[j] : NEG_INF;
-          transpose_reduce(tm, lane, OpMax());
-          s_pool[(q * 2 + 0) * BN + c * 32 + lane] = tm[0];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tm[j] = valid ? v[j] : POS_INF;
-          transpose_reduce(tm, lane, OpMin());
-          s_pool[(q * 2 + 1) * BN + c * 32 + lane] = tm[0];
-        }
-      }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
-      if (G) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
-        const int et = tid - 128;                         // 0..127
-        const int wpg = G / 32;                           // warps (quarters) per pool group: 1, 2 or 4
-        const int groups = 4 / wpg;
-        for (int e = et; e < groups * BN; e += 128) {
-          const int g = e / BN, col = e - g * BN;
-          const int grow = m0 + g * G;
-          if (grow < a.M && n0 + col < a.N) {
-            float mx = NEG_INF, mn = POS_INF;
-            for (int w = 0; w < wpg; ++w) {
-              mx = fmaxf(mx, s_pool[((g * wpg + w) * 2 + 0) * BN + col]);
-              mn = fminf(mn, s_pool[((g * wpg + w) * 2 + 1) * BN + col]);
+          // pool groups are 32, 64 or 128 consecutive rows and tiles start on group boundaries
+          gmx = fmaxf(gmx, mx); gmn = fminf(gmn, mn);
+          const int rows_done = c * 32 + 32;
+          if (rows_done % G == 0) {
+            if (n_ok) {
+              const size_t o = (size_t)((mrow + 32 - G) / G) * a.N + n;
+              a.Ymax[o] = gmx;
+              a.Ymin[o] = gmn;
             }
-            const size_t o = (size_t)(grow / G) * a.N + n0 + col;
-            a.Ymax[o] = mx;
-            a.Ymin[o] = mn;
+            gmx = NEG_INF; gmn = POS_INF;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // s_pool is rewritten by the next tile
+        if (ch == 0) dbg_mark(a.dbg, 2, dbg_n, t * 100 + c);
       }
+      s1 += (double)t1;
+      s2 += (double)t2;
     }
-    if (a.stats) {
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col = n0 + c * 32 + lane;
-        if (col < a.N) {
-          atomicAdd(a.stats + col, s1[c]);
-          atomicAdd(a.stats + a.N + col, s2[c]);
-        }
-      }
+    if (y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (a.stats && n_ok) {
+      atomicAdd(a.stats + n, s1);
+      atomicAdd(a.stats + a.N + n, s2);
     }
   }
 
   // ---- teardown ------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (tid == 96) dbg_mark(a.dbg, 3, dbg_k, 9002);          // all roles finished
+  cta_mark(2);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -460,55 +542,53 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& tm, TcArgs a, int n_tiles, cudaStream_t st) {
-  const SmemLayout L = tc_smem_layout(BN, a.KB, a.raw_stages);
-  auto k = linear_tc_kernel<BN>;
-  P2C_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024));
-  int sms = 148;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int gx = sms / n_tiles;
-  if (gx < 1) gx = 1;
-  if (gx > a.m_tiles) gx = a.m_tiles;
-  dim3 grid(gx, n_tiles);
-  k<<<grid, TC_THREADS, L.total + 1024, st>>>(tm, a);
-  P2C_RETURN_IF_CUDA_ERROR();
-  return 0;
+long long* g_tc_dbg = nullptr;
+
+struct TcPlan { int KB, raw_stages, xt_stages, acc_bufs; };
+
+inline int tc_raw_stages(int KB, int xt, int y_stage) {
+  int raw = MAX_RAW;
+  while (raw >= 2 && tc_smem_layout(KB, raw, xt, y_stage).total + 1024 > 227 * 1024) --raw;
+  return raw;
 }
 
-}  // namespace
-
 // Which kernel takes a given layer shape: 0 = fp32 SIMT, 1 = tcgen05 3xTF32.  Pure function of its arguments.
-static int tc_plan(int64_t ldx, int x_aligned16, int M, int N, int K, int has_mask, int pool_group, int precision,
-                   int* BN_out, int* KB_out, int* stages_out) {
-  (void)M;
+int tc_plan(int64_t ldx, int x_aligned16, int M, int N, int K, int has_mask, int pool_group, int precision,
+            TcPlan* out) {
+  (void)M; (void)N;
   if (precision != P2C_PREC_3XTF32) return 0;                      // bf16 variant: DESIGN.md, next
   if (has_mask) return 0;
   if ((ldx % 4) != 0 || !x_aligned16) return 0;                    // TMA global strides are multiples of 16 B
   if (K < 16) return 0;                                            // xyz-only first layers stay on the SIMT kernel
   if (pool_group && pool_group != 32 && pool_group != 64 && pool_group != 128) return 0;
-  const int BN = N > 64 ? 128 : (N > 32 ? 64 : 32);
   const int KB = (K + TC_BK - 1) / TC_BK;
-  int raw_stages = 4;
-  while (raw_stages >= 2 && tc_smem_layout(BN, KB, raw_stages).total + 1024 > 227 * 1024) --raw_stages;
-  if (raw_stages < 2) return 0;                                    // W not resident: SIMT (streaming-W variant next)
-  if (BN_out) { *BN_out = BN; *KB_out = KB; *stages_out = raw_stages; }
+  const int KPAD = KB * TC_BK;
+  int acc = 0;
+  if (2 * KPAD + 2 * TC_BM <= 512) acc = 2;                        // TMEM: accumulators + W_hi + W_lo
+  else if (2 * KPAD + TC_BM <= 512) acc = 1;
+  else return 0;                                                   // K > 192: W does not fit TMEM (SIMT for now)
+  const int xt = 3;
+  const int raw = tc_raw_stages(KB, xt, 1);
+  if (raw < 2) return 0;
+  if (out) { out->KB = KB; out->raw_stages = raw; out->xt_stages = xt; out->acc_bufs = acc; }
   return 1;
 }
 
+}  // namespace
+
+// tools only: timeline buffer (4 roles x 256 x {tag, globaltimer ns} + 256 x 4 per-CTA times)
+extern "C" int p2c_debug_set_timeline(void* buf) { g_tc_dbg = reinterpret_cast<long long*>(buf); return 0; }
+
 extern "C" int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision) {
-  return tc_plan(ldx, 1, M, N, K, has_mask, pool_group, precision, nullptr, nullptr, nullptr);
+  return tc_plan(ldx, 1, M, N, K, has_mask, pool_group, precision, nullptr);
 }
 
 int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias, const float* in_scale,
                   const float* in_shift, const float* in_mask, int64_t ldmask, float* Y, int64_t ldy, int M, int N,
                   int K, double* stats, int pool_group, float* Ymax, float* Ymin, int precision, cudaStream_t st) {
   (void)ldmask;
-  int BN, KB, raw_stages;
-  if (!tc_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, M, N, K, in_mask != nullptr, pool_group, precision,
-               &BN, &KB, &raw_stages))
+  TcPlan p;
+  if (!tc_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, M, N, K, in_mask != nullptr, pool_group, precision, &p))
     return P2C_EUNSUPPORTED;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return (int)cudaErrorNotSupported;
@@ -523,10 +603,39 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
 
-  TcArgs a{W, bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw_stages,
-           (M + TC_BM - 1) / TC_BM};
-  const int n_tiles = (N + BN - 1) / BN;
-  if (BN == 128) return launch_tc<128>(tm, a, n_tiles, st);
-  if (BN == 64) return launch_tc<64>(tm, a, n_tiles, st);
-  return launch_tc<32>(tm, a, n_tiles, st);
+  CUtensorMap tmY = tm;
+  int y_tma = 0;
+  if (Y && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+    // rows of Y beyond M and channels beyond N are clipped by the TMA unit
+    const cuuint64_t ydim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t ystride[1] = {(cuuint64_t)ldy * 4};
+    const cuuint32_t ybox[2] = {32, 32};
+    r = enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Y, ydim, ystride, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+    y_tma = 1;
+  }
+  const char* dm = getenv("P2C_TC_DBG");
+  p.raw_stages = tc_raw_stages(p.KB, p.xt_stages, y_tma);
+  TcArgs a{W, bias, in_scale, in_shift, Y, ldy, M, N, K, p.KB, stats, pool_group, Ymax, Ymin,
+           p.raw_stages, p.xt_stages, p.acc_bufs, (M + TC_BM - 1) / TC_BM, y_tma, g_tc_dbg, dm ? atoi(dm) : 0};
+  const SmemLayout L = tc_smem_layout(p.KB, p.raw_stages, p.xt_stages, y_tma);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int sms_of[64] = {0};   // per-device one-time setup (idempotent, so a race is harmless)
+  if (dev < 64 && sms_of[dev] == 0) {
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms_of[dev] = n;
+  }
+  const int sms = dev < 64 ? sms_of[dev] : 148;
+  const int n_tiles = (N + TC_BN - 1) / TC_BN;
+  int gx = sms / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > a.m_tiles) gx = a.m_tiles;
+  dim3 grid(gx, n_tiles);
+  linear_tc_kernel<<<grid, TC_THREADS, L.total + 1024, st>>>(tm, tmY, a);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
 }

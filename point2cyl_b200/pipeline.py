@@ -21,7 +21,7 @@ from . import _lib, ops
 Tensor = torch.Tensor
 
 _PRECISIONS = {"fp32": _lib.PREC_FP32, "3xtf32": _lib.PREC_3XTF32, "bf16": _lib.PREC_BF16}
-_default_precision = "fp32"
+_default_precision = "3xtf32"   # tcgen05, fp32-faithful; layers it does not take run the fp32 SIMT kernel
 
 
 def set_precision(name: str) -> None:
