@@ -126,6 +126,12 @@ int p2c_segfit_stats(const float* X_raw, int64_t ldx, const float* W_raw, int64_
 /* Hungarian cost (losses.py:39-42): cost (B,K,K) = D / max(cnt_g + colsum_k - D, 1e-10), n_gt (B). */
 int p2c_segfit_cost(const float* stats, int B, int K, float* cost, int32_t* n_gt, void* stream);
 
+/* On-device assignment — replaces scipy.optimize.linear_sum_assignment(-cost) at losses.py:43-45:
+ * match[b, g] = column assigned to gt row g < n_gt[b] (maximising the summed score), 0 for g >= n_gt[b].
+ * Exact optimum (Hungarian algorithm, float64); K <= 16. */
+int p2c_hungarian(const float* score /* (B,K,K) */, const int32_t* n_gt /* (B) */, int B, int K,
+                  int64_t* match /* (B,K) */, void* stream);
+
 /* Loss pass 2 — the base/barrel loss of train_Point2Cyl_without_sketch.py:283-313 given the match,
  * summed per cloud (the sort at :292 cancels out of the sum). bb_sum: (B). */
 int p2c_bb_loss(const float* W_raw, int64_t ldw, const int64_t* bb, const int64_t* match,

@@ -1,0 +1,73 @@
+"""CUDA-graph replay of one forward+loss step.
+
+The step is ~80 short kernels; launched one by one from Python their launch latency is a visible part of
+the step.  With the on-device assignment (p2c_hungarian) nothing in the step needs the host, so the whole
+sequence - every libp2c kernel, the dropout-mask op and the small torch glue - is captured once into a CUDA
+graph and replayed.  The only per-step host work mirrors the reference: the first FPS centroid of each level
+is drawn from the CPU generator (models/pointnet_util.py:75) and copied to the device.
+
+Re-capture is needed when anything baked into the launch arguments changes: batch shape, loss weights,
+train/eval mode, or the BatchNorm momentum (train scripts change it via update_momentum).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import BATCH_KEYS, pipeline
+
+
+class GraphedForwardLoss:
+    def __init__(self, net, example: Dict[str, torch.Tensor], weights=(1.0,) * 5, norm_eig: bool = False,
+                 precision: Optional[str] = None, warmup: int = 2):
+        self.net = net
+        dev = next(net.parameters()).device
+        self.device = dev
+        self.static = {k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS}
+        B, N, _ = self.static["pcs"].shape
+        self.B, self.N, self.S1 = B, N, net.sa1.npoint
+        self.start_host = [torch.zeros(B, dtype=torch.long).pin_memory() for _ in range(2)]
+        self.start_dev = [torch.zeros(B, dtype=torch.long, device=dev) for _ in range(2)]
+        self._key = self._state_key()
+        self.weights, self.norm_eig, self.precision = weights, norm_eig, precision
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                       # one-time lazy init (func attributes, allocator) outside capture
+                self._draw_starts()
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = self._run()
+
+    def _state_key(self):
+        return (self.net.training,) + tuple(m.momentum for m in self.net.modules()
+                                            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+
+    def _run(self):
+        return pipeline.forward_loss(self.net, self.static, fps_start=self.start_dev, weights=self.weights,
+                                     norm_eig=self.norm_eig, precision=self.precision)
+
+    def _draw_starts(self):
+        # same calls, same order as the reference: sa1 draws from [0,N), then sa2 from [0,npoint1)
+        self.start_host[0].copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
+        self.start_host[1].copy_(torch.randint(0, self.S1, (self.B,), dtype=torch.long))
+        for h, d in zip(self.start_host, self.start_dev):
+            d.copy_(h, non_blocking=True)
+
+    def stale(self) -> bool:
+        return self._key != self._state_key()
+
+    def __call__(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """batch: host (pinned) or device tensors copied into the graph's static inputs; None = reuse them."""
+        if self.stale():
+            raise RuntimeError("GraphedForwardLoss: mode or BatchNorm momentum changed since capture; build a new one")
+        if batch is not None:
+            for k in BATCH_KEYS:
+                self.static[k].copy_(batch[k], non_blocking=True)
+        self._draw_starts()
+        self.graph.replay()
+        return self.out

@@ -222,6 +222,14 @@ def segfit_cost(stats: Tensor, K: int) -> Tuple[Tensor, Tensor]:
     return cost, n_gt
 
 
+def hungarian(cost: Tensor, n_gt: Tensor) -> Tensor:
+    """cost (B,K,K) scores, n_gt (B) int32 -> match (B,K) int64, on the device (no host sync)."""
+    B, K, _ = cost.shape
+    match = torch.empty(B, K, dtype=torch.long, device=cost.device)
+    call("p2c_hungarian", ptr(cost.contiguous()), ptr(n_gt), B, K, ptr(match), stream_ptr())
+    return match
+
+
 def bb_loss_sums(W_raw: Tensor, bb: Tensor, match: Tensor, n_gt: Tensor, K: int) -> Tensor:
     B, N = bb.shape
     Wr = _rows(_as_rows(W_raw))

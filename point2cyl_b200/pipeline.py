@@ -198,15 +198,17 @@ def hungarian_from_cost(cost: Tensor, n_gt: Tensor, K: int) -> Tensor:
 
 def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, gt_inst: Tensor,
                  gt_bb: Tensor, gt_axes: Tensor, gt_centers: Tensor,
-                 weights=(1.0, 1.0, 1.0, 1.0, 1.0), norm_eig: bool = False) -> Dict[str, Tensor]:
+                 weights=(1.0, 1.0, 1.0, 1.0, 1.0), norm_eig: bool = False,
+                 matcher: str = "device") -> Dict[str, Tensor]:
     """train_Point2Cyl_without_sketch.py:246-353 with all five --pred_* branches on.
-    weights = (seg, normal, bb, extrusion, centre)."""
+    weights = (seg, normal, bb, extrusion, centre).  matcher: 'device' (p2c_hungarian, no host sync) or
+    'scipy' (the reference's host call on one D2H copy of the score tensor)."""
     B, N, twoK = W_raw.shape
     K = twoK // 2
     _lib.set_tag("loss")
     stats = ops.segfit_stats(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, K)
     cost, n_gt = ops.segfit_cost(stats, K)
-    match = hungarian_from_cost(cost, n_gt, K)
+    match = ops.hungarian(cost, n_gt) if matcher == "device" else hungarian_from_cost(cost, n_gt, K)
     bb_sum = ops.bb_loss_sums(W_raw, gt_bb, match, n_gt, K)
     losses, E_AX, centers, per_seg, per_cloud = ops.loss_finalize(
         stats, bb_sum, match, n_gt, gt_axes, gt_centers, N, K, norm_eig, weights)
@@ -217,10 +219,11 @@ def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, 
 
 
 def forward_loss(net, batch: Dict[str, Tensor], fps_start=None, weights=(1.0,) * 5,
-                 norm_eig: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
+                 norm_eig: bool = False, precision: Optional[str] = None,
+                 matcher: str = "device") -> Dict[str, Tensor]:
     """One forward+loss pass: the unit BASELINE.json's clouds/s metric counts."""
     X_raw, W_raw = backbone_forward(net, batch["pcs"], fps_start, precision=precision)
     out = loss_forward(batch["pcs"], X_raw, W_raw, batch["normals"], batch["inst"], batch["bb"],
-                       batch["axes"], batch["centers"], weights, norm_eig)
+                       batch["axes"], batch["centers"], weights, norm_eig, matcher)
     out.update(X_raw=X_raw, W_raw=W_raw)
     return out

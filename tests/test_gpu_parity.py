@@ -283,3 +283,46 @@ def test_forward_loss_config2_properties():
     assert torch.equal(m, ref["matching_indices"])
     for k in ("total", "normal", "miou", "bb", "axis", "center"):
         assert rel_err(out[k], ref[k]) <= TOL, k
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8, 13, 16])
+def test_hungarian_matches_scipy(K):
+    from scipy.optimize import linear_sum_assignment
+    g = torch.Generator().manual_seed(K)
+    B = 64
+    cost = torch.rand(B, K, K, generator=g)
+    cost[3] = torch.rand(K, K, generator=g).round(decimals=1)        # many near-ties
+    n_gt = torch.randint(0, K + 1, (B,), generator=g).int()
+    n_gt[0], n_gt[1] = K, 0
+    got = ops.hungarian(cost.to(DEV), n_gt.to(DEV)).cpu()
+    for b in range(B):
+        n = int(n_gt[b])
+        assert bool((got[b, n:] == 0).all())
+        if n == 0:
+            continue
+        rows, cols = linear_sum_assignment(-cost[b, :n].double().numpy())
+        ref_val = float(cost[b, :n].double()[rows, cols].sum())
+        assert len(set(got[b, :n].tolist())) == n
+        val = float(cost[b, :n].double()[torch.arange(n), got[b, :n]].sum())
+        assert abs(val - ref_val) <= 1e-9                              # same optimum
+        if b != 3:
+            assert got[b, :n].tolist() == cols.tolist()                # generic scores: same assignment
+
+
+def test_graph_replay_matches_eager(monkeypatch):
+    from point2cyl_b200.graph import GraphedForwardLoss
+    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: x)
+    B, N, K = 4, 2048, 4
+    data = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, 77).items()}
+    net = make_net(K, 1, "eval")
+    g = GraphedForwardLoss(net, data)
+    torch.manual_seed(5)
+    out = g(data)
+    got = {k: out[k].clone() for k in ("losses", "matching_indices", "E_AX")}
+    torch.manual_seed(5)
+    with torch.no_grad():
+        ref = pipeline.forward_loss(net, data, matcher="scipy")
+    assert torch.equal(got["matching_indices"], ref["matching_indices"])
+    assert rel_err(got["losses"], ref["losses"]) <= 1e-6
+    net.train()
+    assert g.stale()
