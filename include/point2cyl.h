@@ -73,11 +73,17 @@ int p2c_group(const float* xyz, const float* feats, int64_t ldf, const float* ne
 int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                const float* in_scale, const float* in_shift, const float* in_mask, int64_t ldmask,
                float* Y, int64_t ldy, int M, int N, int K, double* stats, int pool_group,
-               float* Ymax, float* Ymin, int precision, void* stream);
+               float* Ymax, float* Ymin, int precision, const float* w_split, int64_t ldws, void* stream);
 
-/* Which kernel p2c_linear dispatches a (16-byte aligned) layer to: 0 = fp32 SIMT, 1 = tcgen05 3xTF32.
+/* hi/lo tf32 split of a weight matrix for the large-K tensor-core kernel: out[0][n][k] = w with the low 13
+ * mantissa bits cleared, out[1][n][k] = w - hi; rows padded with zeros to ldw (multiple of 4) floats.
+ * Pass the result as w_split/ldws to p2c_linear; NULL keeps large-K layers on the fp32 SIMT kernel. */
+int p2c_split_tf32(const float* W, int N, int K, float* out /* (2,N,ldw) */, int64_t ldw, void* stream);
+
+/* Which kernel p2c_linear dispatches a (16-byte aligned) layer to: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 with the
+ * weights resident in tensor memory (K <= 192), 2 = tcgen05 3xTF32 with streamed weights (needs w_split).
  * Pure function of the shape; lets tests assert that the tensor-core path really ran. */
-int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision);
+int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision, int has_split);
 
 /* Tools only (tools/tc_timeline.py): device buffer of 4*512 int64 that CTA 0 of subsequent tensor-core
  * launches fills with (tag, globaltimer) pairs per warp role; NULL (default) disables the probes. */

@@ -9,12 +9,14 @@
 // round is enough).  Tie-break and rounding follow the reference bit for bit:
 //   dist = (dx*dx + dy*dy) + dz*dz, every op rounded (intrinsics: never contracted to FMA);
 //   running = dist < running ? dist : running (init 1e10); farthest = FIRST index of the max.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-template <int PPT, bool XYZ_IN_REGS>
-__global__ void __launch_bounds__(1024, 1)
+template <int PPT, bool XYZ_IN_REGS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int N, int npoint,
            int64_t* __restrict__ out_idx, float* __restrict__ out_xyz) {
   extern __shared__ float s_xyz[];  // xs[N] ys[N] zs[N]
@@ -107,11 +109,11 @@ fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int
   }
 }
 
-template <int PPT, bool R>
+template <int PPT, bool R, int MAXT>
 int launch_fps(const float* xyz, const int64_t* start, int B, int N, int npoint, int64_t* out_idx,
                float* out_xyz, int T, cudaStream_t st) {
   size_t smem = (size_t)N * 3 * sizeof(float);
-  auto k = fps_kernel<PPT, R>;
+  auto k = fps_kernel<PPT, R, MAXT>;
   if (smem > 48 * 1024) P2C_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<B, T, smem, st>>>(xyz, start, N, npoint, out_idx, out_xyz);
   P2C_RETURN_IF_CUDA_ERROR();
@@ -125,14 +127,22 @@ extern "C" int p2c_fps(const float* xyz, const int64_t* start, int B, int N, int
   if (!xyz || !start || !out_idx || !out_xyz || B <= 0 || N <= 0 || npoint <= 0) return P2C_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   auto round32 = [](int v) { return (v + 31) / 32 * 32; };
+  const char* ev = getenv("P2C_FPS_PPT");   // tools only: force points-per-thread (8, 16 or 32)
+  const int force = ev ? atoi(ev) : 0;
+  if (force == 16 && N <= 8192)
+    return launch_fps<16, true, 512>(xyz, start, B, N, npoint, out_idx, out_xyz, round32((N + 15) / 16), st);
+  if (force == 32 && N <= 8192)
+    return launch_fps<32, true, 256>(xyz, start, B, N, npoint, out_idx, out_xyz, round32((N + 31) / 32), st);
   if (N <= 1024) {
     int T = round32((N + 3) / 4);
-    return launch_fps<4, true>(xyz, start, B, N, npoint, out_idx, out_xyz, T, st);
+    return launch_fps<4, true, 256>(xyz, start, B, N, npoint, out_idx, out_xyz, T, st);
   }
-  if (N <= 8192) {
+  if (N <= 4096) {
     int T = round32((N + 7) / 8);
-    return launch_fps<8, true>(xyz, start, B, N, npoint, out_idx, out_xyz, T, st);
+    return launch_fps<8, true, 1024>(xyz, start, B, N, npoint, out_idx, out_xyz, T, st);
   }
-  if (N <= 16384) return launch_fps<16, false>(xyz, start, B, N, npoint, out_idx, out_xyz, 1024, st);
+  if (N <= 8192)   // measured on B200 at N=8192: 32 points/thread (8 warps) 329 us, 16: 332 us, 8: 375 us per 512 rounds
+    return launch_fps<32, true, 256>(xyz, start, B, N, npoint, out_idx, out_xyz, round32((N + 31) / 32), st);
+  if (N <= 16384) return launch_fps<16, false, 1024>(xyz, start, B, N, npoint, out_idx, out_xyz, 1024, st);
   return P2C_EUNSUPPORTED;  // larger clouds need the cluster variant
 }

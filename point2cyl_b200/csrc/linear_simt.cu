@@ -361,11 +361,16 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
                   const float* in_scale, const float* in_shift, const float* in_mask,
                   int64_t ldmask, float* Y, int64_t ldy, int M, int N, int K, double* stats,
                   int pool_group, float* Ymax, float* Ymin, int precision, cudaStream_t st);
+int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int pool_group, int precision);
+int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
+                     const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
+                     double* stats, int pool_group, float* Ymax, float* Ymin, cudaStream_t st);
 
 extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                           const float* in_scale, const float* in_shift, const float* in_mask,
                           int64_t ldmask, float* Y, int64_t ldy, int M, int N, int K, double* stats,
-                          int pool_group, float* Ymax, float* Ymin, int precision, void* stream) {
+                          int pool_group, float* Ymax, float* Ymin, int precision, const float* w_split,
+                          int64_t ldws, void* stream) {
   if (!X || !W || M <= 0 || N <= 0 || K <= 0 || ldx < K) return P2C_EINVAL;
   if ((in_scale == nullptr) != (in_shift == nullptr)) return P2C_EINVAL;
   if (!Y && !pool_group && !stats) return P2C_EINVAL;
@@ -379,7 +384,13 @@ extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const flo
     int rc = p2c_linear_tc(X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
                            stats, pool_group, Ymax, Ymin, precision, st);
     if (rc != P2C_EUNSUPPORTED) return rc;
-    // shapes the tensor-core kernel does not take fall through to the fp32 SIMT kernel (still CUDA)
+    if (w_split && p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, in_mask != nullptr,
+                                         pool_group, precision)) {
+      rc = p2c_linear_tc_ss(X, ldx, w_split, ldws, bias, in_scale, in_shift, Y, ldy, M, N, K, stats, pool_group,
+                            Ymax, Ymin, st);
+      if (rc != P2C_EUNSUPPORTED) return rc;
+    }
+    // shapes the tensor-core kernels do not take fall through to the fp32 SIMT kernel (still CUDA)
   }
   LinearArgs a{X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
                stats, pool_group, Ymax, Ymin};

@@ -1,0 +1,380 @@
+// tcgen05 MLP layer for LARGE K (K > 192: sa3, fp3, fp2 of the backbone), where the weight matrix no longer
+// fits tensor memory.  Same transposed formulation and epilogue as linear_tc.cu (D[n, m] = sum_k W[n,k] f(X)[m,k],
+// one output channel per TMEM lane), but both UMMA operands come from shared memory:
+//   A = W_hi / W_lo k-blocks [128 channels x 32 floats], TMA-loaded from a pre-split copy of the weights
+//       (p2c_split_tf32: hi = low 13 mantissa bits cleared, lo = w - hi, rows padded to 16 bytes for TMA);
+//   B = transformed activation k-blocks (hi | lo), as in linear_tc.cu.
+// These layers have few rows (B*128 or B*512), so the work list is (row tile, channel tile) pairs handed out
+// round-robin to a persistent grid; consecutive CTAs share a row tile (L2 reuse of X).
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+using namespace p2c_tc;
+
+namespace {
+
+constexpr int SS_THREADS = 384;
+constexpr int SS_MAX_RAW = 4, SS_MAX_XT = 3;
+
+struct SsArgs {
+  const float* bias;
+  const float* in_scale; const float* in_shift;
+  float* Y; int64_t ldy;
+  int M, N, K, KB;
+  double* stats;
+  int pool_group;
+  float* Ymax; float* Ymin;
+  int raw_stages, xt_stages;
+  int m_tiles, n_tiles;
+  int y_tma;
+};
+
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct SsSmem {
+  uint32_t raw_off, xt_off, w_off, ystage_off, scale_off, shift_off, bar_off, total;
+};
+__host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_stages, int y_stage) {
+  SsSmem L;
+  uint32_t o = 0;
+  L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES;
+  L.xt_off = o;     o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
+  L.w_off = o;      o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
+  L.ystage_off = o; o += y_stage ? 4u * 2u * 4096u : 0u;
+  L.scale_off = o;  o += (uint32_t)KB * TC_BK * 4u;
+  L.shift_off = o;  o += (uint32_t)KB * TC_BK * 4u;
+  L.bar_off = o;    o += 512u;
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(SS_THREADS, 1)
+linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
+                    const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmY,
+                    const SsArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma);
+  uint8_t* raw_sm = smem + L.raw_off;
+  uint8_t* xt_sm = smem + L.xt_off;
+  uint8_t* w_sm = smem + L.w_off;
+  uint8_t* ystage = smem + L.ystage_off;
+  float* s_scale = reinterpret_cast<float*>(smem + L.scale_off);
+  float* s_shift = reinterpret_cast<float*>(smem + L.shift_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* raw_full = bars;                          // [SS_MAX_RAW]
+  uint64_t* raw_empty = raw_full + SS_MAX_RAW;
+  uint64_t* xt_full = raw_empty + SS_MAX_RAW;         // [SS_MAX_XT]
+  uint64_t* xt_empty = xt_full + SS_MAX_XT;
+  uint64_t* w_full = xt_empty + SS_MAX_XT;            // [SS_MAX_XT]
+  uint64_t* w_empty = w_full + SS_MAX_XT;
+  uint64_t* acc_full = w_empty + SS_MAX_XT;           // [2]
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int KB = a.KB, KPAD = a.KB * TC_BK;
+  const int RS = a.raw_stages, XS = a.xt_stages;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < XS; ++s) {
+      mbar_init(&xt_full[s], 4); mbar_init(&xt_empty[s], 1);
+      mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  for (int k = tid; k < KPAD; k += SS_THREADS) {
+    const bool ok = a.in_scale != nullptr && k < a.K;
+    s_scale[k] = ok ? __ldg(a.in_scale + k) : 0.f;
+    s_shift[k] = ok ? __ldg(a.in_shift + k) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_mt = [&](int t) { return ((int)blockIdx.x + t * (int)gridDim.x) / a.n_tiles; };
+  auto tile_nt = [&](int t) { return ((int)blockIdx.x + t * (int)gridDim.x) % a.n_tiles; };
+
+  if (warp == 0) {
+    // ===== TMA producer: X k-block -> RAW ring, W_hi / W_lo k-blocks -> W ring =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int ws = 0; uint32_t wph = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          mbar_arrive_expect_tx(&w_full[ws], 2 * RAW_BYTES);
+          tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
+          tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES + RAW_BYTES, &tmWlo, &w_full[ws], kb * TC_BK, n0);
+          if (++ws == XS) { ws = 0; wph ^= 1; }
+          mbar_wait(&raw_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
+          tma_load_2d(raw_sm + (size_t)s * RAW_BYTES, &tmX, &raw_full[s], kb * TC_BK, m0);
+          if (++s == RS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int xs = 0; uint32_t xph = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int ab = t & 1;
+        const uint32_t accph = (uint32_t)(t >> 1) & 1u;
+        mbar_wait(&acc_empty[ab], accph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)ab * TC_BM;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&w_full[xs], xph);
+          mbar_wait(&xt_full[xs], xph);
+          tc_fence_after();
+          const uint32_t x_hi = smem_u32(xt_sm + (size_t)xs * 2 * RAW_BYTES), x_lo = x_hi + RAW_BYTES;
+          const uint32_t w_hi = smem_u32(w_sm + (size_t)xs * 2 * RAW_BYTES), w_lo = w_hi + RAW_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u), blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
+            const uint64_t ahi = make_kmajor_sw128_desc(w_hi + ks * 32u), alo = make_kmajor_sw128_desc(w_lo + ks * 32u);
+            umma_tf32_ss(d, ahi, bhi, TC_IDESC, (kb | ks) != 0);
+            umma_tf32_ss(d, alo, bhi, TC_IDESC, 1u);
+            umma_tf32_ss(d, ahi, blo, TC_IDESC, 1u);
+          }
+          umma_commit(&xt_empty[xs]);
+          umma_commit(&w_empty[xs]);
+          if (kb == KB - 1) umma_commit(&acc_full[ab]);
+          if (++xs == XS) { xs = 0; xph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== operand transform (see linear_tc.cu) =====
+    const int tt = tid - 256;
+    const int cj = tt & 7, rg = tt >> 3;
+    const bool has_affine = a.in_scale != nullptr;
+    int s = 0; uint32_t ph = 0;
+    int xs = 0; uint32_t xph = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      for (int kb = 0; kb < KB; ++kb) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_affine) {
+          sc = *reinterpret_cast<const float4*>(s_scale + kb * TC_BK + cj * 4);
+          sh = *reinterpret_cast<const float4*>(s_shift + kb * TC_BK + cj * 4);
+        }
+        mbar_wait(&raw_full[s], ph);
+        const uint8_t* rawp = raw_sm + (size_t)s * RAW_BYTES;
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rg * 8 + i;
+          x[i] = *reinterpret_cast<const float4*>(rawp + (size_t)r * 128 + ((cj ^ (r & 7)) << 4));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[s]);
+        if (++s == RS) { s = 0; ph ^= 1; }
+        if (has_affine) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x[i].x = fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f);
+            x[i].y = fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f);
+            x[i].z = fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f);
+            x[i].w = fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f);
+          }
+        }
+        mbar_wait(&xt_empty[xs], xph ^ 1);
+        uint8_t* hip = xt_sm + (size_t)xs * 2 * RAW_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rg * 8 + i;
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u); l.x = x[i].x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u); l.y = x[i].y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u); l.z = x[i].z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u); l.w = x[i].w - h.w;
+          const size_t off = (size_t)r * 128 + ((cj ^ (r & 7)) << 4);
+          *reinterpret_cast<float4*>(hip + off) = h;
+          *reinterpret_cast<float4*>(hip + RAW_BYTES + off) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xt_full[xs]);
+        if (++xs == XS) { xs = 0; xph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = output channel of the tile =====
+    const int q = warp & 3;
+    const int ch = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
+    const int G = a.pool_group;
+    int ybuf = 0;
+    float* ystg = reinterpret_cast<float*>(ystage + (size_t)q * 8192);
+    const bool y_tma = a.Y != nullptr && a.y_tma;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int ab = t & 1;
+      const uint32_t accph = (uint32_t)(t >> 1) & 1u;
+      const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
+      const int n = n0 + ch;
+      const bool n_ok = n < a.N;
+      const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
+      float gmx = NEG_INF, gmn = POS_INF;
+      float t1 = 0.f, t2 = 0.f;
+      mbar_wait(&acc_full[ab], accph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
+        tmem_wait_ld();
+        if (c == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+        const int mrow = m0 + c * 32;
+        const int jmax = min(32, a.M - mrow);
+        if (jmax <= 0) continue;
+        float* st = ystg + ybuf * 1024;
+        if (y_tma) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        float* yp = (a.Y && !y_tma && n_ok) ? a.Y + (size_t)mrow * a.ldy + n : nullptr;
+        float mx = NEG_INF, mn = POS_INF;
+        if (jmax == 32) epi_chunk<true>(raw, bias, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        else epi_chunk<false>(raw, bias, jmax, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        if (y_tma) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ybuf ^= 1;
+        }
+        if (G) {
+          gmx = fmaxf(gmx, mx); gmn = fminf(gmn, mn);
+          const int rows_done = c * 32 + 32;
+          if (rows_done % G == 0) {
+            if (n_ok) {
+              const size_t o = (size_t)((mrow + 32 - G) / G) * a.N + n;
+              a.Ymax[o] = gmx;
+              a.Ymin[o] = gmn;
+            }
+            gmx = NEG_INF; gmn = POS_INF;
+          }
+        }
+      }
+      if (a.stats && n_ok) {
+        atomicAdd(a.stats + n, (double)t1);
+        atomicAdd(a.stats + a.N + n, (double)t2);
+      }
+    }
+    if (y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ out, int64_t ldw) {
+  const int64_t total = (int64_t)N * ldw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e / ldw;
+    const int k = (int)(e - n * ldw);
+    const float w = k < K ? __ldg(W + n * K + k) : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    out[e] = hi;
+    out[total + e] = w - hi;
+  }
+}
+
+int ss_stages(int KB, int y_tma, int* raw, int* xt) {
+  const int tries[4][2] = {{4, 3}, {2, 3}, {4, 2}, {2, 2}};
+  for (int i = 0; i < 4; ++i)
+    if (ss_smem_layout(KB, tries[i][0], tries[i][1], y_tma).total + 1024 <= 227 * 1024) {
+      *raw = tries[i][0]; *xt = tries[i][1];
+      return 1;
+    }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int p2c_split_tf32(const float* W, int N, int K, float* out, int64_t ldw, void* stream) {
+  if (!W || !out || N <= 0 || K <= 0 || ldw < K || (ldw % 4) != 0) return P2C_EINVAL;
+  const int64_t total = (int64_t)N * ldw;
+  const int blocks = (int)min((int64_t)148 * 8, (total + 255) / 256);
+  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, N, K, out, ldw);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+// 1 when the streamed-W tensor-core kernel takes the shape (given a pre-split weight copy)
+int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int pool_group, int precision) {
+  if (precision != P2C_PREC_3XTF32 || has_mask) return 0;
+  if ((ldx % 4) != 0 || !x_aligned16 || K < 16) return 0;
+  if (pool_group && pool_group != 32 && pool_group != 64 && pool_group != 128) return 0;
+  int raw, xt;
+  return ss_stages((K + TC_BK - 1) / TC_BK, 1, &raw, &xt);
+}
+
+int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
+                     const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
+                     double* stats, int pool_group, float* Ymax, float* Ymin, cudaStream_t st) {
+  const int KB = (K + TC_BK - 1) / TC_BK;
+  const int y_tma = (Y && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
+  int raw, xt;
+  if (!ss_stages(KB, y_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
+  if ((ldws % 4) != 0 || (reinterpret_cast<uintptr_t>(w_split) & 15) != 0) return P2C_EALIGN;
+  CUtensorMap tmX, tmWhi, tmWlo, tmY;
+  int rc;
+  if ((rc = make_map_2d(&tmX, X, K, M, ldx, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&tmWhi, w_split, K, N, ldws, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_2d(&tmWlo, w_split + (size_t)N * ldws, K, N, ldws, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  tmY = tmX;
+  if (y_tma && (rc = make_map_2d(&tmY, Y, N, M, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
+           (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma};
+  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int sms_of[64] = {0};
+  if (dev < 64 && sms_of[dev] == 0) {
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms_of[dev] = n;
+  }
+  const int sms = dev < 64 ? sms_of[dev] : 148;
+  const int tiles = a.m_tiles * a.n_tiles;
+  linear_tc_ss_kernel<<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}

@@ -89,7 +89,8 @@ def group(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: 
 def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None,
            in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
            in_mask: Optional[Tensor] = None, stats: Optional[Tensor] = None, pool_group: int = 0,
-           out: Optional[Tensor] = None, want_y: bool = True, precision: int = _lib.PREC_FP32):
+           out: Optional[Tensor] = None, want_y: bool = True, precision: int = _lib.PREC_FP32,
+           w_split: Optional[Tensor] = None):
     """One MLP layer.  X (M, >=K) rows, W (N, K) (any trailing singleton dims), returns Y (M,N) or,
     with pool_group, (Y or None, Ymax, Ymin).  stats: float64 (2N,) accumulator (pre-zeroed)."""
     need_cuda(X, W)
@@ -115,10 +116,27 @@ def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None
     call("p2c_linear", 
         ptr(X), X.stride(0), ptr(W2), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(in_mask),
         0 if in_mask is None else in_mask.stride(0), ptr(Y), 0 if Y is None else Y.stride(0), M, N, K,
-        ptr(stats), pool_group, ptr(Ymax), ptr(Ymin), precision, stream_ptr())
+        ptr(stats), pool_group, ptr(Ymax), ptr(Ymin), precision, ptr(w_split),
+        0 if w_split is None else w_split.shape[2], stream_ptr())
     if pool_group:
         return Y, Ymax, Ymin
     return Y
+
+
+def split_tf32(W: Tensor) -> Tensor:
+    """(2, N, pad4(K)) hi/lo copy of a weight matrix for the streamed-weight tensor-core kernel."""
+    W2 = W.reshape(W.shape[0], -1)
+    if not W2.is_contiguous():
+        W2 = W2.contiguous()
+    N, K = W2.shape
+    out = torch.empty(2, N, pad4(K), dtype=torch.float32, device=W.device)
+    call("p2c_split_tf32", ptr(W2), N, K, ptr(out), out.shape[2], stream_ptr())
+    return out
+
+
+def needs_split(X: Tensor, N: int, K: int, has_mask: bool, pool_group: int, precision: int) -> bool:
+    """True when p2c_linear would use the streamed-weight kernel for this layer if given a split copy."""
+    return _lib.load().p2c_linear_path(X.stride(0), X.shape[0], N, K, int(has_mask), pool_group, precision, 1) == 2
 
 
 def bn_finalize(stats: Optional[Tensor], count: int, gamma: Tensor, beta: Tensor, eps: float,

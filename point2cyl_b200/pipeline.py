@@ -68,7 +68,8 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
         stats = torch.zeros(2 * N, dtype=torch.float64, device=X.device) if use_batch_stats else None
         pool = pool_group if i == last else 0
         _lib.set_tag(f"{tag}.{i}")
-        res = ops.linear(X, conv.weight, conv.bias, K=K,
+        wsplit = ops.split_tf32(conv.weight) if ops.needs_split(X, N, K, mask is not None, pool, prec) else None
+        res = ops.linear(X, conv.weight, conv.bias, K=K, w_split=wsplit,
                          in_scale=None if aff is None else aff.scale,
                          in_shift=None if aff is None else aff.shift,
                          in_mask=mask, stats=stats, pool_group=pool, want_y=(pool == 0), precision=prec)

@@ -27,7 +27,7 @@ SHAPES = [  # M, N, K, pool
 def test_linear_tc(M, N, K, pool, prologue):
     g = torch.Generator().manual_seed(M * 7 + N + K)
     ld = ops.pad4(K)
-    assert _lib.load().p2c_linear_path(ld, M, N, K, 0, pool, _lib.PREC_3XTF32) == 1
+    assert _lib.load().p2c_linear_path(ld, M, N, K, 0, pool, _lib.PREC_3XTF32, 0) == 1
     X = torch.zeros(M, ld)
     X[:, :K] = torch.randn(M, K, generator=g)
     W = torch.randn(N, K, generator=g) / K ** 0.5
@@ -50,3 +50,38 @@ def test_linear_tc(M, N, K, pool, prologue):
     if pool:
         assert rel_err(res[1], ref.reshape(M // pool, pool, N).max(1).values) <= 2e-6
         assert rel_err(res[2], ref.reshape(M // pool, pool, N).min(1).values) <= 2e-6
+
+
+SS_SHAPES = [(4096, 256, 259, 0), (4096, 512, 256, 0), (4096, 1024, 512, 128), (4096, 256, 1280, 0),
+             (16384, 256, 384, 0), (16384, 128, 256, 0), (1000, 200, 300, 0), (512, 320, 224, 64)]
+
+
+@pytest.mark.parametrize("M,N,K,pool", SS_SHAPES)
+@pytest.mark.parametrize("prologue", [False, True])
+def test_linear_tc_streamed_weights(M, N, K, pool, prologue):
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    ld = ops.pad4(K)
+    assert _lib.load().p2c_linear_path(ld, M, N, K, 0, pool, _lib.PREC_3XTF32, 1) == 2
+    X = torch.zeros(M, ld)
+    X[:, :K] = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    sc = torch.randn(K, generator=g) if prologue else None
+    sh = torch.randn(K, generator=g) if prologue else None
+    A = X[:, :K].double()
+    if prologue:
+        A = torch.relu(A * sc.double() + sh.double())
+    ref = A @ W.double().t() + b.double()
+    stats = torch.zeros(2 * N, dtype=torch.float64, device=DEV)
+    Wd = W.to(DEV)
+    res = ops.linear(X.to(DEV), Wd, b.to(DEV), K=K, in_scale=None if sc is None else sc.to(DEV),
+                     in_shift=None if sh is None else sh.to(DEV), stats=stats, pool_group=pool, want_y=True,
+                     precision=_lib.PREC_3XTF32, w_split=ops.split_tf32(Wd))
+    torch.cuda.synchronize()
+    Y = res[0] if pool else res
+    assert rel_err(Y, ref) <= 1e-5      # 3xTF32 error grows ~sqrt(K); K is up to 1280 here
+    assert rel_err(stats[:N], ref.sum(0)) <= 1e-5
+    assert rel_err(stats[N:], (ref ** 2).sum(0)) <= 1e-5
+    if pool:
+        assert rel_err(res[1], ref.reshape(M // pool, pool, N).max(1).values) <= 1e-5
+        assert rel_err(res[2], ref.reshape(M // pool, pool, N).min(1).values) <= 1e-5

@@ -20,7 +20,8 @@ for name, M, K, Nn, pool in LAYERS:
     sh = torch.randn(K, device="cuda")
     out = []
     for prec in (_lib.PREC_FP32, _lib.PREC_3XTF32):
-        path = _lib.load().p2c_linear_path(ld, M, Nn, K, 0, pool, prec)
+        path = _lib.load().p2c_linear_path(ld, M, Nn, K, 0, pool, prec, 1)
+        wsp = ops.split_tf32(W) if path == 2 else None
         ts = []
         REP = 8
         stats = torch.zeros(2 * Nn, dtype=torch.float64, device="cuda")
@@ -33,7 +34,7 @@ for name, M, K, Nn, pool in LAYERS:
             flush.zero_()
             s.record()
             for _ in range(REP):
-                ops.linear(X, W, b, K=K, in_scale=sc, in_shift=sh, stats=stats, pool_group=pool, out=Y, want_y=(pool == 0), precision=prec)
+                ops.linear(X, W, b, K=K, in_scale=sc, in_shift=sh, stats=stats, pool_group=pool, out=Y, want_y=(pool == 0), precision=prec, w_split=wsp)
             e.record(); e.synchronize()
             ts.append(s.elapsed_time(e) / REP)
         t = min(ts[1:])
