@@ -89,6 +89,15 @@ int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_gro
  * launches fills with (tag, globaltimer) pairs per warp role; NULL (default) disables the probes. */
 int p2c_debug_set_timeline(void* buf);
 
+/* Output heads — replaces F.dropout + the fc2 Conv1d heads, models/pointnet_extrusion.py:60-65:
+ *   Y[b*N+n, j] = sum_k max(H[b*N+n,k]*scale[k]+shift[k], 0) * mask_cf[b,k,n] * W[j,k] + bias[j]
+ * H: fc1's raw output (B*N, C) rows; scale/shift: folded bn1 (NULL = identity, no ReLU); mask_cf: the
+ * (B, C, N) channel-first multiplicative dropout mask exactly as F.dropout(ones(B,C,N)) returns it, or NULL;
+ * W: the heads' weights concatenated (Nout, C), Nout <= 36, C <= 256, C % 16 == 0. */
+int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
+                    const float* mask_cf, const float* W, const float* bias, float* Y, int64_t ldy,
+                    int B, int N, int C, int Nout, void* stream);
+
 /* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
  * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
  * training != 0: mean/var from stats (count rows), running stats updated in place with `momentum`;

@@ -123,6 +123,21 @@ def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None
     return Y
 
 
+def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mask_cf: Optional[Tensor],
+                W: Tensor, bias: Optional[Tensor], B: int, N: int) -> Tensor:
+    """Output heads: (B*N, C) raw fc1 rows -> (B*N, Nout); mask_cf is the (B, C, N) dropout mask."""
+    H = _rows(H)
+    C_ = H.shape[1]
+    W2 = W.reshape(W.shape[0], -1).contiguous()
+    Nout = W2.shape[0]
+    if mask_cf is not None and (tuple(mask_cf.shape) != (B, C_, N) or not mask_cf.is_contiguous()):
+        raise _lib.P2CError(f"head_masked: mask must be contiguous (B,C,N)=({B},{C_},{N}), got {tuple(mask_cf.shape)}")
+    Y = torch.empty(B * N, Nout, dtype=torch.float32, device=H.device)
+    call("p2c_head_masked", ptr(H), H.stride(0), ptr(scale), ptr(shift), ptr(mask_cf), ptr(W2), ptr(bias), ptr(Y),
+         Nout, B, N, C_, Nout, stream_ptr())
+    return Y
+
+
 def split_tf32(W: Tensor) -> Tensor:
     """(2, N, pad4(K)) hi/lo copy of a weight matrix for the streamed-weight tensor-core kernel."""
     W2 = W.reshape(W.shape[0], -1)

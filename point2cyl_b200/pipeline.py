@@ -159,16 +159,15 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     # FC head: fc1 -> bn1 -> ReLU -> dropout(p=.5, always on, :60) -> fc2 heads
     h, aff_h = mlp_stack(y6, y6.shape[1], [net.fc1], [net.bn1], net.training, in_affine=aff6,
                          precision=precision, tag="fc1")
-    # Same torch op on the same (B,128,N) shape as the reference so a shared seed gives the same mask.
+    # Same torch op on the same (B,128,N) shape as the reference so a shared seed gives the same mask; the head
+    # kernel consumes it in that channel-first layout (no transpose copy).
     mask_cf = F.dropout(torch.ones(B, h.shape[1], N, dtype=torch.float32, device=dev), p=0.5)
-    mask = mask_cf.permute(0, 2, 1).reshape(B * N, h.shape[1])
-    if not mask.is_contiguous():
-        mask = mask.contiguous()
+    if tuple(mask_cf.shape) != (B, h.shape[1], N):
+        raise _lib.P2CError("dropout mask must keep the (B,128,N) shape")
     Wcat = torch.cat([fc.weight.reshape(fc.weight.shape[0], -1) for fc in net.fc2], dim=0)
     bcat = torch.cat([fc.bias for fc in net.fc2], dim=0)
-    prec = _PRECISIONS[precision or _default_precision]
     _lib.set_tag("fc2")
-    out = ops.linear(h, Wcat, bcat, in_scale=aff_h.scale, in_shift=aff_h.shift, in_mask=mask, precision=prec)
+    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf.contiguous(), Wcat, bcat, B, N)
     if trace is not None:
         trace.update(sa1=t1, sa2=t2, l1_xyz=l1_xyz, l1=l1, l2_xyz=l2_xyz, l2=l2, l3=l3, l4=l4, l5=l5,
                      y6=y6, aff6=aff6, h=h, aff_h=aff_h)

@@ -81,7 +81,7 @@ def test_linear_tc_streamed_weights(M, N, K, pool, prologue):
     Y = res[0] if pool else res
     assert rel_err(Y, ref) <= 1e-5      # 3xTF32 error grows ~sqrt(K); K is up to 1280 here
     assert rel_err(stats[:N], ref.sum(0)) <= 1e-5
-    assert rel_err(stats[N:], (ref ** 2).sum(0)) <= 1e-5
+    assert rel_err(stats[N:], (ref ** 2).sum(0)) <= 3e-5
     if pool:
         assert rel_err(res[1], ref.reshape(M // pool, pool, N).max(1).values) <= 1e-5
         assert rel_err(res[2], ref.reshape(M // pool, pool, N).min(1).values) <= 1e-5

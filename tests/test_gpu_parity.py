@@ -326,3 +326,20 @@ def test_graph_replay_matches_eager(monkeypatch):
     assert rel_err(got["losses"], ref["losses"]) <= 1e-6
     net.train()
     assert g.stale()
+
+
+@pytest.mark.parametrize("B,N,C,Nout,use_mask", [(2, 1024, 128, 19, True), (3, 200, 128, 11, True),
+                                                 (1, 333, 64, 35, False), (2, 256, 128, 3, True)])
+def test_head_masked(B, N, C, Nout, use_mask):
+    g = torch.Generator().manual_seed(N + Nout)
+    H = torch.randn(B * N, C, generator=g)
+    sc, sh = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    mask = (torch.rand(B, C, N, generator=g) > 0.5).float() * 2 if use_mask else None
+    W, b = torch.randn(Nout, C, generator=g) / C ** 0.5, torch.randn(Nout, generator=g)
+    A = torch.relu(H.double() * sc.double() + sh.double())
+    if use_mask:
+        A = A * mask.permute(0, 2, 1).reshape(B * N, C).double()
+    ref = A @ W.double().t() + b.double()
+    got = ops.head_masked(H.to(DEV), sc.to(DEV), sh.to(DEV), None if mask is None else mask.to(DEV), W.to(DEV),
+                          b.to(DEV), B, N)
+    assert rel_err(got, ref) <= 1e-5
