@@ -163,8 +163,14 @@ def algorithmic_work(name, tag, B):
     if name == "p2c_linear":
         stage, _, li = tag.partition(".")
         rows, layers = mlp[stage]
+        if li == "q":   # feature half of a level's first conv, once per source point (conv linearity)
+            k, n = layers[0]
+            return "tensor", 2.0 * (rows // 64) * (k - 3) * n
         k, n = layers[int(li) if li else 0]
         return "tensor", 2.0 * rows * k * n
+    if name == "p2c_sa_first_layer":   # fused gather + first conv: HBM bound on its output rows (+ 8-byte index)
+        rows, layers = mlp[tag.partition(".")[0]]
+        return "hbm", rows * (4.0 * layers[0][1] + 8.0)
     if name == "p2c_fps":
         return "hbm", B * (12 * N + 8 * 512) if tag == "sa1" else B * (12 * 512 + 8 * 128)
     if name == "p2c_ball_query":

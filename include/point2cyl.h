@@ -57,6 +57,16 @@ int p2c_group(const float* xyz, const float* feats, int64_t ldf, const float* ne
               const int64_t* idx, int B, int N, int S, int nsample, int D, float* out, int64_t ldo,
               void* stream);
 
+/* First MLP layer of a set-abstraction level fused with the grouping gather — replaces index_points + centring
+ * + concat + the first Conv2d (models/pointnet_util.py:130-139, 200-201):
+ *   Y[(b,s,j), c] = sum_d W[c,d] * (xyz[b,p,d] - new_xyz[b,s,d]) + Qf[b*N+p, c] + bias[c],  p = idx[b,s,j]
+ * W: the conv weight (C, 3+D) with row stride ldw — only its first three (xyz) columns are read here; the
+ * feature columns act through Qf = feats * W[:, 3:]^T (N rows per cloud, from p2c_linear; NULL when D = 0).
+ * stats as in p2c_linear.  C is 64 or 128. */
+int p2c_sa_first_layer(const float* xyz, const float* new_xyz, const int64_t* idx, const float* Qf, int64_t ldq,
+                       const float* W, int64_t ldw, const float* bias, int B, int N, int S, int nsample, int C,
+                       float* Y, int64_t ldy, double* stats, void* stream);
+
 /* One 1x1-conv layer of a per-point MLP — replaces Conv2d/Conv1d (kernel 1) at
  * models/pointnet_util.py:200-203, :317-319 and models/pointnet_extrusion.py:58-65, with the
  * previous layer's BatchNorm+ReLU (and the head's dropout mask) folded into the operand load and

@@ -86,6 +86,23 @@ def group(xyz: Tensor, feats: Optional[Tensor], new_xyz: Optional[Tensor], idx: 
     return out
 
 
+def sa_first_layer(xyz: Tensor, new_xyz: Tensor, idx: Tensor, Qf: Optional[Tensor], W: Tensor,
+                   bias: Optional[Tensor], stats: Optional[Tensor]) -> Tensor:
+    """Fused grouping gather + first SA conv.  W (C, 3+D[,1,1]); Qf = feats @ W[:, 3:].T rows or None (D = 0)."""
+    xyz, new_xyz = _cloud(xyz), _cloud(new_xyz)
+    B, N, _ = xyz.shape
+    idx = idx.contiguous()
+    S, ns = idx.shape[1], idx.shape[2]
+    W2 = W.reshape(W.shape[0], -1)
+    if not W2.is_contiguous():
+        W2 = W2.contiguous()
+    C_ = W2.shape[0]
+    Y = torch.empty(B * S * ns, C_, dtype=torch.float32, device=xyz.device)
+    call("p2c_sa_first_layer", ptr(xyz), ptr(new_xyz), ptr(idx), ptr(Qf), 0 if Qf is None else Qf.stride(0), ptr(W2),
+         W2.stride(0), ptr(bias), B, N, S, ns, C_, ptr(Y), Y.stride(0), ptr(stats), stream_ptr())
+    return Y
+
+
 def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None,
            in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
            in_mask: Optional[Tensor] = None, stats: Optional[Tensor] = None, pool_group: int = 0,

@@ -51,23 +51,34 @@ class Affine:
 
 def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0,
               in_affine: Optional[Affine] = None, in_mask: Optional[Tensor] = None,
-              precision: Optional[str] = None, tag: str = "mlp"):
+              precision: Optional[str] = None, tag: str = "mlp", first_layer=None):
     """Runs [conv1x1 -> BN -> ReLU] * L over the rows of X.
 
     Returns (Y_last_raw, Affine_last) — or, with pool_group, the pooled post-BN/ReLU features
     (rows/pool_group, C_last).  The BN of layer i is applied inside layer i+1's operand load.
     """
     prec = _PRECISIONS[precision or _default_precision]
-    M = X.shape[0]
+    M = X.shape[0] if X is not None else None
     aff = in_affine
     mask = in_mask
     last = len(convs) - 1
     for i, (conv, bn) in enumerate(zip(convs, bns)):
         N = conv.weight.shape[0]
         use_batch_stats = training or (bn.running_mean is None)
-        stats = torch.zeros(2 * N, dtype=torch.float64, device=X.device) if use_batch_stats else None
+        stats = torch.zeros(2 * N, dtype=torch.float64, device=conv.weight.device) if use_batch_stats else None
         pool = pool_group if i == last else 0
         _lib.set_tag(f"{tag}.{i}")
+        if i == 0 and first_layer is not None:
+            # the level's first conv comes fused with the grouping gather (p2c_sa_first_layer)
+            res = first_layer(stats)
+            M = res.shape[0]
+            scale, shift = ops.bn_finalize(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn),
+                                           use_batch_stats, bn.running_mean, bn.running_var)
+            if training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            aff = Affine(scale, shift)
+            X, K = res, N
+            continue
         wsplit = ops.split_tf32(conv.weight) if ops.needs_split(X, N, K, mask is not None, pool, prec) else None
         res = ops.linear(X, conv.weight, conv.bias, K=K, w_split=wsplit,
                          in_scale=None if aff is None else aff.scale,
@@ -88,7 +99,8 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
 
 
 def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Tensor],
-                    trace: Optional[dict] = None, precision: Optional[str] = None, tag: str = "sa"):
+                    trace: Optional[dict] = None, precision: Optional[str] = None, tag: str = "sa",
+                    fused_first: bool = True):
     """PointNetSetAbstraction in point-major form (models/pointnet_util.py:181-207).
     xyz (B,N,3), feats (B*N, D) rows or None -> (new_xyz (B,S,3), new_feats (B*S, C))."""
     B, N, _ = xyz.shape
@@ -101,10 +113,28 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
     else:
         fps_idx, new_xyz = ops.fps(xyz, sa.npoint, start)
         gidx = ops.ball_query(sa.radius, sa.nsample, xyz, new_xyz)
-        rows = ops.group(xyz, feats, new_xyz, gidx)
         pool = sa.nsample
         if trace is not None:
             trace["fps_idx"], trace["group_idx"] = fps_idx, gidx
+        conv0 = sa.mlp_convs[0]
+        C0 = conv0.weight.shape[0]
+        prec = _PRECISIONS[precision or _default_precision]
+        if C0 in (64, 128) and len(sa.mlp_convs) > 1 and fused_first:
+            # linearity of the 1x1 conv: the feature half of the first layer is computed once per source point
+            W0 = conv0.weight.reshape(C0, -1)
+            Qf = None
+            if feats is not None:
+                _lib.set_tag(tag + ".q")
+                Wf = W0[:, 3:].contiguous()
+                Qf = ops.linear(feats, Wf, None, K=D, precision=prec)
+
+            def first_layer(stats):
+                return ops.sa_first_layer(xyz, new_xyz, gidx, Qf, W0, conv0.bias, stats)
+
+            out = mlp_stack(None, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
+                            tag=tag, first_layer=first_layer)
+            return new_xyz, out
+        rows = ops.group(xyz, feats, new_xyz, gidx)
     out = mlp_stack(rows, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
                     tag=tag)
     return new_xyz, out

@@ -343,3 +343,25 @@ def test_head_masked(B, N, C, Nout, use_mask):
     got = ops.head_masked(H.to(DEV), sc.to(DEV), sh.to(DEV), None if mask is None else mask.to(DEV), W.to(DEV),
                           b.to(DEV), B, N)
     assert rel_err(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("D,C", [(0, 64), (10, 128), (128, 128)])
+def test_sa_first_layer_matches_grouped_conv(D, C):
+    """Fused gather + first conv (conv linearity) == conv over the materialised grouped tensor."""
+    B, N, S, ns = 2, 600, 48, 16
+    g = torch.Generator().manual_seed(D + C)
+    xyz = synthetic.s_uniform(B, N, 41)
+    feats = torch.randn(B, N, D, generator=g) if D else None
+    new_xyz, grouped, _, gidx = orc.sample_and_group(S, 0.35, ns, xyz, feats, torch.zeros(B, dtype=torch.long))
+    W = torch.randn(C, 3 + D, generator=g) / (3 + D) ** 0.5
+    b = torch.randn(C, generator=g)
+    ref = grouped.reshape(-1, 3 + D).double() @ W.double().t() + b.double()
+    Wd = W.to(DEV)
+    Qf = None
+    if D:
+        Qf = ops.linear(feats.reshape(B * N, D).to(DEV), Wd[:, 3:].contiguous(), None, K=D)
+    stats = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    Y = ops.sa_first_layer(xyz.to(DEV), new_xyz.to(DEV), gidx.to(DEV), Qf, Wd, b.to(DEV), stats)
+    assert rel_err(Y, ref) <= 1e-5
+    assert rel_err(stats[:C], ref.sum(0)) <= 1e-5
+    assert rel_err(stats[C:], (ref ** 2).sum(0)) <= 1e-5
