@@ -148,6 +148,15 @@ int p2c_segfit_stats(const float* X_raw, int64_t ldx, const float* W_raw, int64_
                      const int64_t* bb, int B, int N, int K, float* partial /* scratch */,
                      int64_t partial_elems /* >= B*ceil(N/1024)*stride */, float* stats, void* stream);
 
+/* Same statistics from soft assignments the caller already holds (function-level losses.py / data_utils.py
+ * API: hungarian_matching, compute_miou_loss, estimate_extrusion_axis, estimate_extrusion_centers).
+ * wb/wc: (B,N,K), row stride ld*, element stride s* (slices such as W_2K[:, :, ::2] are operands); wc, X, pcs,
+ * gt_normals, inst, bb may each be NULL (their statistics are then zero / labels -1). */
+int p2c_segfit_stats_w(const float* X, int64_t ldx, int normalize_x, const float* wb, int64_t ldb, int64_t sb,
+                       const float* wc, int64_t ldc, int64_t sc, const float* pcs, const float* gt_normals,
+                       const int64_t* inst, const int64_t* bb, int B, int N, int K, float* partial,
+                       int64_t partial_elems, float* stats, void* stream);
+
 /* Hungarian cost (losses.py:39-42): cost (B,K,K) = D / max(cnt_g + colsum_k - D, 1e-10), n_gt (B). */
 int p2c_segfit_cost(const float* stats, int B, int K, float* cost, int32_t* n_gt, void* stream);
 

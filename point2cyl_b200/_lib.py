@@ -45,6 +45,8 @@ SIGNATURES = {
     "p2c_segfit_stats_stride": [i32],
     "p2c_segfit_stats": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_i64p, c_i64p, i32, i32, i32, c_f32p,
                          i64, c_f32p, vp],
+    "p2c_segfit_stats_w": [c_f32p, i64, i32, c_f32p, i64, i64, c_f32p, i64, i64, c_f32p, c_f32p, c_i64p, c_i64p, i32, i32,
+                           i32, c_f32p, i64, c_f32p, vp],
     "p2c_segfit_cost": [c_f32p, i32, i32, c_f32p, c_i32p, vp],
     "p2c_hungarian": [c_f32p, c_i32p, i32, i32, c_i64p, vp],
     "p2c_bb_loss": [c_f32p, i64, c_i64p, c_i64p, c_i32p, i32, i32, i32, c_f32p, i64, c_f32p, vp],
@@ -112,7 +114,7 @@ def need_cuda(*tensors) -> None:
 # kernels launched by one call of each entry point (the `gpu_launches` claim of bench.py)
 LAUNCHES_PER_CALL = {
     "p2c_split_tf32": 1, "p2c_sa_first_layer": 1, "p2c_head_masked": 1, "p2c_fps": 1, "p2c_ball_query": 1, "p2c_group": 1, "p2c_linear": 1, "p2c_bn_finalize": 1,
-    "p2c_bn_relu_apply": 1, "p2c_pool_bn_relu": 1, "p2c_three_nn_interp": 1, "p2c_segfit_stats": 2,
+    "p2c_bn_relu_apply": 1, "p2c_pool_bn_relu": 1, "p2c_three_nn_interp": 1, "p2c_segfit_stats": 2, "p2c_segfit_stats_w": 2,
     "p2c_segfit_cost": 1, "p2c_hungarian": 1, "p2c_bb_loss": 2, "p2c_loss_finalize": 2, "p2c_eig3x3_smallest": 1,
     "p2c_square_distance": 1, "p2c_gather_rows": 1,
 }

@@ -182,6 +182,127 @@ segfit_partial_kernel(const float* __restrict__ X_raw, int64_t ldx, const float*
   }
 }
 
+// Function-level variant (drop-in losses.py / data_utils.py API): the caller already holds the soft assignments.
+// wb/wc: (B,N,K) with row stride ld* and element stride s* (slices like W_2K[:, :, ::2] are accepted); wc, X,
+// pcs, gt normals and bb may be NULL - the corresponding statistics are then zero.  X is used as given
+// (normalize_x = 0) or L2-normalised like F.normalize (normalize_x = 1).
+template <int KP>
+__global__ void __launch_bounds__(SEG_THREADS)
+segfit_partial_w_kernel(const float* __restrict__ X, int64_t ldx, int normalize_x, const float* __restrict__ wbp,
+                        int64_t ldb, int64_t sb, const float* __restrict__ wcp, int64_t ldc, int64_t sc,
+                        const float* __restrict__ pcs, const float* __restrict__ gtn,
+                        const int64_t* __restrict__ inst, const int64_t* __restrict__ bb, int N, int K,
+                        float* __restrict__ partial, int nchunks) {
+  constexpr int NACC = KP + 21;
+  constexpr int PPS = SEG_THREADS / KP;
+  __shared__ float s_red[SEG_THREADS / 32][KP][NACC];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int k = tid % KP, pl = tid / KP;
+  const int lane = tid & 31, warp = tid >> 5;
+  float accD[KP];
+#pragma unroll
+  for (int g = 0; g < KP; ++g) accD[g] = 0.f;
+  float colsum = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  float mb[6] = {0, 0, 0, 0, 0, 0}, mc[6] = {0, 0, 0, 0, 0, 0};
+  float cnt = 0.f, cbar = 0.f, cbase = 0.f, nsum = 0.f, maxlab = -1.f;
+  const int n_end = min(N, (chunk + 1) * SEG_CHUNK);
+  for (int n0 = chunk * SEG_CHUNK; n0 < n_end; n0 += PPS) {
+    const int n = n0 + pl;
+    const bool ok = n < n_end;
+    const size_t row = (size_t)b * N + (ok ? n : (n_end - 1));
+    float wb = 0.f, wc = 0.f;
+    if (ok && k < K) {
+      wb = __ldg(wbp + row * ldb + (size_t)k * sb);
+      if (wcp) wc = __ldg(wcp + row * ldc + (size_t)k * sc);
+    }
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (X) {
+      const float* xr = X + row * ldx;
+      x = __ldg(xr); y = __ldg(xr + 1); z = __ldg(xr + 2);
+      if (normalize_x) {
+        const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+        x *= inv; y *= inv; z *= inv;
+      }
+    }
+    const int g = inst ? (int)inst[row] : -1;
+    const int t = bb ? (int)bb[row] : -1;
+    const float w = wb + wc;
+#pragma unroll
+    for (int gg = 0; gg < KP; ++gg) accD[gg] += (g == gg) ? w : 0.f;
+    colsum += w;
+    if (pcs) {
+      const float* pr = pcs + row * 3;
+      C0 = fmaf(w, __ldg(pr), C0); C1 = fmaf(w, __ldg(pr + 1), C1); C2 = fmaf(w, __ldg(pr + 2), C2);
+    }
+    const float b2 = wb * wb, c2 = wc * wc;
+    const float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+    mb[0] = fmaf(b2, xx, mb[0]); mb[1] = fmaf(b2, xy, mb[1]); mb[2] = fmaf(b2, xz, mb[2]);
+    mb[3] = fmaf(b2, yy, mb[3]); mb[4] = fmaf(b2, yz, mb[4]); mb[5] = fmaf(b2, zz, mb[5]);
+    mc[0] = fmaf(c2, xx, mc[0]); mc[1] = fmaf(c2, xy, mc[1]); mc[2] = fmaf(c2, xz, mc[2]);
+    mc[3] = fmaf(c2, yy, mc[3]); mc[4] = fmaf(c2, yz, mc[4]); mc[5] = fmaf(c2, zz, mc[5]);
+    if (ok) {
+      if (g == k) { cnt += 1.f; cbar += (t == 0) ? 1.f : 0.f; cbase += (t == 1) ? 1.f : 0.f; }
+      if (k == 0) {
+        if (gtn && X) {
+          const float* gr = gtn + row * 3;
+          nsum += 1.0f - fabsf(x * __ldg(gr) + y * __ldg(gr + 1) + z * __ldg(gr + 2));
+        }
+        maxlab = fmaxf(maxlab, (float)g);
+      }
+    }
+  }
+  float acc[NACC];
+#pragma unroll
+  for (int g = 0; g < KP; ++g) acc[g] = accD[g];
+  acc[KP] = colsum; acc[KP + 1] = C0; acc[KP + 2] = C1; acc[KP + 3] = C2;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { acc[KP + 4 + i] = mb[i]; acc[KP + 10 + i] = mc[i]; }
+  acc[KP + 16] = cnt; acc[KP + 17] = cbar; acc[KP + 18] = cbase; acc[KP + 19] = nsum;
+#pragma unroll
+  for (int i = 0; i < KP + 20; ++i) acc[i] = column_sum<KP>(acc[i]);
+#pragma unroll
+  for (int o = 16; o >= KP; o >>= 1) maxlab = fmaxf(maxlab, __shfl_xor_sync(P2C_FULL_MASK, maxlab, o));
+  acc[KP + 20] = maxlab;
+  if (lane < KP) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s_red[warp][lane][i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < KP && tid < K) {
+    float tot[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) tot[i] = 0.f;
+    tot[KP + 20] = -1.f;
+    for (int w = 0; w < SEG_THREADS / 32; ++w) {
+#pragma unroll
+      for (int i = 0; i < KP + 20; ++i) tot[i] += s_red[w][tid][i];
+      tot[KP + 20] = fmaxf(tot[KP + 20], s_red[w][tid][KP + 20]);
+    }
+    float* o = partial + ((size_t)b * nchunks + chunk) * seg_stride(K);
+    const int kk = tid;
+#pragma unroll
+    for (int g = 0; g < KP; ++g)
+      if (g < K) o[g * K + kk] = tot[g];
+    o[off_colsum(K) + kk] = tot[KP];
+    o[off_C(K) + kk * 3 + 0] = tot[KP + 1];
+    o[off_C(K) + kk * 3 + 1] = tot[KP + 2];
+    o[off_C(K) + kk * 3 + 2] = tot[KP + 3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      o[off_Mbar(K) + kk * 6 + i] = tot[KP + 4 + i];
+      o[off_Mbase(K) + kk * 6 + i] = tot[KP + 10 + i];
+    }
+    o[off_cnt(K) + kk] = tot[KP + 16];
+    o[off_cbar(K) + kk] = tot[KP + 17];
+    o[off_cbase(K) + kk] = tot[KP + 18];
+    if (kk == 0) {
+      o[off_normal(K)] = tot[KP + 19];
+      o[off_maxlab(K)] = tot[KP + 20];
+    }
+  }
+}
+
 // fixed-order sum of the chunk partials (deterministic); max for the label slot
 __global__ void segfit_reduce_kernel(const float* __restrict__ partial, int nchunks, int K,
                                      float* __restrict__ stats) {
@@ -454,6 +575,29 @@ extern "C" int p2c_segfit_stats(const float* X_raw, int64_t ldx, const float* W_
   if (KP == 2) P2C_SEG_LAUNCH(2); else if (KP == 4) P2C_SEG_LAUNCH(4);
   else if (KP == 8) P2C_SEG_LAUNCH(8); else P2C_SEG_LAUNCH(16);
 #undef P2C_SEG_LAUNCH
+  P2C_RETURN_IF_CUDA_ERROR();
+  segfit_reduce_kernel<<<B, 128, 0, st>>>(partial, nchunks, K, stats);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_segfit_stats_w(const float* X, int64_t ldx, int normalize_x, const float* wb, int64_t ldb,
+                                  int64_t sb, const float* wc, int64_t ldc, int64_t sc, const float* pcs,
+                                  const float* gt_normals, const int64_t* inst, const int64_t* bb, int B, int N,
+                                  int K, float* partial, int64_t partial_elems, float* stats, void* stream) {
+  if (!wb || !partial || !stats || B <= 0 || N <= 0 || K <= 0) return P2C_EINVAL;
+  const int KP = kp_of(K);
+  if (!KP) return P2C_EUNSUPPORTED;
+  const int nchunks = p2c_ceil_div(N, SEG_CHUNK);
+  if (partial_elems < (int64_t)B * nchunks * seg_stride(K)) return P2C_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(nchunks, B);
+#define P2C_SEGW_LAUNCH(KPV)                                                                              \
+  segfit_partial_w_kernel<KPV><<<grid, SEG_THREADS, 0, st>>>(X, ldx, normalize_x, wb, ldb, sb, wc, ldc, sc, pcs, \
+                                                             gt_normals, inst, bb, N, K, partial, nchunks)
+  if (KP == 2) P2C_SEGW_LAUNCH(2); else if (KP == 4) P2C_SEGW_LAUNCH(4);
+  else if (KP == 8) P2C_SEGW_LAUNCH(8); else P2C_SEGW_LAUNCH(16);
+#undef P2C_SEGW_LAUNCH
   P2C_RETURN_IF_CUDA_ERROR();
   segfit_reduce_kernel<<<B, 128, 0, st>>>(partial, nchunks, K, stats);
   P2C_RETURN_IF_CUDA_ERROR();

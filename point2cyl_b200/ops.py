@@ -256,6 +256,47 @@ def segfit_stats(X_raw: Tensor, W_raw: Tensor, pcs: Tensor, gt_normals: Tensor, 
     return stats
 
 
+def _w_operand(t: Optional[Tensor], B: int, N: int):
+    """(pointer tensor, row stride, element stride) of a (B,N,K) soft-assignment tensor, copying only if its
+    batch dimension does not collapse into rows."""
+    if t is None:
+        return None, 0, 0
+    if t.dtype != torch.float32 or t.stride(0) != N * t.stride(1):
+        t = t.contiguous().float()
+    return t, t.stride(1), t.stride(2)
+
+
+def segfit_stats_w(Wb: Tensor, Wc: Optional[Tensor] = None, X: Optional[Tensor] = None, normalize_x: bool = False,
+                   pcs: Optional[Tensor] = None, gt_normals: Optional[Tensor] = None,
+                   inst: Optional[Tensor] = None, bb: Optional[Tensor] = None) -> Tensor:
+    """Per-cloud statistics (layout of p2c_segfit_stats) from soft assignments (B,N,K) the caller holds."""
+    need_cuda(Wb)
+    B, N, K = Wb.shape
+    wb, ldb, sb = _w_operand(Wb, B, N)
+    wc, ldc, sc = _w_operand(Wc, B, N)
+    Xr = None
+    if X is not None:
+        Xr = _rows(_as_rows(X.float()))
+    pcs = None if pcs is None else _cloud(pcs)
+    gt_normals = None if gt_normals is None else _cloud(gt_normals)
+    inst = None if inst is None else inst.contiguous().long()
+    bb = None if bb is None else bb.contiguous().long()
+    stride = segfit_stride(K)
+    nchunks = (N + 1023) // 1024
+    partial = torch.empty(B * nchunks * stride, dtype=torch.float32, device=Wb.device)
+    stats = torch.empty(B, stride, dtype=torch.float32, device=Wb.device)
+    call("p2c_segfit_stats_w", ptr(Xr), 0 if Xr is None else Xr.stride(0), 1 if normalize_x else 0, ptr(wb), ldb, sb,
+         ptr(wc), ldc, sc, ptr(pcs), ptr(gt_normals), ptr(inst), ptr(bb), B, N, K, ptr(partial), partial.numel(),
+         ptr(stats), stream_ptr())
+    return stats
+
+
+def seg_layout(K: int):
+    """Offsets into a stats row (see csrc/segfit.cu)."""
+    return dict(D=0, cnt=K * K, cbar=K * K + K, cbase=K * K + 2 * K, colsum=K * K + 3 * K, C=K * K + 4 * K,
+                Mbar=K * K + 7 * K, Mbase=K * K + 13 * K, normal=K * K + 19 * K, maxlab=K * K + 19 * K + 1)
+
+
 def _as_rows(t: Tensor) -> Tensor:
     """(B,N,C) tensor whose (B,N) dims collapse to one row dim with unit column stride, else copy."""
     B, N, C_ = t.shape

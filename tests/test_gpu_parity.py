@@ -365,3 +365,48 @@ def test_sa_first_layer_matches_grouped_conv(D, C):
     assert rel_err(Y, ref) <= 1e-5
     assert rel_err(stats[:C], ref.sum(0)) <= 1e-5
     assert rel_err(stats[C:], (ref ** 2).sum(0)) <= 1e-5
+
+
+@pytest.mark.parametrize("name", LOSS)
+def test_function_level_dropins(golden_dir, name):
+    """losses.py / data_utils.py drop-in functions against the reference goldens, called the way the training
+    script calls them (train_Point2Cyl_without_sketch.py:246-347), including strided W slices."""
+    from point2cyl_b200.dropin import data_utils as du
+    from point2cyl_b200.dropin import losses as ls
+    g = load(golden_dir, name)
+    B, N, K, seed, norm_eig = (int(v) for v in g["meta"])
+    data = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, seed).items()}
+    X = torch.nn.functional.normalize(torch.from_numpy(g["X_raw"]).to(DEV), p=2, dim=2, eps=1e-12)
+    W_2K = torch.softmax(torch.from_numpy(g["W_raw"]).to(DEV), dim=2)
+    W_barrel, W_base = W_2K[:, :, ::2], W_2K[:, :, 1::2]
+    W = W_barrel + W_base
+    total, l_n, l_seg, match, mask = ls.compute_all_losses(data["pcs"], W, data["inst"], X, data["normals"], 1.0, 1.0,
+                                                           return_match_indices=True)
+    assert np.array_equal(match.cpu().numpy(), g["matching_indices"])
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])
+    assert rel_err(total, g["total"]) <= TOL and rel_err(l_n, g["normal"]) <= TOL and rel_err(l_seg, g["miou"]) <= TOL
+    m2, mask2 = ls.hungarian_matching(W, data["inst"], with_mask=True)
+    assert torch.equal(m2, match) and torch.equal(mask2, mask)
+    gi = match.unsqueeze(1).expand(B, N, K)
+    E_AX = du.estimate_extrusion_axis(X, torch.gather(W_barrel, 2, gi), torch.gather(W_base, 2, gi), data["bb"],
+                                      data["inst"], normalize=bool(norm_eig))
+    mk = torch.from_numpy(g["mask"])
+    dots = (E_AX.cpu() * torch.from_numpy(g["E_AX"])).sum(-1).abs()
+    assert float((1 - dots[mk]).max()) <= TOL
+    # strided operands (W_2K[:, :, ::2]) go to the kernel without a copy
+    E2 = du.estimate_extrusion_axis(X, W_barrel, W_base, data["bb"], data["inst"], normalize=False)
+    E2r = orc.estimate_extrusion_axis(X.cpu(), W_barrel.cpu(), W_base.cpu())
+    assert float((1 - (E2.cpu() * E2r).sum(-1).abs()).max()) <= TOL
+    centers = du.estimate_extrusion_centers(torch.gather(W, 2, gi), data["pcs"])
+    assert rel_err(centers.cpu()[mk], torch.from_numpy(g["centers"])[mk]) <= TOL
+    hard = ls.hard_W_encoding(W, to_null_mask=True)
+    assert np.array_equal(hard.argmax(-1).cpu().numpy().astype(np.int8), g["hard_argmax"])
+    assert np.array_equal(hard.sum(-1).cpu().numpy().astype(np.int8), g["hard_rowsum"])
+    iou = ls.compute_segmentation_iou(W, data["inst"], match, mask.float())
+    assert rel_err(iou, g["seg_iou"]) <= TOL
+    assert rel_err(ls.compute_normal_difference(X, data["normals"]), g["normal_diff"]) <= TOL
+    miou, _, Wr = ls.compute_miou_loss(W, data["inst"], match)
+    ref_miou, _, ref_Wr = orc.compute_miou_loss(W.cpu(), data["inst"].cpu(), match.cpu())
+    assert rel_err(miou, ref_miou) <= TOL and torch.equal(Wr.cpu(), ref_Wr)
+    nl = ls.compute_normal_loss(X, data["normals"], angle_diff=False, collapse=False)
+    assert rel_err(nl, orc.compute_normal_loss(X.cpu(), data["normals"].cpu(), collapse=False)) <= TOL
