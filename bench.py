@@ -202,12 +202,11 @@ def main():
     import torch.distributed as dist
     import point2cyl_b200
     from point2cyl_b200 import _lib, pipeline, synthetic
+    from point2cyl_b200 import dist as pd
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    pd.init("nccl")          # one process per GPU; NCCL is used for the timing barrier / max-reduce only
     pipeline.set_precision(args.precision)
     _lib.load()
 
@@ -216,10 +215,7 @@ def main():
     batch = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = pd.barrier
 
     def timed(fn, steps):
         """per-step CUDA-event time on the current stream, L2 flushed (untimed) between steps"""
@@ -273,14 +269,8 @@ def main():
     barrier()
     clk = clocks.stop()
 
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    total_ms = max_over_ranks(sum(ms))
-    total_ms_e2e = max_over_ranks(sum(ms_e2e))
+    total_ms = pd.reduce_max(sum(ms), dev)
+    total_ms_e2e = pd.reduce_max(sum(ms_e2e), dev)
     clouds = B_PER_GPU * world * args.steps
     value = clouds / (total_ms / 1e3)
     e2e = clouds / (total_ms_e2e / 1e3)
