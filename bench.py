@@ -161,13 +161,18 @@ def algorithmic_work(name, tag, B):
         "fc2": (B * N, [(128, 3 + 2 * K_INST)]),
     }
     if name == "p2c_linear":
+        # (flops, compulsory bytes): a layer reads its raw input rows once and writes its raw output rows once
+        # (pooled last layers write rows/nsample instead); weights are negligible
         stage, _, li = tag.partition(".")
         rows, layers = mlp[stage]
         if li == "q":   # feature half of a level's first conv, once per source point (conv linearity)
             k, n = layers[0]
-            return "tensor", 2.0 * (rows // 64) * (k - 3) * n
-        k, n = layers[int(li) if li else 0]
-        return "tensor", 2.0 * rows * k * n
+            r = rows // 64
+            return "linear", (2.0 * r * (k - 3) * n, 4.0 * r * ((k - 3) + n))
+        i = int(li) if li else 0
+        k, n = layers[i]
+        pooled = stage in ("sa1", "sa2", "sa3") and i == len(layers) - 1
+        return "linear", (2.0 * rows * k * n, 4.0 * rows * k + (8.0 * rows / (128 if stage == "sa3" else 64) * n if pooled else 4.0 * rows * n))
     if name == "p2c_sa_first_layer":   # fused gather + first conv: HBM bound on its output rows (+ 8-byte index)
         rows, layers = mlp[tag.partition(".")[0]]
         return "hbm", rows * (4.0 * layers[0][1] + 8.0)
@@ -291,27 +296,40 @@ def main():
                 a[1] += 1
         per_kernel = {}
         for (name, tag), (t, n) in agg.items():
-            d = per_kernel.setdefault(name, {"ms": 0.0, "work": 0.0, "bound": None, "launches": 0})
+            d = per_kernel.setdefault(name, {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
             bound, work = algorithmic_work(name, tag, B_PER_GPU)
             d["ms"] += t / reps
             d["launches"] += n // reps
-            if work:
-                d["work"] += work
-                d["bound"] = bound
+            if bound == "linear":
+                d["flops"] += work[0]
+                d["bytes"] += work[1]
+            elif work:
+                d["bytes"] += work
+        stages = {}
+        for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"]):
+            e = {"ms": round(v["ms"], 4), "launches": v["launches"]}
+            if v["bytes"]:
+                e["hbm_gbs"] = round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1)
+                e["hbm_frac"] = round(e["hbm_gbs"] / pk["hbm"], 4)
+            if v["flops"]:
+                e["tflops"] = round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)
+            stages[k] = e
         top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
         d = per_kernel[top]
-        if d["bound"] == "tensor":
-            ach = d["work"] / (d["ms"] / 1e3) / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16"], "traffic": None,
-                    "note": f"all {d['launches']} {top} launches of a step: algorithmic MLP FLOPs / summed CUDA-event "
-                            f"time; peak = {pk['src']} sustained bf16 cuBLAS (fp32-faithful path reported against it)"}
-        elif d["work"]:
-            ach = d["work"] / (d["ms"] / 1e3) / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": None, "note": f"peak = {pk['src']} copy bandwidth"}
-        stages = {k: round(v["ms"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])}
-
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "linear_traffic.json")   # ncu dram bytes of the same launches
+        if top == "p2c_linear" and os.path.isfile(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+        ach = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["bytes"] else 0.0
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": traffic,
+                "note": f"the {d['launches']} {top} launches of one step taken together: compulsory bytes "
+                        f"(4*rows*(K+N) per layer) / summed CUDA-event time, peak = {pk['src']} copy bandwidth. "
+                        "These per-point MLP layers are HBM bound on this network (K, N <= 128 on the big row counts)"}
+        if d["flops"]:
+            tf = d["flops"] / (d["ms"] / 1e3) / 1e12
+            roof["tensor_tflops"] = tf
+            roof["tensor_frac_of_bf16_peak"] = tf / pk["bf16"]
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample()
@@ -325,7 +343,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host),
                     "d2h_bytes_per_step": 24 + (0 if graphed is not None else B_PER_GPU * K_INST * K_INST * 4 + B_PER_GPU * 4), "ms_per_step": total_ms_e2e / args.steps},
             "gpu_launches": launches, "launch_mode": "eager" if graphed is None else "cuda_graph", "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "kernel_ms_per_step": stages}), flush=True)
+            "stages": stages}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
