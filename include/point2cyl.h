@@ -197,6 +197,46 @@ int p2c_square_distance(const float* src /* (B,S,3) */, const float* dst /* (B,N
 int p2c_gather_rows(const float* points, int64_t ldp, const int64_t* idx /* (B,Mper) */, int B, int N,
                     int Mper, int C, float* out /* (B,Mper,C) */, void* stream);
 
+/* ---- second wave: projection / scale / extent closed forms and eval helpers (a18) ---- */
+
+/* Order-preserving member lists per (cloud, segment) — replaces the `one_hot` / `where(bb==0)` / `nonzero()`
+ * selection of data_utils.py:1018-1061 (and :1654-1695): point n is a member of list (b,k) iff
+ * seg_label[b,n] == k and (bb == NULL or bb[b,n] == bb_value).  counts (B,K) int32; lists (B,K,N) int32, first
+ * counts[b,k] entries valid, ascending point index (the order nonzero() yields); lists may be NULL (counts only). */
+int p2c_segment_lists(const int64_t* seg_label, const int64_t* bb, int bb_value, int B, int N, int K,
+                      int32_t* counts, int32_t* lists, void* stream);
+
+/* Sketch projection — replaces the body of sketch_implicit_projection / 2 / 3, data_utils.py:1014-1417:
+ * per (segment k, cloud b) gather the sampled member points (member number rand_idx[k,b,s] of list (b,k);
+ * rand_idx == NULL: member s itself, lists == NULL: every point is a member — variant 3), rotate the extrusion axis
+ * onto +z with torchgeometry's angle_axis_to_rotation_matrix applied to (a x z)*angle (the axis is NOT normalised
+ * upstream, :1096-1103 — replicated), drop z, subtract the projected centre (:1127-1131), scale = max 2-norm
+ * (:1136).  Segments with <= 1 member over the batch give zeros / scale 1 (:1042-1044); clouds with <= 1 member
+ * give -centre_projected / scale 1 (:1054-1056 leaves zero rows that are still centred).  X / X_proj may be NULL.
+ * P_proj, X_proj: (K,B,S,2); scales (K,B); found (B,K) 0/1 or NULL. */
+int p2c_sketch_project(const float* P, const float* X, int B, int N, int K, int S, const int32_t* lists,
+                       const int32_t* counts, const int64_t* rand_idx /* (K,B,S) */, const float* axes /* (B,K,3) */,
+                       const float* centers /* (B,K,3) */, float zero_tol, float* P_proj, float* X_proj,
+                       float* scales, float* found, void* stream);
+
+/* Extents along the axis — replaces get_extrusion_extents, data_utils.py:1650-1730: min / max over the sampled
+ * members of (p - c).a; same selection and not-found conventions as above.  extents (K,B,2). */
+int p2c_extrusion_extents(const float* P, int B, int N, int K, int S, const int32_t* lists, const int32_t* counts,
+                          const int64_t* rand_idx, const float* axes, const float* centers, float* extents,
+                          float* found, void* stream);
+
+/* hard_W_encoding, losses.py:55-68: hard[b,n,:] = one-hot(first arg-max_k W[b,n,k]), zeroed when that column's
+ * sum over N (colsum (B,K), from p2c_segfit_stats_w; NULL = keep all) is below null_below = N * threshold.
+ * W rows have stride ldw and element stride sw.  label (B,N) int64 = the arg-max (eval.py:328, :339); either output
+ * may be NULL. */
+int p2c_hard_w_encoding(const float* W, int64_t ldw, int64_t sw, int B, int N, int K, const float* colsum,
+                        float null_below, float* hard /* (B,N,K) */, int64_t* label /* (B,N) */, void* stream);
+
+/* compute_normal_difference / acos_safe, losses.py:123-124, :146-159: scale * acos(clamp(|<x,g>|, +-(1-1e-6))) per
+ * point (per_point (B,N) or NULL) and summed per cloud (per_cloud_sum (B) or NULL). */
+int p2c_normal_angle(const float* X, const float* G, int B, int N, float scale, float* per_point,
+                     float* per_cloud_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

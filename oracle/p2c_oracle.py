@@ -13,6 +13,9 @@ tests/golden/make_golden.py imports the real reference through
 oracle/ref_shim.py, runs both on the same seeded inputs and commits the
 reference outputs under tests/golden/; tests/test_oracle_golden.py checks this
 restatement against those files (indices bit-exact, floats to 1e-6).
+One exception, PARITY UNPINNED: torchgeometry==0.1.2's angle_axis_to_rotation_matrix
+(used only by the projection functions) is absent offline and restated
+from its published algorithm; see the note above `angle_axis_to_rotation_matrix` below.
 
 Every function cites the reference file:line it follows (paths relative to the
 upstream repo root).  Layout conventions are the reference's: clouds are
@@ -542,3 +545,129 @@ def compute_normal_difference(X, X_gt, in_radians=True, collapse=True) -> Tensor
     if not in_radians:
         d = d * 180.0 / math.pi
     return d.mean(dim=1) if collapse else d
+
+
+# projection / scale / extent closed forms -------------------------------------------------------
+#
+# PARITY UNPINNED for the rotation: the reference calls torchgeometry==0.1.2 `angle_axis_to_rotation_matrix`
+# (requirements.txt:15), which is neither under /root/reference nor installable offline.  The function below
+# restates its published algorithm (ceres-style Rodrigues with w = aa / (theta + 1e-6) for theta^2 > 1e-6, the
+# first-order Taylor form otherwise, returned as a 4x4 homogeneous matrix).  oracle/ref_shim.py installs it as the
+# `torchgeometry` stub so that the reference's OWN projection functions (data_utils.py:1014-1417, :1650-1730) can
+# be run here to produce tests/golden/projection_*.npz; everything around the rotation is therefore pinned by the
+# reference's code, the rotation itself only by this restatement.
+
+
+def angle_axis_to_rotation_matrix(angle_axis: Tensor) -> Tensor:
+    """torchgeometry 0.1.2 conversions.angle_axis_to_rotation_matrix: (n,3) -> (n,4,4)."""
+    aa = angle_axis
+    theta2 = (aa * aa).sum(dim=1, keepdim=True)
+    theta = torch.sqrt(theta2)
+    w = aa / (theta + 1e-6)
+    wx, wy, wz = w[:, 0:1], w[:, 1:2], w[:, 2:3]
+    c, s = torch.cos(theta), torch.sin(theta)
+    normal = torch.cat([c + wx * wx * (1 - c), wx * wy * (1 - c) - wz * s, wy * s + wx * wz * (1 - c),
+                        wz * s + wx * wy * (1 - c), c + wy * wy * (1 - c), -wx * s + wy * wz * (1 - c),
+                        -wy * s + wx * wz * (1 - c), wx * s + wy * wz * (1 - c), c + wz * wz * (1 - c)],
+                       dim=1).view(-1, 3, 3)
+    rx, ry, rz = aa[:, 0:1], aa[:, 1:2], aa[:, 2:3]
+    one = torch.ones_like(rx)
+    taylor = torch.cat([one, -rz, ry, rz, one, -rx, -ry, rx, one], dim=1).view(-1, 3, 3)
+    mask = (theta2 > 1e-6).view(-1, 1, 1).to(aa.dtype)
+    out = torch.eye(4, dtype=aa.dtype).view(1, 4, 4).repeat(aa.shape[0], 1, 1)
+    out[:, :3, :3] = mask * normal + (1 - mask) * taylor
+    return out
+
+
+def _member_lists(seg_label: Tensor, bb_labels: Optional[Tensor], K: int):
+    """data_utils.py:1018-1025, :1038-1061: members[b][k] = ascending point indices with label k and bb == 0."""
+    B, N = seg_label.shape
+    out = []
+    for b in range(B):
+        row = []
+        for k in range(K):
+            m = seg_label[b] == k
+            if bb_labels is not None:
+                m = m & (bb_labels[b] == 0)
+            row.append(m.nonzero().reshape(-1))
+        out.append(row)
+    return out
+
+
+def sketch_implicit_projection(P, X, seg_label, bb_labels, axes, centers, S=1024, all_points=False,
+                               zero_tol=1.0e-6):
+    """data_utils.py:1014-1146 (variants 2/3: :1149-1417) -> P_proj (K,B,S,2), X_proj (K,B,S,2), scales (K,B),
+    found (B,K).  Consumes the global CPU generator in the reference's order (:1064)."""
+    B, K, _ = axes.shape
+    N = P.shape[1]
+    members = None if all_points else _member_lists(seg_label, bb_labels, K)
+    P_proj = torch.zeros(K, B, S, 2)
+    X_proj = torch.zeros(K, B, S, 2)
+    found = torch.zeros(B, K)
+    scales = torch.ones(K, B)
+    z = torch.tensor([0.0, 0.0, 1.0])
+    for i in range(K):
+        cnt = [N if all_points else int(members[b][i].numel()) for b in range(B)]
+        if sum(cnt) <= 1:
+            continue
+        pts = torch.zeros(B, S, 3)
+        nrm = torch.zeros(B, S, 3)
+        for j in range(B):
+            if cnt[j] <= 1:
+                continue
+            if all_points:
+                sel = torch.arange(N)
+            else:
+                sel = members[j][i][torch.randint(0, cnt[j], (S,))]
+            pts[j], nrm[j] = P[j, sel], X[j, sel]
+            found[j, i] = 1.0
+        R = torch.eye(3).repeat(B, 1, 1)
+        ang = torch.acos((axes[:, i] * z).sum(-1))
+        for a in range(B):
+            if ang[a] > zero_tol:
+                rot_axis = torch.linalg.cross(axes[a, i], z)
+                R[a] = angle_axis_to_rotation_matrix((rot_axis * ang[a]).unsqueeze(0))[0, :3, :3]
+        pp = torch.bmm(pts, R)[:, :, :2]
+        xp = torch.bmm(nrm, R)[:, :, :2]
+        cp = torch.bmm(centers[:, i].unsqueeze(1), R)[:, :, :2]
+        pp = pp - cp
+        scales[i] = pp.pow(2).sum(-1).sqrt().max(dim=-1)[0]
+        P_proj[i], X_proj[i] = pp, xp
+    scales = torch.where(found.T == 1, scales, torch.ones_like(scales))
+    return P_proj, X_proj, scales, found
+
+
+def get_extrusion_extents(P, seg_label, bb_labels, axes, centers, S=1024):
+    """data_utils.py:1650-1730 -> extents (K,B,2), found (B,K)."""
+    B, K, _ = axes.shape
+    members = _member_lists(seg_label, bb_labels, K)
+    found = torch.zeros(B, K)
+    extents = torch.zeros(K, B, 2)
+    for i in range(K):
+        cnt = [int(members[b][i].numel()) for b in range(B)]
+        if sum(cnt) <= 1:
+            continue
+        pts = torch.zeros(B, S, 3)
+        for j in range(B):
+            if cnt[j] <= 1:
+                continue
+            pts[j] = P[j, members[j][i][torch.randint(0, cnt[j], (S,))]]
+            found[j, i] = 1.0
+        d = ((pts - centers[:, i].unsqueeze(1)) * axes[:, i].unsqueeze(1)).sum(-1)
+        extents[i, :, 0], extents[i, :, 1] = d.min(dim=-1)[0], d.max(dim=-1)[0]
+    return extents, found
+
+
+def segment_centroids(EA_W: Tensor, pcs: Tensor):
+    """eval.py:409-436: mean of the points with EA_W == 1 per (cloud, segment) when there are >= 2 of them."""
+    B, N, K = EA_W.shape
+    cen = torch.zeros(B, K, 3)
+    found = torch.zeros(B, K)
+    for j in range(K):
+        for b in range(B):
+            sel = (EA_W[b, :, j] == 1).nonzero().reshape(-1)
+            if sel.numel() <= 1:
+                continue
+            cen[b, j] = pcs[b, sel].mean(dim=0)
+            found[b, j] = 1.0
+    return cen, found

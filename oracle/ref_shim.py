@@ -9,8 +9,9 @@ smoke() or bench.py imports it.
 
 What it patches:
   * stub modules for dependencies the reference imports at module scope but never
-    uses on the forward+loss path: chamferdist, h5py, trimesh, torchgeometry,
-    plyfile, skimage (data_utils.py:5-24, losses.py:14, utils.py:7-11)
+    uses on the forward+loss path: chamferdist, h5py, trimesh, plyfile, skimage
+    (data_utils.py:5-24, losses.py:14, utils.py:7-11); torchgeometry gets the oracle's
+    restatement of angle_axis_to_rotation_matrix (used by the projection functions)
   * torch.symeig (data_utils.py:170) was removed from torch; symeig defaulted to
     upper=True and returned ascending eigenvalues, which is
     torch.linalg.eigh(A, UPLO='U').
@@ -46,7 +47,10 @@ def _install_stubs():
     _stub("chamferdist", ChamferDistance=_ChamferDistance)
     _stub("h5py")
     _stub("trimesh")
-    _stub("torchgeometry")
+    # torchgeometry==0.1.2 cannot be installed offline; its one function on our path is restated in the oracle
+    # (PARITY UNPINNED for that function, see oracle/p2c_oracle.py) and handed to the reference as `tgm`.
+    from oracle import p2c_oracle as _orc
+    _stub("torchgeometry", angle_axis_to_rotation_matrix=_orc.angle_axis_to_rotation_matrix)
     _stub("plyfile")
     sk = _stub("skimage")
     sk.measure = _stub("skimage.measure")

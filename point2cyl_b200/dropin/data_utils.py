@@ -51,3 +51,80 @@ def estimate_extrusion_centers(W, pcs):
     st = ops.segfit_stats_w(W, None, None, False, pcs, None, None, None)
     L = ops.seg_layout(K)
     return st[:, L["C"]:L["C"] + 3 * K].reshape(B, K, 3) / N
+
+
+# ---- projection / scale / extent closed forms -------------------------------------------------
+
+
+def _draw_member_samples(counts, S):
+    """The reference's random stream, data_utils.py:1064: for every segment i (outer) and cloud j (inner) that pass
+    the two `<= 1 member` checks (:1042, :1054), one `torch.randint(0, n_members, (S,))` on the CPU generator.
+    One device->host copy of the (B,K) member counts replaces the reference's K*B `nonzero()` syncs."""
+    cnt = counts.cpu()
+    B, K = cnt.shape
+    rnd = torch.zeros(K, B, S, dtype=torch.long)
+    tot = cnt.sum(dim=0)
+    for i in range(K):
+        if int(tot[i]) <= 1:
+            continue
+        for j in range(B):
+            n = int(cnt[j, i])
+            if n <= 1:
+                continue
+            rnd[i, j] = torch.randint(0, n, (S,))
+    return rnd.to(counts.device, non_blocking=True)
+
+
+def _project(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers, S, all_points):
+    B, K, _ = extrusion_axes.shape
+    N = P.shape[1]
+    if all_points:
+        # variant 3 (:1294): every point is a member of every segment and is used in order, so N must equal S
+        if N != S:
+            raise RuntimeError(f"sketch_implicit_projection3 needs num_points_to_sample == N ({S} vs {N})")
+        counts = torch.full((B, K), N, dtype=torch.int32, device=P.device)
+        lists = rnd = None
+    else:
+        counts, lists = ops.segment_lists(seg_label, bb_labels, 0, K)
+        rnd = _draw_member_samples(counts, S)
+    return ops.sketch_project(P, X, lists, counts, rnd, extrusion_axes, extrusion_centers, S, g_zero_tol)  # noqa: F405
+
+
+def sketch_implicit_projection(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers,
+                               num_points_to_sample=1024):
+    """data_utils.py:1014-1146 -> P_projected (K,B,S,2), X_projected (K,B,S,2), scales (K,B)."""
+    Pp, Xp, sc, _ = _project(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers, num_points_to_sample, False)
+    return Pp, Xp, sc
+
+
+def sketch_implicit_projection2(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers,
+                                num_points_to_sample=1024):
+    """data_utils.py:1149-1281: as above plus found_centers_mask (B,K)."""
+    return _project(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers, num_points_to_sample, False)
+
+
+def sketch_implicit_projection3(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers,
+                                num_points_to_sample=8192):
+    """data_utils.py:1284-1417: all points of the cloud, unsampled, for every segment."""
+    return _project(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers, num_points_to_sample, True)
+
+
+def get_extrusion_extents(P, seg_label, bb_labels, extrusion_axes, extrusion_centers, num_points_to_sample=1024):
+    """data_utils.py:1650-1730 -> extents (K,B,2) = min/max of (p - c).a over the sampled barrel points, found (B,K)."""
+    B, K, _ = extrusion_axes.shape
+    counts, lists = ops.segment_lists(seg_label, bb_labels, 0, K)
+    rnd = _draw_member_samples(counts, num_points_to_sample)
+    return ops.extrusion_extents(P, lists, counts, rnd, extrusion_axes, extrusion_centers, num_points_to_sample)
+
+
+def estimate_segment_centroids(EA_W, pcs):
+    """Function form of the inline centroid loop of eval.py:409-436: per (cloud, segment) the mean of the points with
+    EA_W == 1 when there are at least two of them -> predicted_centroids (B,K,3), found_centers_mask (B,K)."""
+    B, N, K = EA_W.shape
+    hard = (EA_W == 1).float()
+    st = ops.segfit_stats_w(hard, None, None, False, pcs, None, None, None)
+    L = ops.seg_layout(K)
+    cnt = st[:, L["colsum"]:L["colsum"] + K]
+    found = cnt > 1.5
+    cen = st[:, L["C"]:L["C"] + 3 * K].reshape(B, K, 3) / cnt.clamp_min(1.0)[:, :, None]
+    return torch.where(found[:, :, None], cen, torch.zeros_like(cen)), found.float()

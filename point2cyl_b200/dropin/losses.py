@@ -33,15 +33,13 @@ def hungarian_matching(W_pred, I_gt, with_mask=False):
 
 
 def hard_W_encoding(W, to_null_mask=False, W_null_threshold=0.005):
-    """losses.py:55-68: arg-max one-hot, columns with sum W < threshold*N zeroed when asked."""
+    """losses.py:55-68: arg-max one-hot, columns with sum W < threshold*N zeroed when asked (p2c_hard_w_encoding)."""
     B, N, K = W.shape
-    hard = torch.zeros_like(W, dtype=torch.float32)
-    hard.scatter_(2, torch.argmax(W, dim=2, keepdim=True), 1.0)
+    colsum = None
     if to_null_mask:
         st, L, _ = _stats(W)
         colsum = st[:, L["colsum"]:L["colsum"] + K]
-        hard = hard * (1.0 - (colsum < float(N) * W_null_threshold).float())[:, None, :]
-    return hard
+    return ops.hard_w_encoding(W, colsum, float(N) * W_null_threshold)
 
 
 def sequence_mask(lengths, maxlen=None):
@@ -102,11 +100,9 @@ def compute_normal_loss(normal, normal_gt, angle_diff, collapse=True):
 
 
 def compute_normal_difference(X, X_gt, in_radians=True, collapse=True):
-    """losses.py:146-159."""
-    d = acos_safe(torch.abs(torch.sum(X * X_gt, dim=2)))
-    if not in_radians:
-        d = d * 180.0 / TORCH_PI
-    return torch.mean(d, dim=1) if collapse else d
+    """losses.py:146-159 (p2c_normal_angle)."""
+    scale = 1.0 if in_radians else 180.0 / TORCH_PI
+    return ops.normal_angle(X, X_gt, scale, collapse)
 
 
 def compute_all_losses(P, W, I_gt, X, X_gt, normal_loss_multiplier, miou_loss_multiplier,

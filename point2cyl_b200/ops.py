@@ -381,3 +381,87 @@ def gather_rows(points: Tensor, idx: Tensor) -> Tensor:
     out = torch.empty(B, Mper, C_, dtype=torch.float32, device=points.device)
     call("p2c_gather_rows", ptr(pts), pts.stride(1), ptr(flat), B, N, Mper, C_, ptr(out), stream_ptr())
     return out.reshape(*idx.shape, C_)
+
+
+# ---- second wave: projections / extents / eval helpers ----------------------------------
+
+
+def segment_lists(seg_label: Tensor, bb: Optional[Tensor], bb_value: int, K: int, want_lists: bool = True):
+    """counts (B,K) int32 [, lists (B,K,N) int32]: members of (b,k) are points with seg_label == k (and bb == bb_value),
+    ascending point index."""
+    need_cuda(seg_label, bb)
+    B, N = seg_label.shape
+    seg_label = seg_label.contiguous().long()
+    bb = None if bb is None else bb.contiguous().long()
+    counts = torch.empty(B, K, dtype=torch.int32, device=seg_label.device)
+    lists = torch.empty(B, K, N, dtype=torch.int32, device=seg_label.device) if want_lists else None
+    call("p2c_segment_lists", ptr(seg_label), ptr(bb), bb_value, B, N, K, ptr(counts), ptr(lists), stream_ptr())
+    return counts, lists
+
+
+def sketch_project(P: Tensor, X: Optional[Tensor], lists: Optional[Tensor], counts: Tensor, rand_idx: Optional[Tensor],
+                   axes: Tensor, centers: Tensor, S: int, zero_tol: float):
+    """-> P_proj (K,B,S,2), X_proj (K,B,S,2) | None, scales (K,B), found (B,K)."""
+    need_cuda(P, X, counts, axes, centers)
+    P = _cloud(P)
+    X = None if X is None else _cloud(X)
+    B, N, _ = P.shape
+    K = axes.shape[1]
+    dev = P.device
+    P_proj = torch.empty(K, B, S, 2, dtype=torch.float32, device=dev)
+    X_proj = torch.empty(K, B, S, 2, dtype=torch.float32, device=dev) if X is not None else None
+    scales = torch.empty(K, B, dtype=torch.float32, device=dev)
+    found = torch.empty(B, K, dtype=torch.float32, device=dev)
+    if rand_idx is not None:
+        rand_idx = rand_idx.to(device=dev, dtype=torch.long).contiguous()
+    call("p2c_sketch_project", ptr(P), ptr(X), B, N, K, S, ptr(lists), ptr(counts), ptr(rand_idx),
+         ptr(axes.contiguous().float()), ptr(centers.contiguous().float()), float(zero_tol), ptr(P_proj), ptr(X_proj),
+         ptr(scales), ptr(found), stream_ptr())
+    return P_proj, X_proj, scales, found
+
+
+def extrusion_extents(P: Tensor, lists: Optional[Tensor], counts: Tensor, rand_idx: Optional[Tensor], axes: Tensor,
+                      centers: Tensor, S: int):
+    """-> extents (K,B,2) [min, max of (p-c).a], found (B,K)."""
+    need_cuda(P, counts, axes, centers)
+    P = _cloud(P)
+    B, N, _ = P.shape
+    K = axes.shape[1]
+    extents = torch.empty(K, B, 2, dtype=torch.float32, device=P.device)
+    found = torch.empty(B, K, dtype=torch.float32, device=P.device)
+    if rand_idx is not None:
+        rand_idx = rand_idx.to(device=P.device, dtype=torch.long).contiguous()
+    call("p2c_extrusion_extents", ptr(P), B, N, K, S, ptr(lists), ptr(counts), ptr(rand_idx),
+         ptr(axes.contiguous().float()), ptr(centers.contiguous().float()), ptr(extents), ptr(found), stream_ptr())
+    return extents, found
+
+
+def hard_w_encoding(W: Tensor, colsum: Optional[Tensor], null_below: float, want_hard: bool = True,
+                    want_label: bool = False):
+    """W (B,N,K) (strided ok) -> hard (B,N,K) one-hot of the arg-max with nulled columns zeroed [, label (B,N)]."""
+    need_cuda(W)
+    B, N, K = W.shape
+    w, ldw, sw = _w_operand(W, B, N)
+    hard = torch.empty(B, N, K, dtype=torch.float32, device=W.device) if want_hard else None
+    label = torch.empty(B, N, dtype=torch.long, device=W.device) if want_label else None
+    if colsum is not None:
+        colsum = colsum.contiguous().float()
+    call("p2c_hard_w_encoding", ptr(w), ldw, sw, B, N, K, ptr(colsum), float(null_below), ptr(hard), ptr(label),
+         stream_ptr())
+    if want_hard and want_label:
+        return hard, label
+    return hard if want_hard else label
+
+
+def normal_angle(X: Tensor, G: Tensor, scale: float = 1.0, collapse: bool = True) -> Tensor:
+    """scale * acos_safe(|<x,g>|): per point (B,N) or its mean over N (B,)."""
+    need_cuda(X, G)
+    X, G = _cloud(X), _cloud(G)
+    B, N, _ = X.shape
+    if collapse:
+        out = torch.empty(B, dtype=torch.float32, device=X.device)
+        call("p2c_normal_angle", ptr(X), ptr(G), B, N, float(scale), None, ptr(out), stream_ptr())
+        return out / N
+    out = torch.empty(B, N, dtype=torch.float32, device=X.device)
+    call("p2c_normal_angle", ptr(X), ptr(G), B, N, float(scale), ptr(out), None, stream_ptr())
+    return out

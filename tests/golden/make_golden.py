@@ -153,6 +153,48 @@ def loss_case(ref, name, B, N, K, seed, norm_eig):
     print("wrote", name)
 
 
+def projection_case(ref, name, B, N, K, S, seed):
+    """Second-wave closed forms run by the reference's own code (data_utils.py:1014-1417, :1650-1730); the CPU
+    generator is re-seeded before each call so the consumer can reproduce the randint stream.  Cloud 0 loses one
+    segment entirely except for a single point and one segment is relabelled base-only, so both `<= 1 member`
+    branches (:1042, :1054) are exercised; the axes include an exact +z, a near +z and a -z axis."""
+    data = synthetic.s_cyl(B, N, K, seed)
+    P, X, inst, bb = data["pcs"], data["normals"], data["inst"].clone(), data["bb"].clone()
+    axes, centers = data["axes"].clone(), data["centers"].clone()
+    g = torch.Generator().manual_seed(seed + 11)
+    # fill the zero-padded gt slots with random unit axes / centres so every (b,k) rotation is non-trivial
+    pad = axes.norm(dim=-1) == 0
+    rnd_ax = torch.nn.functional.normalize(torch.randn(B, K, 3, generator=g), dim=-1)
+    axes[pad] = rnd_ax[pad]
+    centers[pad] = (torch.rand(B, K, 3, generator=g) - 0.5)[pad]
+    axes[0, 0] = torch.tensor([0.0, 0.0, 1.0])
+    axes[1, 0] = torch.nn.functional.normalize(torch.tensor([1e-4, -2e-4, 1.0]), dim=-1)
+    axes[min(2, B - 1), 1 % K] = torch.tensor([0.0, 0.0, -1.0])
+    bb[0][inst[0] == 0] = 1                       # segment 0 of cloud 0: no barrel point at all
+    first = (bb[0] == 1).nonzero()[0]
+    bb[0, first] = 0
+    inst[0, first] = 0                            # ... except exactly one (still "not found")
+    out = {}
+    torch.manual_seed(seed)
+    Pp, Xp, sc = ref.data_utils.sketch_implicit_projection(P, X, inst, bb, axes, centers, num_points_to_sample=S)
+    out.update(P_proj=np32(Pp), X_proj=np32(Xp), scales=np32(sc))
+    torch.manual_seed(seed)
+    Pp2, Xp2, sc2, found2 = ref.data_utils.sketch_implicit_projection2(P, X, inst, bb, axes, centers,
+                                                                       num_points_to_sample=S)
+    assert torch.equal(Pp2, Pp) and torch.equal(sc2, sc)
+    out.update(found=np32(found2))
+    Pp3, Xp3, sc3, found3 = ref.data_utils.sketch_implicit_projection3(P, X, inst, bb, axes, centers,
+                                                                       num_points_to_sample=N)
+    out.update(P_proj3=np32(Pp3), X_proj3=np32(Xp3), scales3=np32(sc3), found3=np32(found3))
+    torch.manual_seed(seed + 1)
+    ext, found_e = ref.data_utils.get_extrusion_extents(P, inst, bb, axes, centers, num_points_to_sample=S)
+    out.update(extents=np32(ext), found_ext=np32(found_e))
+    np.savez_compressed(os.path.join(HERE, name), inst=np32(inst).astype(np.int8), bb=np32(bb).astype(np.int8),
+                        axes=np32(axes), centers=np32(centers), meta=np.array([B, N, K, S, seed], dtype=np.int64),
+                        **out)
+    print("wrote", name)
+
+
 def main():
     assert ref_shim.available(), "reference tree not present"
     torch.set_num_threads(8)
@@ -165,6 +207,7 @@ def main():
     backbone_case(ref, "backbone_b1_n1024_k4.npz", 1, 1024, 4, seed=3)   # BASELINE.json config 1
     loss_case(ref, "loss_b2_n1024_k4.npz", 2, 1024, 4, seed=0, norm_eig=False)
     loss_case(ref, "loss_b3_n2048_k8_normeig.npz", 3, 2048, 8, seed=5, norm_eig=True)
+    projection_case(ref, "projection_b3_n512_k4.npz", 3, 512, 4, 128, seed=2)
 
 
 if __name__ == "__main__":

@@ -410,3 +410,91 @@ def test_function_level_dropins(golden_dir, name):
     assert rel_err(miou, ref_miou) <= TOL and torch.equal(Wr.cpu(), ref_Wr)
     nl = ls.compute_normal_loss(X, data["normals"], angle_diff=False, collapse=False)
     assert rel_err(nl, orc.compute_normal_loss(X.cpu(), data["normals"].cpu(), collapse=False)) <= TOL
+
+
+def _projection_inputs(g):
+    B, N, K, S, seed = (int(v) for v in g["meta"])
+    data = synthetic.s_cyl(B, N, K, seed)
+    return (data["pcs"], data["normals"], torch.from_numpy(g["inst"]).long(), torch.from_numpy(g["bb"]).long(),
+            torch.from_numpy(g["axes"]), torch.from_numpy(g["centers"]), S, seed)
+
+
+def test_projection_dropins_golden(golden_dir):
+    """a19 through the drop-in data_utils functions against the reference's outputs (same CPU random stream)."""
+    from point2cyl_b200.dropin import data_utils as du
+    g = load(golden_dir, "projection_b3_n512_k4.npz")
+    P, X, inst, bb, axes, centers, S, seed = (t.to(DEV) if torch.is_tensor(t) else t for t in _projection_inputs(g))
+    torch.manual_seed(seed)
+    Pp, Xp, sc = du.sketch_implicit_projection(P, X, inst, bb, axes, centers, num_points_to_sample=S)
+    assert rel_err(Pp, g["P_proj"]) <= TOL and rel_err(Xp, g["X_proj"]) <= TOL and rel_err(sc, g["scales"]) <= TOL
+    assert float((Pp.cpu() - torch.from_numpy(g["P_proj"])).abs().max()) <= 1e-5
+    torch.manual_seed(seed)
+    Pp2, Xp2, sc2, found = du.sketch_implicit_projection2(P, X, inst, bb, axes, centers, num_points_to_sample=S)
+    assert torch.equal(Pp2, Pp) and torch.equal(sc2, sc)
+    assert np.array_equal(found.cpu().numpy(), g["found"])
+    Pp3, Xp3, sc3, found3 = du.sketch_implicit_projection3(P, X, inst, bb, axes, centers,
+                                                           num_points_to_sample=P.shape[1])
+    assert np.array_equal(found3.cpu().numpy(), g["found3"])
+    assert rel_err(Pp3, g["P_proj3"]) <= TOL and rel_err(Xp3, g["X_proj3"]) <= TOL and rel_err(sc3, g["scales3"]) <= TOL
+    torch.manual_seed(seed + 1)
+    ext, found_e = du.get_extrusion_extents(P, inst, bb, axes, centers, num_points_to_sample=S)
+    assert np.array_equal(found_e.cpu().numpy(), g["found_ext"])
+    assert rel_err(ext, g["extents"]) <= TOL
+
+
+def test_projection_config2_vs_oracle():
+    """a19 at B=32, N=8192, K=8 with the training script's 1024 samples: member lists exact, projections within TOL."""
+    from point2cyl_b200.dropin import data_utils as du
+    B, N, K, S = 32, 8192, 8, 1024
+    data = synthetic.s_cyl(B, N, K, seed=21)
+    g = torch.Generator().manual_seed(5)
+    axes = torch.nn.functional.normalize(torch.randn(B, K, 3, generator=g), dim=-1)
+    centers = torch.rand(B, K, 3, generator=g) - 0.5
+    counts, lists = ops.segment_lists(data["inst"].to(DEV), data["bb"].to(DEV), 0, K)
+    mem = orc._member_lists(data["inst"], data["bb"], K)
+    for b in (0, 7, 31):
+        for k in range(K):
+            n = int(counts[b, k])
+            assert n == mem[b][k].numel()
+            assert torch.equal(lists[b, k, :n].cpu().long(), mem[b][k])
+    torch.manual_seed(9)
+    ref = orc.sketch_implicit_projection(data["pcs"], data["normals"], data["inst"], data["bb"], axes, centers, S)
+    torch.manual_seed(9)
+    got = du.sketch_implicit_projection2(data["pcs"].to(DEV), data["normals"].to(DEV), data["inst"].to(DEV),
+                                         data["bb"].to(DEV), axes.to(DEV), centers.to(DEV), num_points_to_sample=S)
+    assert torch.equal(got[3].cpu(), ref[3])
+    for a, r in zip(got[:3], ref[:3]):
+        assert rel_err(a, r) <= TOL
+    torch.manual_seed(10)
+    ext_ref, _ = orc.get_extrusion_extents(data["pcs"], data["inst"], data["bb"], axes, centers, S)
+    torch.manual_seed(10)
+    ext, _ = du.get_extrusion_extents(data["pcs"].to(DEV), data["inst"].to(DEV), data["bb"].to(DEV), axes.to(DEV),
+                                      centers.to(DEV), num_points_to_sample=S)
+    assert rel_err(ext, ext_ref) <= TOL
+
+
+def test_eval_helpers_kernels():
+    """a18: hard_W_encoding (+labels), normal difference in degrees / uncollapsed, segment centroids."""
+    from point2cyl_b200.dropin import data_utils as du
+    from point2cyl_b200.dropin import losses as ls
+    B, N, K = 4, 3000, 8
+    data = synthetic.s_cyl(B, N, K, seed=4)
+    g = torch.Generator().manual_seed(1)
+    W = torch.softmax(3 * torch.randn(B, N, K, generator=g), dim=2)
+    W[:, :, 5] *= 1e-3                                      # a column that falls under the null threshold
+    for null in (False, True):
+        hard = ls.hard_W_encoding(W.to(DEV), to_null_mask=null)
+        assert torch.equal(hard.cpu(), orc.hard_W_encoding(W, to_null_mask=null))
+    hard, label = ops.hard_w_encoding(W.to(DEV)[:, :, ::2], None, 0.0, want_label=True)   # strided operand
+    assert torch.equal(label.cpu(), W[:, :, ::2].argmax(-1))
+    X = torch.nn.functional.normalize(data["normals"] + 0.2 * torch.randn(B, N, 3, generator=g), dim=-1)
+    for rad in (True, False):
+        for col in (True, False):
+            got = ls.compute_normal_difference(X.to(DEV), data["normals"].to(DEV), in_radians=rad, collapse=col)
+            assert rel_err(got, orc.compute_normal_difference(X, data["normals"], rad, col)) <= TOL
+    EA_W = orc.hard_W_encoding(W, to_null_mask=True)
+    EA_W[0, 1:, 2] = 0                                      # at most one point left in (0, 2)
+    cen, found = du.estimate_segment_centroids(EA_W.to(DEV), data["pcs"].to(DEV))
+    cen_ref, found_ref = orc.segment_centroids(EA_W, data["pcs"])
+    assert torch.equal(found.cpu(), found_ref)
+    assert float((cen.cpu() - cen_ref).abs().max()) <= 1e-5

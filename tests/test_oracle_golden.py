@@ -133,3 +133,43 @@ def test_eval_helpers(golden_dir, name):
     assert rel_err(iou, g["seg_iou"]) <= 2e-6
     nd = orc.compute_normal_difference(X, data["normals"])
     assert rel_err(nd, g["normal_diff"]) <= 2e-6
+
+
+def projection_inputs(g):
+    B, N, K, S, seed = (int(v) for v in g["meta"])
+    data = synthetic.s_cyl(B, N, K, seed)
+    return (data["pcs"], data["normals"], torch.from_numpy(g["inst"]).long(), torch.from_numpy(g["bb"]).long(),
+            torch.from_numpy(g["axes"]), torch.from_numpy(g["centers"]), S, seed)
+
+
+def test_projection_closed_forms(golden_dir):
+    """a19: sketch_implicit_projection{,2,3} and get_extrusion_extents of the reference (run with the restated
+    torchgeometry rotation) vs the oracle, same CPU random stream."""
+    g = load(golden_dir, "projection_b3_n512_k4.npz")
+    P, X, inst, bb, axes, centers, S, seed = projection_inputs(g)
+    torch.manual_seed(seed)
+    Pp, Xp, sc, found = orc.sketch_implicit_projection(P, X, inst, bb, axes, centers, S)
+    assert np.array_equal(found.numpy(), g["found"])
+    assert found.numpy().min() == 0 and found.numpy().max() == 1      # both branches present
+    assert rel_err(Pp, g["P_proj"]) <= FLOAT_TOL and rel_err(Xp, g["X_proj"]) <= FLOAT_TOL
+    assert rel_err(sc, g["scales"]) <= FLOAT_TOL
+    Pp3, Xp3, sc3, found3 = orc.sketch_implicit_projection(P, X, inst, bb, axes, centers, P.shape[1], all_points=True)
+    assert np.array_equal(found3.numpy(), g["found3"])
+    assert rel_err(Pp3, g["P_proj3"]) <= FLOAT_TOL and rel_err(Xp3, g["X_proj3"]) <= FLOAT_TOL
+    assert rel_err(sc3, g["scales3"]) <= FLOAT_TOL
+    torch.manual_seed(seed + 1)
+    ext, found_e = orc.get_extrusion_extents(P, inst, bb, axes, centers, S)
+    assert np.array_equal(found_e.numpy(), g["found_ext"])
+    assert rel_err(ext, g["extents"]) <= FLOAT_TOL
+
+
+def test_rotation_restatement_is_a_rotation_only_for_unit_axis():
+    """Documents the reference quirk (data_utils.py:1096-1103): the rotation vector is (a x z)*angle with a x z NOT
+    normalised, so the matrix rotates by angle*sin(angle), and only takes a to +z when the two coincide."""
+    a = torch.nn.functional.normalize(torch.tensor([[0.3, -0.5, 0.6]]), dim=-1)
+    z = torch.tensor([[0.0, 0.0, 1.0]])
+    ang = torch.acos((a * z).sum(-1))
+    R = orc.angle_axis_to_rotation_matrix(torch.linalg.cross(a, z) * ang[:, None])[0, :3, :3]
+    assert torch.allclose(R @ R.T, torch.eye(3), atol=1e-5)            # still orthonormal
+    got = torch.acos(((R @ R @ R).trace() - 1) / 2)                    # 3 * rotation angle
+    assert abs(float(got) - 3 * float(ang * torch.sin(ang))) < 1e-4
