@@ -237,6 +237,37 @@ int p2c_hard_w_encoding(const float* W, int64_t ldw, int64_t sw, int B, int N, i
 int p2c_normal_angle(const float* X, const float* G, int B, int N, float scale, float* per_point,
                      float* per_cloud_sum, void* stream);
 
+/* ---- backward of the forward+loss path (the training step) ---- */
+
+/* d total / d statistics for the loss block — backward of p2c_loss_finalize (relaxed IoU losses.py:95-101,
+ * centre data_utils.py:253-266, axis data_utils.py:162-172 through the eigenvector sensitivity that
+ * torch.symeig's backward implements, normal loss losses.py:130).  eff_weights: DEVICE pointer to 5 floats
+ * {seg, normal, bb, axis, centre} = loss multipliers times the upstream gradient.  dstats: (B, stride(K)),
+ * fully overwritten. */
+int p2c_loss_backward_coef(const float* stats, const int64_t* match, const int32_t* n_gt, const float* gt_axes,
+                           const float* gt_centers, const float* eff_weights, int B, int N, int K, int norm_eig,
+                           float* dstats, void* stream);
+
+/* Backward of p2c_segfit_stats (+ p2c_bb_loss when match/n_gt are given): one sweep over the points from the
+ * statistics' gradient to the network outputs — through W = barrel + base, the squared weights of the 3x3
+ * scatters, softmax over 2K (train_...:254), F.normalize (:247) and the base/barrel cross entropy (:286-307).
+ * dX_raw (B*N rows, stride lddx >= 3), dW_raw (B*N rows, stride lddw >= 2K): both fully written. */
+int p2c_segfit_backward(const float* X_raw, int64_t ldx, const float* W_raw, int64_t ldw, const float* pcs,
+                        const float* gt_normals, const int64_t* inst, const int64_t* bb, const float* dstats,
+                        const int64_t* match, const int32_t* n_gt, const float* eff_weights, int B, int N, int K,
+                        float* dX_raw, int64_t lddx, float* dW_raw, int64_t lddw, void* stream);
+
+/* Backward of p2c_segfit_stats_w (function-level losses.py / data_utils.py API): dX (rows, stride lddx) or NULL,
+ * dWb / dWc contiguous (B,N,K) or NULL. */
+int p2c_segfit_backward_w(const float* X, int64_t ldx, int normalize_x, const float* wb, int64_t ldb, int64_t sb,
+                          const float* wc, int64_t ldc, int64_t sc, const float* pcs, const float* gt_normals,
+                          const int64_t* inst, const float* dstats, int B, int N, int K, float* dX, int64_t lddx,
+                          float* dWb, float* dWc, void* stream);
+
+/* Backward of p2c_eig3x3_smallest: dM (n,3,3) symmetric from gvec = d L / d vec (n,3) — what autograd does for
+ * torch.symeig(...)[1][:, :, 0] at data_utils.py:170-171. */
+int p2c_eig3x3_backward(const float* M, const float* gvec, int n, float* dM, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,12 @@ SIGNATURES = {
     "p2c_extrusion_extents": [c_f32p, i32, i32, i32, i32, c_i32p, c_i32p, c_i64p, c_f32p, c_f32p, c_f32p, c_f32p, vp],
     "p2c_hard_w_encoding": [c_f32p, i64, i64, i32, i32, i32, c_f32p, f32, c_f32p, c_i64p, vp],
     "p2c_normal_angle": [c_f32p, c_f32p, i32, i32, f32, c_f32p, c_f32p, vp],
+    "p2c_loss_backward_coef": [c_f32p, c_i64p, c_i32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, vp],
+    "p2c_segfit_backward": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_i64p, c_i64p, c_f32p, c_i64p, c_i32p, c_f32p,
+                            i32, i32, i32, c_f32p, i64, c_f32p, i64, vp],
+    "p2c_segfit_backward_w": [c_f32p, i64, i32, c_f32p, i64, i64, c_f32p, i64, i64, c_f32p, c_f32p, c_i64p, c_f32p,
+                              i32, i32, i32, c_f32p, i64, c_f32p, c_f32p, vp],
+    "p2c_eig3x3_backward": [c_f32p, c_f32p, i32, c_f32p, vp],
 }
 
 P2C_ERRORS = {-1: "P2C_EINVAL (bad size / null pointer)", -2: "P2C_EUNSUPPORTED (shape not covered)",

@@ -1,0 +1,98 @@
+"""torch.autograd.Function wrappers: each forward AND backward runs libp2c.so kernels (no torch-eager math on the
+point dimension).  This is what lets the unmodified training scripts call `total_loss.backward()` on results of the
+drop-in modules (train_Point2Cyl_without_sketch.py:367).
+
+  SegfitStatsW     per-cloud sufficient statistics of soft assignments (function-level losses.py / data_utils.py)
+  Eig3x3Smallest   eigenvector of the smallest eigenvalue (torch.symeig(...)[1][:, :, 0], data_utils.py:170-171)
+  FusedLoss        the whole loss block of the training script on the network's raw outputs
+  Backbone         the whole PointNet++ backbone as ONE autograd node (point2cyl_b200.backward does the work)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+class SegfitStatsW(torch.autograd.Function):
+    """stats (B, stride(K)) = p2c_segfit_stats_w(...); differentiable w.r.t. Wb, Wc and X."""
+
+    @staticmethod
+    def forward(ctx, Wb, Wc, X, normalize_x, pcs, gt_normals, inst, bb):
+        ctx.save_for_backward(Wb, Wc, X, pcs, gt_normals, inst)
+        ctx.normalize_x = bool(normalize_x)
+        return ops.segfit_stats_w(Wb, Wc, X, normalize_x, pcs, gt_normals, inst, bb)
+
+    @staticmethod
+    def backward(ctx, dstats):
+        Wb, Wc, X, pcs, gt_normals, inst = ctx.saved_tensors
+        need_wb, need_wc, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dX, dWb, dWc = ops.segfit_backward_w(dstats, Wb, Wc, X, ctx.normalize_x, pcs, gt_normals, inst,
+                                             want_dx=need_x, want_dwc=need_wc)
+        return (dWb if need_wb else None, dWc if need_wc else None, dX if need_x else None, None, None, None, None,
+                None)
+
+
+def segfit_stats_w(Wb, Wc=None, X=None, normalize_x=False, pcs=None, gt_normals=None, inst=None, bb=None):
+    return SegfitStatsW.apply(Wb, Wc, X, normalize_x, pcs, gt_normals, inst, bb)
+
+
+class Eig3x3Smallest(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, M):
+        vec, ev = ops.eig3x3_smallest(M)
+        ctx.save_for_backward(M)
+        ctx.mark_non_differentiable(ev)
+        return vec, ev
+
+    @staticmethod
+    def backward(ctx, gvec, _gev):
+        (M,) = ctx.saved_tensors
+        return ops.eig3x3_backward(M, gvec)
+
+
+def eig3x3_smallest(M):
+    return Eig3x3Smallest.apply(M)
+
+
+class FusedLoss(torch.autograd.Function):
+    """train_Point2Cyl_without_sketch.py:246-353 on (X_raw, W_raw): losses (6,) = {total, normal, miou, bb, axis,
+    centre} plus non-differentiable by-products."""
+
+    @staticmethod
+    def forward(ctx, X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher):
+        from . import pipeline
+        B, N, twoK = W_raw.shape
+        K = twoK // 2
+        stats = ops.segfit_stats(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, K)
+        cost, n_gt = ops.segfit_cost(stats, K)
+        match = ops.hungarian(cost, n_gt) if matcher == "device" else pipeline.hungarian_from_cost(cost, n_gt, K)
+        bb_sum = ops.bb_loss_sums(W_raw, gt_bb, match, n_gt, K)
+        losses, E_AX, centers, per_seg, per_cloud = ops.loss_finalize(
+            stats, bb_sum, match, n_gt, gt_axes, gt_centers, N, K, norm_eig, weights)
+        ctx.save_for_backward(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, stats, match, n_gt)
+        ctx.weights, ctx.norm_eig, ctx.K, ctx.N = tuple(float(w) for w in weights), bool(norm_eig), K, N
+        ctx.mark_non_differentiable(match, n_gt, E_AX, centers, per_seg, per_cloud, stats)
+        return losses, match, n_gt, E_AX, centers, per_seg, per_cloud, stats
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, stats, match, n_gt = ctx.saved_tensors
+        w = torch.tensor(ctx.weights, dtype=torch.float32, device=g.device)
+        g = g.float()
+        # losses = {total, normal, miou, bb, axis, centre}; weights = {seg, normal, bb, axis, centre}
+        eff = w * g[0] + torch.stack([g[2], g[1], g[3], g[4], g[5]])
+        dstats = ops.loss_backward_coef(stats, match, n_gt, gt_axes, gt_centers, eff, ctx.N, ctx.K, ctx.norm_eig)
+        d_out = ops.segfit_backward(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, dstats, match, n_gt, eff, ctx.K)
+        B, N = gt_inst.shape
+        d3 = d_out.reshape(B, N, -1)
+        return (d3[:, :, :3], d3[:, :, 3:]) + (None,) * 9
+
+
+def fused_loss(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher):
+    return FusedLoss.apply(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, tuple(weights),
+                           norm_eig, matcher)

@@ -2,11 +2,13 @@
 
 estimate_extrusion_axis never builds the reference's (B,N,N) diag_embed matrices: BtB - CtC is the 3x3 scatter
 sum_n (w_barrel^2 - w_base^2) x x^T, accumulated by p2c_segfit_stats_w, and the eigenvector of its smallest
-eigenvalue comes from p2c_eig3x3_smallest (Jacobi, float64).  Forward only this round.
+eigenvalue comes from p2c_eig3x3_smallest (Jacobi, float64).  Differentiable: the backward kernels are
+p2c_segfit_backward_w and p2c_eig3x3_backward (point2cyl_b200.autograd).
 """
 import numpy as np
 import torch
 
+from point2cyl_b200 import autograd as ag
 from point2cyl_b200 import ops
 from point2cyl_b200.dropin.global_variables import *  # noqa: F401,F403
 
@@ -31,7 +33,7 @@ def estimate_extrusion_axis(X, W_barrel, W_base, gt_bb_labels, gt_extrusion_inst
     """data_utils.py:99-177 -> E_AX (B,K,3): unit eigenvector of the smallest eigenvalue of BtB - CtC per
     segment.  The eigenvector sign is arbitrary (the loss uses |dot|); here the largest component is positive."""
     B, N, K = W_barrel.shape
-    st = ops.segfit_stats_w(W_barrel, W_base, X, False, None, None,
+    st = ag.segfit_stats_w(W_barrel, W_base, X, False, None, None,
                             gt_extrusion_instances if normalize else None, gt_bb_labels if normalize else None)
     L = ops.seg_layout(K)
     Mb = st[:, L["Mbar"]:L["Mbar"] + 6 * K].reshape(B, K, 6)
@@ -41,14 +43,14 @@ def estimate_extrusion_axis(X, W_barrel, W_base, gt_bb_labels, gt_extrusion_inst
         nc = torch.sqrt(st[:, L["cbase"]:L["cbase"] + K]) + 1.0
         Mb = Mb / (nb * nb)[:, :, None]
         Mc = Mc / (nc * nc)[:, :, None]
-    vec, _ = ops.eig3x3_smallest(_sym3(Mb - Mc))
+    vec, _ = ag.eig3x3_smallest(_sym3(Mb - Mc))
     return vec
 
 
 def estimate_extrusion_centers(W, pcs):
     """data_utils.py:253-266 -> (B,K,3): mean_n W[b,n,k] * p[b,n]  (a plain mean over N, not / sum W)."""
     B, N, K = W.shape
-    st = ops.segfit_stats_w(W, None, None, False, pcs, None, None, None)
+    st = ag.segfit_stats_w(W, None, None, False, pcs, None, None, None)
     L = ops.seg_layout(K)
     return st[:, L["C"]:L["C"] + 3 * K].reshape(B, K, 3) / N
 

@@ -1,14 +1,15 @@
 """Drop-in for the LIVE functions of the reference's losses.py (same names, signatures, return shapes).
 
 All reductions over the N points run in the libp2c.so statistics kernel (p2c_segfit_stats_w), the assignment in
-p2c_hungarian; what is left in torch are (B,K)-sized elementwise formulas.  Forward only this round: results
-carry no autograd graph.  Dead reference code (sketch / chamfer / axis-regularisation losses,
+p2c_hungarian; what is left in torch are (B,K)-sized elementwise formulas.  Results carry an autograd graph whose backward runs
+the p2c_segfit_backward_w kernel (point2cyl_b200.autograd).  Dead reference code (sketch / chamfer / axis-regularisation losses,
 losses.py:165-312) is intentionally absent.
 """
 import math
 
 import torch
 
+from point2cyl_b200 import autograd as ag
 from point2cyl_b200 import ops
 from point2cyl_b200.dropin.global_variables import *  # noqa: F401,F403  (the reference re-exports these)
 
@@ -17,14 +18,14 @@ TORCH_PI = math.pi
 
 def _stats(W, I_gt=None, X=None, X_gt=None):
     K = W.shape[2]
-    st = ops.segfit_stats_w(W, None, X, False, None, X_gt, I_gt, None)
+    st = ag.segfit_stats_w(W, None, X, False, None, X_gt, I_gt, None)
     return st, ops.seg_layout(K), K
 
 
 def hungarian_matching(W_pred, I_gt, with_mask=False):
     """losses.py:22-52 -> matching_indices (B,K) int64 [, mask (B,K) bool].  No gradient (like the reference)."""
     st, L, K = _stats(W_pred.detach(), I_gt)
-    cost, n_gt = ops.segfit_cost(st, K)
+    cost, n_gt = ops.segfit_cost(st.detach(), K)
     match = ops.hungarian(cost, n_gt)
     if not with_mask:
         return match
@@ -92,7 +93,7 @@ def compute_normal_loss(normal, normal_gt, angle_diff, collapse=True):
         # mean_n (1 - |<x, x_gt>|) straight from the statistics kernel
         B, N, _ = normal.shape
         dummy = normal.new_zeros(B, N, 1)
-        st = ops.segfit_stats_w(dummy, None, normal, False, None, normal_gt, None, None)
+        st = ag.segfit_stats_w(dummy, None, normal, False, None, normal_gt, None, None)
         return st[:, ops.seg_layout(1)["normal"]] / N
     dot_abs = torch.abs(torch.sum(normal * normal_gt, dim=2))
     val = acos_safe(dot_abs) if angle_diff else 1.0 - dot_abs
@@ -110,7 +111,7 @@ def compute_all_losses(P, W, I_gt, X, X_gt, normal_loss_multiplier, miou_loss_mu
     """losses.py:317-351."""
     B, N, K = W.shape
     mask_gt = get_mask_gt(I_gt, K)
-    st = ops.segfit_stats_w(W, None, X, False, None, X_gt, I_gt, None)   # one pass: D, counts, sums, normal loss
+    st = ag.segfit_stats_w(W, None, X, False, None, X_gt, I_gt, None)   # one pass: D, counts, sums, normal loss
     L = ops.seg_layout(K)
     if normal_loss_multiplier > 0:
         normal_loss = st[:, L["normal"]] / N
@@ -118,7 +119,7 @@ def compute_all_losses(P, W, I_gt, X, X_gt, normal_loss_multiplier, miou_loss_mu
         normal_loss = torch.zeros([B, K], device=P.device)
     matching_indices = mask = None
     if miou_loss_multiplier > 0:
-        cost, n_gt = ops.segfit_cost(st, K)
+        cost, n_gt = ops.segfit_cost(st.detach(), K)
         matching_indices = ops.hungarian(cost, n_gt)
         mask = torch.arange(K, device=W.device)[None, :] < n_gt[:, None]
         D = st[:, :K * K].reshape(B, K, K)

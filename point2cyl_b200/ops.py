@@ -465,3 +465,61 @@ def normal_angle(X: Tensor, G: Tensor, scale: float = 1.0, collapse: bool = True
     out = torch.empty(B, N, dtype=torch.float32, device=X.device)
     call("p2c_normal_angle", ptr(X), ptr(G), B, N, float(scale), ptr(out), None, stream_ptr())
     return out
+
+
+# ---- backward of the loss block -------------------------------------------------------------------------------
+
+
+def loss_backward_coef(stats: Tensor, match: Tensor, n_gt: Tensor, gt_axes: Tensor, gt_centers: Tensor,
+                       eff_weights: Tensor, N: int, K: int, norm_eig: bool) -> Tensor:
+    """d total / d stats (B, stride).  eff_weights: device (5,) float32 {seg, normal, bb, axis, centre}."""
+    B = stats.shape[0]
+    dstats = torch.empty_like(stats)
+    call("p2c_loss_backward_coef", ptr(stats), ptr(match.contiguous()), ptr(n_gt), ptr(gt_axes.contiguous().float()),
+         ptr(gt_centers.contiguous().float()), ptr(eff_weights), B, N, K, 1 if norm_eig else 0, ptr(dstats),
+         stream_ptr())
+    return dstats
+
+
+def segfit_backward(X_raw: Tensor, W_raw: Tensor, pcs: Tensor, gt_normals: Tensor, inst: Tensor, bb: Tensor,
+                    dstats: Tensor, match: Optional[Tensor], n_gt: Optional[Tensor], eff_weights: Optional[Tensor],
+                    K: int, out: Optional[Tensor] = None) -> Tensor:
+    """-> d(out) rows (B*N, 3 + 2K): gradient w.r.t. [X_raw | W_raw] in the head's output layout."""
+    B, N = inst.shape
+    Xr = _rows(_as_rows(X_raw))
+    Wr = _rows(_as_rows(W_raw))
+    if out is None:
+        out = torch.empty(B * N, 3 + 2 * K, dtype=torch.float32, device=pcs.device)
+    dX, dW = out[:, :3], out[:, 3:]
+    call("p2c_segfit_backward", ptr(Xr), Xr.stride(0), ptr(Wr), Wr.stride(0), ptr(_cloud(pcs)), ptr(_cloud(gt_normals)),
+         ptr(inst.contiguous()), ptr(bb.contiguous()), ptr(dstats), ptr(None if match is None else match.contiguous()),
+         ptr(n_gt), ptr(eff_weights), B, N, K, ptr(dX), out.stride(0), ptr(dW), out.stride(0), stream_ptr())
+    return out
+
+
+def segfit_backward_w(dstats: Tensor, Wb: Tensor, Wc: Optional[Tensor], X: Optional[Tensor], normalize_x: bool,
+                      pcs: Optional[Tensor], gt_normals: Optional[Tensor], inst: Optional[Tensor],
+                      want_dx: bool, want_dwc: bool):
+    """Backward of segfit_stats_w -> (dX (B,N,3) | None, dWb (B,N,K), dWc (B,N,K) | None)."""
+    B, N, K = Wb.shape
+    wb, ldb, sb = _w_operand(Wb, B, N)
+    wc, ldc, sc = _w_operand(Wc, B, N)
+    Xr = None if X is None else _rows(_as_rows(X.float()))
+    dev = Wb.device
+    dX = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if (want_dx and Xr is not None) else None
+    dWb = torch.empty(B, N, K, dtype=torch.float32, device=dev)
+    dWc = torch.empty(B, N, K, dtype=torch.float32, device=dev) if (want_dwc and wc is not None) else None
+    call("p2c_segfit_backward_w", ptr(Xr), 0 if Xr is None else Xr.stride(0), 1 if normalize_x else 0, ptr(wb), ldb, sb,
+         ptr(wc), ldc, sc, ptr(None if pcs is None else _cloud(pcs)),
+         ptr(None if gt_normals is None else _cloud(gt_normals)),
+         ptr(None if inst is None else inst.contiguous().long()), ptr(dstats.contiguous()), B, N, K, ptr(dX), 3,
+         ptr(dWb), ptr(dWc), stream_ptr())
+    return dX, dWb, dWc
+
+
+def eig3x3_backward(M: Tensor, gvec: Tensor) -> Tensor:
+    flat = M.reshape(-1, 9).contiguous().float()
+    g = gvec.reshape(-1, 3).contiguous().float()
+    dM = torch.empty_like(flat)
+    call("p2c_eig3x3_backward", ptr(flat), ptr(g), flat.shape[0], ptr(dM), stream_ptr())
+    return dM.reshape(M.shape)

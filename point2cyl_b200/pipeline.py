@@ -236,12 +236,9 @@ def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, 
     B, N, twoK = W_raw.shape
     K = twoK // 2
     _lib.set_tag("loss")
-    stats = ops.segfit_stats(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, K)
-    cost, n_gt = ops.segfit_cost(stats, K)
-    match = ops.hungarian(cost, n_gt) if matcher == "device" else hungarian_from_cost(cost, n_gt, K)
-    bb_sum = ops.bb_loss_sums(W_raw, gt_bb, match, n_gt, K)
-    losses, E_AX, centers, per_seg, per_cloud = ops.loss_finalize(
-        stats, bb_sum, match, n_gt, gt_axes, gt_centers, N, K, norm_eig, weights)
+    from . import autograd as ag
+    losses, match, n_gt, E_AX, centers, per_seg, per_cloud, stats = ag.fused_loss(
+        X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher)
     mask = torch.arange(K, device=pcs.device)[None, :] < n_gt[:, None]
     return dict(total=losses[0], normal=losses[1], miou=losses[2], bb=losses[3], axis=losses[4],
                 center=losses[5], losses=losses, matching_indices=match, mask=mask, E_AX=E_AX,

@@ -116,6 +116,8 @@ def loss_case(ref, name, B, N, K, seed, norm_eig):
     W_raw.scatter_add_(2, col[:, :, None], torch.full((B, N, 1), 2.5))
     pcs, gt_normals = data["pcs"], data["normals"]
     gt_extrusion_instances, gt_bb_labels = data["inst"], data["bb"]
+    X_raw.requires_grad_(True)     # the reference's own autograd gives the gradient goldens (dX_raw, dW_raw)
+    W_raw.requires_grad_(True)
 
     X = F.normalize(X_raw, p=2, dim=2, eps=1e-12)
     W_2K = torch.softmax(W_raw, dim=2)
@@ -139,10 +141,16 @@ def loss_case(ref, name, B, N, K, seed, norm_eig):
     centers = ref.data_utils.estimate_extrusion_centers(torch.gather(W, 2, gi), pcs)
     cd = torch.square(centers - data["centers"]).sum(dim=-1)
     l_c = torch.mean(ref.losses.reduce_mean_masked_instance(cd, mask_gt))
+    # total of the training script with all five multipliers = 1 (train_...:314,339,353)
+    (total + l_bb + l_ax + l_c).backward()
+    dX_raw, dW_raw = X_raw.grad.clone(), W_raw.grad.clone()
+    X_raw, W_raw, X, W, W_barrel, W_base = (t.detach() for t in (X_raw, W_raw, X, W, W_barrel, W_base))
+    total, l_n, l_seg, l_bb, l_ax, l_c, E_AX, centers = (t.detach() for t in (total, l_n, l_seg, l_bb, l_ax, l_c,
+                                                                                E_AX, centers))
     hard = ref.losses.hard_W_encoding(W, to_null_mask=True)
     np.savez_compressed(
         os.path.join(HERE, name),
-        X_raw=np32(X_raw), W_raw=np32(W_raw), total=np32(total), normal=np32(l_n), miou=np32(l_seg),
+        X_raw=np32(X_raw), W_raw=np32(W_raw), dX_raw=np32(dX_raw), dW_raw=np32(dW_raw), total=np32(total), normal=np32(l_n), miou=np32(l_seg),
         bb=np32(l_bb), axis=np32(l_ax), center=np32(l_c), matching_indices=np32(matching_indices),
         mask=np32(ns["mask"] > 0), E_AX=np32(E_AX), centers=np32(centers),
         hard_argmax=np32(hard.argmax(-1)).astype(np.int8), hard_rowsum=np32(hard.sum(-1)).astype(np.int8),

@@ -173,3 +173,18 @@ def test_rotation_restatement_is_a_rotation_only_for_unit_axis():
     assert torch.allclose(R @ R.T, torch.eye(3), atol=1e-5)            # still orthonormal
     got = torch.acos(((R @ R @ R).trace() - 1) / 2)                    # 3 * rotation angle
     assert abs(float(got) - 3 * float(ang * torch.sin(ang))) < 1e-4
+
+
+@pytest.mark.parametrize("name", LOSS)
+def test_loss_gradients(golden_dir, name):
+    """Autograd through the oracle's loss block reproduces the reference's own gradients w.r.t. the network
+    outputs (pins the checker used for the backward kernels)."""
+    g = load(golden_dir, name)
+    data, X_raw, W_raw, norm_eig = loss_inputs(g)
+    X_raw = X_raw.clone().requires_grad_(True)
+    W_raw = W_raw.clone().requires_grad_(True)
+    out = orc.loss_block(data["pcs"], X_raw, W_raw, data["normals"], data["inst"], data["bb"],
+                         data["axes"], data["centers"], norm_eig=norm_eig)
+    out["total"].backward()
+    assert rel_err(X_raw.grad, g["dX_raw"]) <= 2e-5
+    assert rel_err(W_raw.grad, g["dW_raw"]) <= 2e-5
