@@ -268,6 +268,62 @@ int p2c_segfit_backward_w(const float* X, int64_t ldx, int normalize_x, const fl
  * torch.symeig(...)[1][:, :, 0] at data_utils.py:170-171. */
 int p2c_eig3x3_backward(const float* M, const float* gvec, int n, float* dM, void* stream);
 
+/* BatchNorm+ReLU backward, pass 1 — autograd of models/pointnet_util.py:203 / :319 (F.relu(bn(conv(x)))):
+ * sums[c] = sum_m g, sums[C+c] = sum_m g*Y[m,c] with g = dA[m,c] * [scale[c]*Y[m,c]+shift[c] > 0]
+ * (scale == NULL: no ReLU gate).  sums: float64 (2C), zeroed here.  C: 32..1024, power of two. */
+int p2c_bn_bwd_reduce(const float* dA, int64_t ldda, const float* Y, int64_t ldy, const float* scale,
+                      const float* shift, int64_t M, int C, double* sums, void* stream);
+
+/* Same sums for a max-pooled layer (torch.max(new_points, 2)[0], models/pointnet_util.py:205): only the arg-max
+ * row of each group carries gradient and its raw value is Ymax (Ymin when scale < 0), so the pooled tensors
+ * suffice.  dOut: (G, C) gradient of the pooled post-BN/ReLU output. */
+int p2c_pool_bwd_reduce(const float* dOut, int64_t ldd, const float* Ymax, const float* Ymin, const float* scale,
+                        const float* shift, int64_t G, int C, double* sums, void* stream);
+
+/* BatchNorm backward, per-channel part: dgamma[c] += invstd*(s2 - mean*s1), dbeta[c] += s1 (either may be NULL) and
+ * coef (3C) = {a, b, c} with dY = a*g + b*Y + c (training: batch statistics over `count` rows; eval: b = c = 0). */
+int p2c_bn_bwd_coef(const double* sums, int64_t count, const float* gamma, const float* mean, const float* invstd,
+                    int training, float* coef, float* dgamma, float* dbeta, int C, void* stream);
+
+/* BatchNorm+ReLU backward, pass 2: dY[m,c] = a*g + b*Y + c (may run in place over dA). */
+int p2c_bn_bwd_apply(const float* dA, int64_t ldda, const float* Y, int64_t ldy, const float* scale,
+                     const float* shift, const float* coef, int64_t M, int C, float* dY, int64_t lddy, void* stream);
+
+/* Pass 2 for a max-pooled layer: dY (G*group, C) from dOut (G, C); the gradient is routed to the first row of the
+ * group whose raw value equals the pooled one. */
+int p2c_pool_bwd_apply(const float* dOut, int64_t ldd, const float* Ymax, const float* Ymin, const float* Y,
+                       int64_t ldy, const float* scale, const float* shift, const float* coef, int64_t G, int group,
+                       int C, float* dY, int64_t lddy, void* stream);
+
+/* Weight / bias gradient of a 1x1 conv — autograd of Conv2d/Conv1d at models/pointnet_util.py:201, :317,
+ * pointnet_extrusion.py:58-65:  dW[n,k] += sum_m dY[m,n] * A[m,k], db[n] += sum_m dY[m,n], with the layer input
+ * A recomputed from the raw previous activation exactly as p2c_linear's operand load does
+ * (A = max(X*in_scale+in_shift, 0) [* mask_cf[b,k,n], m = b*mask_N + n]).  dW/db are accumulated (atomics). */
+int p2c_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* in_scale,
+              const float* in_shift, const float* mask_cf, int mask_N, int64_t M, int N, int K, float* dW,
+              int64_t lddw, float* db, void* stream);
+
+/* Backward of p2c_sa_first_layer: dQf[b*N+p, :] += dY[r, :] (NULL when the level has no input features; pre-zeroed
+ * by the caller), dW[:, 0:3] += dY^T * (xyz[p] - centre), dbias += column sums. */
+int p2c_sa_first_bwd(const float* dY, int64_t lddy, const float* xyz, const float* new_xyz, const int64_t* idx, int B,
+                     int N, int S, int nsample, int C, float* dQf, int64_t ldq, float* dW, int64_t lddw, float* dbias,
+                     void* stream);
+
+/* Backward of p2c_three_nn_interp: dfeats2[b*S + idx[b,n,j], :] += w[b,n,j] * dInterp[b*N+n, :] (S == 1: the
+ * broadcast of models/pointnet_util.py:298-299, idx/w unused).  dfeats2 is fully defined on return. */
+int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const int64_t* idx, const float* w, int B, int N, int S,
+                            int D, float* dfeats2, int64_t ldf, void* stream);
+
+/* Data gradient of p2c_head_masked: dA[m,k] = mask_cf[b,k,n] * sum_j dOut[m,j] * W[j,k] (the ReLU/BN part is then the
+ * generic p2c_bn_bwd_* on fc1's raw output; the heads' dW/db come from p2c_wgrad with the same mask). */
+int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const float* W, int B, int N, int C, int Nout,
+                 float* dA, int64_t ldda, void* stream);
+
+/* torch.optim.Adam step (train_Point2Cyl_without_sketch.py:189, :368) over a flat fp32 parameter buffer:
+ * g = grads*grad_scale (+ weight_decay*p), m/v updated in place, bias-corrected with `step` (1-based). */
+int p2c_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

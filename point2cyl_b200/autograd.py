@@ -96,3 +96,40 @@ class FusedLoss(torch.autograd.Function):
 def fused_loss(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher):
     return FusedLoss.apply(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, tuple(weights),
                            norm_eig, matcher)
+
+
+class Backbone(torch.autograd.Function):
+    """models/pointnet_extrusion.py:37-66 as one autograd node: forward records a tape, backward walks it with the
+    csrc/backward.cu kernels.  `params` are net.parameters() in order, passed only so that autograd routes their
+    gradients; BatchNorm running statistics are updated in place by the forward like nn.BatchNorm does."""
+
+    @staticmethod
+    def forward(ctx, net, x, fps_start, precision, *params):
+        from . import pipeline
+        tape = {}
+        pipeline.backbone_forward(net, x, fps_start, precision=precision, tape=tape)
+        ctx.tape, ctx.net, ctx.precision = tape, net, precision
+        ctx.n_params = len(params)
+        B, N = tape["B"], tape["N"]
+        out = tape["out"]
+        return out.reshape(B, N, out.shape[1])
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from . import backward as bw
+        params = list(ctx.net.parameters())
+        grads = {id(p): torch.zeros_like(p) for p in params}
+        bw.backbone_backward(ctx.tape, d_out, lambda p: grads[id(p)], ctx.precision)
+        ctx.tape = None
+        return (None, None, None, None) + tuple(grads[id(p)] for p in params)
+
+
+def backbone_apply(net, x, fps_start=None, precision=None):
+    """-> list of (B,N,o_i) views, differentiable w.r.t. net.parameters()."""
+    out = Backbone.apply(net, x, fps_start, precision, *list(net.parameters()))
+    results, c0 = [], 0
+    for fc in net.fc2:
+        o = fc.weight.shape[0]
+        results.append(out[:, :, c0:c0 + o])
+        c0 += o
+    return results

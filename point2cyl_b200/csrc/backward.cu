@@ -1,0 +1,567 @@
+// Backward of the PointNet++ backbone: what autograd runs for
+// models/pointnet_util.py:181-207 (set abstraction), :283-320 (feature propagation) and
+// models/pointnet_extrusion.py:58-65 (head) in the reference, restated on the forward's own data layout:
+// activations are raw (pre-BatchNorm) row matrices, BatchNorm+ReLU of layer i lives in layer i+1's operand load.
+//
+// Per MLP layer, given dA = d L / d relu(bn(Y)):
+//   p2c_bn_bwd_reduce   s1 = sum_m dYh, s2 = sum_m dYh * Y with dYh = dA * [scale*Y + shift > 0]      (1 pass)
+//   p2c_bn_bwd_coef     dgamma, dbeta and the per-channel affine (a, b, c) of BatchNorm's backward:
+//                       dY = a*dYh + b*Y + c   (train: a = gamma*invstd, b = -a*invstd*dgamma/M,
+//                       c = -a*dbeta/M - b*mean; eval: b = c = 0)
+//   p2c_bn_bwd_apply    dY materialised once (in place over dA)
+//   p2c_linear          dA_prev = dY * W   (the forward's tcgen05 kernel on the transposed weight)
+//   p2c_wgrad           dW += dY^T * A_prev with A_prev = relu(bn(X_prev)) recomputed in the operand load, db += sum dY
+// Max-pooled layers (last layer of a set-abstraction level): the gradient enters only at the arg-max row of each
+// group, recovered as the first row whose raw value equals the pooled max (min when scale < 0) — the forward
+// stores no indices (p2c_pool_bwd_reduce / p2c_pool_bwd_apply).
+// The fused gather + first SA conv runs backward as a scatter-add into the per-source-point product Qf
+// (p2c_sa_first_bwd), the 3-NN interpolation as a weighted scatter-add (p2c_three_nn_interp_bwd), the heads as
+// p2c_head_bwd + p2c_wgrad with the channel-first dropout mask.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward reductions
+// ---------------------------------------------------------------------------------------------------------
+
+constexpr int RED_THREADS = 256;
+constexpr int RED_ROWS = 512;   // rows per CTA
+
+// thread t: channel (t % CW) + i*CW, row lane t / CW
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldda, const float* __restrict__ Y, int64_t ldy,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int64_t M, int C,
+                     double* __restrict__ sums) {
+  __shared__ float s_red[2][RED_THREADS];
+  const int CW = C < RED_THREADS ? C : RED_THREADS;      // C is a multiple of 32 and <= 1024; CW divides 256 or equals it
+  const int RL = RED_THREADS / CW;
+  const int cl = threadIdx.x % CW, rl = threadIdx.x / CW;
+  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS;
+  const int64_t r1 = r0 + RED_ROWS < M ? r0 + RED_ROWS : M;
+  for (int c = cl; c < C; c += CW) {
+    const float sc = scale ? __ldg(scale + c) : 1.f, sh = shift ? __ldg(shift + c) : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+    if (rl < RL) {
+      for (int64_t r = r0 + rl; r < r1; r += RL) {
+        const float y = __ldg(Y + r * ldy + c);
+        float g = __ldg(dA + r * ldda + c);
+        if (scale && !(fmaf(y, sc, sh) > 0.f)) g = 0.f;
+        s1 += g;
+        s2 = fmaf(g, y, s2);
+      }
+    }
+    s_red[0][threadIdx.x] = s1;
+    s_red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (rl == 0) {
+      for (int j = 1; j < RL; ++j) { s1 += s_red[0][j * CW + cl]; s2 += s_red[1][j * CW + cl]; }
+      atomicAdd(sums + c, (double)s1);
+      atomicAdd(sums + C + c, (double)s2);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pool_bwd_reduce_kernel(const float* __restrict__ dOut, int64_t ldd, const float* __restrict__ Ymax,
+                       const float* __restrict__ Ymin, const float* __restrict__ scale,
+                       const float* __restrict__ shift, int64_t G, int C, double* __restrict__ sums) {
+  // one thread per channel (grid.x over channel blocks), grid.y over group slabs
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t g0 = (int64_t)blockIdx.y * 64;
+  const int64_t g1 = g0 + 64 < G ? g0 + 64 : G;
+  const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t g = g0; g < g1; ++g) {
+    const float y = sc >= 0.f ? __ldg(Ymax + g * C + c) : __ldg(Ymin + g * C + c);
+    float d = __ldg(dOut + g * ldd + c);
+    if (!(fmaf(y, sc, sh) > 0.f)) d = 0.f;
+    s1 += d;
+    s2 = fmaf(d, y, s2);
+  }
+  atomicAdd(sums + c, (double)s1);
+  atomicAdd(sums + C + c, (double)s2);
+}
+
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd, int training,
+                                   float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sums[c], s2 = sums[C + c];
+  const double mu = mean[c], is = invstd[c], g = gamma ? (double)gamma[c] : 1.0;
+  const double dg = is * (s2 - mu * s1);
+  const double a = g * is;
+  double b = 0.0, cc = 0.0;
+  if (training) {
+    b = -a * is * dg / count;
+    cc = -a * s1 / count - b * mu;
+  }
+  coef[c] = (float)a;
+  coef[C + c] = (float)b;
+  coef[2 * C + c] = (float)cc;
+  if (dgamma) dgamma[c] += (float)dg;
+  if (dbeta) dbeta[c] += (float)s1;
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dA, int64_t ldda, const float* __restrict__ Y, int64_t ldy,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ coef, int64_t M, int C, float* __restrict__ dY, int64_t lddy) {
+  const int C4 = C >> 2;
+  const int64_t total = M * C4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / C4;
+    const int c = (int)(e - m * C4) * 4;
+    const float4 y = __ldg(reinterpret_cast<const float4*>(Y + m * ldy + c));
+    float4 g = __ldg(reinterpret_cast<const float4*>(dA + m * ldda + c));
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(coef + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(coef + C + c));
+    const float4 k = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c));
+    if (!(fmaf(y.x, sc.x, sh.x) > 0.f)) g.x = 0.f;
+    if (!(fmaf(y.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
+    if (!(fmaf(y.z, sc.z, sh.z) > 0.f)) g.z = 0.f;
+    if (!(fmaf(y.w, sc.w, sh.w) > 0.f)) g.w = 0.f;
+    float4 o;
+    o.x = fmaf(a.x, g.x, fmaf(b.x, y.x, k.x));
+    o.y = fmaf(a.y, g.y, fmaf(b.y, y.y, k.y));
+    o.z = fmaf(a.z, g.z, fmaf(b.z, y.z, k.z));
+    o.w = fmaf(a.w, g.w, fmaf(b.w, y.w, k.w));
+    *reinterpret_cast<float4*>(dY + m * lddy + c) = o;
+  }
+}
+
+// one thread per (group, channel): walk the group's rows, route dOut to the first row that attains the pooled value
+__global__ void __launch_bounds__(256)
+pool_bwd_apply_kernel(const float* __restrict__ dOut, int64_t ldd, const float* __restrict__ Ymax,
+                      const float* __restrict__ Ymin, const float* __restrict__ Y, int64_t ldy,
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ coef, int64_t G, int group, int C, float* __restrict__ dY,
+                      int64_t lddy) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= G * C) return;
+  const int64_t g = e / C;
+  const int c = (int)(e - g * C);
+  const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+  const float a = __ldg(coef + c), b = __ldg(coef + C + c), k = __ldg(coef + 2 * C + c);
+  const float ysel = sc >= 0.f ? __ldg(Ymax + g * C + c) : __ldg(Ymin + g * C + c);
+  float d = __ldg(dOut + g * ldd + c);
+  if (!(fmaf(ysel, sc, sh) > 0.f)) d = 0.f;
+  bool hit = false;
+  const int64_t r0 = g * group;
+  for (int j = 0; j < group; ++j) {
+    const float y = __ldg(Y + (r0 + j) * ldy + c);
+    float o = fmaf(b, y, k);
+    if (!hit && y == ysel) { o = fmaf(a, d, o); hit = true; }
+    dY[(r0 + j) * lddy + c] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient: dW[n,k] += sum_m dY[m,n] * A[m,k],  A = f(X) (BN+ReLU fold, optional channel-first mask)
+// SIMT register-tiled, the row dimension split over the grid, fp32 atomics into dW.
+// ---------------------------------------------------------------------------------------------------------
+
+constexpr int WG_RS = 16;   // rows per shared-memory stage
+
+template <int TN, int TK>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ X, int64_t ldx,
+             const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+             const float* __restrict__ mask_cf, int mask_N, int64_t M, int N, int K, int rows_per_cta,
+             float* __restrict__ dW, int64_t lddw, float* __restrict__ db) {
+  constexpr int RN = TN / 16, RK = TK / 16;
+  __shared__ __align__(16) float s_dy[WG_RS][TN];
+  __shared__ __align__(16) float s_a[WG_RS][TK];
+  const int n0 = blockIdx.x * TN, k0 = blockIdx.y * TK;
+  const int64_t m0 = (int64_t)blockIdx.z * rows_per_cta;
+  const int64_t m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
+  const int tid = threadIdx.x;
+  const int tn = tid / 16, tk = tid % 16;     // thread owns n = n0 + tn*RN + i, k = k0 + tk*RK + j
+  float acc[RN][RK];
+#pragma unroll
+  for (int i = 0; i < RN; ++i)
+#pragma unroll
+    for (int j = 0; j < RK; ++j) acc[i][j] = 0.f;
+  float bsum[RN];
+#pragma unroll
+  for (int i = 0; i < RN; ++i) bsum[i] = 0.f;
+
+  for (int64_t ms = m0; ms < m1; ms += WG_RS) {
+    // stage WG_RS rows of dY (TN wide) and A (TK wide)
+    for (int e = tid; e < WG_RS * TN; e += 256) {
+      const int r = e / TN, c = e - r * TN;
+      const int64_t m = ms + r;
+      s_dy[r][c] = (m < m1 && n0 + c < N) ? __ldg(dY + m * lddy + n0 + c) : 0.f;
+    }
+    for (int e = tid; e < WG_RS * TK; e += 256) {
+      const int r = e / TK, c = e - r * TK;
+      const int64_t m = ms + r;
+      float v = 0.f;
+      if (m < m1 && k0 + c < K) {
+        v = __ldg(X + m * ldx + k0 + c);
+        if (in_scale) v = fmaxf(fmaf(v, __ldg(in_scale + k0 + c), __ldg(in_shift + k0 + c)), 0.f);
+        if (mask_cf) {
+          const int64_t b = m / mask_N;
+          v *= __ldg(mask_cf + ((size_t)b * K + (k0 + c)) * mask_N + (m - b * mask_N));
+        }
+      }
+      s_a[r][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < WG_RS; ++r) {
+      float dyv[RN], av[RK];
+#pragma unroll
+      for (int i = 0; i < RN; ++i) dyv[i] = s_dy[r][tn * RN + i];
+#pragma unroll
+      for (int j = 0; j < RK; ++j) av[j] = s_a[r][tk * RK + j];
+#pragma unroll
+      for (int i = 0; i < RN; ++i) {
+        bsum[i] += dyv[i];
+#pragma unroll
+        for (int j = 0; j < RK; ++j) acc[i][j] = fmaf(dyv[i], av[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < RN; ++i) {
+    const int n = n0 + tn * RN + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < RK; ++j) {
+      const int k = k0 + tk * RK + j;
+      if (k < K) atomicAdd(dW + (size_t)n * lddw + k, acc[i][j]);
+    }
+    if (db && blockIdx.y == 0 && tk == 0) atomicAdd(db + n, bsum[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused gather + first SA conv, backward: dQf[p] += dY0[r], dWx += dY0^T * (xyz[p] - centre), dbias += sum dY0
+// ---------------------------------------------------------------------------------------------------------
+
+template <int CPL>
+__global__ void __launch_bounds__(256)
+sa_first_bwd_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ xyz,
+                    const float* __restrict__ new_xyz, const int64_t* __restrict__ idx, int N, int S, int ns,
+                    int64_t rows, float* __restrict__ dQf, int64_t ldq, float* __restrict__ dW, int64_t lddw,
+                    float* __restrict__ dbias) {
+  constexpr int C = 32 * CPL;
+  __shared__ float s_red[8][4][C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * CPL;
+  float gw[CPL][3], gb[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) { gw[i][0] = gw[i][1] = gw[i][2] = 0.f; gb[i] = 0.f; }
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows; r += wstride) {
+    const int64_t bs = r / ns, b = bs / S;
+    int64_t p = __ldg(idx + r);
+    p = (p < 0 || p >= N) ? 0 : p;
+    const float* pp = xyz + ((size_t)b * N + p) * 3;
+    const float* cc = new_xyz + (size_t)bs * 3;
+    const float d0 = __ldg(pp) - __ldg(cc), d1 = __ldg(pp + 1) - __ldg(cc + 1), d2 = __ldg(pp + 2) - __ldg(cc + 2);
+    float g[CPL];
+    const float* gr = dY + r * lddy + c0;
+    if (CPL == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(gr));
+      g[0] = t.x; g[1] = t.y; g[2] = t.z; g[CPL - 1] = t.w;
+    } else {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(gr));
+      g[0] = t.x; g[1] = t.y;
+    }
+    if (dQf) {
+      float* q = dQf + ((size_t)b * N + p) * ldq + c0;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      gw[i][0] = fmaf(g[i], d0, gw[i][0]); gw[i][1] = fmaf(g[i], d1, gw[i][1]); gw[i][2] = fmaf(g[i], d2, gw[i][2]);
+      gb[i] += g[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    s_red[warp][0][c0 + i] = gw[i][0]; s_red[warp][1][c0 + i] = gw[i][1]; s_red[warp][2][c0 + i] = gw[i][2];
+    s_red[warp][3][c0 + i] = gb[i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 4 * C; e += 256) {
+    const int which = e / C, c = e - which * C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][which][c];
+    if (which < 3) atomicAdd(dW + (size_t)c * lddw + which, t);
+    else if (dbias) atomicAdd(dbias + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 3-NN interpolation backward: dfeats2[b, idx[b,n,j], :] += w[b,n,j] * dInterp[b*N+n, :]
+// ---------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+interp_bwd_kernel(const float* __restrict__ dI, int64_t ldi, const int64_t* __restrict__ idx,
+                  const float* __restrict__ w, int N, int S, int D, int64_t rows, float* __restrict__ dF,
+                  int64_t ldf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t b = r / N;
+  int64_t i0 = __ldg(idx + r * 3), i1 = __ldg(idx + r * 3 + 1), i2 = __ldg(idx + r * 3 + 2);
+  const float w0 = __ldg(w + r * 3), w1 = __ldg(w + r * 3 + 1), w2 = __ldg(w + r * 3 + 2);
+  float* f0 = dF + ((size_t)b * S + i0) * ldf;
+  float* f1 = dF + ((size_t)b * S + i1) * ldf;
+  float* f2 = dF + ((size_t)b * S + i2) * ldf;
+  const float* g = dI + r * ldi;
+  for (int c = lane; c < D; c += 32) {
+    const float v = __ldg(g + c);
+    atomicAdd(f0 + c, w0 * v);
+    atomicAdd(f1 + c, w1 * v);
+    atomicAdd(f2 + c, w2 * v);
+  }
+}
+
+// S == 1 (broadcast, models/pointnet_util.py:298-299): dfeats2[b, :] = sum_n dInterp[b*N+n, :]
+__global__ void __launch_bounds__(256)
+broadcast_bwd_kernel(const float* __restrict__ dI, int64_t ldi, int N, int D, float* __restrict__ dF, int64_t ldf) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  __shared__ float s[8][32];
+  float t = 0.f;
+  if (c < D)
+    for (int n = rl; n < N; n += 8) t += __ldg(dI + ((size_t)b * N + n) * ldi + c);
+  s[rl][threadIdx.x & 31] = t;
+  __syncthreads();
+  if (rl == 0 && c < D) {
+    for (int j = 1; j < 8; ++j) t += s[j][threadIdx.x & 31];
+    dF[(size_t)b * ldf + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Heads backward (data gradient): dA[m,k] = mask[b,k,n] * sum_j dOut[m,j] * W[j,k]
+// ---------------------------------------------------------------------------------------------------------
+
+template <int NP>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ dOut, int64_t ldo, const float* __restrict__ mask_cf,
+                const float* __restrict__ W, int64_t M, int N, int C, int Nout, float* __restrict__ dA,
+                int64_t ldda) {
+  extern __shared__ __align__(16) float s_w[];   // [C][NP]  (W transposed)
+  for (int e = threadIdx.x; e < C * NP; e += 256) {
+    const int k = e / NP, j = e - k * NP;
+    s_w[e] = j < Nout ? __ldg(W + (size_t)j * C + k) : 0.f;
+  }
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (m >= M) return;
+  const int64_t b = m / N;
+  const int n = (int)(m - b * N);
+  float g[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) g[j] = j < Nout ? __ldg(dOut + m * ldo + j) : 0.f;
+  const float* mk = mask_cf ? mask_cf + (size_t)b * C * N + n : nullptr;
+  float* out = dA + m * ldda;
+  for (int k0 = 0; k0 < C; k0 += 4) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* wr = s_w + (k0 + i) * NP;
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) t = fmaf(g[j], wr[j], t);
+      v[i] = mk ? t * __ldg(mk + (size_t)(k0 + i) * N) : t;
+    }
+    *reinterpret_cast<float4*>(out + k0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam defaults of train_...:189: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad)
+// over the flat parameter buffer: one launch for the whole model.
+// ---------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace
+
+extern "C" int p2c_bn_bwd_reduce(const float* dA, int64_t ldda, const float* Y, int64_t ldy, const float* scale,
+                                 const float* shift, int64_t M, int C, double* sums, void* stream) {
+  if (!dA || !Y || !sums || M <= 0 || C <= 0 || ldda < C || ldy < C) return P2C_EINVAL;
+  if ((scale == nullptr) != (shift == nullptr)) return P2C_EINVAL;
+  if (C > 1024 || (C < RED_THREADS && RED_THREADS % C != 0) || (C > RED_THREADS && C % RED_THREADS != 0))
+    return P2C_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  P2C_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  bn_bwd_reduce_kernel<<<p2c_ceil_div(M, RED_ROWS), RED_THREADS, 0, st>>>(dA, ldda, Y, ldy, scale, shift, M, C, sums);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_pool_bwd_reduce(const float* dOut, int64_t ldd, const float* Ymax, const float* Ymin,
+                                   const float* scale, const float* shift, int64_t G, int C, double* sums,
+                                   void* stream) {
+  if (!dOut || !Ymax || !Ymin || !scale || !shift || !sums || G <= 0 || C <= 0 || ldd < C) return P2C_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  P2C_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  dim3 grid(p2c_ceil_div(C, 128), p2c_ceil_div(G, 64));
+  pool_bwd_reduce_kernel<<<grid, 128, 0, st>>>(dOut, ldd, Ymax, Ymin, scale, shift, G, C, sums);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_bn_bwd_coef(const double* sums, int64_t count, const float* gamma, const float* mean,
+                               const float* invstd, int training, float* coef, float* dgamma, float* dbeta, int C,
+                               void* stream) {
+  if (!sums || !mean || !invstd || !coef || count <= 0 || C <= 0) return P2C_EINVAL;
+  bn_bwd_coef_kernel<<<p2c_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)count, gamma, mean, invstd,
+                                                                            training, coef, dgamma, dbeta, C);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_bn_bwd_apply(const float* dA, int64_t ldda, const float* Y, int64_t ldy, const float* scale,
+                                const float* shift, const float* coef, int64_t M, int C, float* dY, int64_t lddy,
+                                void* stream) {
+  if (!dA || !Y || !scale || !shift || !coef || !dY || M <= 0 || C <= 0) return P2C_EINVAL;
+  if (C % 4 || ldda % 4 || ldy % 4 || lddy % 4 ||
+      ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY) |
+        reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(coef)) & 15))
+    return P2C_EALIGN;
+  const int64_t total = M * (C / 4);
+  const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
+  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dA, ldda, Y, ldy, scale, shift, coef, M, C, dY, lddy);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_pool_bwd_apply(const float* dOut, int64_t ldd, const float* Ymax, const float* Ymin, const float* Y,
+                                  int64_t ldy, const float* scale, const float* shift, const float* coef, int64_t G,
+                                  int group, int C, float* dY, int64_t lddy, void* stream) {
+  if (!dOut || !Ymax || !Ymin || !Y || !scale || !shift || !coef || !dY || G <= 0 || group <= 0 || C <= 0)
+    return P2C_EINVAL;
+  pool_bwd_apply_kernel<<<p2c_ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(dOut, ldd, Ymax, Ymin, Y, ldy, scale,
+                                                                                    shift, coef, G, group, C, dY, lddy);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* in_scale,
+                         const float* in_shift, const float* mask_cf, int mask_N, int64_t M, int N, int K, float* dW,
+                         int64_t lddw, float* db, void* stream) {
+  if (!dY || !X || !dW || M <= 0 || N <= 0 || K <= 0 || lddy < N || ldx < K || lddw < K) return P2C_EINVAL;
+  if ((in_scale == nullptr) != (in_shift == nullptr)) return P2C_EINVAL;
+  if (mask_cf && mask_N <= 0) return P2C_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool big = N >= 128 && K >= 128;
+  const int TN = big ? 128 : 64, TK = big ? 128 : 64;
+  const int gx = p2c_ceil_div(N, TN), gy = p2c_ceil_div(K, TK);
+  // split the rows so that the grid fills the 148 SMs a few times over; at least 256 rows per CTA
+  int64_t want = (int64_t)148 * 4 / ((int64_t)gx * gy);
+  if (want < 1) want = 1;
+  int64_t rows_per_cta = (M + want - 1) / want;
+  if (rows_per_cta < 256) rows_per_cta = 256;
+  rows_per_cta = (rows_per_cta + WG_RS - 1) / WG_RS * WG_RS;
+  const int gz = p2c_ceil_div(M, rows_per_cta);
+  dim3 grid(gx, gy, gz);
+  if (big)
+    wgrad_kernel<128, 128><<<grid, 256, 0, st>>>(dY, lddy, X, ldx, in_scale, in_shift, mask_cf, mask_N, M, N, K,
+                                                 (int)rows_per_cta, dW, lddw, db);
+  else
+    wgrad_kernel<64, 64><<<grid, 256, 0, st>>>(dY, lddy, X, ldx, in_scale, in_shift, mask_cf, mask_N, M, N, K,
+                                               (int)rows_per_cta, dW, lddw, db);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_sa_first_bwd(const float* dY, int64_t lddy, const float* xyz, const float* new_xyz,
+                                const int64_t* idx, int B, int N, int S, int nsample, int C, float* dQf, int64_t ldq,
+                                float* dW, int64_t lddw, float* dbias, void* stream) {
+  if (!dY || !xyz || !new_xyz || !idx || !dW || B <= 0 || N <= 0 || S <= 0 || nsample <= 0 || lddw < 3 || lddy < C)
+    return P2C_EINVAL;
+  if (C != 64 && C != 128) return P2C_EUNSUPPORTED;
+  if ((lddy % 4) != 0 || (reinterpret_cast<uintptr_t>(dY) & 15) != 0) return P2C_EALIGN;
+  const int64_t rows = (int64_t)B * S * nsample;
+  const int blocks = (int)min((int64_t)148 * 8, (rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 128)
+    sa_first_bwd_kernel<4><<<blocks, 256, 0, st>>>(dY, lddy, xyz, new_xyz, idx, N, S, nsample, rows, dQf, ldq, dW, lddw,
+                                                   dbias);
+  else
+    sa_first_bwd_kernel<2><<<blocks, 256, 0, st>>>(dY, lddy, xyz, new_xyz, idx, N, S, nsample, rows, dQf, ldq, dW, lddw,
+                                                   dbias);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const int64_t* idx, const float* w, int B,
+                                       int N, int S, int D, float* dfeats2, int64_t ldf, void* stream) {
+  if (!dInterp || !dfeats2 || B <= 0 || N <= 0 || S <= 0 || D <= 0 || ldi < D || ldf < D) return P2C_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 1) {
+    broadcast_bwd_kernel<<<dim3(p2c_ceil_div(D, 32), B), 256, 0, st>>>(dInterp, ldi, N, D, dfeats2, ldf);
+  } else {
+    if (!idx || !w) return P2C_EINVAL;
+    P2C_CUDA_TRY(cudaMemset2DAsync(dfeats2, sizeof(float) * ldf, 0, sizeof(float) * D, (size_t)B * S, st));
+    const int64_t rows = (int64_t)B * N;
+    interp_bwd_kernel<<<p2c_ceil_div(rows, 8), 256, 0, st>>>(dInterp, ldi, idx, w, N, S, D, rows, dfeats2, ldf);
+  }
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const float* W, int B, int N, int C,
+                            int Nout, float* dA, int64_t ldda, void* stream) {
+  if (!dOut || !W || !dA || B <= 0 || N <= 0 || C <= 0 || Nout <= 0 || ldo < Nout || ldda < C) return P2C_EINVAL;
+  if (C % 4 || ldda % 4 || (reinterpret_cast<uintptr_t>(dA) & 15)) return P2C_EALIGN;
+  if (C > 256 || Nout > 36) return P2C_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = (int64_t)B * N;
+#define P2C_HB(NPV)                                                                                              \
+  do {                                                                                                           \
+    const size_t smem = (size_t)C * NPV * sizeof(float);                                                         \
+    head_bwd_kernel<NPV><<<p2c_ceil_div(M, 256), 256, smem, st>>>(dOut, ldo, mask_cf, W, M, N, C, Nout, dA, ldda); \
+  } while (0)
+  if (Nout <= 4) P2C_HB(4); else if (Nout <= 8) P2C_HB(8); else if (Nout <= 12) P2C_HB(12);
+  else if (Nout <= 20) P2C_HB(20); else if (Nout <= 28) P2C_HB(28); else P2C_HB(36);
+#undef P2C_HB
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                             void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step <= 0) return P2C_EINVAL;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  const int blocks = (int)min((int64_t)148 * 8, (n + 255) / 256);
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                        weight_decay, bc1, bc2_sqrt, grad_scale);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}

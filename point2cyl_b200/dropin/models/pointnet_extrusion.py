@@ -3,7 +3,7 @@ forward signature and state_dict keys (123 entries for output_sizes=[3,16]), run
 import torch
 import torch.nn as nn
 
-from point2cyl_b200 import pipeline
+from point2cyl_b200 import autograd, pipeline
 from point2cyl_b200.dropin.models.pointnet_util import (PointNetFeaturePropagation,  # noqa: F401
                                                         PointNetSetAbstraction,
                                                         PointNetSetAbstractionMsg)
@@ -33,4 +33,6 @@ class backbone(nn.Module):
     def forward(self, x, fps_start=None):
         """fps_start: optional ((B,) int64, (B,) int64) first FPS centroids for sa1/sa2; default draws
         them from the CPU generator in the reference's order."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return autograd.backbone_apply(self, x, fps_start)        # backward = csrc/backward.cu kernels
         return pipeline.backbone_forward(self, x, fps_start)

@@ -523,3 +523,106 @@ def eig3x3_backward(M: Tensor, gvec: Tensor) -> Tensor:
     dM = torch.empty_like(flat)
     call("p2c_eig3x3_backward", ptr(flat), ptr(g), flat.shape[0], ptr(dM), stream_ptr())
     return dM.reshape(M.shape)
+
+
+# ---- backward of the backbone (kernels in csrc/backward.cu) ----------------------------------------------------
+
+
+def bn_bwd_reduce(dA: Tensor, Y: Tensor, scale: Optional[Tensor], shift: Optional[Tensor]) -> Tensor:
+    dA, Y = _rows(dA), _rows(Y)
+    M, C_ = Y.shape
+    sums = torch.empty(2 * C_, dtype=torch.float64, device=Y.device)
+    call("p2c_bn_bwd_reduce", ptr(dA), dA.stride(0), ptr(Y), Y.stride(0), ptr(scale), ptr(shift), M, C_, ptr(sums),
+         stream_ptr())
+    return sums
+
+
+def pool_bwd_reduce(dOut: Tensor, Ymax: Tensor, Ymin: Tensor, scale: Tensor, shift: Tensor) -> Tensor:
+    dOut = _rows(dOut)
+    G, C_ = Ymax.shape
+    sums = torch.empty(2 * C_, dtype=torch.float64, device=Ymax.device)
+    call("p2c_pool_bwd_reduce", ptr(dOut), dOut.stride(0), ptr(Ymax), ptr(Ymin), ptr(scale), ptr(shift), G, C_, ptr(sums),
+         stream_ptr())
+    return sums
+
+
+def bn_bwd_coef(sums: Tensor, count: int, gamma: Tensor, mean: Tensor, invstd: Tensor, training: bool,
+                dgamma: Optional[Tensor], dbeta: Optional[Tensor]) -> Tensor:
+    C_ = mean.shape[0]
+    coef = torch.empty(3 * C_, dtype=torch.float32, device=mean.device)
+    call("p2c_bn_bwd_coef", ptr(sums), count, ptr(gamma), ptr(mean), ptr(invstd), 1 if training else 0, ptr(coef),
+         ptr(dgamma), ptr(dbeta), C_, stream_ptr())
+    return coef
+
+
+def bn_bwd_apply(dA: Tensor, Y: Tensor, scale: Tensor, shift: Tensor, coef: Tensor, out: Optional[Tensor] = None):
+    dA, Y = _rows(dA), _rows(Y)
+    M, C_ = Y.shape
+    if out is None:
+        out = torch.empty(M, C_, dtype=torch.float32, device=Y.device)
+    call("p2c_bn_bwd_apply", ptr(dA), dA.stride(0), ptr(Y), Y.stride(0), ptr(scale), ptr(shift), ptr(coef), M, C_,
+         ptr(out), out.stride(0), stream_ptr())
+    return out
+
+
+def pool_bwd_apply(dOut: Tensor, Ymax: Tensor, Ymin: Tensor, Y: Tensor, scale: Tensor, shift: Tensor, coef: Tensor,
+                   group: int) -> Tensor:
+    dOut, Y = _rows(dOut), _rows(Y)
+    G, C_ = Ymax.shape
+    dY = torch.empty(G * group, C_, dtype=torch.float32, device=Y.device)
+    call("p2c_pool_bwd_apply", ptr(dOut), dOut.stride(0), ptr(Ymax), ptr(Ymin), ptr(Y), Y.stride(0), ptr(scale),
+         ptr(shift), ptr(coef), G, group, C_, ptr(dY), dY.stride(0), stream_ptr())
+    return dY
+
+
+def wgrad(dY: Tensor, X: Tensor, K: int, dW: Tensor, db: Optional[Tensor], in_scale: Optional[Tensor] = None,
+          in_shift: Optional[Tensor] = None, mask_cf: Optional[Tensor] = None) -> None:
+    """dW (N, >=K rows of stride dW.stride(0)) += dY^T f(X);  db (N) += column sums of dY."""
+    dY, X = _rows(dY), _rows(X)
+    M, N = dY.shape
+    dW2 = dW if dW.dim() == 2 else dW.reshape(dW.shape[0], -1)
+    if dW2.stride(1) != 1 or dW2.shape[0] != N or dW2.shape[1] < K:
+        raise _lib.P2CError(f"wgrad: dW {tuple(dW.shape)} does not match N={N}, K={K}")
+    call("p2c_wgrad", ptr(dY), dY.stride(0), ptr(X), X.stride(0), ptr(in_scale), ptr(in_shift), ptr(mask_cf),
+         0 if mask_cf is None else mask_cf.shape[2], M, N, K, ptr(dW2), dW2.stride(0), ptr(db), stream_ptr())
+
+
+def sa_first_bwd(dY: Tensor, xyz: Tensor, new_xyz: Tensor, idx: Tensor, dQf: Optional[Tensor], dW: Tensor,
+                 dbias: Optional[Tensor]) -> None:
+    dY = _rows(dY)
+    B, N, _ = xyz.shape
+    S, ns = idx.shape[1], idx.shape[2]
+    dW2 = dW.reshape(dW.shape[0], -1)
+    call("p2c_sa_first_bwd", ptr(dY), dY.stride(0), ptr(xyz), ptr(new_xyz), ptr(idx), B, N, S, ns, dY.shape[1], ptr(dQf),
+         0 if dQf is None else dQf.stride(0), ptr(dW2), dW2.stride(0), ptr(dbias), stream_ptr())
+
+
+def three_nn_interp_bwd(dInterp: Tensor, idx: Optional[Tensor], w: Optional[Tensor], B: int, N: int, S: int) -> Tensor:
+    dInterp = _rows(dInterp)
+    D = dInterp.shape[1]
+    dF = torch.empty(B * S, D, dtype=torch.float32, device=dInterp.device)
+    call("p2c_three_nn_interp_bwd", ptr(dInterp), dInterp.stride(0), ptr(idx), ptr(w), B, N, S, D, ptr(dF), dF.stride(0),
+         stream_ptr())
+    return dF
+
+
+def head_bwd(dOut: Tensor, mask_cf: Optional[Tensor], W: Tensor, B: int, N: int) -> Tensor:
+    dOut = _rows(dOut)
+    W2 = W.reshape(W.shape[0], -1).contiguous()
+    Nout, C_ = W2.shape
+    dA = torch.empty(B * N, C_, dtype=torch.float32, device=dOut.device)
+    call("p2c_head_bwd", ptr(dOut), dOut.stride(0), ptr(mask_cf), ptr(W2), B, N, C_, Nout, ptr(dA), dA.stride(0),
+         stream_ptr())
+    return dA
+
+
+def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int,
+              betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    """In-place Adam on flat fp32 buffers (torch.optim.Adam semantics, no amsgrad)."""
+    need_cuda(params, grads, exp_avg, exp_avg_sq)
+    n = params.numel()
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if t.numel() != n or not t.is_contiguous() or t.dtype != torch.float32:
+            raise _lib.P2CError("adam_step: flat contiguous float32 buffers of equal length expected")
+    call("p2c_adam_step", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), n, float(lr), float(betas[0]),
+         float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), stream_ptr())

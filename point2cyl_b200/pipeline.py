@@ -51,61 +51,73 @@ class Affine:
 
 def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0,
               in_affine: Optional[Affine] = None, in_mask: Optional[Tensor] = None,
-              precision: Optional[str] = None, tag: str = "mlp", first_layer=None):
+              precision: Optional[str] = None, tag: str = "mlp", first_layer=None, tape: Optional[list] = None):
     """Runs [conv1x1 -> BN -> ReLU] * L over the rows of X.
 
     Returns (Y_last_raw, Affine_last) — or, with pool_group, the pooled post-BN/ReLU features
     (rows/pool_group, C_last).  The BN of layer i is applied inside layer i+1's operand load.
+    tape: when given, every layer appends what point2cyl_b200.backward needs (raw input/output, folded BN,
+    batch mean / invstd, pooled extrema) and pooled layers keep their raw output.
     """
     prec = _PRECISIONS[precision or _default_precision]
     M = X.shape[0] if X is not None else None
     aff = in_affine
     mask = in_mask
     last = len(convs) - 1
+    save = tape is not None
     for i, (conv, bn) in enumerate(zip(convs, bns)):
         N = conv.weight.shape[0]
         use_batch_stats = training or (bn.running_mean is None)
         stats = torch.zeros(2 * N, dtype=torch.float64, device=conv.weight.device) if use_batch_stats else None
         pool = pool_group if i == last else 0
         _lib.set_tag(f"{tag}.{i}")
-        if i == 0 and first_layer is not None:
+        fused_first = i == 0 and first_layer is not None
+        Ymax = Ymin = None
+        if fused_first:
             # the level's first conv comes fused with the grouping gather (p2c_sa_first_layer)
-            res = first_layer(stats)
-            M = res.shape[0]
-            scale, shift = ops.bn_finalize(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn),
-                                           use_batch_stats, bn.running_mean, bn.running_var)
-            if training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)
-            aff = Affine(scale, shift)
-            X, K = res, N
-            continue
-        wsplit = ops.split_tf32(conv.weight) if ops.needs_split(X, N, K, mask is not None, pool, prec) else None
-        res = ops.linear(X, conv.weight, conv.bias, K=K, w_split=wsplit,
-                         in_scale=None if aff is None else aff.scale,
-                         in_shift=None if aff is None else aff.shift,
-                         in_mask=mask, stats=stats, pool_group=pool, want_y=(pool == 0), precision=prec)
-        scale, shift = ops.bn_finalize(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn),
-                                       use_batch_stats, bn.running_mean, bn.running_var)
+            Y = first_layer(stats)
+            M = Y.shape[0]
+        else:
+            wsplit = ops.split_tf32(conv.weight) if ops.needs_split(X, N, K, mask is not None, pool, prec) else None
+            res = ops.linear(X, conv.weight, conv.bias, K=K, w_split=wsplit,
+                             in_scale=None if aff is None else aff.scale,
+                             in_shift=None if aff is None else aff.shift,
+                             in_mask=mask, stats=stats, pool_group=pool, want_y=(pool == 0 or save), precision=prec)
+            if pool:
+                Y, Ymax, Ymin = res
+            else:
+                Y = res
+        fin = ops.bn_finalize(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn), use_batch_stats,
+                              bn.running_mean, bn.running_var, save=save)
+        scale, shift = fin[0], fin[1]
         if training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
+        if save:
+            tape.append(dict(X=None if fused_first else X, K=K, in_aff=aff, in_mask=mask, conv=conv, bn=bn, Y=Y,
+                             scale=scale, shift=shift, mean=fin[2], invstd=fin[3], M=M, pool=pool, Ymax=Ymax, Ymin=Ymin,
+                             batch_stats=use_batch_stats, fused_first=fused_first))
         aff = Affine(scale, shift)
         mask = None
         if pool:
-            _, Ymax, Ymin = res
             return ops.pool_bn_relu(Ymax, Ymin, scale, shift)
-        X = res
+        X = Y
         K = N
     return X, aff
 
 
 def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Tensor],
                     trace: Optional[dict] = None, precision: Optional[str] = None, tag: str = "sa",
-                    fused_first: bool = True):
+                    fused_first: bool = True, tape: Optional[dict] = None):
     """PointNetSetAbstraction in point-major form (models/pointnet_util.py:181-207).
-    xyz (B,N,3), feats (B*N, D) rows or None -> (new_xyz (B,S,3), new_feats (B*S, C))."""
+    xyz (B,N,3), feats (B*N, D) rows or None -> (new_xyz (B,S,3), new_feats (B*S, C)).
+    tape: dict filled with what the backward of this level needs."""
     B, N, _ = xyz.shape
     D = 0 if feats is None else feats.shape[1]
     _lib.set_tag(tag)
+    layers = None
+    if tape is not None:
+        layers = []
+        tape.update(kind="sa", module=sa, xyz=xyz, feats=feats, B=B, N=N, D=D, layers=layers, fused=False)
     if sa.group_all:
         rows = ops.group(xyz, feats, None, None)
         new_xyz = torch.zeros(B, 1, 3, dtype=torch.float32, device=xyz.device)
@@ -131,29 +143,41 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
             def first_layer(stats):
                 return ops.sa_first_layer(xyz, new_xyz, gidx, Qf, W0, conv0.bias, stats)
 
+            if tape is not None:
+                tape.update(fused=True, new_xyz=new_xyz, gidx=gidx)
             out = mlp_stack(None, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
-                            tag=tag, first_layer=first_layer)
+                            tag=tag, first_layer=first_layer, tape=layers)
             return new_xyz, out
+        if tape is not None:
+            raise _lib.P2CError("training through the un-fused grouping path (first SA width not 64/128) is not built")
         rows = ops.group(xyz, feats, new_xyz, gidx)
     out = mlp_stack(rows, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
-                    tag=tag)
+                    tag=tag, tape=layers)
     return new_xyz, out
 
 
 def feature_propagation(fp, xyz1: Tensor, xyz2: Tensor, feats1: Optional[Tensor], feats2: Tensor,
-                        materialize: bool = True, precision: Optional[str] = None, tag: str = "fp"):
+                        materialize: bool = True, precision: Optional[str] = None, tag: str = "fp",
+                        tape: Optional[dict] = None):
     """PointNetFeaturePropagation in point-major form (models/pointnet_util.py:283-320).
     feats1 (B*N, D1) or None, feats2 (B*S, D2) -> (B*N, C) post-BN/ReLU rows (materialize=True) or
     (raw rows, Affine) for a consumer that folds the last BN+ReLU into its own load."""
     B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
     D1 = 0 if feats1 is None else feats1.shape[1]
     D2 = feats2.shape[1]
     _lib.set_tag(tag)
     buf = torch.empty(B * N, D1 + D2, dtype=torch.float32, device=xyz1.device)
     if feats1 is not None:
         buf[:, :D1].copy_(feats1)           # skip features first (:312)
-    ops.three_nn_interp(xyz1, xyz2, feats2, out=buf[:, D1:])
-    Y, aff = mlp_stack(buf, D1 + D2, fp.mlp_convs, fp.mlp_bns, fp.training, precision=precision, tag=tag)
+    layers = None
+    if tape is not None:
+        layers = []
+        _, nn_idx, nn_w = ops.three_nn_interp(xyz1, xyz2, feats2, out=buf[:, D1:], want_idx=True)
+        tape.update(kind="fp", module=fp, B=B, N=N, S=S, D1=D1, D2=D2, nn_idx=nn_idx, nn_w=nn_w, layers=layers)
+    else:
+        ops.three_nn_interp(xyz1, xyz2, feats2, out=buf[:, D1:])
+    Y, aff = mlp_stack(buf, D1 + D2, fp.mlp_convs, fp.mlp_bns, fp.training, precision=precision, tag=tag, tape=layers)
     _lib.set_tag(tag)
     if materialize:
         return ops.bn_relu_apply(Y, aff.scale, aff.shift)
@@ -167,40 +191,50 @@ def draw_fps_start(B: int, N: int, device) -> Tensor:
 
 
 def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = None,
-                     trace: Optional[dict] = None, precision: Optional[str] = None) -> List[Tensor]:
-    """models/pointnet_extrusion.py:37-66.  x (B,N,3[+3]) -> [ (B,N,o_i) ] (views of one buffer)."""
+                     trace: Optional[dict] = None, precision: Optional[str] = None,
+                     tape: Optional[dict] = None) -> List[Tensor]:
+    """models/pointnet_extrusion.py:37-66.  x (B,N,3[+3]) -> [ (B,N,o_i) ] (views of one buffer).
+    tape: dict that receives the per-stage records point2cyl_b200.backward.backbone_backward consumes."""
     _lib.need_cuda(x)
     B, N, Cx = x.shape
     x = x.float()
     xyz = x[:, :, :3].contiguous()
     feats0 = x[:, :, 3:].reshape(B * N, Cx - 3).contiguous() if Cx > 3 else None
     dev = x.device
+    rec = (lambda: {}) if tape is not None else (lambda: None)
+    r_sa1, r_sa2, r_sa3, r_fp3, r_fp2, r_fp1 = rec(), rec(), rec(), rec(), rec(), rec()
     s1 = fps_start[0] if fps_start is not None else draw_fps_start(B, N, dev)
     t1 = {} if trace is not None else None
-    l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, s1, t1, precision, tag="sa1")
+    l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, s1, t1, precision, tag="sa1", tape=r_sa1)
     s2 = fps_start[1] if fps_start is not None else draw_fps_start(B, l1_xyz.shape[1], dev)
     t2 = {} if trace is not None else None
-    l2_xyz, l2 = set_abstraction(net.sa2, l1_xyz, l1, s2, t2, precision, tag="sa2")
-    l3_xyz, l3 = set_abstraction(net.sa3, l2_xyz, l2, None, None, precision, tag="sa3")
-    l4 = feature_propagation(net.fp3, l2_xyz, l3_xyz, l2, l3, precision=precision, tag="fp3")
-    l5 = feature_propagation(net.fp2, l1_xyz, l2_xyz, l1, l4, precision=precision, tag="fp2")
+    l2_xyz, l2 = set_abstraction(net.sa2, l1_xyz, l1, s2, t2, precision, tag="sa2", tape=r_sa2)
+    l3_xyz, l3 = set_abstraction(net.sa3, l2_xyz, l2, None, None, precision, tag="sa3", tape=r_sa3)
+    l4 = feature_propagation(net.fp3, l2_xyz, l3_xyz, l2, l3, precision=precision, tag="fp3", tape=r_fp3)
+    l5 = feature_propagation(net.fp2, l1_xyz, l2_xyz, l1, l4, precision=precision, tag="fp2", tape=r_fp2)
     y6, aff6 = feature_propagation(net.fp1, xyz, l1_xyz, feats0, l5, materialize=False, precision=precision,
-                                    tag="fp1")
+                                    tag="fp1", tape=r_fp1)
     # FC head: fc1 -> bn1 -> ReLU -> dropout(p=.5, always on, :60) -> fc2 heads
+    head_layers = [] if tape is not None else None
     h, aff_h = mlp_stack(y6, y6.shape[1], [net.fc1], [net.bn1], net.training, in_affine=aff6,
-                         precision=precision, tag="fc1")
+                         precision=precision, tag="fc1", tape=head_layers)
     # Same torch op on the same (B,128,N) shape as the reference so a shared seed gives the same mask; the head
     # kernel consumes it in that channel-first layout (no transpose copy).
     mask_cf = F.dropout(torch.ones(B, h.shape[1], N, dtype=torch.float32, device=dev), p=0.5)
     if tuple(mask_cf.shape) != (B, h.shape[1], N):
         raise _lib.P2CError("dropout mask must keep the (B,128,N) shape")
+    mask_cf = mask_cf.contiguous()
     Wcat = torch.cat([fc.weight.reshape(fc.weight.shape[0], -1) for fc in net.fc2], dim=0)
     bcat = torch.cat([fc.bias for fc in net.fc2], dim=0)
     _lib.set_tag("fc2")
-    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf.contiguous(), Wcat, bcat, B, N)
+    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N)
     if trace is not None:
         trace.update(sa1=t1, sa2=t2, l1_xyz=l1_xyz, l1=l1, l2_xyz=l2_xyz, l2=l2, l3=l3, l4=l4, l5=l5,
                      y6=y6, aff6=aff6, h=h, aff_h=aff_h)
+    if tape is not None:
+        tape.update(B=B, N=N, sa1=r_sa1, sa2=r_sa2, sa3=r_sa3, fp3=r_fp3, fp2=r_fp2, fp1=r_fp1,
+                    head=dict(layers=head_layers, h=h, aff_h=aff_h, mask_cf=mask_cf, Wcat=Wcat, fc2=list(net.fc2)),
+                    out=out, feats0=feats0)
     results, c0 = [], 0
     out3 = out.reshape(B, N, out.shape[1])
     for fc in net.fc2:

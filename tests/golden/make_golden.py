@@ -161,6 +161,64 @@ def loss_case(ref, name, B, N, K, seed, norm_eig):
     print("wrote", name)
 
 
+def sample_grad(g, limit=2048):
+    """Parameter gradients are stored whole when small, else as their first `limit` entries plus the L2 norm."""
+    flat = g.detach().reshape(-1)
+    return np32(flat[:limit]), np.float64(flat.double().norm())
+
+
+def train_case(ref, name, B, N, K, seed, bn_eval=False):
+    """One training step of the reference (train_Point2Cyl_without_sketch.py:244-367, all five multipliers 1):
+    real backbone module in train mode, a fixed seeded dropout mask, the reference's loss functions and inline bb
+    loss, torch autograd -> gradients of every parameter."""
+    data = synthetic.s_cyl(B, N, K, seed)
+    sd = orc.init_state_dict(output_sizes=(3, 2 * K), seed=seed)
+    net = ref.net.backbone(output_sizes=[3, 2 * K])
+    net.load_state_dict(sd, strict=True)
+    net.train(not bn_eval)      # bn_eval: BatchNorm on running statistics (F.dropout stays active, :60) - the
+    #                             well-conditioned variant of the same step, see tests/test_gpu_backward.py
+    mask = (torch.rand(B, 128, N, generator=torch.Generator().manual_seed(seed + 3)) > 0.5).float() * 2.0
+    real_dropout = ref.net.F.dropout
+    ref.net.F.dropout = lambda x, p=0.5, **kw: x * mask
+    try:
+        torch.manual_seed(seed)
+        s1 = torch.randint(0, N, (B,), dtype=torch.long)
+        s2 = torch.randint(0, 512, (B,), dtype=torch.long)
+        torch.manual_seed(seed)
+        X_raw, W_raw = net(data["pcs"])
+    finally:
+        ref.net.F.dropout = real_dropout
+    pcs, gt_normals, inst, bb = data["pcs"], data["normals"], data["inst"], data["bb"]
+    X = F.normalize(X_raw, p=2, dim=2, eps=1e-12)
+    W_2K = torch.softmax(W_raw, dim=2)
+    W_barrel, W_barrel_bb = W_2K[:, :, ::2], W_raw[:, :, ::2]
+    W_base, W_base_bb = W_2K[:, :, 1::2], W_raw[:, :, 1::2]
+    W = W_barrel + W_base
+    total, l_n, l_seg, matching_indices, mask_m = ref.losses.compute_all_losses(
+        pcs, W, inst, X, gt_normals, 1.0, 1.0, return_match_indices=True)
+    ns = dict(torch=torch, F=F, W=W, matching_indices=matching_indices, mask=mask_m, K=K, NUM_POINT=N,
+              batch_size=B, sampled_pcs=pcs, W_barrel_bb=W_barrel_bb, W_base_bb=W_base_bb, gt_bb_labels=bb)
+    exec(_inline_bb_loss_source(), ns)
+    l_bb = ns["total_bb_loss"]
+    mask_gt = ref.losses.get_mask_gt(inst, K)
+    gi = matching_indices.unsqueeze(1).expand(B, N, K)
+    E_AX = ref.data_utils.estimate_extrusion_axis(X, torch.gather(W_barrel, 2, gi), torch.gather(W_base, 2, gi), bb,
+                                                  inst, normalize=False)
+    ext = ref.losses.compute_normal_loss(E_AX, data["axes"], angle_diff=False, collapse=False)
+    l_ax = torch.mean(ref.losses.reduce_mean_masked_instance(ext, mask_gt))
+    centers = ref.data_utils.estimate_extrusion_centers(torch.gather(W, 2, gi), pcs)
+    l_c = torch.mean(ref.losses.reduce_mean_masked_instance(torch.square(centers - data["centers"]).sum(dim=-1),
+                                                            mask_gt))
+    loss = total + l_bb + l_ax + l_c
+    loss.backward()
+    out = dict(loss=np32(loss), s1=np32(s1), s2=np32(s2), matching_indices=np32(matching_indices),
+               X_raw=np32(X_raw), W_raw=np32(W_raw), meta=np.array([B, N, K, seed], dtype=np.int64))
+    for k, p in net.named_parameters():
+        out["grad_" + k], out["gnorm_" + k] = sample_grad(p.grad)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name)
+
+
 def projection_case(ref, name, B, N, K, S, seed):
     """Second-wave closed forms run by the reference's own code (data_utils.py:1014-1417, :1650-1730); the CPU
     generator is re-seeded before each call so the consumer can reproduce the randint stream.  Cloud 0 loses one
@@ -216,6 +274,8 @@ def main():
     loss_case(ref, "loss_b2_n1024_k4.npz", 2, 1024, 4, seed=0, norm_eig=False)
     loss_case(ref, "loss_b3_n2048_k8_normeig.npz", 3, 2048, 8, seed=5, norm_eig=True)
     projection_case(ref, "projection_b3_n512_k4.npz", 3, 512, 4, 128, seed=2)
+    train_case(ref, "train_b2_n1024_k4.npz", 2, 1024, 4, seed=0)
+    train_case(ref, "train_bneval_b2_n1024_k4.npz", 2, 1024, 4, seed=0, bn_eval=True)
 
 
 if __name__ == "__main__":

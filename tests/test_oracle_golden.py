@@ -188,3 +188,48 @@ def test_loss_gradients(golden_dir, name):
     out["total"].backward()
     assert rel_err(X_raw.grad, g["dX_raw"]) <= 2e-5
     assert rel_err(W_raw.grad, g["dW_raw"]) <= 2e-5
+
+
+def grad_errors(got, g, key):
+    """(relative L2 error, median |err| / max|ref|, norm error) of a parameter gradient against its stored sample
+    (first 2048 entries + L2 norm)."""
+    ref = torch.from_numpy(g["grad_" + key]).double()
+    flat = got.detach().reshape(-1).double().cpu()
+    d = flat[:ref.numel()] - ref
+    scale = max(float(ref.abs().max()), 1e-30)
+    return (float(d.norm() / ref.norm().clamp_min(1e-30)), float(d.abs().median()) / scale,
+            abs(float(flat.norm()) - float(g["gnorm_" + key])) / max(float(g["gnorm_" + key]), 1e-30))
+
+
+def live_keys(g, training):
+    """Parameters whose gradient is not mathematically zero: with train-mode BatchNorm a conv bias in front of it,
+    or a shift that a later BatchNorm removes (sa3's last beta), only carries rounding noise."""
+    gmax = max(float(g[k]) for k in g.files if k.startswith("gnorm_"))
+    keys = [k[5:] for k in g.files if k.startswith("grad_") and float(g["gnorm_" + k[5:]]) > 1e-5 * gmax]
+    if training:
+        keys = [k for k in keys if not (k.endswith("bias") and ("mlp_convs" in k or k.startswith("fc1")))]
+    return keys
+
+
+@pytest.mark.parametrize("name,training", [("train_b2_n1024_k4.npz", True), ("train_bneval_b2_n1024_k4.npz", False)])
+def test_training_step_gradients(golden_dir, name, training):
+    """Autograd through the oracle's backbone + loss block reproduces the reference's parameter gradients for one
+    training step (pins the checker of the backward kernels).  Same torch ops in the same order, so this holds to
+    1e-3 even though the step is ill-conditioned (see test_gpu_backward.py)."""
+    g = load(golden_dir, name)
+    B, N, K, seed = (int(v) for v in g["meta"])
+    data = synthetic.s_cyl(B, N, K, seed)
+    sd = orc.init_state_dict((3, 2 * K), seed=seed)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd.items()}
+    mask = (torch.rand(B, 128, N, generator=torch.Generator().manual_seed(seed + 3)) > 0.5).float() * 2.0
+    starts = (torch.from_numpy(g["s1"]), torch.from_numpy(g["s2"]))
+    out = orc.forward_loss(sd, data, training=training, fps_start=starts, dropout_mask=mask)
+    assert rel_err(out["total"].detach(), g["loss"]) <= 1e-5
+    out["total"].backward()
+    assert len([k for k in g.files if k.startswith("grad_")]) == 72
+    keys = live_keys(g, training)
+    assert len(keys) >= 40
+    for k in keys:
+        l2, med, nerr = grad_errors(sd[k].grad, g, k)
+        assert l2 <= 1e-3 and nerr <= 1e-3, (k, l2, med, nerr)
