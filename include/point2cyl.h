@@ -298,10 +298,18 @@ int p2c_pool_bwd_apply(const float* dOut, int64_t ldd, const float* Ymax, const 
 /* Weight / bias gradient of a 1x1 conv — autograd of Conv2d/Conv1d at models/pointnet_util.py:201, :317,
  * pointnet_extrusion.py:58-65:  dW[n,k] += sum_m dY[m,n] * A[m,k], db[n] += sum_m dY[m,n], with the layer input
  * A recomputed from the raw previous activation exactly as p2c_linear's operand load does
- * (A = max(X*in_scale+in_shift, 0) [* mask_cf[b,k,n], m = b*mask_N + n]).  dW/db are accumulated (atomics). */
+ * (A = max(X*in_scale+in_shift, 0) [* mask_cf[b,k,n], m = b*mask_N + n]).  dW/db are accumulated (atomics).
+ * P2C_PREC_3XTF32: split-over-rows tcgen05 kernel (csrc/wgrad_tc.cu: MN-major operands straight from TMA boxes,
+ * accumulator in tensor memory, error-compensated tf32 like the forward); masked / unaligned / tiny calls and
+ * P2C_PREC_FP32 take the register-tiled SIMT kernel. */
 int p2c_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* in_scale,
               const float* in_shift, const float* mask_cf, int mask_N, int64_t M, int N, int K, float* dW,
-              int64_t lddw, float* db, void* stream);
+              int64_t lddw, float* db, int precision /* P2C_PREC_FP32: SIMT; P2C_PREC_3XTF32: tcgen05 */,
+              void* stream);
+
+/* 1 when p2c_wgrad(P2C_PREC_3XTF32) runs on the tensor cores for these strides / sizes (16-byte aligned operands
+ * assumed), 0 when it takes the fp32 SIMT kernel.  Lets tests assert that the tcgen05 path really ran. */
+int p2c_wgrad_path(int64_t lddy, int64_t ldx, int64_t M, int N, int K, int has_mask);
 
 /* Backward of p2c_sa_first_layer: dQf[b*N+p, :] += dY[r, :] (NULL when the level has no input features; pre-zeroed
  * by the caller), dW[:, 0:3] += dY^T * (xyz[p] - centre), dbias += column sums. */

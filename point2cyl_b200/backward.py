@@ -21,6 +21,11 @@ Tensor = torch.Tensor
 GradOf = Callable[[torch.nn.Parameter], Tensor]
 
 
+def _wprec(precision: int) -> int:
+    """wgrad follows the forward's precision: tensor cores (3xTF32) unless the fp32 SIMT path was asked for."""
+    return _lib.PREC_FP32 if precision == _lib.PREC_FP32 else _lib.PREC_3XTF32
+
+
 def _w2(conv) -> Tensor:
     return conv.weight.reshape(conv.weight.shape[0], -1)
 
@@ -52,7 +57,7 @@ def _layer_backward(rec: dict, dA: Tensor, grad_of: GradOf, precision: int, need
         return dY, None
     aff = rec["in_aff"]
     ops.wgrad(dY, rec["X"], rec["K"], grad_of(conv.weight), grad_of(conv.bias),
-              None if aff is None else aff.scale, None if aff is None else aff.shift)
+              None if aff is None else aff.scale, None if aff is None else aff.shift, precision=_wprec(precision))
     dA_prev = _dgrad(dY, _w2(conv), precision) if need_input_grad else None
     return dY, dA_prev
 
@@ -87,7 +92,7 @@ def _sa_backward(rec: dict, d_out: Tensor, grad_of: GradOf, precision: int) -> O
     if feats is None:
         return None
     # Qf = feats @ W0[:, 3:].T  (computed once per source point in the forward)
-    ops.wgrad(dQf, feats, D, gW0[:, 3:], None)
+    ops.wgrad(dQf, feats, D, gW0[:, 3:], None, precision=_wprec(precision))
     return _dgrad(dQf, _w2(conv0)[:, 3:], precision)
 
 

@@ -470,13 +470,20 @@ extern "C" int p2c_pool_bwd_apply(const float* dOut, int64_t ldd, const float* Y
   return 0;
 }
 
+int p2c_wgrad_tc(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* in_scale,
+                 const float* in_shift, int64_t M, int N, int K, float* dW, int64_t lddw, float* db, cudaStream_t st);
+
 extern "C" int p2c_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* in_scale,
                          const float* in_shift, const float* mask_cf, int mask_N, int64_t M, int N, int K, float* dW,
-                         int64_t lddw, float* db, void* stream) {
+                         int64_t lddw, float* db, int precision, void* stream) {
   if (!dY || !X || !dW || M <= 0 || N <= 0 || K <= 0 || lddy < N || ldx < K || lddw < K) return P2C_EINVAL;
   if ((in_scale == nullptr) != (in_shift == nullptr)) return P2C_EINVAL;
   if (mask_cf && mask_N <= 0) return P2C_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == P2C_PREC_3XTF32 && !mask_cf) {
+    const int rc = p2c_wgrad_tc(dY, lddy, X, ldx, in_scale, in_shift, M, N, K, dW, lddw, db, st);
+    if (rc != P2C_EUNSUPPORTED) return rc;       // taken by the tensor-core kernel (or a real error)
+  }
   const bool big = N >= 128 && K >= 128;
   const int TN = big ? 128 : 64, TK = big ? 128 : 64;
   const int gx = p2c_ceil_div(N, TN), gy = p2c_ceil_div(K, TK);

@@ -576,7 +576,8 @@ def pool_bwd_apply(dOut: Tensor, Ymax: Tensor, Ymin: Tensor, Y: Tensor, scale: T
 
 
 def wgrad(dY: Tensor, X: Tensor, K: int, dW: Tensor, db: Optional[Tensor], in_scale: Optional[Tensor] = None,
-          in_shift: Optional[Tensor] = None, mask_cf: Optional[Tensor] = None) -> None:
+          in_shift: Optional[Tensor] = None, mask_cf: Optional[Tensor] = None,
+          precision: int = _lib.PREC_3XTF32) -> None:
     """dW (N, >=K rows of stride dW.stride(0)) += dY^T f(X);  db (N) += column sums of dY."""
     dY, X = _rows(dY), _rows(X)
     M, N = dY.shape
@@ -584,7 +585,13 @@ def wgrad(dY: Tensor, X: Tensor, K: int, dW: Tensor, db: Optional[Tensor], in_sc
     if dW2.stride(1) != 1 or dW2.shape[0] != N or dW2.shape[1] < K:
         raise _lib.P2CError(f"wgrad: dW {tuple(dW.shape)} does not match N={N}, K={K}")
     call("p2c_wgrad", ptr(dY), dY.stride(0), ptr(X), X.stride(0), ptr(in_scale), ptr(in_shift), ptr(mask_cf),
-         0 if mask_cf is None else mask_cf.shape[2], M, N, K, ptr(dW2), dW2.stride(0), ptr(db), stream_ptr())
+         0 if mask_cf is None else mask_cf.shape[2], M, N, K, ptr(dW2), dW2.stride(0), ptr(db), precision,
+         stream_ptr())
+
+
+def wgrad_on_tensor_cores(dY: Tensor, X: Tensor, K: int, has_mask: bool = False) -> bool:
+    return bool(_lib.load().p2c_wgrad_path(dY.stride(0), X.stride(0), dY.shape[0], dY.shape[1], K, int(has_mask))) \
+        and dY.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0
 
 
 def sa_first_bwd(dY: Tensor, xyz: Tensor, new_xyz: Tensor, idx: Tensor, dQf: Optional[Tensor], dW: Tensor,

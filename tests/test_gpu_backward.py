@@ -292,19 +292,33 @@ def test_head_backward_vs_autograd():
     assert rel_err(dW, Wd.grad) <= 1e-5 and rel_err(db, dOut.double().sum(0)) <= 1e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(5000, 64, 64), (3000, 128, 131), (1024, 256, 259), (700, 19, 128)])
-def test_wgrad_kernel(M, N, K):
+@pytest.mark.parametrize("M,N,K", [(5000, 64, 64), (3000, 128, 131), (1024, 256, 259), (700, 19, 128),
+                                   (40000, 128, 128), (33001, 64, 64), (20000, 256, 131), (4096, 512, 1024)])
+@pytest.mark.parametrize("tc", [False, True])
+def test_wgrad_kernel(M, N, K, tc):
+    """dW = dY^T relu(bn(X)), db = column sums: fp32 SIMT kernel and the tcgen05 split-over-rows kernel (3xTF32)."""
+    from point2cyl_b200 import _lib
     g = torch.Generator().manual_seed(M)
-    dY = torch.randn(M, N, generator=g)
-    ld = ops.pad4(K)
+    ldn, ld = ops.pad4(N), ops.pad4(K)
+    dY = torch.randn(M, ldn, generator=g)[:, :N]
     X = torch.randn(M, ld, generator=g)
     sc, sh = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.1
     A = torch.relu(X[:, :K] * sc + sh)
     dW = torch.zeros(N, K, device=DEV)
     db = torch.zeros(N, device=DEV)
-    ops.wgrad(dY.to(DEV), X.to(DEV), K, dW, db, sc.to(DEV), sh.to(DEV))
+    dYd, Xd = dY.to(DEV), X.to(DEV)                       # .to keeps the padded row stride of the slice
+    if dYd.stride(0) != ldn:
+        dYd = torch.zeros(M, ldn, device=DEV)[:, :N].copy_(dY)
+    on_tc = ops.wgrad_on_tensor_cores(dYd, Xd, K)
+    assert on_tc == (M >= 1024)
+    ops.wgrad(dYd, Xd, K, dW, db, sc.to(DEV), sh.to(DEV), precision=_lib.PREC_3XTF32 if tc else _lib.PREC_FP32)
     assert rel_err(dW, dY.double().T @ A.double()) <= 1e-5
     assert rel_err(db, dY.double().sum(0)) <= 1e-5
+    # no-affine operand and accumulation into a strided dW view (the Qf half of a fused first layer)
+    dWs = torch.ones(N, K + 3, device=DEV)
+    ops.wgrad(dYd, Xd, K, dWs[:, 3:], None, precision=_lib.PREC_3XTF32 if tc else _lib.PREC_FP32)
+    assert rel_err(dWs[:, 3:] - 1.0, dY.double().T @ X[:, :K].double()) <= 1e-5
+    assert float((dWs[:, :3] - 1.0).abs().max()) == 0.0
 
 
 def test_bn_relu_backward_kernels_vs_autograd():
