@@ -185,6 +185,126 @@ def algorithmic_work(name, tag, B):
     return "hbm", None
 
 
+def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, warmup):
+    """forward + loss + backward + gradient all-reduce (NCCL) + Adam through point2cyl_b200.train.Trainer:
+    device-resident and end-to-end (pinned host batch -> H2D -> step -> loss scalar D2H) clouds/s over all ranks."""
+    import point2cyl_b200
+    from point2cyl_b200 import _lib
+    from point2cyl_b200.train import Trainer
+    tr = Trainer(net, lr=1e-3)
+
+    def step_resident():
+        return tr.step(batch)
+
+    def step_e2e():
+        dev_batch = {k: host[k].to(dev, non_blocking=True) for k in point2cyl_b200.BATCH_KEYS}
+        out = tr.step(dev_batch)
+        out["loss_host"] = out["losses"].cpu()
+        return out
+
+    for _ in range(warmup):
+        step_resident()
+    step_e2e()
+    pd.barrier()
+    ms = timed(step_resident, steps)
+    l0 = _lib.launch_count
+    step_resident()
+    launches = _lib.launch_count - l0
+    pd.barrier()
+    ms_e2e = timed(step_e2e, steps)
+    pd.barrier()
+    tot, tot_e2e = pd.reduce_max(sum(ms), dev), pd.reduce_max(sum(ms_e2e), dev)
+    clouds = B_PER_GPU * world * steps
+    n_param = tr.flat_param.numel()
+    return {"metric": "point-clouds/sec training step (forward+loss+backward+grad all-reduce+Adam), B=32/GPU N=8192 K=8",
+            "value": clouds / (tot / 1e3), "unit": UNIT, "ms_per_step": tot / steps,
+            "e2e": {"value": clouds / (tot_e2e / 1e3), "unit": UNIT, "ms_per_step": tot_e2e / steps,
+                    "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host), "d2h_bytes_per_step": 24},
+            "gpu_launches": launches, "steps": steps, "warmup": warmup, "launch_mode": "eager",
+            "collective": None if world == 1 else f"one NCCL sum all-reduce of the flat fp32 gradient ({n_param} floats)",
+            "parameters": n_param, "global_batch": B_PER_GPU * world}
+
+
+def run_train(args, rank, world, dev, pd, net, host, batch, flush, timed):
+    """--workload train: BASELINE.json configs[3] (data-parallel training step, 32 clouds per GPU)."""
+    import torch.distributed as dist
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    t = train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps=args.steps, warmup=args.warmup)
+    clk = clocks.stop()
+    if rank == 0:
+        cfg = workload_config(world, args.precision)
+        cfg["workload"] = ("training step: forward+loss+backward+NCCL gradient all-reduce+Adam, S-cyl synthetic clouds, "
+                           f"B={B_PER_GPU}/GPU x N={N_POINTS}, K={K_INST} (BASELINE.json configs[3])")
+        cfg["parallelism"] = f"dp{world} (clouds sharded; one flat-gradient all-reduce per step)"
+        print(json.dumps({"metric": t["metric"], "value": t["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": t["ms_per_step"], "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
+                          "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "launch_mode": "eager", "clocks": clk,
+                          "collective": t["collective"]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_stress(args, rank, world, dev, pd):
+    """--workload stress: BASELINE.json configs[4] - FPS + ball query of both set-abstraction levels on
+    B=128 x N=32768 uniform clouds (sparse balls: the padding path), clouds sharded over the ranks; achieved HBM GB/s
+    on the algorithmic bytes of SURVEY.md 8d (1,139,200 B per cloud)."""
+    import torch.distributed as dist
+    from point2cyl_b200 import ops, synthetic
+    B_total, N = 128, 32768
+    lo, hi = pd.shard_range(B_total, rank, world)
+    xyz = synthetic.s_uniform(hi - lo, N, seed=77 + rank).to(dev)
+    s1 = torch.zeros(hi - lo, dtype=torch.long, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        _, c1 = ops.fps(xyz, 512, s1)
+        g1 = ops.ball_query(0.2, 64, xyz, c1)
+        _, c2 = ops.fps(c1, 128, s1)
+        g2 = ops.ball_query(0.4, 64, c1, c2)
+        return g1, g2
+
+    for _ in range(args.warmup):
+        step()
+    pd.barrier()
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step()
+        e.record()
+        e.synchronize()
+        ms.append(s.elapsed_time(e))
+    pd.barrier()
+    clk = clocks.stop()
+    tot = pd.reduce_max(sum(ms), dev)
+    if rank == 0:
+        pk = peaks()
+        per_cloud = 12 * N + 8 * 512 + 12 * 512 + 8 * 128 + (12 * N + 12 * 512 + 8 * 512 * 64) + (12 * 512 + 12 * 128 + 8 * 128 * 64)
+        clouds = B_total * args.steps
+        gbs = per_cloud * clouds / (tot / 1e3) / 1e9
+        print(json.dumps({"metric": "FPS+ball-query clouds/sec at B=128 N=32768 (stress sweep)", "value": clouds / (tot / 1e3),
+                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": tot / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                          "config": {"workload": "FPS (N->512->128) + ball query (r=.2/.4, nsample 64) on S-uniform clouds, "
+                                                 "B=128 total x N=32768 (BASELINE.json configs[4])",
+                                     "global_batch": B_total, "points": N, "parallelism": f"dp{world} (clouds sharded)",
+                                     "l2": "flushed between timed steps (512 MiB write)"},
+                          "roofline": {"kernel": "p2c_fps + p2c_ball_query", "bound": "hbm", "achieved": gbs,
+                                       "peak": pk["hbm"] * world, "unit": "GB/s", "frac": gbs / (pk["hbm"] * world),
+                                       "traffic": None,
+                                       "note": f"algorithmic bytes {per_cloud} per cloud (SURVEY.md 8d); FPS is bound by "
+                                               "its 640 dependent arg-max rounds, not by HBM"},
+                          "gpu_launches": 4, "clocks": clk}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,6 +314,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("P2C_PRECISION", "3xtf32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--workload", default="forward_loss", choices=["forward_loss", "train", "stress"],
+                    help="forward_loss = BASELINE.json configs[1] (the headline metric, default); train = configs[3], "
+                         "the data-parallel training step (32 clouds per GPU); stress = configs[4], FPS + ball query "
+                         "at B=128 x N=32768")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -214,6 +338,10 @@ def main():
     pd.init("nccl")          # one process per GPU; NCCL is used for the timing barrier / max-reduce only
     pipeline.set_precision(args.precision)
     _lib.load()
+
+    if args.workload == "stress":
+        run_stress(args, rank, world, dev, pd)
+        return
 
     net = make_net(dev)
     host = point2cyl_b200.pin_batch(synthetic.s_cyl(B_PER_GPU, N_POINTS, K_INST, seed=1234 + rank))
@@ -256,6 +384,10 @@ def main():
             return out
         with torch.no_grad():
             return point2cyl_b200.forward_loss_host(net, host, device=dev)
+
+    if args.workload == "train":
+        run_train(args, rank, world, dev, pd, net, host, batch, flush, timed)
+        return
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -330,6 +462,8 @@ def main():
             tf = d["flops"] / (d["ms"] / 1e3) / 1e12
             roof["tensor_tflops"] = tf
             roof["tensor_frac_of_bf16_peak"] = tf / pk["bf16"]
+    # ---- the training step of configs[3] on the same batch (all ranks: it contains the gradient all-reduce) ----
+    train = train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps=10, warmup=3)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample()
@@ -343,7 +477,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host),
                     "d2h_bytes_per_step": 24 + (0 if graphed is not None else B_PER_GPU * K_INST * K_INST * 4 + B_PER_GPU * 4), "ms_per_step": total_ms_e2e / args.steps},
             "gpu_launches": launches, "launch_mode": "eager" if graphed is None else "cuda_graph", "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "stages": stages}), flush=True)
+            "stages": stages, "train_step": train}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

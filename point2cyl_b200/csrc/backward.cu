@@ -26,40 +26,50 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 
 constexpr int RED_THREADS = 256;
-constexpr int RED_ROWS = 512;   // rows per CTA
+constexpr int RED_CB = 128;     // channels per CTA (32 float4 lanes); C < 128 uses C/4 lanes and more row lanes
 
-// thread t: channel (t % CW) + i*CW, row lane t / CW
+// CTA = (row slab blockIdx.x, channel block blockIdx.y); thread = (float4 channel lane, row lane); float4 loads
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldda, const float* __restrict__ Y, int64_t ldy,
                      const float* __restrict__ scale, const float* __restrict__ shift, int64_t M, int C,
-                     double* __restrict__ sums) {
-  __shared__ float s_red[2][RED_THREADS];
-  const int CW = C < RED_THREADS ? C : RED_THREADS;      // C is a multiple of 32 and <= 1024; CW divides 256 or equals it
-  const int RL = RED_THREADS / CW;
-  const int cl = threadIdx.x % CW, rl = threadIdx.x / CW;
-  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS;
-  const int64_t r1 = r0 + RED_ROWS < M ? r0 + RED_ROWS : M;
-  for (int c = cl; c < C; c += CW) {
-    const float sc = scale ? __ldg(scale + c) : 1.f, sh = shift ? __ldg(shift + c) : 0.f;
-    float s1 = 0.f, s2 = 0.f;
-    if (rl < RL) {
-      for (int64_t r = r0 + rl; r < r1; r += RL) {
-        const float y = __ldg(Y + r * ldy + c);
-        float g = __ldg(dA + r * ldda + c);
-        if (scale && !(fmaf(y, sc, sh) > 0.f)) g = 0.f;
-        s1 += g;
-        s2 = fmaf(g, y, s2);
-      }
+                     int rows_per_cta, double* __restrict__ sums) {
+  __shared__ float s_red[RED_THREADS][8];
+  const int cb = C < RED_CB ? C : RED_CB;            // channels of this CTA's block
+  const int CL = cb >> 2;                            // float4 lanes (8, 16 or 32)
+  const int RL = RED_THREADS / CL;                   // row lanes
+  const int cl = threadIdx.x % CL, rl = threadIdx.x / CL;
+  const int c = blockIdx.y * cb + cl * 4;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scale) {
+    sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+    sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+  }
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  for (int64_t r = r0 + rl; r < r1; r += RL) {
+    const float4 y = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
+    float4 g = __ldg(reinterpret_cast<const float4*>(dA + r * ldda + c));
+    if (scale) {
+      if (!(fmaf(y.x, sc.x, sh.x) > 0.f)) g.x = 0.f;
+      if (!(fmaf(y.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
+      if (!(fmaf(y.z, sc.z, sh.z) > 0.f)) g.z = 0.f;
+      if (!(fmaf(y.w, sc.w, sh.w) > 0.f)) g.w = 0.f;
     }
-    s_red[0][threadIdx.x] = s1;
-    s_red[1][threadIdx.x] = s2;
-    __syncthreads();
-    if (rl == 0) {
-      for (int j = 1; j < RL; ++j) { s1 += s_red[0][j * CW + cl]; s2 += s_red[1][j * CW + cl]; }
-      atomicAdd(sums + c, (double)s1);
-      atomicAdd(sums + C + c, (double)s2);
-    }
-    __syncthreads();
+    s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+    s2.x = fmaf(g.x, y.x, s2.x); s2.y = fmaf(g.y, y.y, s2.y); s2.z = fmaf(g.z, y.z, s2.z); s2.w = fmaf(g.w, y.w, s2.w);
+  }
+  float* mine = s_red[threadIdx.x];
+  mine[0] = s1.x; mine[1] = s1.y; mine[2] = s1.z; mine[3] = s1.w;
+  mine[4] = s2.x; mine[5] = s2.y; mine[6] = s2.z; mine[7] = s2.w;
+  __syncthreads();
+  // thread t < 8*CL: (lane cl', component q) summed over the row lanes
+  for (int e = threadIdx.x; e < 8 * CL; e += RED_THREADS) {
+    const int l = e >> 3, q = e & 7;
+    float t = 0.f;
+    for (int j = 0; j < RL; ++j) t += s_red[j * CL + l][q];
+    const int ch = blockIdx.y * cb + l * 4 + (q & 3);
+    atomicAdd(sums + (q < 4 ? 0 : C) + ch, (double)t);
   }
 }
 
@@ -260,32 +270,47 @@ sa_first_bwd_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
   float gw[CPL][3], gb[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) { gw[i][0] = gw[i][1] = gw[i][2] = 0.f; gb[i] = 0.f; }
-  const int64_t wstride = (int64_t)gridDim.x * 8;
-  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows; r += wstride) {
-    const int64_t bs = r / ns, b = bs / S;
-    int64_t p = __ldg(idx + r);
-    p = (p < 0 || p >= N) ? 0 : p;
-    const float* pp = xyz + ((size_t)b * N + p) * 3;
-    const float* cc = new_xyz + (size_t)bs * 3;
-    const float d0 = __ldg(pp) - __ldg(cc), d1 = __ldg(pp + 1) - __ldg(cc + 1), d2 = __ldg(pp + 2) - __ldg(cc + 2);
-    float g[CPL];
-    const float* gr = dY + r * lddy + c0;
-    if (CPL == 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(gr));
-      g[0] = t.x; g[1] = t.y; g[2] = t.z; g[CPL - 1] = t.w;
-    } else {
-      const float2 t = __ldg(reinterpret_cast<const float2*>(gr));
-      g[0] = t.x; g[1] = t.y;
-    }
-    if (dQf) {
-      float* q = dQf + ((size_t)b * N + p) * ldq + c0;
+  // UNR rows per warp and step: index -> coordinates -> gradient row are dependent L2 / HBM round trips
+  constexpr int UNR = 4;
+  const int64_t wstride = (int64_t)gridDim.x * 8 * UNR;
+  for (int64_t rb = ((int64_t)blockIdx.x * 8 + warp) * UNR; rb < rows; rb += wstride) {
+    int64_t p[UNR], bs[UNR], bq[UNR];
+    bool ok[UNR];
+    float g[UNR][CPL];
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[i]);
+    for (int u = 0; u < UNR; ++u) {
+      ok[u] = rb + u < rows;
+      const int64_t r = ok[u] ? rb + u : rows - 1;
+      bs[u] = r / ns;
+      bq[u] = bs[u] / S;
+      p[u] = __ldg(idx + r);
+      const float* gr = dY + r * lddy + c0;
+      if (CPL == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gr));
+        g[u][0] = t.x; g[u][1] = t.y; g[u][2] = t.z; g[u][CPL - 1] = t.w;
+      } else {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(gr));
+        g[u][0] = t.x; g[u][1] = t.y;
+      }
     }
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      gw[i][0] = fmaf(g[i], d0, gw[i][0]); gw[i][1] = fmaf(g[i], d1, gw[i][1]); gw[i][2] = fmaf(g[i], d2, gw[i][2]);
-      gb[i] += g[i];
+    for (int u = 0; u < UNR; ++u) {
+      if (!ok[u]) continue;
+      const int64_t pu = (p[u] < 0 || p[u] >= N) ? 0 : p[u];
+      const float* pp = xyz + ((size_t)bq[u] * N + pu) * 3;
+      const float* cc = new_xyz + (size_t)bs[u] * 3;
+      const float d0 = __ldg(pp) - __ldg(cc), d1 = __ldg(pp + 1) - __ldg(cc + 1), d2 = __ldg(pp + 2) - __ldg(cc + 2);
+      if (dQf) {
+        float* q = dQf + ((size_t)bq[u] * N + pu) * ldq + c0;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[u][i]);
+      }
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        gw[i][0] = fmaf(g[u][i], d0, gw[i][0]); gw[i][1] = fmaf(g[u][i], d1, gw[i][1]);
+        gw[i][2] = fmaf(g[u][i], d2, gw[i][2]);
+        gb[i] += g[u][i];
+      }
     }
   }
 #pragma unroll
@@ -413,11 +438,20 @@ extern "C" int p2c_bn_bwd_reduce(const float* dA, int64_t ldda, const float* Y, 
                                  const float* shift, int64_t M, int C, double* sums, void* stream) {
   if (!dA || !Y || !sums || M <= 0 || C <= 0 || ldda < C || ldy < C) return P2C_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return P2C_EINVAL;
-  if (C > 1024 || (C < RED_THREADS && RED_THREADS % C != 0) || (C > RED_THREADS && C % RED_THREADS != 0))
-    return P2C_EUNSUPPORTED;
+  if (C != 32 && C != 64 && (C % RED_CB) != 0) return P2C_EUNSUPPORTED;
+  if ((ldda % 4) || (ldy % 4) ||
+      ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(scale) |
+        reinterpret_cast<uintptr_t>(shift)) & 15))
+    return P2C_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   P2C_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-  bn_bwd_reduce_kernel<<<p2c_ceil_div(M, RED_ROWS), RED_THREADS, 0, st>>>(dA, ldda, Y, ldy, scale, shift, M, C, sums);
+  const int cblocks = C < RED_CB ? 1 : C / RED_CB;
+  // enough CTAs to fill the 148 SMs a few times over, at least 64 rows each
+  int64_t rows_per_cta = M / ((int64_t)148 * 8 / cblocks + 1) + 1;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  if (rows_per_cta > 2048) rows_per_cta = 2048;
+  dim3 grid(p2c_ceil_div(M, rows_per_cta), cblocks);
+  bn_bwd_reduce_kernel<<<grid, RED_THREADS, 0, st>>>(dA, ldda, Y, ldy, scale, shift, M, C, (int)rows_per_cta, sums);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }
@@ -513,7 +547,7 @@ extern "C" int p2c_sa_first_bwd(const float* dY, int64_t lddy, const float* xyz,
   if (C != 64 && C != 128) return P2C_EUNSUPPORTED;
   if ((lddy % 4) != 0 || (reinterpret_cast<uintptr_t>(dY) & 15) != 0) return P2C_EALIGN;
   const int64_t rows = (int64_t)B * S * nsample;
-  const int blocks = (int)min((int64_t)148 * 8, (rows + 7) / 8);
+  const int blocks = (int)min((int64_t)148 * 8, (rows + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 128)
     sa_first_bwd_kernel<4><<<blocks, 256, 0, st>>>(dY, lddy, xyz, new_xyz, idx, N, S, nsample, rows, dQf, ldq, dW, lddw,

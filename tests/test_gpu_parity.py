@@ -498,3 +498,32 @@ def test_eval_helpers_kernels():
     cen_ref, found_ref = orc.segment_centroids(EA_W, data["pcs"])
     assert torch.equal(found.cpu(), found_ref)
     assert float((cen.cpu() - cen_ref).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("N,npoint,cs", [(4096, 64, 0), (8192, 512, 2), (8192, 512, 4), (5000, 300, 8), (32768, 512, 0), (20000, 128, 0)])
+def test_fps_cluster_kernel_bit_exact(monkeypatch, N, npoint, cs):
+    """Thread-block-cluster FPS (CS CTAs per cloud, candidates exchanged through distributed shared memory): forced
+    on clouds the single-CTA kernel also takes, and as the default path above 16384 points (stress config N=32768)."""
+    B = 3
+    xyz = synthetic.s_uniform(B, N, seed=N) if N > 8192 else synthetic.s_cyl(B, N, 4, seed=3)["pcs"]
+    start = torch.tensor([0, N - 1, N // 2])
+    ref = orc.farthest_point_sample(xyz, npoint, start)
+    if cs:
+        single, _ = ops.fps(xyz.to(DEV), npoint, start.to(DEV))
+        monkeypatch.setenv("P2C_FPS_CLUSTER", str(cs))
+    idx, new_xyz = ops.fps(xyz.to(DEV), npoint, start.to(DEV))
+    assert torch.equal(idx.cpu(), ref)
+    if cs:
+        assert torch.equal(idx, single)
+    assert torch.equal(new_xyz.cpu(), torch.gather(xyz, 1, ref[:, :, None].expand(B, npoint, 3)))
+
+
+def test_stress_config_ball_query_large_cloud():
+    """configs[4] shapes (N=32768, S=512, r=0.2, nsample 64): ball query against the oracle on one cloud."""
+    N = 32768
+    xyz = synthetic.s_uniform(1, N, seed=5)
+    start = torch.tensor([7])
+    idx, new_xyz = ops.fps(xyz.to(DEV), 512, start.to(DEV))
+    got = ops.ball_query(0.2, 64, xyz.to(DEV), new_xyz)
+    ref = orc.query_ball_point(0.2, 64, xyz, new_xyz.cpu())
+    assert torch.equal(got.cpu(), ref)
