@@ -323,9 +323,12 @@ int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const int64_t* id
                             int D, float* dfeats2, int64_t ldf, void* stream);
 
 /* Data gradient of p2c_head_masked: dA[m,k] = mask_cf[b,k,n] * sum_j dOut[m,j] * W[j,k] (the ReLU/BN part is then the
- * generic p2c_bn_bwd_* on fc1's raw output; the heads' dW/db come from p2c_wgrad with the same mask). */
+ * generic p2c_bn_bwd_* on fc1's raw output).  With A_out != NULL the kernel also writes the heads' input
+ * A[m,k] = max(H[m,k]*scale[k]+shift[k], 0) * mask_cf[b,k,n] (H: fc1's raw output), so that the heads' dW/db come
+ * from the tensor-core p2c_wgrad on a plain row matrix. */
 int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const float* W, int B, int N, int C, int Nout,
-                 float* dA, int64_t ldda, void* stream);
+                 float* dA, int64_t ldda, const float* H, int64_t ldh, const float* scale, const float* shift,
+                 float* A_out, int64_t lda, void* stream);
 
 /* torch.optim.Adam step (train_Point2Cyl_without_sketch.py:189, :368) over a flat fp32 parameter buffer:
  * g = grads*grad_scale (+ weight_decay*p), m/v updated in place, bias-corrected with `step` (1-based). */

@@ -78,7 +78,8 @@ SIGNATURES = {
     "p2c_sa_first_bwd": [c_f32p, i64, c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64,
                          c_f32p, vp],
     "p2c_three_nn_interp_bwd": [c_f32p, i64, c_i64p, c_f32p, i32, i32, i32, i32, c_f32p, i64, vp],
-    "p2c_head_bwd": [c_f32p, i64, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, i64, vp],
+    "p2c_head_bwd": [c_f32p, i64, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p,
+                     i64, vp],
     "p2c_adam_step": [c_f32p, c_f32p, c_f32p, c_f32p, i64, f32, f32, f32, f32, f32, i32, f32, vp],
 }
 

@@ -112,22 +112,30 @@ def backbone_backward(tape: Dict, d_out: Tensor, grad_of: GradOf, precision: Opt
     prec = pipeline._PRECISIONS[precision or pipeline.get_precision()]
     B, N = tape["B"], tape["N"]
     head = tape["head"]
-    d_out = d_out.contiguous() if d_out.stride(-1) != 1 else d_out
-    d_rows = d_out.reshape(B * N, -1)
+    if d_out.dim() == 3:
+        d_out = d_out.contiguous().reshape(B * N, -1)
+    d_rows = d_out                                   # (B*N, C) rows, possibly with a padded row stride
     _lib.set_tag("bwd.head")
-    # heads: weights / biases from p2c_wgrad with the dropout mask, data gradient from p2c_head_bwd
+    # heads: p2c_head_bwd gives the data gradient and re-materialises the heads' input relu(bn1(fc1)) * dropout mask;
+    # their weights / biases then come from p2c_wgrad on plain row matrices (tensor cores when d_out rows are 16-byte
+    # aligned - the Trainer allocates them padded; a contiguous autograd gradient is copied into a padded buffer)
     Wcat = head["Wcat"]
+    aff_h = head["aff_h"]
+    dA, A_h = ops.head_bwd(d_rows, head["mask_cf"], Wcat, B, N, head["h"], aff_h.scale, aff_h.shift)
+    if d_rows.stride(0) % 4:
+        padded = torch.zeros(B * N, ops.pad4(d_rows.shape[1]), dtype=torch.float32, device=d_rows.device)
+        padded[:, :d_rows.shape[1]].copy_(d_rows)
+        d_rows = padded[:, :d_rows.shape[1]]
     gWcat = torch.zeros_like(Wcat)
     gbcat = torch.zeros(Wcat.shape[0], dtype=torch.float32, device=Wcat.device)
-    aff_h = head["aff_h"]
-    ops.wgrad(d_rows, head["h"], Wcat.shape[1], gWcat, gbcat, aff_h.scale, aff_h.shift, head["mask_cf"])
+    ops.wgrad(d_rows, A_h, Wcat.shape[1], gWcat, gbcat, precision=_wprec(prec))
+    del A_h
     c0 = 0
     for fc in head["fc2"]:
         o = fc.weight.shape[0]
         grad_of(fc.weight).reshape(o, -1).add_(gWcat[c0:c0 + o])
         grad_of(fc.bias).add_(gbcat[c0:c0 + o])
         c0 += o
-    dA = ops.head_bwd(d_rows, head["mask_cf"], Wcat, B, N)
     dA = _stack_backward(head["layers"], dA, grad_of, prec, need_input_grad=True)        # fc1 / bn1
     _lib.set_tag("bwd.fp1")
     d_feats0, d_l5 = _fp_backward(tape["fp1"], dA, grad_of, prec)                        # d_feats0: input normals, unused

@@ -381,11 +381,18 @@ template <int NP>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dOut, int64_t ldo, const float* __restrict__ mask_cf,
                 const float* __restrict__ W, int64_t M, int N, int C, int Nout, float* __restrict__ dA,
-                int64_t ldda) {
-  extern __shared__ __align__(16) float s_w[];   // [C][NP]  (W transposed)
+                int64_t ldda, const float* __restrict__ H, int64_t ldh, const float* __restrict__ scale,
+                const float* __restrict__ shift, float* __restrict__ A_out, int64_t lda) {
+  extern __shared__ __align__(16) float s_w[];   // [C][NP]  (W transposed), then scale[C], shift[C]
+  float* s_sc = s_w + C * NP;
+  float* s_sh = s_sc + C;
   for (int e = threadIdx.x; e < C * NP; e += 256) {
     const int k = e / NP, j = e - k * NP;
     s_w[e] = j < Nout ? __ldg(W + (size_t)j * C + k) : 0.f;
+  }
+  for (int k = threadIdx.x; k < C; k += 256) {
+    s_sc[k] = scale ? __ldg(scale + k) : 1.f;
+    s_sh[k] = shift ? __ldg(shift + k) : 0.f;
   }
   __syncthreads();
   const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -398,16 +405,27 @@ head_bwd_kernel(const float* __restrict__ dOut, int64_t ldo, const float* __rest
   const float* mk = mask_cf ? mask_cf + (size_t)b * C * N + n : nullptr;
   float* out = dA + m * ldda;
   for (int k0 = 0; k0 < C; k0 += 4) {
-    float v[4];
+    float v[4], mq[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float* wr = s_w + (k0 + i) * NP;
       float t = 0.f;
 #pragma unroll
       for (int j = 0; j < NP; ++j) t = fmaf(g[j], wr[j], t);
-      v[i] = mk ? t * __ldg(mk + (size_t)(k0 + i) * N) : t;
+      mq[i] = mk ? __ldg(mk + (size_t)(k0 + i) * N) : 1.f;
+      v[i] = t * mq[i];
     }
     *reinterpret_cast<float4*>(out + k0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (A_out) {
+      // the heads' input, relu(bn1(fc1)) * dropout mask, for their weight gradient (p2c_wgrad on the tensor cores)
+      const float4 h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + k0));
+      float4 a;
+      a.x = (scale ? fmaxf(fmaf(h.x, s_sc[k0], s_sh[k0]), 0.f) : h.x) * mq[0];
+      a.y = (scale ? fmaxf(fmaf(h.y, s_sc[k0 + 1], s_sh[k0 + 1]), 0.f) : h.y) * mq[1];
+      a.z = (scale ? fmaxf(fmaf(h.z, s_sc[k0 + 2], s_sh[k0 + 2]), 0.f) : h.z) * mq[2];
+      a.w = (scale ? fmaxf(fmaf(h.w, s_sc[k0 + 3], s_sh[k0 + 3]), 0.f) : h.w) * mq[3];
+      *reinterpret_cast<float4*>(A_out + m * lda + k0) = a;
+    }
   }
 }
 
@@ -576,16 +594,22 @@ extern "C" int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const 
 }
 
 extern "C" int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const float* W, int B, int N, int C,
-                            int Nout, float* dA, int64_t ldda, void* stream) {
+                            int Nout, float* dA, int64_t ldda, const float* H, int64_t ldh, const float* scale,
+                            const float* shift, float* A_out, int64_t lda, void* stream) {
   if (!dOut || !W || !dA || B <= 0 || N <= 0 || C <= 0 || Nout <= 0 || ldo < Nout || ldda < C) return P2C_EINVAL;
+  if ((scale == nullptr) != (shift == nullptr)) return P2C_EINVAL;
+  if (A_out && (!H || ldh < C || lda < C)) return P2C_EINVAL;
   if (C % 4 || ldda % 4 || (reinterpret_cast<uintptr_t>(dA) & 15)) return P2C_EALIGN;
+  if (A_out && (ldh % 4 || lda % 4 || ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(A_out)) & 15)))
+    return P2C_EALIGN;
   if (C > 256 || Nout > 36) return P2C_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = (int64_t)B * N;
 #define P2C_HB(NPV)                                                                                              \
   do {                                                                                                           \
-    const size_t smem = (size_t)C * NPV * sizeof(float);                                                         \
-    head_bwd_kernel<NPV><<<p2c_ceil_div(M, 256), 256, smem, st>>>(dOut, ldo, mask_cf, W, M, N, C, Nout, dA, ldda); \
+    const size_t smem = ((size_t)C * NPV + 2 * C) * sizeof(float);                                               \
+    head_bwd_kernel<NPV><<<p2c_ceil_div(M, 256), 256, smem, st>>>(dOut, ldo, mask_cf, W, M, N, C, Nout, dA, ldda, H, \
+                                                                  ldh, scale, shift, A_out, lda);                \
   } while (0)
   if (Nout <= 4) P2C_HB(4); else if (Nout <= 8) P2C_HB(8); else if (Nout <= 12) P2C_HB(12);
   else if (Nout <= 20) P2C_HB(20); else if (Nout <= 28) P2C_HB(28); else P2C_HB(36);

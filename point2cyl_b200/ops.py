@@ -613,14 +613,21 @@ def three_nn_interp_bwd(dInterp: Tensor, idx: Optional[Tensor], w: Optional[Tens
     return dF
 
 
-def head_bwd(dOut: Tensor, mask_cf: Optional[Tensor], W: Tensor, B: int, N: int) -> Tensor:
+def head_bwd(dOut: Tensor, mask_cf: Optional[Tensor], W: Tensor, B: int, N: int, H: Optional[Tensor] = None,
+             scale: Optional[Tensor] = None, shift: Optional[Tensor] = None):
+    """-> dA (B*N, C) [, A (B*N, C) = relu(bn(H)) * mask when H is given: the heads' input for their wgrad]."""
     dOut = _rows(dOut)
     W2 = W.reshape(W.shape[0], -1).contiguous()
     Nout, C_ = W2.shape
     dA = torch.empty(B * N, C_, dtype=torch.float32, device=dOut.device)
+    A = None
+    if H is not None:
+        H = _rows(H)
+        A = torch.empty(B * N, C_, dtype=torch.float32, device=dOut.device)
     call("p2c_head_bwd", ptr(dOut), dOut.stride(0), ptr(mask_cf), ptr(W2), B, N, C_, Nout, ptr(dA), dA.stride(0),
+         ptr(H), 0 if H is None else H.stride(0), ptr(scale), ptr(shift), ptr(A), 0 if A is None else A.stride(0),
          stream_ptr())
-    return dA
+    return dA if H is None else (dA, A)
 
 
 def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int,

@@ -68,8 +68,10 @@ class Trainer:
             self._ones = torch.tensor(self.weights, dtype=torch.float32, device=stats.device)
         dstats = ops.loss_backward_coef(stats, match, n_gt, batch["axes"], batch["centers"], self._ones, N, K,
                                         self.norm_eig)
+        C_out = 3 + 2 * K                                 # rows padded to 16 bytes: TMA operand of the heads' wgrad
+        d_buf = torch.empty(B * N, ops.pad4(C_out), dtype=torch.float32, device=stats.device)
         d_out = ops.segfit_backward(X_raw, W_raw, batch["pcs"], batch["normals"], batch["inst"], batch["bb"], dstats,
-                                    match, n_gt, self._ones, K)
+                                    match, n_gt, self._ones, K, out=d_buf[:, :C_out])
         bw.backbone_backward(tape, d_out, lambda p: p.grad, self.precision)
         return dict(total=losses[0], losses=losses, matching_indices=match, E_AX=E_AX, centers=centers)
 

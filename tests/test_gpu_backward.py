@@ -283,6 +283,8 @@ def test_head_backward_vs_autograd():
     A = torch.relu(Hd * sc.double() + sh.double()) * mask.double().permute(0, 2, 1).reshape(B * N, C)
     ((A @ Wd.T) * dOut.double()).sum().backward()
     dA = ops.head_bwd(dOut.to(DEV), mask.to(DEV), W.to(DEV), B, N)
+    dA2, A_h = ops.head_bwd(dOut.to(DEV), mask.to(DEV), W.to(DEV), B, N, H.to(DEV), sc.to(DEV), sh.to(DEV))
+    assert torch.equal(dA, dA2) and rel_err(A_h, A) <= 1e-6
     # dA is the gradient w.r.t. relu(bn(H)) (mask applied); gate it like the BN/ReLU stage does
     gate = ((H * sc + sh) > 0).double() * sc.double()
     assert rel_err(dA.cpu().double() * gate, Hd.grad) <= 1e-5
