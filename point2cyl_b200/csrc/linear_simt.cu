@@ -7,6 +7,8 @@
 // Classic 128 x BN x 16 register-tiled GEMM, 256 threads, 8 x BN/16 outputs per thread, double
 // buffered through shared memory.  The tensor-core paths (tcgen05) live in linear_tc.cu; this
 // one is the full-fp32 fallback for shapes they do not take and the in-library cross-check.
+#include <cstdlib>
+
 #include "common.cuh"
 
 #include <math_constants.h>
@@ -381,8 +383,11 @@ extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const flo
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != P2C_PREC_FP32) {
-    int rc = p2c_linear_tc(X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
-                           stats, pool_group, Ymax, Ymin, precision, st);
+    static const bool force_ss = getenv("P2C_TC_FORCE_SS") != nullptr;   // tools only: streamed-weight kernel first
+    int rc = P2C_EUNSUPPORTED;
+    if (!(force_ss && w_split))
+      rc = p2c_linear_tc(X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
+                         stats, pool_group, Ymax, Ymin, precision, st);
     if (rc != P2C_EUNSUPPORTED) return rc;
     if (w_split && p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, in_mask != nullptr,
                                          pool_group, precision)) {

@@ -37,6 +37,8 @@ using namespace p2c_tc;
 
 namespace {
 
+constexpr int LTC_THREADS = 512;   // 16 warps: producer, MMA, alloc, idle, 4 epilogue (even tiles), 4 transform, 4 epilogue (odd tiles)
+
 struct TcArgs {
   const float* W; const float* bias;
   const float* in_scale; const float* in_shift;
@@ -60,7 +62,7 @@ __host__ __device__ inline SmemLayout tc_smem_layout(int KB, int raw_stages, int
   uint32_t o = 0;
   L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES;       // [stage][128 rows][128 B]
   L.xt_off = o;     o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo][128 rows][128 B]
-  L.ystage_off = o; o += y_stage ? 4u * 2u * 4096u : 0u;         // [epilogue warp][buf][32 rows][32 channels]
+  L.ystage_off = o; o += y_stage ? 8u * 2u * 4096u : 0u;         // [epilogue warp (2 groups x 4)][buf][32 rows][32 channels]
   L.scale_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.shift_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.bar_off = o;    o += 512u;
@@ -68,7 +70,7 @@ __host__ __device__ inline SmemLayout tc_smem_layout(int KB, int raw_stages, int
   return L;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(LTC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmY, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms (TMA destination, UMMA descriptors) need 1024-byte aligned shared addresses
@@ -114,7 +116,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
-  for (int k = tid; k < KPAD; k += TC_THREADS) {
+  for (int k = tid; k < KPAD; k += LTC_THREADS) {
     const bool ok = a.in_scale != nullptr && k < a.K;
     s_scale[k] = ok ? __ldg(a.in_scale + k) : 0.f;
     s_shift[k] = ok ? __ldg(a.in_shift + k) : 0.f;
@@ -127,7 +129,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tm_w = tmem_base + (uint32_t)ACC * TC_BM;         // W_hi at +k, W_lo at +KPAD+k
 
   // weights -> TMEM (thread = output channel; hi | lo), zero padded in n and k
-  if (warp >= 8) {
+  if (warp >= 8 && warp < 12) {
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -218,7 +220,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===== operand transform: RAW ring -> BN+ReLU -> hi/lo -> XT ring =====
     // thread = (16-byte column chunk cj, 8-row group rg): its four k columns are fixed, so the folded
     // BatchNorm scale/shift are 8 registers per k-block instead of shared-memory loads per element
@@ -279,6 +281,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread = output channel n; accumulator columns = rows of Y =====
+    // Two groups of four warps (warps 4-7 and 12-15; warp % 4 = TMEM lane quadrant): with two accumulator buffers
+    // group g drains the tiles t = g (mod 2), so two tiles are in the epilogue at once.  One warp per scheduler
+    // issues the ~260 dependent instructions of a 32-row chunk at ~0.27 IPC (ncu: 36 % fixed-latency waits), which
+    // made the epilogue - not HBM, not the tensor pipe - pace the K = 64 layers; a second warp per scheduler
+    // overlaps those stalls.
+    const int grp = warp >= 12 ? 1 : 0;
     const int q = warp & 3;
     const int ch = q * 32 + lane;                      // channel within the CTA's 128
     const int n = n0 + ch;
@@ -291,20 +299,35 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float gmx = NEG_INF, gmn = POS_INF;                // running pool over the current group
     int dbg_n = 0;
     int ybuf = 0;
-    float* ystg = reinterpret_cast<float*>(ystage + (size_t)q * 8192);   // this warp's two 4 KB staging tiles
+    float* ystg = reinterpret_cast<float*>(ystage + (size_t)(grp * 4 + q) * 8192);   // this warp's two 4 KB staging tiles
     const bool y_tma = a.Y != nullptr && a.y_tma;
-    for (int t = 0; t < my_tiles; ++t) {
+    const bool warp_live = n0 + q * 32 < a.N;          // warp-uniform
+    float f1 = 0.f, f2 = 0.f;                          // fp32 partial sums, flushed to fp64 every few tiles
+    int since_flush = 0;
+    for (int t = (ACC == 2 ? grp : 0); t < ((ACC == 2 || grp == 0) ? my_tiles : 0); t += (ACC == 2 ? 2 : 1)) {
       const int ab = ACC == 2 ? (t & 1) : 0;
       const uint32_t accph = (ACC == 2 ? (uint32_t)(t >> 1) : (uint32_t)t) & 1u;
       const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BM;
       mbar_wait(&acc_full[ab], accph);
       tc_fence_after();
-      if (ch == 0) dbg_mark(a.dbg, 2, dbg_n, t * 100 + 99);
+      if (ch == 0 && grp == 0) dbg_mark(a.dbg, 2, dbg_n, t * 100 + 99);
       float t1 = 0.f, t2 = 0.f;
-#pragma unroll
+      if (!warp_live) {
+        // every channel of this warp lies beyond N (e.g. N = 64 on a 128-lane tile): nothing to read or reduce -
+        // only hand the accumulator back, which also leaves the TMEM read port to the live warps
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        continue;
+      }
+      // The chunk loop is deliberately NOT unrolled: one chunk is ~250 straight-line instructions (4 KB); unrolled
+      // four times (x the FULL / partial variants) the epilogue alone overflowed the instruction cache and the
+      // whole kernel ran at ~0.25 IPC (K = 64 layers: 177 us -> see profiles/README.md).
+      const uint32_t acc_addr = tm_acc + (uint32_t)ab * TC_BM + lane_addr;
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tm_acc + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
+        tmem_ld32(acc_addr + (uint32_t)c * 32u, raw);
         tmem_wait_ld();
         if (c == 3) {                                  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
@@ -323,7 +346,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         float* yp = (a.Y && !y_tma && n_ok) ? a.Y + (size_t)mrow * a.ldy + n : nullptr;
         float mx = NEG_INF, mn = POS_INF;
-        if (jmax == 32) epi_chunk<true>(raw, bias, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        if (jmax == 32) epi_chunk<true>(raw, bias, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr && !(a.dbg_mode & 4), G != 0 && !(a.dbg_mode & 8), t1, t2, mx, mn);
         else epi_chunk<false>(raw, bias, jmax, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
         if (y_tma) {
           // [32 rows][32 channels] staged (lanes = channels: conflict-free); the TMA engine writes it out:
@@ -350,11 +373,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             gmx = NEG_INF; gmn = POS_INF;
           }
         }
-        if (ch == 0) dbg_mark(a.dbg, 2, dbg_n, t * 100 + c);
+        if (ch == 0 && grp == 0) dbg_mark(a.dbg, 2, dbg_n, t * 100 + c);
       }
-      s1 += (double)t1;
-      s2 += (double)t2;
+      f1 += t1;
+      f2 += t2;
+      if (++since_flush == 4) {                        // fp64 adds are slow here: one pair per four tiles (512 rows)
+        s1 += (double)f1; s2 += (double)f2;
+        f1 = f2 = 0.f; since_flush = 0;
+      }
     }
+    s1 += (double)f1;
+    s2 += (double)f2;
     if (y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (a.stats && n_ok) {
       atomicAdd(a.stats + n, s1);
@@ -471,7 +500,7 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
   dim3 grid(gx, n_tiles);
-  linear_tc_kernel<<<grid, TC_THREADS, L.total + 1024, st>>>(tm, tmY, a);
+  linear_tc_kernel<<<grid, LTC_THREADS, L.total + 1024, st>>>(tm, tmY, a);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

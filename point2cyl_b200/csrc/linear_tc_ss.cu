@@ -241,7 +241,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       float t1 = 0.f, t2 = 0.f;
       mbar_wait(&acc_full[ab], accph);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1                                       // rolled on purpose: instruction-cache footprint (see linear_tc.cu)
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
