@@ -295,6 +295,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     const int G = a.pool_group;
+    const int gshift = G ? 31 - __clz(G) : 0;
     double s1 = 0.0, s2 = 0.0;
     float gmx = NEG_INF, gmn = POS_INF;                // running pool over the current group
     int dbg_n = 0;
@@ -364,9 +365,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // pool groups are 32, 64 or 128 consecutive rows and tiles start on group boundaries
           gmx = fmaxf(gmx, mx); gmn = fminf(gmn, mn);
           const int rows_done = c * 32 + 32;
-          if (rows_done % G == 0) {
+          if ((rows_done & (G - 1)) == 0) {            // G is 32, 64 or 128
             if (n_ok) {
-              const size_t o = (size_t)((mrow + 32 - G) / G) * a.N + n;
+              const size_t o = (size_t)((mrow + 32 - G) >> gshift) * a.N + n;
               a.Ymax[o] = gmx;
               a.Ymin[o] = gmn;
             }

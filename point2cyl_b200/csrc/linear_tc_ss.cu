@@ -227,6 +227,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     const int G = a.pool_group;
+    const int gshift = G ? 31 - __clz(G) : 0;
     int ybuf = 0;
     float* ystg = reinterpret_cast<float*>(ystage + (size_t)q * 8192);
     const bool y_tma = a.Y != nullptr && a.y_tma;
@@ -276,9 +277,9 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (G) {
           gmx = fmaxf(gmx, mx); gmn = fminf(gmn, mn);
           const int rows_done = c * 32 + 32;
-          if (rows_done % G == 0) {
+          if ((rows_done & (G - 1)) == 0) {            // G is 32, 64 or 128
             if (n_ok) {
-              const size_t o = (size_t)((mrow + 32 - G) / G) * a.N + n;
+              const size_t o = (size_t)((mrow + 32 - G) >> gshift) * a.N + n;
               a.Ymax[o] = gmx;
               a.Ymin[o] = gmn;
             }

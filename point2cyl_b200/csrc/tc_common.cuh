@@ -126,34 +126,45 @@ template <bool FULL>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&raw)[32], float bias, int jmax, float* stage,
                                           float* yp, int64_t ldy, bool do_stats, bool do_pool, float& t1,
                                           float& t2, float& mx_out, float& mn_out) {
-  float v[32];
+  // packed fp32 pairs (FADD2 / FFMA2 on sm_100): half the issue slots of the bias add and of the statistics
+  float2 v2[16];
+  const float2 b2 = make_float2(bias, bias);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + bias;
+  for (int i = 0; i < 16; ++i)
+    v2[i] = __fadd2_rn(make_float2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1])), b2);
   if (stage) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) stage[j * 32] = v[j];           // rows past M are clipped by the TMA store
+    for (int i = 0; i < 16; ++i) {                               // rows past M are clipped by the TMA store
+      stage[(2 * i) * 32] = v2[i].x;
+      stage[(2 * i + 1) * 32] = v2[i].y;
+    }
   } else if (yp) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (FULL || j < jmax) yp[(size_t)j * ldy] = v[j];
+    for (int i = 0; i < 16; ++i) {
+      if (FULL || 2 * i < jmax) yp[(size_t)(2 * i) * ldy] = v2[i].x;
+      if (FULL || 2 * i + 1 < jmax) yp[(size_t)(2 * i + 1) * ldy] = v2[i].y;
+    }
   }
   if (do_stats) {
-    float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // short dependency chains
+    float2 p1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // four scalar chains in two packed ones
+    float2 p2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float y = (FULL || j < jmax) ? v[j] : 0.f;
-      p1[j & 3] += y;
-      p2[j & 3] = fmaf(y, y, p2[j & 3]);
+    for (int i = 0; i < 16; ++i) {
+      float2 y = v2[i];
+      if (!FULL) { y.x = (2 * i < jmax) ? y.x : 0.f; y.y = (2 * i + 1 < jmax) ? y.y : 0.f; }
+      p1[i & 1] = __fadd2_rn(p1[i & 1], y);
+      p2[i & 1] = __ffma2_rn(y, y, p2[i & 1]);
     }
-    t1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
-    t2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+    t1 += (p1[0].x + p1[0].y) + (p1[1].x + p1[1].y);
+    t2 += (p2[0].x + p2[0].y) + (p2[1].x + p2[1].y);
   }
   if (do_pool) {
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     float mx[4] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF}, mn[4] = {POS_INF, POS_INF, POS_INF, POS_INF};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (FULL || j < jmax) { mx[j & 3] = fmaxf(mx[j & 3], v[j]); mn[j & 3] = fminf(mn[j & 3], v[j]); }
+    for (int i = 0; i < 16; ++i) {
+      if (FULL || 2 * i < jmax) { mx[i & 3] = fmaxf(mx[i & 3], v2[i].x); mn[i & 3] = fminf(mn[i & 3], v2[i].x); }
+      if (FULL || 2 * i + 1 < jmax) { mx[i & 3] = fmaxf(mx[i & 3], v2[i].y); mn[i & 3] = fminf(mn[i & 3], v2[i].y); }
     }
     mx_out = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
     mn_out = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
