@@ -270,46 +270,45 @@ sa_first_bwd_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
   float gw[CPL][3], gb[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) { gw[i][0] = gw[i][1] = gw[i][2] = 0.f; gb[i] = 0.f; }
-  // UNR rows per warp and step: index -> coordinates -> gradient row are dependent L2 / HBM round trips
-  constexpr int UNR = 4;
-  const int64_t wstride = (int64_t)gridDim.x * 8 * UNR;
-  for (int64_t rb = ((int64_t)blockIdx.x * 8 + warp) * UNR; rb < rows; rb += wstride) {
-    int64_t p[UNR], bs[UNR], bq[UNR];
-    bool ok[UNR];
-    float g[UNR][CPL];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      ok[u] = rb + u < rows;
-      const int64_t r = ok[u] ? rb + u : rows - 1;
-      bs[u] = r / ns;
-      bq[u] = bs[u] / S;
-      p[u] = __ldg(idx + r);
-      const float* gr = dY + r * lddy + c0;
+  // 32 rows per warp and step (same scheme as the forward kernel): lane l resolves row r0 + l's index and centred
+  // coordinates, the warp then walks the rows with shuffled broadcasts; lane = CPL consecutive channels.
+  const int64_t wstride = (int64_t)gridDim.x * 8 * 32;
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * 32; r0 < rows; r0 += wstride) {
+    const int64_t rl = r0 + lane;
+    const bool okl = rl < rows;
+    const unsigned rr = (unsigned)(okl ? rl : rows - 1);
+    const unsigned bsl = rr / (unsigned)ns, bl = bsl / (unsigned)S;
+    int64_t pl = __ldg(idx + rr);
+    pl = (pl < 0 || pl >= N) ? 0 : pl;
+    const unsigned src = bl * (unsigned)N + (unsigned)pl;
+    const float* pp = xyz + (size_t)src * 3;
+    const float* cc = new_xyz + (size_t)bsl * 3;
+    const float dl0 = __ldg(pp) - __ldg(cc), dl1 = __ldg(pp + 1) - __ldg(cc + 1), dl2 = __ldg(pp + 2) - __ldg(cc + 2);
+    const int nrow = (int)min((int64_t)32, rows - r0);
+#pragma unroll 4
+    for (int j = 0; j < nrow; ++j) {
+      const float d0 = __shfl_sync(P2C_FULL_MASK, dl0, j), d1 = __shfl_sync(P2C_FULL_MASK, dl1, j),
+                  d2 = __shfl_sync(P2C_FULL_MASK, dl2, j);
+      float g[CPL];
+      const float* gr = dY + (r0 + j) * lddy + c0;
       if (CPL == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(gr));
-        g[u][0] = t.x; g[u][1] = t.y; g[u][2] = t.z; g[u][CPL - 1] = t.w;
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[CPL - 1] = t.w;
       } else {
         const float2 t = __ldg(reinterpret_cast<const float2*>(gr));
-        g[u][0] = t.x; g[u][1] = t.y;
+        g[0] = t.x; g[1] = t.y;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (!ok[u]) continue;
-      const int64_t pu = (p[u] < 0 || p[u] >= N) ? 0 : p[u];
-      const float* pp = xyz + ((size_t)bq[u] * N + pu) * 3;
-      const float* cc = new_xyz + (size_t)bs[u] * 3;
-      const float d0 = __ldg(pp) - __ldg(cc), d1 = __ldg(pp + 1) - __ldg(cc + 1), d2 = __ldg(pp + 2) - __ldg(cc + 2);
       if (dQf) {
-        float* q = dQf + ((size_t)bq[u] * N + pu) * ldq + c0;
+        const unsigned sj = __shfl_sync(P2C_FULL_MASK, src, j);
+        float* q = dQf + (size_t)sj * ldq + c0;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[u][i]);
+        for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[i]);
       }
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
-        gw[i][0] = fmaf(g[u][i], d0, gw[i][0]); gw[i][1] = fmaf(g[u][i], d1, gw[i][1]);
-        gw[i][2] = fmaf(g[u][i], d2, gw[i][2]);
-        gb[i] += g[u][i];
+        gw[i][0] = fmaf(g[i], d0, gw[i][0]); gw[i][1] = fmaf(g[i], d1, gw[i][1]);
+        gw[i][2] = fmaf(g[i], d2, gw[i][2]);
+        gb[i] += g[i];
       }
     }
   }
@@ -565,7 +564,8 @@ extern "C" int p2c_sa_first_bwd(const float* dY, int64_t lddy, const float* xyz,
   if (C != 64 && C != 128) return P2C_EUNSUPPORTED;
   if ((lddy % 4) != 0 || (reinterpret_cast<uintptr_t>(dY) & 15) != 0) return P2C_EALIGN;
   const int64_t rows = (int64_t)B * S * nsample;
-  const int blocks = (int)min((int64_t)148 * 8, (rows + 31) / 32);
+  if (rows >= ((int64_t)1 << 31) || (int64_t)B * N >= ((int64_t)1 << 32)) return P2C_EUNSUPPORTED;
+  const int blocks = (int)min((int64_t)148 * 8, (rows + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 128)
     sa_first_bwd_kernel<4><<<blocks, 256, 0, st>>>(dY, lddy, xyz, new_xyz, idx, N, S, nsample, rows, dQf, ldq, dW, lddw,

@@ -20,16 +20,15 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
                        const float* __restrict__ feats2, int64_t ldf, int N, int S, int D,
                        float* __restrict__ out, int64_t ldo, int64_t* __restrict__ idx_out,
                        float* __restrict__ w_out) {
-  extern __shared__ float sm[];  // sx[S] sy[S] sz[S] sn[S]
+  extern __shared__ float4 sm4[];  // (x, y, z, |p|^2) per source point: one broadcast LDS.128 per candidate
   __shared__ int s_idx[QPB][3];
   __shared__ float s_w[QPB][3];
-  float* sx = sm; float* sy = sm + S; float* sz = sm + 2 * S; float* sn = sm + 3 * S;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const float* p2 = xyz2 + (size_t)b * S * 3;
   for (int i = tid; i < S; i += QPB) {
     float x = __ldg(p2 + i * 3), y = __ldg(p2 + i * 3 + 1), z = __ldg(p2 + i * 3 + 2);
-    sx[i] = x; sy[i] = y; sz[i] = z; sn[i] = p2c_norm2_rn(x, y, z);
+    sm4[i] = make_float4(x, y, z, p2c_norm2_rn(x, y, z));
   }
   __syncthreads();
 
@@ -40,8 +39,10 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
     const float na = p2c_norm2_rn(ax, ay, az);
     float d0 = __int_as_float(0x7f800000), d1 = d0, d2 = d0;  // +inf
     int i0 = 0, i1 = 0, i2 = 0;
+#pragma unroll 4
     for (int j = 0; j < S; ++j) {
-      const float d = p2c_sqdist_expanded(ax, ay, az, na, sx[j], sy[j], sz[j], sn[j]);
+      const float4 sp = sm4[j];
+      const float d = p2c_sqdist_expanded(ax, ay, az, na, sp.x, sp.y, sp.z, sp.w);
       if (d < d2) {
         if (d < d1) {
           d2 = d1; i2 = i1;

@@ -22,7 +22,7 @@ sa_first_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz
                 const float* __restrict__ bias, int N, int S, int ns, int64_t rows, float* __restrict__ Y,
                 int64_t ldy, double* __restrict__ stats) {
   constexpr int C = 32 * CPL;
-  __shared__ float s_red[8][2][C];
+  __shared__ double s_red[8][2][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = lane * CPL;
   float wx[CPL][3], bj[CPL];
@@ -33,60 +33,62 @@ sa_first_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz
     wx[i][2] = __ldg(W + (size_t)(c0 + i) * ldw + 2);
     bj[i] = bias ? __ldg(bias + c0 + i) : 0.f;
   }
-  float s1[CPL], s2[CPL];
+  // BatchNorm sums: fp32 within a 32-row step, fp64 across steps (var = E[y^2] - mean^2 cancels, so the sums must
+  // carry more than fp32 once a lane has seen hundreds of rows)
+  double s1[CPL], s2[CPL];
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  for (int i = 0; i < CPL; ++i) { s1[i] = 0.0; s2[i] = 0.0; }
 
-  // UNR rows per warp and step: the index -> coordinates / Qf row -> store chain is two dependent L2 round
-  // trips, so independent rows are kept in flight
-  constexpr int UNR = 4;
-  const int64_t wstride = (int64_t)gridDim.x * 8 * UNR;
-  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * UNR; r0 < rows; r0 += wstride) {
-    int64_t p[UNR], bs[UNR], bb[UNR];
-    bool ok[UNR];
+  // 32 rows per warp and step: lane l fetches the index and the centred coordinates of row r0 + l (one coalesced
+  // 256-byte index load and three gathers for 32 rows instead of a dependent L2 round-trip chain per row), then the
+  // warp walks the 32 rows with the coordinates broadcast by shuffles; lane = CPL consecutive output channels.
+  const int64_t wstride = (int64_t)gridDim.x * 8 * 32;
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * 32; r0 < rows; r0 += wstride) {
+    const int64_t rl = r0 + lane;
+    const bool okl = rl < rows;
+    const unsigned rr = (unsigned)(okl ? rl : rows - 1);             // rows < 2^31 (checked by the entry point)
+    const unsigned bsl = rr / (unsigned)ns, bl = bsl / (unsigned)S;
+    int64_t pl = __ldg(idx + rr);
+    pl = (pl < 0 || pl >= N) ? 0 : pl;
+    const unsigned src = bl * (unsigned)N + (unsigned)pl;            // source row of xyz / Qf (B*N < 2^32)
+    const float* pp = xyz + (size_t)src * 3;
+    const float* cc = new_xyz + (size_t)bsl * 3;
+    const float dl0 = __ldg(pp) - __ldg(cc), dl1 = __ldg(pp + 1) - __ldg(cc + 1), dl2 = __ldg(pp + 2) - __ldg(cc + 2);
+    const int nrow = (int)min((int64_t)32, rows - r0);
+    float t1[CPL], t2[CPL];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      ok[u] = r0 + u < rows;
-      const int64_t r = ok[u] ? r0 + u : rows - 1;
-      bs[u] = r / ns;
-      bb[u] = bs[u] / S;
-      p[u] = __ldg(idx + r);
-    }
-    float d[UNR][3];
-    float y[UNR][CPL];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      p[u] = (p[u] < 0 || p[u] >= N) ? 0 : p[u];
-      const float* pp = xyz + ((size_t)bb[u] * N + p[u]) * 3;
-      const float* cc = new_xyz + (size_t)bs[u] * 3;
-      d[u][0] = __ldg(pp) - __ldg(cc); d[u][1] = __ldg(pp + 1) - __ldg(cc + 1); d[u][2] = __ldg(pp + 2) - __ldg(cc + 2);
+    for (int i = 0; i < CPL; ++i) { t1[i] = 0.f; t2[i] = 0.f; }
+#pragma unroll 4
+    for (int j = 0; j < nrow; ++j) {
+      const float d0 = __shfl_sync(P2C_FULL_MASK, dl0, j), d1 = __shfl_sync(P2C_FULL_MASK, dl1, j),
+                  d2 = __shfl_sync(P2C_FULL_MASK, dl2, j);
+      float y[CPL];
       if (Qf) {
-        const float* q = Qf + ((size_t)bb[u] * N + p[u]) * ldq + c0;
+        const unsigned sj = __shfl_sync(P2C_FULL_MASK, src, j);
+        const float* q = Qf + (size_t)sj * ldq + c0;
         if (CPL == 4) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(q));
-          y[u][0] = t.x; y[u][1] = t.y; y[u][2] = t.z; y[u][CPL - 1] = t.w;
+          y[0] = t.x; y[1] = t.y; y[2] = t.z; y[CPL - 1] = t.w;
         } else {
           const float2 t = __ldg(reinterpret_cast<const float2*>(q));
-          y[u][0] = t.x; y[u][1] = t.y;
+          y[0] = t.x; y[1] = t.y;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) y[u][i] = 0.f;
+        for (int i = 0; i < CPL; ++i) y[i] = 0.f;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (!ok[u]) continue;
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
-        y[u][i] += fmaf(wx[i][2], d[u][2], fmaf(wx[i][1], d[u][1], wx[i][0] * d[u][0])) + bj[i];
-        s1[i] += y[u][i];
-        s2[i] = fmaf(y[u][i], y[u][i], s2[i]);
+        y[i] += fmaf(wx[i][2], d2, fmaf(wx[i][1], d1, wx[i][0] * d0)) + bj[i];
+        t1[i] += y[i];
+        t2[i] = fmaf(y[i], y[i], t2[i]);
       }
-      float* yo = Y + (size_t)(r0 + u) * ldy + c0;
-      if (CPL == 4) *reinterpret_cast<float4*>(yo) = make_float4(y[u][0], y[u][1], y[u][2], y[u][CPL - 1]);
-      else *reinterpret_cast<float2*>(yo) = make_float2(y[u][0], y[u][1]);
+      float* yo = Y + (size_t)(r0 + j) * ldy + c0;
+      if (CPL == 4) *reinterpret_cast<float4*>(yo) = make_float4(y[0], y[1], y[2], y[CPL - 1]);
+      else *reinterpret_cast<float2*>(yo) = make_float2(y[0], y[1]);
     }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { s1[i] += (double)t1[i]; s2[i] += (double)t2[i]; }
   }
   if (stats) {
 #pragma unroll
@@ -96,7 +98,7 @@ sa_first_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz
       const int which = e / C, c = e - which * C;
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += (double)s_red[w][which][c];
+      for (int w = 0; w < 8; ++w) t += s_red[w][which][c];
       atomicAdd(stats + which * C + c, t);
     }
   }
@@ -113,7 +115,8 @@ extern "C" int p2c_sa_first_layer(const float* xyz, const float* new_xyz, const 
   if ((ldy % 4) != 0 || (reinterpret_cast<uintptr_t>(Y) & 15) != 0) return P2C_EALIGN;
   if (Qf && ((ldq % 4) != 0 || (reinterpret_cast<uintptr_t>(Qf) & 15) != 0 || ldq < C)) return P2C_EALIGN;
   const int64_t rows = (int64_t)B * S * nsample;
-  const int blocks = (int)min((int64_t)148 * 8, (rows + 31) / 32);
+  if (rows >= ((int64_t)1 << 31) || (int64_t)B * N >= ((int64_t)1 << 32)) return P2C_EUNSUPPORTED;
+  const int blocks = (int)min((int64_t)148 * 8, (rows + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (C == 128)
     sa_first_kernel<4><<<blocks, 256, 0, st>>>(xyz, new_xyz, idx, Qf, ldq, W, ldw, bias, N, S, nsample, rows, Y, ldy, stats);

@@ -187,10 +187,11 @@ def test_backbone_backward_autograd_golden(golden_dir, monkeypatch, name, traini
     net, data, starts, K = _train_setup(g, monkeypatch, training)
     X_raw, W_raw = net(data["pcs"], fps_start=starts)
     assert X_raw.requires_grad and W_raw.requires_grad
-    assert rel_err(X_raw, g["X_raw"]) <= TOL and rel_err(W_raw, g["W_raw"]) <= TOL
+    ftol = 1e-3 if training else TOL          # train-mode forward conditioning: see tests/test_gpu_parity.py TRAIN_TOL
+    assert rel_err(X_raw, g["X_raw"]) <= ftol and rel_err(W_raw, g["W_raw"]) <= ftol
     out = pipeline.loss_forward(data["pcs"], X_raw, W_raw, data["normals"], data["inst"], data["bb"], data["axes"],
                                 data["centers"])
-    assert rel_err(out["total"], g["loss"]) <= TOL
+    assert rel_err(out["total"], g["loss"]) <= ftol
     out["total"].backward()
     _assert_param_grads([(k, p.grad) for k, p in net.named_parameters()], g, training)
 

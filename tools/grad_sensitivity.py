@@ -29,7 +29,23 @@ def grads(B, N, K, seed, training, noise):
     return {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
 
 
+def forward_outputs(B, N, K, seed, training, noise):
+    data = synthetic.s_cyl(B, N, K, seed)
+    torch.manual_seed(seed)
+    starts = (torch.randint(0, N, (B,)), torch.randint(0, 512, (B,)))
+    gen = torch.Generator().manual_seed(5)
+    sd = {k: (v * (1 + noise * torch.randn(v.shape, generator=gen)) if v.is_floating_point() and "running" not in k
+              else v.clone()) for k, v in orc.init_state_dict((3, 2 * K), seed=seed).items()}
+    with torch.no_grad():
+        return orc.backbone_forward(sd, data["pcs"], training=training, fps_start=starts,
+                                    dropout_mask=torch.ones(B, 128, N))
+
+
 if __name__ == "__main__":
+    for B, training in ((2, True), (1, True), (2, False)):
+        (X0, W0), (X1, W1) = forward_outputs(B, 1024, 4, 0, training, 0.0), forward_outputs(B, 1024, 4, 0, training, 1e-6)
+        print(f"FORWARD B={B} N=1024 train-mode BN={training}: output change under a 1e-6 relative weight perturbation: "
+              f"X {float((X1 - X0).abs().max() / X0.abs().max()):.1e}  W_raw {float((W1 - W0).abs().max() / W0.abs().max()):.1e}")
     KEYS = ("fc2.1.weight", "bn1.bias", "fc1.weight", "fp1.mlp_convs.0.weight", "fp2.mlp_convs.0.weight",
             "sa2.mlp_convs.1.weight", "sa1.mlp_convs.1.weight", "sa1.mlp_bns.0.bias")
     for B, training in ((2, True), (8, True), (2, False)):
