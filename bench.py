@@ -190,15 +190,18 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
     device-resident and end-to-end (pinned host batch -> H2D -> step -> loss scalar D2H) clouds/s over all ranks."""
     import point2cyl_b200
     from point2cyl_b200 import _lib
-    from point2cyl_b200.train import Trainer
-    tr = Trainer(net, lr=1e-3)
+    from point2cyl_b200.train import GraphedTrainer, Trainer
+    graphed = not getattr(train_step_numbers, "no_graph", False)
+    tr = GraphedTrainer(net, batch, lr=1e-3) if graphed else Trainer(net, lr=1e-3)
 
     def step_resident():
-        return tr.step(batch)
+        return tr.step(None if graphed else batch)      # the graph's static inputs already hold `batch`
 
     def step_e2e():
-        dev_batch = {k: host[k].to(dev, non_blocking=True) for k in point2cyl_b200.BATCH_KEYS}
-        out = tr.step(dev_batch)
+        if graphed:
+            out = tr.step(host)                           # H2D of the six batch tensors into the static inputs, replay
+        else:
+            out = tr.step({k: host[k].to(dev, non_blocking=True) for k in point2cyl_b200.BATCH_KEYS})
         out["loss_host"] = out["losses"].cpu()
         return out
 
@@ -208,8 +211,8 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
     pd.barrier()
     ms = timed(step_resident, steps)
     l0 = _lib.launch_count
-    step_resident()
-    launches = _lib.launch_count - l0
+    Trainer.forward_backward(tr, batch)                 # launches per step, counted on one eager pass
+    launches = _lib.launch_count - l0 + 1               # + the Adam kernel
     pd.barrier()
     ms_e2e = timed(step_e2e, steps)
     pd.barrier()
@@ -220,7 +223,8 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
             "value": clouds / (tot / 1e3), "unit": UNIT, "ms_per_step": tot / steps,
             "e2e": {"value": clouds / (tot_e2e / 1e3), "unit": UNIT, "ms_per_step": tot_e2e / steps,
                     "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host), "d2h_bytes_per_step": 24},
-            "gpu_launches": launches, "steps": steps, "warmup": warmup, "launch_mode": "eager",
+            "gpu_launches": launches, "steps": steps, "warmup": warmup,
+            "launch_mode": "cuda_graph (forward+loss+backward) + all-reduce + Adam" if graphed else "eager",
             "collective": None if world == 1 else f"one NCCL sum all-reduce of the flat fp32 gradient ({n_param} floats)",
             "parameters": n_param, "global_batch": B_PER_GPU * world}
 
@@ -240,7 +244,7 @@ def run_train(args, rank, world, dev, pd, net, host, batch, flush, timed):
         print(json.dumps({"metric": t["metric"], "value": t["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": t["ms_per_step"], "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
-                          "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "launch_mode": "eager", "clocks": clk,
+                          "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "launch_mode": t["launch_mode"], "clocks": clk,
                           "collective": t["collective"]}), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -385,6 +389,7 @@ def main():
         with torch.no_grad():
             return point2cyl_b200.forward_loss_host(net, host, device=dev)
 
+    train_step_numbers.no_graph = args.no_graph
     if args.workload == "train":
         run_train(args, rank, world, dev, pd, net, host, batch, flush, timed)
         return

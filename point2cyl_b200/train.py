@@ -76,7 +76,7 @@ class Trainer:
         return dict(total=losses[0], losses=losses, matching_indices=match, E_AX=E_AX, centers=centers)
 
     @torch.no_grad()
-    def step(self, batch: Dict[str, Tensor], fps_start=None) -> Dict[str, Tensor]:
+    def step(self, batch: Optional[Dict[str, Tensor]], fps_start=None) -> Dict[str, Tensor]:
         """forward + loss + backward + gradient all-reduce + Adam.  Gradients are averaged over ranks like DDP."""
         out = self.forward_backward(batch, fps_start)
         world = self.world()
@@ -86,3 +86,67 @@ class Trainer:
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.step_count,
                       self.betas, self.eps, self.weight_decay, grad_scale=1.0 / world)
         return out
+
+
+class GraphedTrainer(Trainer):
+    """Trainer whose forward + loss + backward (about 230 launches of short kernels) is captured ONCE into a CUDA
+    graph and replayed; the gradient all-reduce and the Adam kernel (its bias correction is a launch argument that
+    changes every step) stay outside the graph.  Per-step host work mirrors the reference: the first FPS centroid of
+    each level is drawn from the CPU generator (models/pointnet_util.py:75) and copied to the device.
+
+    Re-capture (build a new object) when the batch shape, train/eval mode or the BatchNorm momentum changes."""
+
+    def __init__(self, net, example: Dict[str, Tensor], warmup: int = 2, **kw):
+        super().__init__(net, **kw)
+        from . import BATCH_KEYS
+        dev = self.flat_param.device
+        self.keys = BATCH_KEYS
+        self.static = {k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS}
+        B, N, _ = self.static["pcs"].shape
+        self.B, self.N, self.S1 = B, N, net.sa1.npoint
+        self.start_host = [torch.zeros(B, dtype=torch.long).pin_memory() for _ in range(2)]
+        self.start_dev = [torch.zeros(B, dtype=torch.long, device=dev) for _ in range(2)]
+        self._key = self._state_key()
+        # eager warm-up outside the capture (one-time cudaFuncSetAttribute calls, allocator growth); BatchNorm buffers
+        # are restored afterwards so that building the graph does not count as training steps
+        buffers = {k: v.clone() for k, v in net.named_buffers()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._draw_starts()
+                Trainer.forward_backward(self, self.static, self.start_dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = Trainer.forward_backward(self, self.static, self.start_dev)
+        with torch.no_grad():
+            for k, v in net.named_buffers():
+                v.copy_(buffers[k])
+
+    def _state_key(self):
+        return (self.net.training,) + tuple(m.momentum for m in self.net.modules()
+                                            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+
+    def _draw_starts(self):
+        self.start_host[0].copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
+        self.start_host[1].copy_(torch.randint(0, self.S1, (self.B,), dtype=torch.long))
+        for h, d in zip(self.start_host, self.start_dev):
+            d.copy_(h, non_blocking=True)
+
+    @torch.no_grad()
+    def forward_backward(self, batch: Optional[Dict[str, Tensor]] = None, fps_start=None) -> Dict[str, Tensor]:
+        if self._key != self._state_key():
+            raise RuntimeError("GraphedTrainer: mode or BatchNorm momentum changed since capture; build a new one")
+        if batch is not None:
+            for k in self.keys:
+                if batch[k] is not self.static[k]:
+                    self.static[k].copy_(batch[k], non_blocking=True)
+        if fps_start is None:
+            self._draw_starts()
+        else:
+            for d, s in zip(self.start_dev, fps_start):
+                d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.out

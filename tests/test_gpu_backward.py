@@ -358,3 +358,29 @@ def test_bn_relu_backward_kernels_vs_autograd():
     coef = ops.bn_bwd_coef(sums, M, dev(gamma), dev(mean), dev(invstd), True, dgam, dbet)
     dY = ops.pool_bwd_apply(dev(dO), dev(Ymax), dev(Ymin), dev(Y), dev(scale), dev(shift), coef, G)
     assert rel_err(dY, Yd2.grad) <= 1e-4 and rel_err(dgam, gd2.grad) <= 1e-4 and rel_err(dbet, bd2.grad) <= 1e-4
+
+
+def test_graphed_trainer_matches_eager(monkeypatch):
+    """CUDA-graph replay of forward+loss+backward gives the gradients of the eager Trainer (same dropout mask, same FPS
+    starts), keeps BatchNorm buffers untouched by the capture, and trains."""
+    from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
+    from point2cyl_b200.train import GraphedTrainer, Trainer
+    B, N, K = 4, 2048, 4
+    data = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, seed=2).items()}
+    mask = ((torch.rand(B, 128, N, generator=torch.Generator().manual_seed(1)) > 0.5).float() * 2.0).to(DEV)
+    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: mask)
+    starts = (torch.arange(B, device=DEV), torch.arange(B, device=DEV) + 3)
+    nets = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        nets.append(backbone(output_sizes=[3, 2 * K]).to(DEV).train())
+    eager = Trainer(nets[0], lr=1e-3)
+    graphed = GraphedTrainer(nets[1], data, lr=1e-3)
+    for (k, a), (_, b) in zip(nets[0].named_buffers(), nets[1].named_buffers()):
+        assert torch.equal(a, b), k                        # capture + warm-up left the running statistics alone
+    o1 = eager.forward_backward(data, fps_start=starts)
+    o2 = graphed.forward_backward(None, fps_start=starts)
+    assert rel_err(o2["total"], o1["total"]) <= 1e-6
+    assert rel_err(graphed.flat_grad, eager.flat_grad) <= 1e-4      # atomics order differs run to run
+    losses = [float(graphed.step(data, fps_start=starts)["total"]) for _ in range(8)]
+    assert losses[-1] < losses[0]
