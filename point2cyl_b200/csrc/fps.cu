@@ -74,6 +74,21 @@ fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int
       oxyz[it * 3 + 2] = cz;
     }
     float best = 0.0f;
+    if (XYZ_IN_REGS && (PPT % 2 == 0)) {
+      // two points per instruction: FADD2 / FMUL2 round each half exactly like the scalar ops (round-to-nearest,
+      // no contraction), so the distances are bit-identical while the issue slots per point drop from 10 to 6
+      const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+#pragma unroll
+      for (int j = 0; j < PPT; j += 2) {
+        const float2 dx = __fadd2_rn(make_float2(px[j], px[j + 1]), ncx);
+        const float2 dy = __fadd2_rn(make_float2(py[j], py[j + 1]), ncy);
+        const float2 dz = __fadd2_rn(make_float2(pz[j], pz[j + 1]), ncz);
+        const float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+        run[j] = fminf(run[j], d.x);
+        run[j + 1] = fminf(run[j + 1], d.y);
+        best = fmaxf(best, fmaxf(run[j], run[j + 1]));
+      }
+    } else {
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       float x, y, z;
@@ -89,6 +104,7 @@ fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int
       if (!XYZ_IN_REGS) d = (j * T + tid < N) ? d : 0.0f;
       run[j] = fminf(run[j], d);
       best = fmaxf(best, run[j]);
+    }
     }
     // distances are >= +0, so their bit patterns order like unsigned integers
     const unsigned vb = __float_as_uint(best);
