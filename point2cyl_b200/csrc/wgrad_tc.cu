@@ -15,6 +15,10 @@
 // operand are one box = 4096 B apart along MN (= LBO), so no transposition is ever done: the transform warps only apply the folded BatchNorm +
 // ReLU of the previous layer to the X boxes and split both operands into tf32 hi / lo halves in place-shaped
 // buffers.  3xTF32 like the forward: dYhi*Ahi + dYlo*Ahi + dYhi*Alo, fp32 accumulate (fp32-faithful).
+// kind::tf32 reads the upper 19 bits of an fp32 word and ignores the low 13 mantissa bits, so the RAW fp32 tile IS
+// the "hi" operand: only lo = x - trunc(x) is written by the transform (and Ahi when the operand load folds a
+// BatchNorm+ReLU).  That keeps three 32 KB TMA stages in flight per SM instead of two; a RAW stage is released by
+// the MMA's commit, not by the transform.
 //
 // Warp roles (384 threads, 1 CTA/SM): warp 0 TMA producer (8 boxes = 32 KB per 32-row stage), warp 1 MMA issuer,
 // warp 2 TMEM allocator, warps 4-11 operand transform, warps 4-7 afterwards the epilogue (thread = dW row n).
@@ -28,9 +32,9 @@ constexpr int WG_THREADS = 384;
 constexpr int WG_ROWS = 32;                  // rows per stage = 4 UMMA k-steps of 8 rows
 constexpr int WG_BOX = WG_ROWS * 128;        // bytes of one [32 rows x 32 channels] box
 constexpr int WG_OP = 4 * WG_BOX;            // one operand stage: 128 channels = 16 KB
-constexpr int WG_RAW_STAGE = 2 * WG_OP;      // dY | X
-constexpr int WG_XT_STAGE = 4 * WG_OP;       // dYhi | dYlo | Ahi | Alo
-constexpr int WG_RAW = 2, WG_XT = 2;
+constexpr int WG_RAW_STAGE = 2 * WG_OP;      // dY | X      (TMA destination; also the tf32 "hi" operands, see below)
+constexpr int WG_XT_STAGE = 3 * WG_OP;       // dYlo | Alo | Ahi (Ahi only when a BatchNorm+ReLU fold changes X)
+constexpr int WG_RAW = 3, WG_XT = 2;
 constexpr int WG_TILE = 128;
 
 // kind::tf32, fp32 accumulate, A and B MN-major, M = 128, N = 128
@@ -96,7 +100,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDY)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
-    for (int s = 0; s < WG_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
+    for (int s = 0; s < WG_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
     for (int s = 0; s < WG_XT; ++s) { mbar_init(&xt_full[s], 8); mbar_init(&xt_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -131,24 +135,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
+      const bool affine = a.in_scale != nullptr;
       int xs = 0; uint32_t xph = 0;
+      int rs = 0;
       for (int t = 0; t < my_stages; ++t) {
-        mbar_wait(&xt_full[xs], xph);
+        mbar_wait(&xt_full[xs], xph);               // implies raw_full[rs]: the transform read that stage
         tc_fence_after();
-        const uint32_t base = smem_u32(xt_sm + (size_t)xs * WG_XT_STAGE);
+        const uint32_t rawb = smem_u32(raw_sm + (size_t)rs * WG_RAW_STAGE);
+        const uint32_t xtb = smem_u32(xt_sm + (size_t)xs * WG_XT_STAGE);
+        const uint32_t ahib = affine ? xtb + 2 * WG_OP : rawb + WG_OP;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t dyhi = make_mnmajor_sw128_desc(base + ks * 1024u);
-          const uint64_t dylo = make_mnmajor_sw128_desc(base + WG_OP + ks * 1024u);
-          const uint64_t ahi = make_mnmajor_sw128_desc(base + 2 * WG_OP + ks * 1024u);
-          const uint64_t alo = make_mnmajor_sw128_desc(base + 3 * WG_OP + ks * 1024u);
+          const uint64_t dyhi = make_mnmajor_sw128_desc(rawb + ks * 1024u);
+          const uint64_t dylo = make_mnmajor_sw128_desc(xtb + ks * 1024u);
+          const uint64_t ahi = make_mnmajor_sw128_desc(ahib + ks * 1024u);
+          const uint64_t alo = make_mnmajor_sw128_desc(xtb + WG_OP + ks * 1024u);
           umma_tf32_ss(tm_acc, dyhi, ahi, WG_IDESC, (t | ks) != 0);
           umma_tf32_ss(tm_acc, dylo, ahi, WG_IDESC, 1u);
           umma_tf32_ss(tm_acc, dyhi, alo, WG_IDESC, 1u);
         }
         umma_commit(&xt_empty[xs]);
+        umma_commit(&raw_empty[rs]);                // the tensor core has read the RAW stage: TMA may refill it
         if (t == my_stages - 1) umma_commit(acc_full);
         if (++xs == WG_XT) { xs = 0; xph ^= 1; }
+        if (++rs == WG_RAW) rs = 0;
       }
     }
   } else if (warp >= 4) {
@@ -166,7 +176,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const bool do_bias = !is_x && a.db != nullptr && blockIdx.z == 0;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t raw_op = is_x ? WG_OP : 0;
-    const uint32_t xt_op = is_x ? 2 * WG_OP : 0;
+    const uint32_t xt_op = is_x ? WG_OP : 0;       // lo half of this operand; Ahi sits at 2 * WG_OP
     const uint32_t box_off = (uint32_t)(box & 3) * WG_BOX;
     int s = 0; uint32_t ph = 0;
     int xs = 0; uint32_t xph = 0;
@@ -179,8 +189,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const int r = rg * 8 + i;
         x[i] = *reinterpret_cast<const float4*>(rawp + box_off32(r, cj));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[s]);
       if (++s == WG_RAW) { s = 0; ph ^= 1; }
       if (has_affine) {
 #pragma unroll
@@ -196,18 +204,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         for (int i = 0; i < 8; ++i) { bsum.x += x[i].x; bsum.y += x[i].y; bsum.z += x[i].z; bsum.w += x[i].w; }
       }
       mbar_wait(&xt_empty[xs], xph ^ 1);
-      uint8_t* hip = xt_sm + (size_t)xs * WG_XT_STAGE + xt_op + box_off;
+      uint8_t* lop = xt_sm + (size_t)xs * WG_XT_STAGE + xt_op + box_off;
+      uint8_t* hip = xt_sm + (size_t)xs * WG_XT_STAGE + 2 * WG_OP + box_off;   // Ahi (X boxes with an affine fold only)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rg * 8 + i;
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u); l.x = x[i].x - h.x;
-        h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u); l.y = x[i].y - h.y;
-        h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u); l.z = x[i].z - h.z;
-        h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u); l.w = x[i].w - h.w;
+        float4 l;
+        l.x = x[i].x - __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u);
+        l.y = x[i].y - __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u);
+        l.z = x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u);
+        l.w = x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u);
         const uint32_t off = box_off32(r, cj);
-        *reinterpret_cast<float4*>(hip + off) = h;
-        *reinterpret_cast<float4*>(hip + WG_OP + off) = l;
+        *reinterpret_cast<float4*>(lop + off) = l;
+        if (has_affine) *reinterpret_cast<float4*>(hip + off) = x[i];   // the tensor core drops the low 13 bits itself
       }
       fence_proxy_async();
       __syncwarp();
