@@ -540,3 +540,43 @@ def test_stress_config_ball_query_large_cloud():
     got = ops.ball_query(0.2, 64, xyz.to(DEV), new_xyz)
     ref = orc.query_ball_point(0.2, 64, xyz, new_xyz.cpu())
     assert torch.equal(got.cpu(), ref)
+
+
+def test_loss_with_background_points_and_single_instance():
+    """Edge cases of the loss block the reference tolerates (losses.py:38,42): points labelled -1 (background: they
+    count in no ground-truth row but still in the predicted column sums), and a cloud with a single instance."""
+    B, N, K = 3, 1500, 8
+    data = synthetic.s_cyl(B, N, K, seed=12)
+    inst = data["inst"].clone()
+    inst[0, ::7] = -1                                   # background points in cloud 0
+    inst[1] = 0                                         # cloud 1: one instance only
+    g = torch.Generator().manual_seed(3)
+    X_raw = data["normals"] + 0.2 * torch.randn(B, N, 3, generator=g)
+    W_raw = torch.randn(B, N, 2 * K, generator=g)
+    col = inst.clamp_min(0) * 2 + data["bb"]
+    W_raw.scatter_add_(2, col[:, :, None], torch.full((B, N, 1), 2.0))
+    ref = orc.loss_block(data["pcs"], X_raw, W_raw, data["normals"], inst, data["bb"], data["axes"], data["centers"])
+    d = {k: v.to(DEV) for k, v in data.items()}
+    out = pipeline.loss_forward(d["pcs"], X_raw.to(DEV), W_raw.to(DEV), d["normals"], inst.to(DEV), d["bb"], d["axes"],
+                                d["centers"])
+    assert torch.equal(out["matching_indices"].cpu(), ref["matching_indices"])
+    assert torch.equal(out["mask"].cpu(), ref["mask"])
+    assert int(out["n_gt"][1]) == 1
+    for k in ("total", "normal", "miou", "bb", "axis", "center"):
+        assert rel_err(out[k], ref[k]) <= TOL, k
+
+
+def test_cpu_tensors_and_bad_shapes_raise():
+    """No CPU path and no silent fallback: host tensors and malformed arguments raise P2CError."""
+    from point2cyl_b200._lib import P2CError
+    xyz = torch.rand(1, 64, 3)
+    with pytest.raises(P2CError):
+        ops.fps(xyz, 8, torch.zeros(1, dtype=torch.long))
+    with pytest.raises(P2CError):
+        ops.ball_query(0.2, 8, xyz, xyz[:, :4])
+    with pytest.raises(P2CError):
+        ops.fps(torch.rand(1, 64, 2, device=DEV), 8, torch.zeros(1, dtype=torch.long, device=DEV))
+    with pytest.raises(P2CError):                        # K beyond the 16 columns the assignment kernel covers
+        ops.hungarian(torch.rand(1, 17, 17, device=DEV), torch.tensor([3], dtype=torch.int32, device=DEV))
+    with pytest.raises(P2CError):                        # feature matrix with a non-unit column stride
+        ops.linear(torch.rand(64, 8, device=DEV).t(), torch.rand(4, 64, device=DEV), None)
