@@ -90,8 +90,15 @@ int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
  * Pass the result as w_split/ldws to p2c_linear; NULL keeps large-K layers on the fp32 SIMT kernel. */
 int p2c_split_tf32(const float* W, int N, int K, float* out /* (2,N,ldw) */, int64_t ldw, void* stream);
 
+/* bf16 copy of a weight matrix for P2C_PREC_BF16: out (N, ldw) bf16 (round-to-nearest), rows zero padded to ldw
+ * (multiple of 8) elements.  Pass it as w_split (ldws = ldw) to p2c_linear with precision P2C_PREC_BF16: the layer then
+ * runs ONE tcgen05 kind::f16 pass on bf16 operands with fp32 accumulation (not fp32-faithful; BASELINE.json's bf16
+ * MLP-stack configuration). */
+int p2c_cast_bf16(const float* W, int N, int K, void* out /* (N,ldw) bf16 */, int64_t ldw, void* stream);
+
 /* Which kernel p2c_linear dispatches a (16-byte aligned) layer to: 0 = fp32 SIMT, 1 = tcgen05 3xTF32 with the
- * weights resident in tensor memory (K <= 192), 2 = tcgen05 3xTF32 with streamed weights (needs w_split).
+ * weights resident in tensor memory (K <= 192), 2 = tcgen05 3xTF32 with streamed weights (needs w_split),
+ * 3 = tcgen05 bf16 with streamed weights (P2C_PREC_BF16, needs the p2c_cast_bf16 copy as w_split).
  * Pure function of the shape; lets tests assert that the tensor-core path really ran. */
 int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision, int has_split);
 

@@ -34,7 +34,7 @@ def _dgrad(dY: Tensor, W: Tensor, precision: int) -> Tensor:
     """dA_prev (M, K) = dY (M, N) @ W (N, K): the forward kernel on the transposed weight."""
     Wt = W.t().contiguous()                      # (K, N): 'output channels' = K, reduction over N
     Kout, Nred = Wt.shape
-    wsplit = ops.split_tf32(Wt) if ops.needs_split(dY, Kout, Nred, False, 0, precision) else None
+    wsplit = ops.weight_operand(dY, Wt, Kout, Nred, False, 0, precision)
     return ops.linear(dY, Wt, None, K=Nred, precision=precision, w_split=wsplit)
 
 

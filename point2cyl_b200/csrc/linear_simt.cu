@@ -366,7 +366,7 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
 int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int pool_group, int precision);
 int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                      const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
-                     double* stats, int pool_group, float* Ymax, float* Ymin, cudaStream_t st);
+                     double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, cudaStream_t st);
 
 extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                           const float* in_scale, const float* in_shift, const float* in_mask,
@@ -385,14 +385,14 @@ extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const flo
   if (precision != P2C_PREC_FP32) {
     static const bool force_ss = getenv("P2C_TC_FORCE_SS") != nullptr;   // tools only: streamed-weight kernel first
     int rc = P2C_EUNSUPPORTED;
-    if (!(force_ss && w_split))
+    if (!(force_ss && w_split) && precision != P2C_PREC_BF16)
       rc = p2c_linear_tc(X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
                          stats, pool_group, Ymax, Ymin, precision, st);
     if (rc != P2C_EUNSUPPORTED) return rc;
     if (w_split && p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, in_mask != nullptr,
                                          pool_group, precision)) {
       rc = p2c_linear_tc_ss(X, ldx, w_split, ldws, bias, in_scale, in_shift, Y, ldy, M, N, K, stats, pool_group,
-                            Ymax, Ymin, st);
+                            Ymax, Ymin, precision == P2C_PREC_BF16 ? 1 : 0, st);
       if (rc != P2C_EUNSUPPORTED) return rc;
     }
     // shapes the tensor-core kernels do not take fall through to the fp32 SIMT kernel (still CUDA)

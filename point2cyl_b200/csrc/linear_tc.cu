@@ -417,7 +417,7 @@ inline int tc_raw_stages(int KB, int xt, int y_stage) {
 int tc_plan(int64_t ldx, int x_aligned16, int M, int N, int K, int has_mask, int pool_group, int precision,
             TcPlan* out) {
   (void)M; (void)N;
-  if (precision != P2C_PREC_3XTF32) return 0;                      // bf16 variant: DESIGN.md, next
+  if (precision != P2C_PREC_3XTF32) return 0;                      // bf16: streamed-weight kernel (linear_tc_ss.cu)
   if (has_mask) return 0;
   if ((ldx % 4) != 0 || !x_aligned16) return 0;                    // TMA global strides are multiples of 16 B
   if (K < 16) return 0;                                            // xyz-only first layers stay on the SIMT kernel
@@ -445,7 +445,8 @@ int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int
 extern "C" int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, int pool_group, int precision,
                                int has_split) {
   if (tc_plan(ldx, 1, M, N, K, has_mask, pool_group, precision, nullptr)) return 1;
-  if (has_split && p2c_linear_tc_ss_plan(ldx, 1, K, has_mask, pool_group, precision)) return 2;
+  if (has_split && p2c_linear_tc_ss_plan(ldx, 1, K, has_mask, pool_group, precision))
+    return precision == P2C_PREC_BF16 ? 3 : 2;
   return 0;
 }
 

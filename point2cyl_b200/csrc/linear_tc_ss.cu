@@ -30,6 +30,40 @@ struct SsArgs {
   int y_tma;
 };
 
+// ---- bf16 mode (P2C_PREC_BF16): one kind::f16 MMA pass on bf16 operands instead of the three tf32 passes ----
+// The fp32 activations still arrive as [128 rows x 32 floats] TMA boxes; the transform warps apply the BatchNorm+ReLU
+// fold and write a bf16 tile [128 rows x 32 bf16 = 64 B] in the K-major SWIZZLE_64B layout (16-byte chunk index XOR
+// (row >> 1) & 3); the weights come from a bf16 copy (p2c_cast_bf16) through a bf16 TMA map with the same swizzle.
+// Two MMAs (K = 16) per k-block, fp32 accumulate; epilogue unchanged.  Not fp32-faithful (8-bit mantissa): it exists
+// for BASELINE.json's bf16 MLP-stack configuration, not for the parity path.
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;         // 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
+  return d;
+}
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 3) << 17) |
+                                   ((uint32_t)(TC_BN >> 4) << 24);
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+constexpr int W_BF16_BYTES = TC_BN * TC_BK * 2;   // 8 KB
+
 __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -58,6 +92,7 @@ __host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_
   return L;
 }
 
+template <bool BF16>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmY,
@@ -124,9 +159,14 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&w_empty[ws], wph ^ 1);
-          mbar_arrive_expect_tx(&w_full[ws], 2 * RAW_BYTES);
-          tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
-          tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES + RAW_BYTES, &tmWlo, &w_full[ws], kb * TC_BK, n0);
+          if (BF16) {
+            mbar_arrive_expect_tx(&w_full[ws], W_BF16_BYTES);
+            tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
+          } else {
+            mbar_arrive_expect_tx(&w_full[ws], 2 * RAW_BYTES);
+            tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
+            tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES + RAW_BYTES, &tmWlo, &w_full[ws], kb * TC_BK, n0);
+          }
           if (++ws == XS) { ws = 0; wph ^= 1; }
           mbar_wait(&raw_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
@@ -151,6 +191,12 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tc_fence_after();
           const uint32_t x_hi = smem_u32(xt_sm + (size_t)xs * 2 * RAW_BYTES), x_lo = x_hi + RAW_BYTES;
           const uint32_t w_hi = smem_u32(w_sm + (size_t)xs * 2 * RAW_BYTES), w_lo = w_hi + RAW_BYTES;
+          if (BF16) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)           // 16 bf16 = 32 bytes per k-step
+              umma_bf16_ss(d, make_kmajor_sw64_desc(w_hi + ks * 32u), make_kmajor_sw64_desc(x_hi + ks * 32u),
+                           TC_IDESC_BF16, (kb | ks) != 0);
+          } else {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u), blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
@@ -158,6 +204,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             umma_tf32_ss(d, ahi, bhi, TC_IDESC, (kb | ks) != 0);
             umma_tf32_ss(d, alo, bhi, TC_IDESC, 1u);
             umma_tf32_ss(d, ahi, blo, TC_IDESC, 1u);
+          }
           }
           umma_commit(&xt_empty[xs]);
           umma_commit(&w_empty[xs]);
@@ -202,6 +249,15 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         mbar_wait(&xt_empty[xs], xph ^ 1);
         uint8_t* hip = xt_sm + (size_t)xs * 2 * RAW_BYTES;
+        if (BF16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg * 8 + i;
+            // fp32 chunk cj (columns 4cj..4cj+3) -> half (cj & 1) of 16-byte bf16 chunk cj >> 1, rows of 64 bytes
+            const size_t off = (size_t)r * 64 + ((((unsigned)cj >> 1) ^ (((unsigned)r >> 1) & 3u)) << 4) + ((cj & 1) << 3);
+            *reinterpret_cast<uint2*>(hip + off) = make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = rg * 8 + i;
@@ -213,6 +269,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const size_t off = (size_t)r * 128 + ((cj ^ (r & 7)) << 4);
           *reinterpret_cast<float4*>(hip + off) = h;
           *reinterpret_cast<float4*>(hip + RAW_BYTES + off) = l;
+        }
         }
         fence_proxy_async();
         __syncwarp();
@@ -316,6 +373,17 @@ split_tf32_kernel(const float* __restrict__ W, int N, int K, float* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ W, int N, int K, uint16_t* __restrict__ out, int64_t ldw) {
+  const int64_t total = (int64_t)N * ldw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e / ldw;
+    const int k = (int)(e - n * ldw);
+    const float w = k < K ? __ldg(W + n * K + k) : 0.f;
+    out[e] = (uint16_t)(pack_bf16(w, 0.f) & 0xffffu);
+  }
+}
+
 int ss_stages(int KB, int y_tma, int* raw, int* xt) {
   const int tries[4][2] = {{4, 3}, {2, 3}, {4, 2}, {2, 2}};
   for (int i = 0; i < 4; ++i)
@@ -337,9 +405,18 @@ extern "C" int p2c_split_tf32(const float* W, int N, int K, float* out, int64_t 
   return 0;
 }
 
-// 1 when the streamed-W tensor-core kernel takes the shape (given a pre-split weight copy)
+extern "C" int p2c_cast_bf16(const float* W, int N, int K, void* out, int64_t ldw, void* stream) {
+  if (!W || !out || N <= 0 || K <= 0 || ldw < K || (ldw % 8) != 0) return P2C_EINVAL;
+  const int64_t total = (int64_t)N * ldw;
+  const int blocks = (int)min((int64_t)148 * 8, (total + 255) / 256);
+  cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, N, K, reinterpret_cast<uint16_t*>(out), ldw);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+// 1 when the streamed-W tensor-core kernel takes the shape (given a pre-split / bf16 weight copy)
 int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int pool_group, int precision) {
-  if (precision != P2C_PREC_3XTF32 || has_mask) return 0;
+  if ((precision != P2C_PREC_3XTF32 && precision != P2C_PREC_BF16) || has_mask) return 0;
   if ((ldx % 4) != 0 || !x_aligned16 || K < 16) return 0;
   if (pool_group && pool_group != 32 && pool_group != 64 && pool_group != 128) return 0;
   int raw, xt;
@@ -348,17 +425,32 @@ int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int
 
 int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                      const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
-                     double* stats, int pool_group, float* Ymax, float* Ymin, cudaStream_t st) {
+                     double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, cudaStream_t st) {
   const int KB = (K + TC_BK - 1) / TC_BK;
   const int y_tma = (Y && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
   int raw, xt;
   if (!ss_stages(KB, y_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
-  if ((ldws % 4) != 0 || (reinterpret_cast<uintptr_t>(w_split) & 15) != 0) return P2C_EALIGN;
+  if ((ldws % (bf16 ? 8 : 4)) != 0 || (reinterpret_cast<uintptr_t>(w_split) & 15) != 0) return P2C_EALIGN;
   CUtensorMap tmX, tmWhi, tmWlo, tmY;
   int rc;
   if ((rc = make_map_2d(&tmX, X, K, M, ldx, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&tmWhi, w_split, K, N, ldws, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map_2d(&tmWlo, w_split + (size_t)N * ldws, K, N, ldws, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if (bf16) {
+    // bf16 weight copy (N, ldws) bf16: boxes of [128 channels x 32 bf16 = 64 B], SWIZZLE_64B
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldws * 2};
+    const cuuint32_t box[2] = {TC_BK, TC_BN};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmWhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(w_split), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+    tmWlo = tmWhi;
+  } else {
+    if ((rc = make_map_2d(&tmWhi, w_split, K, N, ldws, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&tmWlo, w_split + (size_t)N * ldws, K, N, ldws, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
   tmY = tmX;
   if (y_tma && (rc = make_map_2d(&tmY, Y, N, M, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
@@ -368,14 +460,18 @@ int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t 
   cudaGetDevice(&dev);
   static int sms_of[64] = {0};
   if (dev < 64 && sms_of[dev] == 0) {
-    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
   }
   const int sms = dev < 64 ? sms_of[dev] : 148;
   const int tiles = a.m_tiles * a.n_tiles;
-  linear_tc_ss_kernel<<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);
+  if (bf16)
+    linear_tc_ss_kernel<true><<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);
+  else
+    linear_tc_ss_kernel<false><<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

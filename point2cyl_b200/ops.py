@@ -134,7 +134,7 @@ def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None
         ptr(X), X.stride(0), ptr(W2), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(in_mask),
         0 if in_mask is None else in_mask.stride(0), ptr(Y), 0 if Y is None else Y.stride(0), M, N, K,
         ptr(stats), pool_group, ptr(Ymax), ptr(Ymin), precision, ptr(w_split),
-        0 if w_split is None else w_split.shape[2], stream_ptr())
+        0 if w_split is None else w_split.shape[-1], stream_ptr())
     if pool_group:
         return Y, Ymax, Ymin
     return Y
@@ -164,6 +164,29 @@ def split_tf32(W: Tensor) -> Tensor:
     out = torch.empty(2, N, pad4(K), dtype=torch.float32, device=W.device)
     call("p2c_split_tf32", ptr(W2), N, K, ptr(out), out.shape[2], stream_ptr())
     return out
+
+
+def cast_bf16(W: Tensor) -> Tensor:
+    """(N, pad8(K)) bf16 copy of a weight matrix for the bf16 tensor-core path (P2C_PREC_BF16)."""
+    W2 = W.reshape(W.shape[0], -1)
+    if not W2.is_contiguous():
+        W2 = W2.contiguous()
+    N, K = W2.shape
+    out = torch.empty(N, (K + 7) // 8 * 8, dtype=torch.bfloat16, device=W.device)
+    call("p2c_cast_bf16", ptr(W2), N, K, ptr(out), out.shape[1], stream_ptr())
+    return out
+
+
+def weight_operand(X: Tensor, W: Tensor, N: int, K: int, has_mask: bool, pool_group: int,
+                   precision: int) -> Optional[Tensor]:
+    """The pre-processed weight copy p2c_linear wants as `w_split` for this layer: hi/lo tf32 split (streamed-weight
+    3xTF32 kernel), bf16 copy (bf16 kernel) or None."""
+    path = _lib.load().p2c_linear_path(X.stride(0), X.shape[0], N, K, int(has_mask), pool_group, precision, 1)
+    if path == 2:
+        return split_tf32(W)
+    if path == 3:
+        return cast_bf16(W)
+    return None
 
 
 def needs_split(X: Tensor, N: int, K: int, has_mask: bool, pool_group: int, precision: int) -> bool:

@@ -25,7 +25,8 @@ _default_precision = "3xtf32"   # tcgen05, fp32-faithful; layers it does not tak
 
 
 def set_precision(name: str) -> None:
-    """'fp32' (SIMT), '3xtf32' (tcgen05, fp32-faithful) or 'bf16' (tcgen05)."""
+    """'fp32' (SIMT), '3xtf32' (tcgen05, fp32-faithful; default) or 'bf16' (tcgen05 kind::f16 on bf16 operands with
+    fp32 accumulation - BASELINE.json's bf16 MLP-stack configuration, NOT within the 1e-4 parity bar)."""
     global _default_precision
     if name not in _PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
@@ -78,7 +79,7 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
             Y = first_layer(stats)
             M = Y.shape[0]
         else:
-            wsplit = ops.split_tf32(conv.weight) if ops.needs_split(X, N, K, mask is not None, pool, prec) else None
+            wsplit = ops.weight_operand(X, conv.weight, N, K, mask is not None, pool, prec)
             res = ops.linear(X, conv.weight, conv.bias, K=K, w_split=wsplit,
                              in_scale=None if aff is None else aff.scale,
                              in_shift=None if aff is None else aff.shift,
@@ -138,7 +139,8 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
             if feats is not None:
                 _lib.set_tag(tag + ".q")
                 Wf = W0[:, 3:].contiguous()
-                Qf = ops.linear(feats, Wf, None, K=D, precision=prec)
+                Qf = ops.linear(feats, Wf, None, K=D, precision=prec,
+                                w_split=ops.weight_operand(feats, Wf, C0, D, False, 0, prec))
 
             def first_layer(stats):
                 return ops.sa_first_layer(xyz, new_xyz, gidx, Qf, W0, conv0.bias, stats)

@@ -85,3 +85,32 @@ def test_linear_tc_streamed_weights(M, N, K, pool, prologue):
     if pool:
         assert rel_err(res[1], ref.reshape(M // pool, pool, N).max(1).values) <= 1e-5
         assert rel_err(res[2], ref.reshape(M // pool, pool, N).min(1).values) <= 1e-5
+
+
+@pytest.mark.parametrize("M,K,N,pool", [(4096, 128, 128, 0), (5000, 64, 64, 0), (8192, 259, 256, 64), (4096, 1280, 256, 0)])
+def test_linear_bf16_path(M, K, N, pool):
+    """P2C_PREC_BF16: one kind::f16 pass on bf16 operands (BASELINE.json configs[2]); compared with the same product of
+    bf16-rounded operands in float64 (tight) and with the fp32 product (bf16-level tolerance)."""
+    g = torch.Generator().manual_seed(K)
+    ld = ops.pad4(K)
+    X = torch.randn(M, ld, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    sc, sh = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.2
+    Xd, Wd = X.to(DEV), W.to(DEV)
+    wop = ops.weight_operand(Xd, Wd, N, K, False, pool, _lib.PREC_BF16)
+    assert wop is not None and wop.dtype == torch.bfloat16
+    stats = torch.zeros(2 * N, dtype=torch.float64, device=DEV)
+    res = ops.linear(Xd, Wd, b.to(DEV), K=K, in_scale=sc.to(DEV), in_shift=sh.to(DEV), stats=stats, pool_group=pool,
+                     precision=_lib.PREC_BF16, w_split=wop)
+    Y = res[0] if pool else res
+    A = torch.relu(X[:, :K] * sc + sh)
+    ref_bf = A.bfloat16().double() @ W.bfloat16().double().T + b.double()
+    ref32 = A.double() @ W.double().T + b.double()
+    # (the operand fold is an fma on the device and mul+add on the host: a one-ulp fp32 difference now and then flips
+    # a bf16 rounding, hence 2e-3 rather than accumulation-order noise)
+    assert rel_err(Y, ref_bf) <= 2e-3
+    assert rel_err(Y, ref32) <= 2e-2
+    assert rel_err(stats[:N], Y.double().sum(0)) <= 1e-5
+    if pool:
+        assert rel_err(res[1], Y.reshape(M // pool, pool, N).max(1)[0]) == 0.0
