@@ -8,6 +8,11 @@ is drawn from the CPU generator (models/pointnet_util.py:75) and copied to the d
 
 Re-capture is needed when anything baked into the launch arguments changes: batch shape, loss weights,
 train/eval mode, or the BatchNorm momentum (train scripts change it via update_momentum).
+
+The step is captured as TWO graphs - backbone, then loss - so that a batch arriving from host memory can overlap
+its copies with the compute: only the point coordinates (3 of the 10.5 MB per step) have to be on the device before the
+backbone starts; normals, labels and ground-truth axes / centres are copied on a side stream while the backbone
+runs and the loss graph waits for that stream's event.
 """
 from __future__ import annotations
 
@@ -39,9 +44,18 @@ class GraphedForwardLoss:
                 self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = torch.cuda.Event()
+        self.graph = torch.cuda.CUDAGraph()            # backbone
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out = self._run()
+            self.X_raw, self.W_raw = pipeline.backbone_forward(self.net, self.static["pcs"], self.start_dev,
+                                                               precision=self.precision)
+        self.loss_graph = torch.cuda.CUDAGraph()       # loss block on the backbone's static outputs
+        with torch.no_grad(), torch.cuda.graph(self.loss_graph, pool=self.graph.pool()):
+            self.out = pipeline.loss_forward(self.static["pcs"], self.X_raw, self.W_raw, self.static["normals"],
+                                             self.static["inst"], self.static["bb"], self.static["axes"],
+                                             self.static["centers"], self.weights, self.norm_eig)
+            self.out.update(X_raw=self.X_raw, W_raw=self.W_raw)
 
     def _state_key(self):
         return (self.net.training,) + tuple(m.momentum for m in self.net.modules()
@@ -65,9 +79,18 @@ class GraphedForwardLoss:
         """batch: host (pinned) or device tensors copied into the graph's static inputs; None = reuse them."""
         if self.stale():
             raise RuntimeError("GraphedForwardLoss: mode or BatchNorm momentum changed since capture; build a new one")
+        cur = torch.cuda.current_stream(self.device)
         if batch is not None:
-            for k in BATCH_KEYS:
-                self.static[k].copy_(batch[k], non_blocking=True)
+            self.static["pcs"].copy_(batch["pcs"], non_blocking=True)      # the backbone needs only the coordinates
+            self.copy_stream.wait_stream(cur)                              # (the previous step's loss has read the labels)
+            with torch.cuda.stream(self.copy_stream):
+                for k in BATCH_KEYS:
+                    if k != "pcs":
+                        self.static[k].copy_(batch[k], non_blocking=True)
+                self.copied.record(self.copy_stream)
         self._draw_starts()
         self.graph.replay()
+        if batch is not None:
+            cur.wait_event(self.copied)
+        self.loss_graph.replay()
         return self.out

@@ -51,11 +51,16 @@ class Trainer:
         return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
     @torch.no_grad()
-    def forward_backward(self, batch: Dict[str, Tensor], fps_start=None) -> Dict[str, Tensor]:
-        """Gradients of the total loss into the flat buffer (zeroed first).  Returns the loss dict."""
+    def _forward(self, pcs: Tensor, fps_start=None):
+        """Backbone forward with a tape (needs only the point coordinates of the batch)."""
         self.flat_grad.zero_()
         tape: Dict = {}
-        X_raw, W_raw = pipeline.backbone_forward(self.net, batch["pcs"], fps_start, precision=self.precision, tape=tape)
+        X_raw, W_raw = pipeline.backbone_forward(self.net, pcs, fps_start, precision=self.precision, tape=tape)
+        return tape, X_raw, W_raw
+
+    @torch.no_grad()
+    def _loss_backward(self, batch: Dict[str, Tensor], tape: Dict, X_raw: Tensor, W_raw: Tensor) -> Dict[str, Tensor]:
+        """Loss block, its backward and the backbone backward: gradients land in the flat buffer."""
         B, N, twoK = W_raw.shape
         K = twoK // 2
         stats = ops.segfit_stats(X_raw, W_raw, batch["pcs"], batch["normals"], batch["inst"], batch["bb"], K)
@@ -74,6 +79,12 @@ class Trainer:
                                     match, n_gt, self._ones, K, out=d_buf[:, :C_out])
         bw.backbone_backward(tape, d_out, lambda p: p.grad, self.precision)
         return dict(total=losses[0], losses=losses, matching_indices=match, E_AX=E_AX, centers=centers)
+
+    @torch.no_grad()
+    def forward_backward(self, batch: Dict[str, Tensor], fps_start=None) -> Dict[str, Tensor]:
+        """Gradients of the total loss into the flat buffer (zeroed first).  Returns the loss dict."""
+        tape, X_raw, W_raw = self._forward(batch["pcs"], fps_start)
+        return self._loss_backward(batch, tape, X_raw, W_raw)
 
     @torch.no_grad()
     def step(self, batch: Optional[Dict[str, Tensor]], fps_start=None) -> Dict[str, Tensor]:
@@ -118,9 +129,17 @@ class GraphedTrainer(Trainer):
                 Trainer.forward_backward(self, self.static, self.start_dev)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # two graphs, like graph.GraphedForwardLoss: the backbone forward needs only the coordinates, so the labels /
+        # normals of a host batch are copied on a side stream while it runs
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = torch.cuda.Event()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = Trainer.forward_backward(self, self.static, self.start_dev)
+            tape, X_raw, W_raw = Trainer._forward(self, self.static["pcs"], self.start_dev)
+        self.bwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.bwd_graph, pool=self.graph.pool()):
+            self.out = Trainer._loss_backward(self, self.static, tape, X_raw, W_raw)
+        self._tape = tape                                  # keeps the forward's activations alive for the replay
         with torch.no_grad():
             for k, v in net.named_buffers():
                 v.copy_(buffers[k])
@@ -139,14 +158,23 @@ class GraphedTrainer(Trainer):
     def forward_backward(self, batch: Optional[Dict[str, Tensor]] = None, fps_start=None) -> Dict[str, Tensor]:
         if self._key != self._state_key():
             raise RuntimeError("GraphedTrainer: mode or BatchNorm momentum changed since capture; build a new one")
-        if batch is not None:
-            for k in self.keys:
-                if batch[k] is not self.static[k]:
-                    self.static[k].copy_(batch[k], non_blocking=True)
+        cur = torch.cuda.current_stream(self.flat_param.device)
+        copying = batch is not None and batch["pcs"] is not self.static["pcs"]
+        if copying:
+            self.static["pcs"].copy_(batch["pcs"], non_blocking=True)
+            self.copy_stream.wait_stream(cur)
+            with torch.cuda.stream(self.copy_stream):
+                for k in self.keys:
+                    if k != "pcs":
+                        self.static[k].copy_(batch[k], non_blocking=True)
+                self.copied.record(self.copy_stream)
         if fps_start is None:
             self._draw_starts()
         else:
             for d, s in zip(self.start_dev, fps_start):
                 d.copy_(s, non_blocking=True)
         self.graph.replay()
+        if copying:
+            cur.wait_event(self.copied)
+        self.bwd_graph.replay()
         return self.out
