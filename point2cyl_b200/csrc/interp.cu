@@ -20,15 +20,23 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
                        const float* __restrict__ feats2, int64_t ldf, int N, int S, int D,
                        float* __restrict__ out, int64_t ldo, int64_t* __restrict__ idx_out,
                        float* __restrict__ w_out) {
-  extern __shared__ float4 sm4[];  // (x, y, z, |p|^2) per source point: one broadcast LDS.128 per candidate
+  // sources in PAIRS: sA[p] = (x0, x1, y0, y1), sB[p] = (z0, z1, |p0|^2, |p1|^2) for sources 2p, 2p+1 - two broadcast
+  // LDS.128 feed six packed FMUL2 / FFMA2 / FADD2 (same rounding per half as the scalar ops: bit-identical distances)
+  extern __shared__ float4 sm4[];
+  float4* sA = sm4;
+  float4* sB = sm4 + (S + 1) / 2;
   __shared__ int s_idx[QPB][3];
   __shared__ float s_w[QPB][3];
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const float* p2 = xyz2 + (size_t)b * S * 3;
-  for (int i = tid; i < S; i += QPB) {
-    float x = __ldg(p2 + i * 3), y = __ldg(p2 + i * 3 + 1), z = __ldg(p2 + i * 3 + 2);
-    sm4[i] = make_float4(x, y, z, p2c_norm2_rn(x, y, z));
+  for (int pr = tid; pr < (S + 1) / 2; pr += QPB) {
+    const int i0 = 2 * pr, i1 = 2 * pr + 1;
+    const float x0 = __ldg(p2 + i0 * 3), y0 = __ldg(p2 + i0 * 3 + 1), z0 = __ldg(p2 + i0 * 3 + 2);
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = __int_as_float(0x7f800000);   // odd S: the pad never enters the top 3
+    if (i1 < S) { x1 = __ldg(p2 + i1 * 3); y1 = __ldg(p2 + i1 * 3 + 1); z1 = __ldg(p2 + i1 * 3 + 2); n1 = p2c_norm2_rn(x1, y1, z1); }
+    sA[pr] = make_float4(x0, x1, y0, y1);
+    sB[pr] = make_float4(z0, z1, p2c_norm2_rn(x0, y0, z0), n1);
   }
   __syncthreads();
 
@@ -39,17 +47,24 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
     const float na = p2c_norm2_rn(ax, ay, az);
     float d0 = __int_as_float(0x7f800000), d1 = d0, d2 = d0;  // +inf
     int i0 = 0, i1 = 0, i2 = 0;
+    const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
+    const float2 na2 = make_float2(na, na), m2 = make_float2(-2.0f, -2.0f);
+    auto insert = [&](float d, int j) {
+      if (d < d1) {
+        d2 = d1; i2 = i1;
+        if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+        else { d1 = d; i1 = j; }
+      } else { d2 = d; i2 = j; }
+    };
 #pragma unroll 4
-    for (int j = 0; j < S; ++j) {
-      const float4 sp = sm4[j];
-      const float d = p2c_sqdist_expanded(ax, ay, az, na, sp.x, sp.y, sp.z, sp.w);
-      if (d < d2) {
-        if (d < d1) {
-          d2 = d1; i2 = i1;
-          if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
-          else { d1 = d; i1 = j; }
-        } else { d2 = d; i2 = j; }
-      }
+    for (int pr = 0; pr < (S + 1) / 2; ++pr) {
+      const float4 A = sA[pr], Bv = sB[pr];
+      // ((-2*dot) + |q|^2) + |p|^2 with dot = fma(az,bz, fma(ay,by, ax*bx)): p2c_sqdist_expanded on both halves
+      const float2 dot = __ffma2_rn(az2, make_float2(Bv.x, Bv.y),
+                                    __ffma2_rn(ay2, make_float2(A.z, A.w), __fmul2_rn(ax2, make_float2(A.x, A.y))));
+      const float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(m2, dot), na2), make_float2(Bv.z, Bv.w));
+      if (d.x < d2) insert(d.x, 2 * pr);
+      if (d.y < d2) insert(d.y, 2 * pr + 1);
     }
     // w = (1/(d+1e-8)) / sum, same op order as :305-307
     const float r0 = __fdiv_rn(1.0f, __fadd_rn(d0, 1e-8f));
@@ -131,7 +146,7 @@ extern "C" int p2c_three_nn_interp(const float* xyz1, const float* xyz2, const f
   }
   if (!xyz1 || !xyz2) return P2C_EINVAL;
   if (S < 3) return P2C_EUNSUPPORTED;
-  const size_t smem = (size_t)S * 4 * sizeof(float);
+  const size_t smem = (size_t)((S + 1) / 2) * 2 * sizeof(float4);
   if (smem > 200 * 1024) return P2C_EUNSUPPORTED;
   if (smem > 48 * 1024)
     P2C_CUDA_TRY(cudaFuncSetAttribute(three_nn_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
