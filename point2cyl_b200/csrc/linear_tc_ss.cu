@@ -14,7 +14,7 @@ using namespace p2c_tc;
 
 namespace {
 
-constexpr int SS_THREADS = 384;
+constexpr int SS_THREADS = 512;   // 16 warps: producer, MMA, alloc, idle, 4 epilogue, 4 transform, 4 epilogue (second group)
 constexpr int SS_MAX_RAW = 4, SS_MAX_XT = 3;
 
 struct SsArgs {
@@ -213,7 +213,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===== operand transform (see linear_tc.cu) =====
     const int tt = tid - 256;
     const int cj = tt & 7, rg = tt >> 3;
@@ -278,17 +278,18 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = output channel of the tile =====
+    // ===== epilogue: thread = output channel of the tile; two groups of four warps (4-7, 12-15) drain the two
+    // accumulator buffers alternately, like linear_tc.cu =====
+    const int grp = warp >= 12 ? 1 : 0;
     const int q = warp & 3;
     const int ch = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     const int G = a.pool_group;
     const int gshift = G ? 31 - __clz(G) : 0;
-    int ybuf = 0;
-    float* ystg = reinterpret_cast<float*>(ystage + (size_t)q * 8192);
+    float* ystg = reinterpret_cast<float*>(ystage + (size_t)(grp * 4 + q) * 4096);   // one 4 KB staging tile per warp
     const bool y_tma = a.Y != nullptr && a.y_tma;
-    for (int t = 0; t < my_tiles; ++t) {
+    for (int t = grp; t < my_tiles; t += 2) {
       const int ab = t & 1;
       const uint32_t accph = (uint32_t)(t >> 1) & 1u;
       const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
@@ -312,9 +313,9 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int mrow = m0 + c * 32;
         const int jmax = min(32, a.M - mrow);
         if (jmax <= 0) continue;
-        float* st = ystg + ybuf * 1024;
+        float* st = ystg;
         if (y_tma) {
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
           __syncwarp();
         }
         float* yp = (a.Y && !y_tma && n_ok) ? a.Y + (size_t)mrow * a.ldy + n : nullptr;
@@ -329,7 +330,6 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                          ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          ybuf ^= 1;
         }
         if (G) {
           gmx = fmaxf(gmx, mx); gmn = fminf(gmn, mn);
