@@ -16,7 +16,9 @@
 // stores no indices (p2c_pool_bwd_reduce / p2c_pool_bwd_apply).
 // The fused gather + first SA conv runs backward as a scatter-add into the per-source-point product Qf
 // (p2c_sa_first_bwd), the 3-NN interpolation as a weighted scatter-add (p2c_three_nn_interp_bwd), the heads as
-// p2c_head_bwd + p2c_wgrad with the channel-first dropout mask.
+// p2c_head_bwd (data gradient + re-materialised masked input) followed by p2c_wgrad on plain row matrices.
+// p2c_wgrad dispatches to the tcgen05 kernel of wgrad_tc.cu; the SIMT kernel below takes masked / unaligned / tiny
+// calls and P2C_PREC_FP32.
 #include "common.cuh"
 
 namespace {
