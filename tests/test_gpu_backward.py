@@ -143,7 +143,7 @@ def test_eig3x3_backward_matches_eigh():
 # upstream of the heads); with BatchNorm on running statistics the same perturbation moves them by <= 5e-4 (isolated
 # ReLU / arg-max flips, median 0).  No implementation with a different summation order can therefore match the
 # train-mode gradients of the reference tighter than a few per cent, so the end-to-end bars are:
-#   * BatchNorm on running statistics: relative L2 error <= 5e-3 per parameter, median entry error <= 1e-4 of max;
+#   * BatchNorm on running statistics: relative L2 error <= 5e-3 per parameter, median entry error <= 2e-4 of max;
 #   * train-mode BatchNorm: relative L2 error <= 2e-1 per parameter (2048-entry samples; measured worst 8.8e-2),
 #     heads (fc2.*) <= 1e-2 (measured 3.3e-3), loss <= 1e-3;
 # and every backward kernel is checked on its own against torch autograd to 1e-4 (tests further down).
@@ -174,7 +174,7 @@ def _assert_param_grads(named_grads, g, training):
             bar = 1e-2 if k.startswith("fc2") else 2e-1
             ok = l2 <= bar and nerr <= bar
         else:
-            ok = l2 <= 5e-3 and med <= 1e-4 and nerr <= 5e-3
+            ok = l2 <= 5e-3 and med <= 2e-4 and nerr <= 5e-3   # measured worst: 2.1e-3, 6e-5, 2.4e-4
         if not ok:
             worst.append((k, l2, med, nerr))
     assert not worst, worst
