@@ -133,3 +133,52 @@ def backbone_apply(net, x, fps_start=None, precision=None):
         results.append(out[:, :, c0:c0 + o])
         c0 += o
     return results
+
+
+class SetAbstractionFn(torch.autograd.Function):
+    """One PointNetSetAbstraction level (models/pointnet_util.py:181-207) as an autograd node: differentiable w.r.t.
+    the input features (rows) and the level's parameters (not w.r.t. the coordinates, which are data)."""
+
+    @staticmethod
+    def forward(ctx, sa, xyz, feats, start, *params):
+        from . import pipeline
+        tape = {}
+        new_xyz, out = pipeline.set_abstraction(sa, xyz, feats, start, tape=tape)
+        ctx.tape, ctx.sa = tape, sa
+        ctx.mark_non_differentiable(new_xyz)
+        return new_xyz, out
+
+    @staticmethod
+    def backward(ctx, _d_xyz, d_out):
+        from . import backward as bw
+        from . import pipeline
+        params = list(ctx.sa.parameters())
+        grads = {id(p): torch.zeros_like(p) for p in params}
+        prec = pipeline._PRECISIONS[pipeline.get_precision()]
+        d_feats = bw._sa_backward(ctx.tape, d_out.contiguous(), lambda p: grads[id(p)], prec)
+        ctx.tape = None
+        return (None, None, d_feats, None) + tuple(grads[id(p)] for p in params)
+
+
+class FeaturePropagationFn(torch.autograd.Function):
+    """One PointNetFeaturePropagation level (models/pointnet_util.py:283-320): differentiable w.r.t. both feature
+    inputs (rows) and the level's parameters."""
+
+    @staticmethod
+    def forward(ctx, fp, xyz1, xyz2, feats1, feats2, *params):
+        from . import pipeline
+        tape = {}
+        out = pipeline.feature_propagation(fp, xyz1, xyz2, feats1, feats2, materialize=True, tape=tape)
+        ctx.tape, ctx.fp = tape, fp
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from . import backward as bw
+        from . import pipeline
+        params = list(ctx.fp.parameters())
+        grads = {id(p): torch.zeros_like(p) for p in params}
+        prec = pipeline._PRECISIONS[pipeline.get_precision()]
+        d_f1, d_f2 = bw._fp_backward(ctx.tape, d_out.contiguous(), lambda p: grads[id(p)], prec)
+        ctx.tape = None
+        return (None, None, None, d_f1, d_f2) + tuple(grads[id(p)] for p in params)

@@ -7,7 +7,7 @@ function level is point-major (B,N,C); nn.Module level is channel-first (B,C,N).
 import torch
 import torch.nn as nn
 
-from point2cyl_b200 import ops, pipeline
+from point2cyl_b200 import autograd, ops, pipeline
 
 
 def square_distance(src, dst):
@@ -88,7 +88,13 @@ class PointNetSetAbstraction(nn.Module):
         B = xyz.shape[0]
         xyz_pm = xyz.permute(0, 2, 1).contiguous().float()
         start = None if self.group_all else pipeline.draw_fps_start(B, xyz_pm.shape[1], xyz.device)
-        new_xyz, feats = pipeline.set_abstraction(self, xyz_pm, _to_rows(points), start)
+        rows = _to_rows(points)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or (rows is not None and rows.requires_grad)):
+            # backward = csrc/backward.cu kernels (gradients w.r.t. the features and the parameters)
+            new_xyz, feats = autograd.SetAbstractionFn.apply(self, xyz_pm, rows, start, *list(self.parameters()))
+        else:
+            new_xyz, feats = pipeline.set_abstraction(self, xyz_pm, rows, start)
         return new_xyz.permute(0, 2, 1), _to_cf(feats, B)
 
 
@@ -146,7 +152,12 @@ class PointNetFeaturePropagation(nn.Module):
 
     def forward(self, xyz1, xyz2, points1, points2):
         B = xyz1.shape[0]
-        out = pipeline.feature_propagation(self, xyz1.permute(0, 2, 1).contiguous().float(),
-                                           xyz2.permute(0, 2, 1).contiguous().float(),
-                                           _to_rows(points1), _to_rows(points2))
+        x1 = xyz1.permute(0, 2, 1).contiguous().float()
+        x2 = xyz2.permute(0, 2, 1).contiguous().float()
+        f1, f2 = _to_rows(points1), _to_rows(points2)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or f2.requires_grad
+                                        or (f1 is not None and f1.requires_grad)):
+            out = autograd.FeaturePropagationFn.apply(self, x1, x2, f1, f2, *list(self.parameters()))
+        else:
+            out = pipeline.feature_propagation(self, x1, x2, f1, f2)
         return _to_cf(out, B)

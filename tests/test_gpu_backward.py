@@ -391,3 +391,71 @@ def test_graphed_trainer_matches_eager(monkeypatch):
     graphed = GraphedTrainer(nets[1], data, lr=1e-3)               # train mode changed: a new capture is required
     losses = [float(graphed.step(data, fps_start=starts)["total"]) for _ in range(8)]
     assert losses[-1] < losses[0]
+
+
+def _l2(got, ref):
+    """relative L2 error: isolated ReLU / arg-max flips move single entries, not the bulk"""
+    return float((got.detach().cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
+
+
+def _module_sd(sd, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
+
+
+def test_module_level_autograd_sa_and_fp(monkeypatch):
+    """Stand-alone PointNetSetAbstraction / PointNetFeaturePropagation drop-in modules are trainable: gradients w.r.t.
+    their input features and parameters against torch autograd through the oracle (BatchNorm on running statistics,
+    the well-conditioned setting)."""
+    from point2cyl_b200.dropin.models import pointnet_util as pu
+    B, N, K = 2, 1024, 4
+    sd = orc.init_state_dict((3, 2 * K), seed=4)
+    g = torch.Generator().manual_seed(8)
+    xyz = synthetic.s_cyl(B, N, K, seed=4)["pcs"]
+    # ---- sa2-shaped level: 512 points with 128 features -> 128 centres ----
+    sa_spec = orc.SA_SPECS[1]
+    xyz1 = xyz[:, :512].contiguous()
+    feats = torch.randn(B, 128, 512, generator=g)
+    start = torch.tensor([3, 7])
+    monkeypatch.setattr(pipeline, "draw_fps_start", lambda B_, N_, dev: start.to(dev))
+    sd_ref = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in sd.items()}
+    f_ref = feats.clone().requires_grad_(True)
+    new_xyz_ref, out_ref = orc.set_abstraction(sd_ref, sa_spec, xyz1.permute(0, 2, 1), f_ref, training=False, start=start)
+    dO = torch.randn(out_ref.shape, generator=g)
+    (out_ref * dO).sum().backward()
+    sa = pu.PointNetSetAbstraction(sa_spec["npoint"], sa_spec["radius"], sa_spec["nsample"], 128 + 3, sa_spec["mlp"], False)
+    sa.load_state_dict(_module_sd(sd, "sa2"), strict=True)
+    sa = sa.to(DEV).eval()
+    f_dev = feats.to(DEV).requires_grad_(True)
+    new_xyz, out = sa(xyz1.permute(0, 2, 1).to(DEV), f_dev)
+    assert rel_err(out, out_ref) <= TOL and rel_err(new_xyz, new_xyz_ref) == 0.0
+    (out * dO.to(DEV)).sum().backward()
+    assert _l2(f_dev.grad, f_ref.grad) <= 5e-3
+    for k, p in sa.named_parameters():
+        ref = sd_ref["sa2." + k].grad
+        d = (p.grad.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30)
+        assert float(d) <= 5e-3, (k, float(d))
+    # ---- fp2-shaped level: 512 query points (128 skip features) <- 128 source points with 256 features ----
+    fp_spec = orc.FP_SPECS[1]
+    xyz2 = xyz[:, 512:640].contiguous()
+    p1 = torch.randn(B, 128, 512, generator=g)
+    p2 = torch.randn(B, 256, 128, generator=g)
+    p1r, p2r = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    for v in sd_ref.values():
+        if v.is_floating_point() and v.grad is not None:
+            v.grad = None
+    o_ref = orc.feature_propagation(sd_ref, fp_spec, xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1), p1r, p2r, training=False)
+    dO2 = torch.randn(o_ref.shape, generator=g)
+    (o_ref * dO2).sum().backward()
+    fp = pu.PointNetFeaturePropagation(384, fp_spec["mlp"])
+    fp.load_state_dict(_module_sd(sd, "fp2"), strict=True)
+    fp = fp.to(DEV).eval()
+    p1d, p2d = p1.to(DEV).requires_grad_(True), p2.to(DEV).requires_grad_(True)
+    o = fp(xyz1.permute(0, 2, 1).to(DEV), xyz2.permute(0, 2, 1).to(DEV), p1d, p2d)
+    assert rel_err(o, o_ref) <= TOL
+    (o * dO2.to(DEV)).sum().backward()
+    assert _l2(p1d.grad, p1r.grad) <= 5e-3 and _l2(p2d.grad, p2r.grad) <= 5e-3
+    for k, p in fp.named_parameters():
+        ref = sd_ref["fp2." + k].grad
+        d = (p.grad.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30)
+        assert float(d) <= 5e-3, (k, float(d))
