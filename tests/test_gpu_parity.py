@@ -337,6 +337,20 @@ def test_graph_replay_matches_eager(monkeypatch):
         ref = pipeline.forward_loss(net, data, matcher="scipy")
     assert torch.equal(got["matching_indices"], ref["matching_indices"])
     assert rel_err(got["losses"], ref["losses"]) <= 1e-6
+    # a DIFFERENT batch arriving from pinned host memory: the coordinates gate the backbone graph, labels / normals are
+    # copied on the side stream and the loss graph waits for them - results must belong to the new batch
+    import point2cyl_b200
+    for seed in (78, 79):
+        host = point2cyl_b200.pin_batch(synthetic.s_cyl(B, N, K, seed))
+        torch.manual_seed(6)
+        out2 = g(host)
+        got2 = {k: out2[k].clone() for k in ("losses", "matching_indices")}
+        torch.manual_seed(6)
+        with torch.no_grad():
+            ref2 = pipeline.forward_loss(net, {k: v.to(DEV) for k, v in host.items()})
+        assert torch.equal(got2["matching_indices"], ref2["matching_indices"])
+        assert rel_err(got2["losses"], ref2["losses"]) <= 1e-6
+        assert rel_err(got2["losses"], got["losses"]) > 1e-3          # and it really is another batch
     net.train()
     assert g.stale()
 
