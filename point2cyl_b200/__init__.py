@@ -1,9 +1,13 @@
 """point2cyl_b200 — B200-native (sm_100a) forward+loss hot path of Point2Cyl.
 
 Public surface:
-  point2cyl_b200.dropin.*        drop-in modules with the reference's names and signatures
+  point2cyl_b200.dropin.*        drop-in modules with the reference's names and signatures (differentiable)
   point2cyl_b200.pipeline        backbone_forward / loss_forward / forward_loss on device tensors
   point2cyl_b200.forward_loss_host   the same call from HOST buffers (H2D in, loss D2H out)
+  point2cyl_b200.graph           GraphedForwardLoss: CUDA-graph replay of the step, host copies overlapped
+  point2cyl_b200.autograd        torch.autograd.Function wrappers whose backward runs the backward kernels
+  point2cyl_b200.train           Trainer / GraphedTrainer: forward + loss + backward + all-reduce + Adam, flat buffers
+  point2cyl_b200.dist            one-process-per-GPU helpers (shards, reductions, buffer broadcast)
   point2cyl_b200.ops             one wrapper per C-ABI entry point (include/point2cyl.h)
 """
 from __future__ import annotations
