@@ -324,6 +324,11 @@ int p2c_sa_first_bwd(const float* dY, int64_t lddy, const float* xyz, const floa
                      int N, int S, int nsample, int C, float* dQf, int64_t ldq, float* dW, int64_t lddw, float* dbias,
                      void* stream);
 
+/* Backward of p2c_group (the un-fused grouping path): dfeats[b*N + idx[b,s,j], :] += dRows[(b,s,j), 3:3+D]; dfeats must
+ * be zeroed by the caller; the three xyz columns carry no gradient (coordinates are data). */
+int p2c_group_bwd(const float* dRows, int64_t ldr, const int64_t* idx, int B, int N, int S, int nsample, int D,
+                  float* dfeats, int64_t ldf, void* stream);
+
 /* Backward of p2c_three_nn_interp: dfeats2[b*S + idx[b,n,j], :] += w[b,n,j] * dInterp[b*N+n, :] (S == 1: the
  * broadcast of models/pointnet_util.py:298-299, idx/w unused).  dfeats2 is fully defined on return. */
 int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const int64_t* idx, const float* w, int B, int N, int S,

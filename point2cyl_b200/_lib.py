@@ -78,6 +78,7 @@ SIGNATURES = {
     "p2c_wgrad_path": [i64, i64, i64, i32, i32, i32],
     "p2c_sa_first_bwd": [c_f32p, i64, c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64,
                          c_f32p, vp],
+    "p2c_group_bwd": [c_f32p, i64, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, vp],
     "p2c_three_nn_interp_bwd": [c_f32p, i64, c_i64p, c_f32p, i32, i32, i32, i32, c_f32p, i64, vp],
     "p2c_head_bwd": [c_f32p, i64, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p,
                      i64, vp],
@@ -146,7 +147,7 @@ LAUNCHES_PER_CALL = {
     "p2c_square_distance": 1, "p2c_gather_rows": 1, "p2c_segment_lists": 1, "p2c_sketch_project": 1,
     "p2c_extrusion_extents": 1, "p2c_hard_w_encoding": 1, "p2c_normal_angle": 1,
     "p2c_bn_bwd_reduce": 1, "p2c_pool_bwd_reduce": 1, "p2c_bn_bwd_coef": 1, "p2c_bn_bwd_apply": 1,
-    "p2c_pool_bwd_apply": 1, "p2c_wgrad": 1, "p2c_sa_first_bwd": 1, "p2c_three_nn_interp_bwd": 1, "p2c_head_bwd": 1,
+    "p2c_pool_bwd_apply": 1, "p2c_wgrad": 1, "p2c_sa_first_bwd": 1, "p2c_group_bwd": 1, "p2c_three_nn_interp_bwd": 1, "p2c_head_bwd": 1,
     "p2c_adam_step": 1, "p2c_loss_backward_coef": 1, "p2c_segfit_backward": 1, "p2c_segfit_backward_w": 1,
     "p2c_eig3x3_backward": 1,
 }

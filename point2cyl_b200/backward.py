@@ -78,9 +78,14 @@ def _sa_backward(rec: dict, d_out: Tensor, grad_of: GradOf, precision: int) -> O
     layers = rec["layers"]
     D = rec["D"]
     if not rec["fused"]:
-        # group-all level: rows = [xyz | feats], plain stack; the feature gradient is a column slice
         d_rows = _stack_backward(layers, d_out, grad_of, precision, need_input_grad=D > 0)
-        return None if D == 0 else d_rows[:, 3:3 + D]
+        if D == 0:
+            return None
+        if rec.get("grouped"):
+            # un-fused ball-query level (first width other than 64 / 128): scatter the rows back to their source points
+            return ops.group_bwd(d_rows, rec["gidx"], rec["B"], rec["N"], D)
+        # group-all level: rows = [xyz | feats] in point order; the feature gradient is a column slice
+        return d_rows[:, 3:3 + D]
     dY0 = _stack_backward(layers, d_out, grad_of, precision, need_input_grad=False)
     conv0 = layers[0]["conv"]
     gW0 = grad_of(conv0.weight).reshape(conv0.weight.shape[0], -1)

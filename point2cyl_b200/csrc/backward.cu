@@ -331,6 +331,25 @@ sa_first_bwd_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Grouping gather backward (the un-fused set-abstraction path: first-layer width other than 64 / 128):
+// dfeats[b*N + idx[r], :] += dRows[r, 3:3+D]   (the xyz columns carry no gradient: coordinates are data)
+// ---------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+group_bwd_kernel(const float* __restrict__ dRows, int64_t ldr, const int64_t* __restrict__ idx, int N, int S, int ns,
+                 int D, int64_t rows, float* __restrict__ dF, int64_t ldf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t b = (r / ns) / S;
+  const int64_t src = __ldg(idx + r);
+  if (src < 0 || src >= N) return;            // a query without hits gathered zeros in the forward
+  const float* g = dRows + r * ldr + 3;
+  float* f = dF + ((size_t)b * N + src) * ldf;
+  for (int c = lane; c < D; c += 32) atomicAdd(f + c, __ldg(g + c));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // 3-NN interpolation backward: dfeats2[b, idx[b,n,j], :] += w[b,n,j] * dInterp[b*N+n, :]
 // ---------------------------------------------------------------------------------------------------------
 
@@ -575,6 +594,17 @@ extern "C" int p2c_sa_first_bwd(const float* dY, int64_t lddy, const float* xyz,
   else
     sa_first_bwd_kernel<2><<<blocks, 256, 0, st>>>(dY, lddy, xyz, new_xyz, idx, N, S, nsample, rows, dQf, ldq, dW, lddw,
                                                    dbias);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_group_bwd(const float* dRows, int64_t ldr, const int64_t* idx, int B, int N, int S, int nsample,
+                             int D, float* dfeats, int64_t ldf, void* stream) {
+  if (!dRows || !idx || !dfeats || B <= 0 || N <= 0 || S <= 0 || nsample <= 0 || D <= 0 || ldr < 3 + D || ldf < D)
+    return P2C_EINVAL;
+  const int64_t rows = (int64_t)B * S * nsample;
+  group_bwd_kernel<<<p2c_ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(dRows, ldr, idx, N, S, nsample, D, rows,
+                                                                           dfeats, ldf);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

@@ -627,6 +627,16 @@ def sa_first_bwd(dY: Tensor, xyz: Tensor, new_xyz: Tensor, idx: Tensor, dQf: Opt
          0 if dQf is None else dQf.stride(0), ptr(dW2), dW2.stride(0), ptr(dbias), stream_ptr())
 
 
+def group_bwd(dRows: Tensor, idx: Tensor, B: int, N: int, D: int) -> Tensor:
+    """Backward of `group` w.r.t. the features: (B*N, D) scatter-add of the feature columns of the grouped rows."""
+    dRows = _rows(dRows)
+    idx = idx.contiguous()
+    S, ns = idx.shape[1], idx.shape[2]
+    dF = torch.zeros(B * N, D, dtype=torch.float32, device=dRows.device)
+    call("p2c_group_bwd", ptr(dRows), dRows.stride(0), ptr(idx), B, N, S, ns, D, ptr(dF), dF.stride(0), stream_ptr())
+    return dF
+
+
 def three_nn_interp_bwd(dInterp: Tensor, idx: Optional[Tensor], w: Optional[Tensor], B: int, N: int, S: int) -> Tensor:
     dInterp = _rows(dInterp)
     D = dInterp.shape[1]

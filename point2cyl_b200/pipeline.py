@@ -151,7 +151,7 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
                             tag=tag, first_layer=first_layer, tape=layers)
             return new_xyz, out
         if tape is not None:
-            raise _lib.P2CError("training through the un-fused grouping path (first SA width not 64/128) is not built")
+            tape.update(gidx=gidx, grouped=True)     # un-fused path: the gather's backward is p2c_group_bwd
         rows = ops.group(xyz, feats, new_xyz, gidx)
     out = mlp_stack(rows, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
                     tag=tag, tape=layers)

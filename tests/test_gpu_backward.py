@@ -459,3 +459,42 @@ def test_module_level_autograd_sa_and_fp(monkeypatch):
         ref = sd_ref["fp2." + k].grad
         d = (p.grad.cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30)
         assert float(d) <= 5e-3, (k, float(d))
+
+
+def test_unfused_set_abstraction_backward(monkeypatch):
+    """A set-abstraction level whose first width is not 64 / 128 runs the materialised grouping path; its backward
+    (p2c_group_bwd scatter + plain stack) against oracle autograd, BatchNorm on running statistics."""
+    from point2cyl_b200.dropin.models import pointnet_util as pu
+    g = torch.Generator().manual_seed(21)
+    B, N, D = 2, 600, 16
+    spec = dict(name="sax", npoint=64, radius=0.35, nsample=16, mlp=(32, 48), group_all=False)
+    xyz = torch.rand(B, N, 3, generator=g)
+    feats = torch.randn(B, D, N, generator=g)
+    sd, cin = {}, 3 + D
+    for i, cout in enumerate(spec["mlp"]):
+        sd[f"sax.mlp_convs.{i}.weight"] = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+        sd[f"sax.mlp_convs.{i}.bias"] = torch.randn(cout, generator=g) * 0.1
+        sd[f"sax.mlp_bns.{i}.weight"] = 1 + 0.2 * torch.randn(cout, generator=g)
+        sd[f"sax.mlp_bns.{i}.bias"] = 0.1 * torch.randn(cout, generator=g)
+        sd[f"sax.mlp_bns.{i}.running_mean"] = 0.1 * torch.randn(cout, generator=g)
+        sd[f"sax.mlp_bns.{i}.running_var"] = 0.5 + torch.rand(cout, generator=g)
+        sd[f"sax.mlp_bns.{i}.num_batches_tracked"] = torch.tensor(0)
+        cin = cout
+    start = torch.tensor([1, 5])
+    monkeypatch.setattr(pipeline, "draw_fps_start", lambda B_, N_, dev: start.to(dev))
+    sd_ref = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in sd.items()}
+    f_ref = feats.clone().requires_grad_(True)
+    _, out_ref = orc.set_abstraction(sd_ref, spec, xyz.permute(0, 2, 1), f_ref, training=False, start=start)
+    dO = torch.randn(out_ref.shape, generator=g)
+    (out_ref * dO).sum().backward()
+    sa = pu.PointNetSetAbstraction(spec["npoint"], spec["radius"], spec["nsample"], 3 + D, list(spec["mlp"]), False)
+    sa.load_state_dict(_module_sd(sd, "sax"), strict=True)
+    sa = sa.to(DEV).eval()
+    f_dev = feats.to(DEV).requires_grad_(True)
+    _, out = sa(xyz.permute(0, 2, 1).to(DEV), f_dev)
+    assert rel_err(out, out_ref) <= TOL
+    (out * dO.to(DEV)).sum().backward()
+    assert _l2(f_dev.grad, f_ref.grad) <= 5e-3
+    for k, p in sa.named_parameters():
+        assert _l2(p.grad, sd_ref["sax." + k].grad) <= 5e-3, k
