@@ -224,7 +224,13 @@ int p2c_segment_lists(const int64_t* seg_label, const int64_t* bb, int bb_value,
 int p2c_sketch_project(const float* P, const float* X, int B, int N, int K, int S, const int32_t* lists,
                        const int32_t* counts, const int64_t* rand_idx /* (K,B,S) */, const float* axes /* (B,K,3) */,
                        const float* centers /* (B,K,3) */, float zero_tol, float* P_proj, float* X_proj,
-                       float* scales, float* found, void* stream);
+                       float* scales, float* found, int32_t* sel_out /* (K,B,S) sampled point or -1, may be NULL */,
+                       float* R_out /* (K,B,9) rotation, may be NULL */, void* stream);
+
+/* Backward of the projected NORMALS w.r.t. X (the with-sketch trainer feeds predicted normals,
+ * train_Point2Cyl.py:549): dX[b, sel[k,b,s], :] += R[k,b][:, 0:2] * dX_proj[k,b,s,:].  dX (B,N,3) is overwritten. */
+int p2c_sketch_project_bwd(const float* dX_proj, const int32_t* sel, const float* R, int B, int N, int K, int S,
+                           float* dX, void* stream);
 
 /* Extents along the axis — replaces get_extrusion_extents, data_utils.py:1650-1730: min / max over the sampled
  * members of (p - c).a; same selection and not-found conventions as above.  extents (K,B,2). */

@@ -58,7 +58,8 @@ SIGNATURES = {
     "p2c_gather_rows": [c_f32p, i64, c_i64p, i32, i32, i32, i32, c_f32p, vp],
     "p2c_segment_lists": [c_i64p, c_i64p, i32, i32, i32, i32, c_i32p, c_i32p, vp],
     "p2c_sketch_project": [c_f32p, c_f32p, i32, i32, i32, i32, c_i32p, c_i32p, c_i64p, c_f32p, c_f32p, f32, c_f32p,
-                           c_f32p, c_f32p, c_f32p, vp],
+                           c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, vp],
+    "p2c_sketch_project_bwd": [c_f32p, c_i32p, c_f32p, i32, i32, i32, i32, c_f32p, vp],
     "p2c_extrusion_extents": [c_f32p, i32, i32, i32, i32, c_i32p, c_i32p, c_i64p, c_f32p, c_f32p, c_f32p, c_f32p, vp],
     "p2c_hard_w_encoding": [c_f32p, i64, i64, i32, i32, i32, c_f32p, f32, c_f32p, c_i64p, vp],
     "p2c_normal_angle": [c_f32p, c_f32p, i32, i32, f32, c_f32p, c_f32p, vp],
@@ -144,7 +145,7 @@ LAUNCHES_PER_CALL = {
     "p2c_split_tf32": 1, "p2c_cast_bf16": 1, "p2c_sa_first_layer": 1, "p2c_head_masked": 1, "p2c_fps": 1, "p2c_ball_query": 1, "p2c_group": 1, "p2c_linear": 1, "p2c_bn_finalize": 1,
     "p2c_bn_relu_apply": 1, "p2c_pool_bn_relu": 1, "p2c_three_nn_interp": 1, "p2c_segfit_stats": 2, "p2c_segfit_stats_w": 2,
     "p2c_segfit_cost": 1, "p2c_hungarian": 1, "p2c_bb_loss": 2, "p2c_loss_finalize": 2, "p2c_eig3x3_smallest": 1,
-    "p2c_square_distance": 1, "p2c_gather_rows": 1, "p2c_segment_lists": 1, "p2c_sketch_project": 1,
+    "p2c_square_distance": 1, "p2c_gather_rows": 1, "p2c_segment_lists": 1, "p2c_sketch_project": 1, "p2c_sketch_project_bwd": 1,
     "p2c_extrusion_extents": 1, "p2c_hard_w_encoding": 1, "p2c_normal_angle": 1,
     "p2c_bn_bwd_reduce": 1, "p2c_pool_bwd_reduce": 1, "p2c_bn_bwd_coef": 1, "p2c_bn_bwd_apply": 1,
     "p2c_pool_bwd_apply": 1, "p2c_wgrad": 1, "p2c_sa_first_bwd": 1, "p2c_group_bwd": 1, "p2c_three_nn_interp_bwd": 1, "p2c_head_bwd": 1,

@@ -182,3 +182,23 @@ class FeaturePropagationFn(torch.autograd.Function):
         d_f1, d_f2 = bw._fp_backward(ctx.tape, d_out.contiguous(), lambda p: grads[id(p)], prec)
         ctx.tape = None
         return (None, None, None, d_f1, d_f2) + tuple(grads[id(p)] for p in params)
+
+
+class SketchProject(torch.autograd.Function):
+    """sketch_implicit_projection (data_utils.py:1014-1146) with the gradient of the projected normals w.r.t. X - the
+    with-sketch trainer projects PREDICTED normals (train_Point2Cyl.py:549).  P, labels, axes and centres are data."""
+
+    @staticmethod
+    def forward(ctx, X, P, lists, counts, rand_idx, axes, centers, S, zero_tol):
+        P_proj, X_proj, scales, found, sel, R = ops.sketch_project(P, X, lists, counts, rand_idx, axes, centers, S,
+                                                                   zero_tol, want_sel=True)
+        ctx.save_for_backward(sel, R)
+        ctx.shape = (P.shape[0], P.shape[1])
+        ctx.mark_non_differentiable(P_proj, scales, found)
+        return P_proj, X_proj, scales, found
+
+    @staticmethod
+    def backward(ctx, _dP, dX_proj, _ds, _df):
+        sel, R = ctx.saved_tensors
+        B, N = ctx.shape
+        return (ops.sketch_project_bwd(dX_proj, sel, R, B, N),) + (None,) * 8

@@ -97,7 +97,8 @@ sketch_project_kernel(const float* __restrict__ P, const float* __restrict__ X, 
                       const int32_t* __restrict__ lists, const int32_t* __restrict__ counts,
                       const int64_t* __restrict__ rand_idx, const float* __restrict__ axes,
                       const float* __restrict__ centers, float zero_tol, float* __restrict__ P_proj,
-                      float* __restrict__ X_proj, float* __restrict__ scales, float* __restrict__ found_out) {
+                      float* __restrict__ X_proj, float* __restrict__ scales, float* __restrict__ found_out,
+                      int32_t* __restrict__ sel_out, float* __restrict__ R_out) {
   const int k = blockIdx.x, b = blockIdx.y;
   __shared__ float R[9];
   __shared__ float cproj[2];
@@ -113,6 +114,8 @@ sketch_project_kernel(const float* __restrict__ P, const float* __restrict__ X, 
     const float* c = centers + ((size_t)b * K + k) * 3;
     cproj[0] = c[0] * r[0] + c[1] * r[3] + c[2] * r[6];
     cproj[1] = c[0] * r[1] + c[1] * r[4] + c[2] * r[7];
+    if (R_out)
+      for (int i = 0; i < 9; ++i) R_out[((size_t)k * B + b) * 9 + i] = r[i];
   }
   __syncthreads();
   const bool seg_active = flags[0], found = flags[1];
@@ -125,11 +128,13 @@ sketch_project_kernel(const float* __restrict__ P, const float* __restrict__ X, 
   float best = 0.f;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     float px = 0.f, py = 0.f, nx = 0.f, ny = 0.f;
+    int32_t chosen = -1;
     if (seg_active) {
       float p0 = 0.f, p1 = 0.f, p2 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (found) {
         const int64_t n = pick_member(list, rnd, s, cnt);
         if (n >= 0 && n < N) {
+          chosen = (int32_t)n;
           p0 = Pb[n * 3]; p1 = Pb[n * 3 + 1]; p2 = Pb[n * 3 + 2];
           if (Xb) { x0 = Xb[n * 3]; x1 = Xb[n * 3 + 1]; x2 = Xb[n * 3 + 2]; }
         }
@@ -145,6 +150,7 @@ sketch_project_kernel(const float* __restrict__ P, const float* __restrict__ X, 
       X_proj[(ob + s) * 2] = nx;
       X_proj[(ob + s) * 2 + 1] = ny;
     }
+    if (sel_out) sel_out[ob + s] = chosen;
     best = fmaxf(best, sqrtf(px * px + py * py));
   }
   best = p2c_warp_max(best);
@@ -198,6 +204,25 @@ extents_kernel(const float* __restrict__ P, int B, int N, int K, int S, const in
     extents[((size_t)k * B + b) * 2 + 1] = seg_active ? hi : 0.f;
     if (found_out) found_out[(size_t)b * K + k] = found ? 1.f : 0.f;
   }
+}
+
+// backward of the projected normals w.r.t. X: X_proj[k,b,s,c] = sum_r X[b, sel, r] * R[r][c]  =>
+// dX[b, sel, r] += R[r][0] * g0 + R[r][1] * g1   (the same point can be sampled many times: atomics)
+__global__ void __launch_bounds__(256)
+sketch_project_bwd_kernel(const float* __restrict__ dXproj, const int32_t* __restrict__ sel,
+                          const float* __restrict__ R, int B, int N, int S, int64_t total, float* __restrict__ dX) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int n = sel[e];
+  if (n < 0) return;
+  const int64_t kb = e / S;                 // k*B + b
+  const int b = (int)(kb % B);
+  const float* r = R + kb * 9;
+  const float g0 = dXproj[e * 2], g1 = dXproj[e * 2 + 1];
+  float* o = dX + ((size_t)b * N + n) * 3;
+  atomicAdd(o + 0, r[0] * g0 + r[1] * g1);
+  atomicAdd(o + 1, r[3] * g0 + r[4] * g1);
+  atomicAdd(o + 2, r[6] * g0 + r[7] * g1);
 }
 
 // hard_W_encoding: one-hot of the first arg-max over K, nulled columns zeroed; also the arg-max label itself
@@ -266,12 +291,24 @@ extern "C" int p2c_segment_lists(const int64_t* seg_label, const int64_t* bb, in
 extern "C" int p2c_sketch_project(const float* P, const float* X, int B, int N, int K, int S, const int32_t* lists,
                                   const int32_t* counts, const int64_t* rand_idx, const float* axes,
                                   const float* centers, float zero_tol, float* P_proj, float* X_proj, float* scales,
-                                  float* found, void* stream) {
+                                  float* found, int32_t* sel_out, float* R_out, void* stream) {
   if (!P || !counts || !axes || !centers || !P_proj || !scales || B <= 0 || N <= 0 || K <= 0 || S <= 0 || B > 65535)
     return P2C_EINVAL;
   if ((X == nullptr) != (X_proj == nullptr)) return P2C_EINVAL;
   sketch_project_kernel<<<dim3(K, B), 256, 0, (cudaStream_t)stream>>>(P, X, B, N, K, S, lists, counts, rand_idx, axes,
-                                                                      centers, zero_tol, P_proj, X_proj, scales, found);
+                                                                      centers, zero_tol, P_proj, X_proj, scales, found,
+                                                                      sel_out, R_out);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_sketch_project_bwd(const float* dX_proj, const int32_t* sel, const float* R, int B, int N, int K, int S,
+                                      float* dX, void* stream) {
+  if (!dX_proj || !sel || !R || !dX || B <= 0 || N <= 0 || K <= 0 || S <= 0) return P2C_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  P2C_CUDA_TRY(cudaMemsetAsync(dX, 0, sizeof(float) * (size_t)B * N * 3, st));
+  const int64_t total = (int64_t)K * B * S;
+  sketch_project_bwd_kernel<<<p2c_ceil_div(total, 256), 256, 0, st>>>(dX_proj, sel, R, B, N, S, total, dX);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

@@ -89,6 +89,9 @@ def _project(P, X, seg_label, bb_labels, extrusion_axes, extrusion_centers, S, a
     else:
         counts, lists = ops.segment_lists(seg_label, bb_labels, 0, K)
         rnd = _draw_member_samples(counts, S)
+    if torch.is_tensor(X) and X.requires_grad:
+        # predicted normals (train_Point2Cyl.py:549): the projected normals carry a gradient back to X
+        return ag.SketchProject.apply(X, P, lists, counts, rnd, extrusion_axes, extrusion_centers, S, g_zero_tol)  # noqa: F405
     return ops.sketch_project(P, X, lists, counts, rnd, extrusion_axes, extrusion_centers, S, g_zero_tol)  # noqa: F405
 
 

@@ -423,8 +423,8 @@ def segment_lists(seg_label: Tensor, bb: Optional[Tensor], bb_value: int, K: int
 
 
 def sketch_project(P: Tensor, X: Optional[Tensor], lists: Optional[Tensor], counts: Tensor, rand_idx: Optional[Tensor],
-                   axes: Tensor, centers: Tensor, S: int, zero_tol: float):
-    """-> P_proj (K,B,S,2), X_proj (K,B,S,2) | None, scales (K,B), found (B,K)."""
+                   axes: Tensor, centers: Tensor, S: int, zero_tol: float, want_sel: bool = False):
+    """-> P_proj (K,B,S,2), X_proj (K,B,S,2) | None, scales (K,B), found (B,K) [, sel (K,B,S) int32, R (K,B,9)]."""
     need_cuda(P, X, counts, axes, centers)
     P = _cloud(P)
     X = None if X is None else _cloud(X)
@@ -435,12 +435,23 @@ def sketch_project(P: Tensor, X: Optional[Tensor], lists: Optional[Tensor], coun
     X_proj = torch.empty(K, B, S, 2, dtype=torch.float32, device=dev) if X is not None else None
     scales = torch.empty(K, B, dtype=torch.float32, device=dev)
     found = torch.empty(B, K, dtype=torch.float32, device=dev)
+    sel = torch.empty(K, B, S, dtype=torch.int32, device=dev) if want_sel else None
+    R = torch.empty(K, B, 9, dtype=torch.float32, device=dev) if want_sel else None
     if rand_idx is not None:
         rand_idx = rand_idx.to(device=dev, dtype=torch.long).contiguous()
     call("p2c_sketch_project", ptr(P), ptr(X), B, N, K, S, ptr(lists), ptr(counts), ptr(rand_idx),
          ptr(axes.contiguous().float()), ptr(centers.contiguous().float()), float(zero_tol), ptr(P_proj), ptr(X_proj),
-         ptr(scales), ptr(found), stream_ptr())
+         ptr(scales), ptr(found), ptr(sel), ptr(R), stream_ptr())
+    if want_sel:
+        return P_proj, X_proj, scales, found, sel, R
     return P_proj, X_proj, scales, found
+
+
+def sketch_project_bwd(dX_proj: Tensor, sel: Tensor, R: Tensor, B: int, N: int) -> Tensor:
+    K, _, S = sel.shape
+    dX = torch.empty(B, N, 3, dtype=torch.float32, device=sel.device)
+    call("p2c_sketch_project_bwd", ptr(dX_proj.contiguous().float()), ptr(sel), ptr(R), B, N, K, S, ptr(dX), stream_ptr())
+    return dX
 
 
 def extrusion_extents(P: Tensor, lists: Optional[Tensor], counts: Tensor, rand_idx: Optional[Tensor], axes: Tensor,

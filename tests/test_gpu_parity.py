@@ -469,6 +469,30 @@ def test_projection_dropins_golden(golden_dir):
     assert rel_err(ext, g["extents"]) <= TOL
 
 
+def test_projection_normal_gradient_vs_oracle():
+    """The with-sketch trainer projects PREDICTED normals (train_Point2Cyl.py:549): d(X_proj)/dX through the drop-in
+    equals the oracle's autograd (same random stream -> same sampled members)."""
+    from point2cyl_b200.dropin import data_utils as du
+    B, N, K, S = 4, 1024, 4, 256
+    data = synthetic.s_cyl(B, N, K, seed=3)
+    g = torch.Generator().manual_seed(6)
+    axes = torch.nn.functional.normalize(torch.randn(B, K, 3, generator=g), dim=-1)
+    centers = torch.rand(B, K, 3, generator=g) - 0.5
+    wgt = torch.randn(K, B, S, 2, generator=g)
+    Xc = data["normals"].clone().requires_grad_(True)
+    torch.manual_seed(4)
+    ref = orc.sketch_implicit_projection(data["pcs"], Xc, data["inst"], data["bb"], axes, centers, S)
+    (ref[1] * wgt).sum().backward()
+    Xg = data["normals"].to(DEV).requires_grad_(True)
+    torch.manual_seed(4)
+    got = du.sketch_implicit_projection(data["pcs"].to(DEV), Xg, data["inst"].to(DEV), data["bb"].to(DEV),
+                                        axes.to(DEV), centers.to(DEV), num_points_to_sample=S)
+    assert rel_err(got[1], ref[1].detach()) <= TOL and not got[0].requires_grad
+    (got[1] * wgt.to(DEV)).sum().backward()
+    assert float(Xc.grad.abs().max()) > 0
+    assert rel_err(Xg.grad, Xc.grad) <= TOL
+
+
 def test_projection_config2_vs_oracle():
     """a19 at B=32, N=8192, K=8 with the training script's 1024 samples: member lists exact, projections within TOL."""
     from point2cyl_b200.dropin import data_utils as du
