@@ -124,9 +124,17 @@ def check(rc: int, what: str) -> None:
     raise P2CError(f"{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else 'no device'})")
 
 
+_alive: list = []
+
+
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
-    return None if t is None else t.data_ptr()
+    """Device pointer of a tensor (None -> NULL).  The tensor is kept alive until the next `call()` has returned, so a
+    temporary made inline (`ptr(x.contiguous())`) cannot be released between taking its address and the launch that
+    reads it; after the launch the allocator's stream ordering protects it."""
+    if t is None:
+        return None
+    _alive.append(t)
+    return t.data_ptr()
 
 
 def stream_ptr() -> int:
@@ -171,6 +179,7 @@ def call(name: str, *args) -> None:
         rc = fn(*args)
         e.record()
         _profile.append((name, _profile_tag, s, e))
+    _alive.clear()
     check(rc, name)
     launch_count += LAUNCHES_PER_CALL.get(name, 1)
 

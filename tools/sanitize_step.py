@@ -1,0 +1,59 @@
+"""One small pass through every product path, meant to run under compute-sanitizer:
+  PYTORCH_NO_CUDA_MEMORY_CACHING=1 compute-sanitizer --tool memcheck python tools/sanitize_step.py
+(the env var gives every tensor its own cudaMalloc so an out-of-bounds access is not hidden inside torch's pool).
+Sizes are the smallest that still take the tcgen05 kernels (rows >= 1024, widths 64..1024)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from point2cyl_b200 import pipeline, synthetic
+from point2cyl_b200.dropin import data_utils as du
+from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
+from point2cyl_b200.train import Trainer
+
+B, N, K = 2, 1024, 4
+torch.manual_seed(0)
+net = backbone(output_sizes=[3, 2 * K]).cuda().train()
+batch = {k: v.cuda() for k, v in synthetic.s_cyl(B, N, K, seed=7).items()}
+for prec in ("3xtf32", "fp32", "bf16"):
+    with torch.no_grad():
+        out = pipeline.forward_loss(net, batch, precision=prec)
+    print("forward+loss", prec, [round(float(v), 5) for v in out["losses"].cpu()], flush=True)
+tr = Trainer(net)
+for i in range(2):
+    print("train step", i, float(tr.step(batch)["losses"][0]), flush=True)
+net.eval()
+with torch.no_grad():
+    out = pipeline.forward_loss(net, batch)
+print("eval forward+loss", float(out["losses"][0]), flush=True)
+X = batch["normals"].clone().requires_grad_(True)
+Pp, Xp, sc = du.sketch_implicit_projection(batch["pcs"], X, batch["inst"], batch["bb"], batch["axes"], batch["centers"],
+                                           num_points_to_sample=256)
+Xp.sum().backward()
+ext, _ = du.get_extrusion_extents(batch["pcs"], batch["inst"], batch["bb"], batch["axes"], batch["centers"],
+                                  num_points_to_sample=256)
+torch.cuda.synchronize()
+print("projection ok", float(sc.max()), float(ext.abs().max()), float(X.grad.abs().max()))
+# function-level drop-ins (training-script call sites) with autograd, and the eval helpers
+from point2cyl_b200.dropin import losses as L
+net.train()
+Xn = torch.nn.functional.normalize(batch["normals"] + 0.1 * torch.randn_like(batch["normals"]), dim=-1).requires_grad_(True)
+Wl = torch.randn(B, N, 2 * K, device="cuda", requires_grad=True)
+W = torch.softmax(Wl[:, :, :K], dim=-1)
+tot, nl, ml, match, mask = L.compute_all_losses(batch["pcs"], W, batch["inst"], Xn, batch["normals"], 1.0, 1.0,
+                                                return_match_indices=True)
+EAX = du.estimate_extrusion_axis(Xn, W, W, batch["bb"], batch["inst"], normalize=False)
+cen = du.estimate_extrusion_centers(W, batch["pcs"])
+(tot + EAX.sum() + cen.sum()).backward()
+hw = L.hard_W_encoding(W.detach(), to_null_mask=True)
+nd = L.compute_normal_difference(Xn.detach(), batch["normals"])
+cc, _ = du.estimate_segment_centroids(hw, batch["pcs"])
+torch.cuda.synchronize()
+print("drop-in functions ok", float(tot), float(Wl.grad.abs().max()), float(nd.mean()), float(cc.abs().max()))
+from point2cyl_b200 import ops
+big = torch.rand(2, 20000, 3, device="cuda")                      # N > 16384: the 8-CTA cluster FPS (DSMEM exchange)
+idx, _ = ops.fps(big, 96, torch.tensor([5, 19999]))
+odd = torch.rand(3, 777, 3, device="cuda")                        # ragged tail: N not a multiple of anything
+idx2, _ = ops.fps(odd, 33, torch.tensor([0, 776, 100]))
+torch.cuda.synchronize()
+print("fps ok", int(idx.max()), int(idx2.max()))
+print("DONE")
