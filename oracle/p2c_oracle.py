@@ -555,7 +555,8 @@ def compute_normal_difference(X, X_gt, in_radians=True, collapse=True) -> Tensor
 # first-order Taylor form otherwise, returned as a 4x4 homogeneous matrix).  oracle/ref_shim.py installs it as the
 # `torchgeometry` stub so that the reference's OWN projection functions (data_utils.py:1014-1417, :1650-1730) can
 # be run here to produce tests/golden/projection_*.npz; everything around the rotation is therefore pinned by the
-# reference's code, the rotation itself only by this restatement.
+# reference's code, the rotation itself only by this restatement (cross-checked against scipy's Rodrigues
+# implementation in tests/test_oracle_golden.py - an independent check of the formula, not of torchgeometry's code).
 
 
 def angle_axis_to_rotation_matrix(angle_axis: Tensor) -> Tensor:

@@ -175,6 +175,23 @@ def test_rotation_restatement_is_a_rotation_only_for_unit_axis():
     assert abs(float(got) - 3 * float(ang * torch.sin(ang))) < 1e-4
 
 
+def test_rotation_restatement_against_scipy_rodrigues():
+    """torchgeometry is not installable offline, so the restated angle_axis_to_rotation_matrix is anchored on an
+    independent implementation of the same published formula (Rodrigues): scipy's Rotation.from_rotvec.  The only
+    difference is torchgeometry's `theta + 1e-6` in the axis normalisation (<= 2e-6 relative)."""
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(11)
+    aa = torch.randn(256, 3, generator=g, dtype=torch.float64) * torch.rand(256, 1, generator=g, dtype=torch.float64) * 3.0
+    R = orc.angle_axis_to_rotation_matrix(aa)[:, :3, :3]
+    ref = torch.from_numpy(Rotation.from_rotvec(aa.numpy()).as_matrix())
+    assert float((R - ref).abs().max()) <= 1e-5
+    tiny = torch.randn(64, 3, generator=g, dtype=torch.float64) * 1e-4          # first-order branch (theta^2 <= 1e-6)
+    Rt = orc.angle_axis_to_rotation_matrix(tiny)[:, :3, :3]
+    reft = torch.from_numpy(Rotation.from_rotvec(tiny.numpy()).as_matrix())
+    assert float((Rt - reft).abs().max()) <= 1e-7                               # second-order terms only
+    assert torch.equal(orc.angle_axis_to_rotation_matrix(aa)[:, 3, :], torch.tensor([0, 0, 0, 1.0], dtype=torch.float64).expand(256, 4))
+
+
 @pytest.mark.parametrize("name", LOSS)
 def test_loss_gradients(golden_dir, name):
     """Autograd through the oracle's loss block reproduces the reference's own gradients w.r.t. the network
