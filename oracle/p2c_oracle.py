@@ -362,7 +362,7 @@ def hungarian_matching(W_pred: Tensor, I_gt: Tensor):
         inter = onehot.t() @ W_pred[b]
         union = onehot.sum(0)[:, None] + W_pred[b].sum(0)[None, :] - inter
         score = (inter / union.clamp(min=1e-10))[:n_gt]
-        _, cols = linear_sum_assignment(-score.detach().numpy())
+        _, cols = linear_sum_assignment(-score.detach().cpu().numpy())   # .cpu(): as losses.py:43
         match[b, :n_gt] = torch.from_numpy(cols).long()
         mask[b, :n_gt] = True
     return match, mask
