@@ -64,13 +64,12 @@ class FusedLoss(torch.autograd.Function):
     centre} plus non-differentiable by-products."""
 
     @staticmethod
-    def forward(ctx, X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher):
-        from . import pipeline
+    def forward(ctx, X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig):
         B, N, twoK = W_raw.shape
         K = twoK // 2
         stats = ops.segfit_stats(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, K)
         cost, n_gt = ops.segfit_cost(stats, K)
-        match = ops.hungarian(cost, n_gt) if matcher == "device" else pipeline.hungarian_from_cost(cost, n_gt, K)
+        match = ops.hungarian(cost, n_gt)
         bb_sum = ops.bb_loss_sums(W_raw, gt_bb, match, n_gt, K)
         losses, E_AX, centers, per_seg, per_cloud = ops.loss_finalize(
             stats, bb_sum, match, n_gt, gt_axes, gt_centers, N, K, norm_eig, weights)
@@ -90,12 +89,12 @@ class FusedLoss(torch.autograd.Function):
         d_out = ops.segfit_backward(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, dstats, match, n_gt, eff, ctx.K)
         B, N = gt_inst.shape
         d3 = d_out.reshape(B, N, -1)
-        return (d3[:, :, :3], d3[:, :, 3:]) + (None,) * 9
+        return (d3[:, :, :3], d3[:, :, 3:]) + (None,) * 8
 
 
-def fused_loss(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher):
+def fused_loss(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig):
     return FusedLoss.apply(X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, tuple(weights),
-                           norm_eig, matcher)
+                           norm_eig)
 
 
 class Backbone(torch.autograd.Function):

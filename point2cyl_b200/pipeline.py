@@ -11,10 +11,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 import torch.nn.functional as F
-from scipy.optimize import linear_sum_assignment
 
 from . import _lib, ops
 
@@ -249,32 +247,18 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
 # ---- loss ----------------------------------------------------------------------------------------
 
 
-def hungarian_from_cost(cost: Tensor, n_gt: Tensor, K: int) -> Tensor:
-    """losses.py:43-45 on the host: one D2H of the (B,K,K) score tensor, scipy per cloud, one H2D."""
-    cost_h = cost.cpu().numpy()
-    n_h = n_gt.cpu().numpy()
-    match = np.zeros((cost_h.shape[0], K), dtype=np.int64)
-    for b in range(cost_h.shape[0]):
-        n = int(n_h[b])
-        if n > 0:
-            _, cols = linear_sum_assignment(-cost_h[b, :n, :])
-            match[b, :n] = cols
-    return torch.from_numpy(match).to(cost.device)
-
-
 def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, gt_inst: Tensor,
                  gt_bb: Tensor, gt_axes: Tensor, gt_centers: Tensor,
-                 weights=(1.0, 1.0, 1.0, 1.0, 1.0), norm_eig: bool = False,
-                 matcher: str = "device") -> Dict[str, Tensor]:
+                 weights=(1.0, 1.0, 1.0, 1.0, 1.0), norm_eig: bool = False) -> Dict[str, Tensor]:
     """train_Point2Cyl_without_sketch.py:246-353 with all five --pred_* branches on.
-    weights = (seg, normal, bb, extrusion, centre).  matcher: 'device' (p2c_hungarian, no host sync) or
-    'scipy' (the reference's host call on one D2H copy of the score tensor)."""
+    weights = (seg, normal, bb, extrusion, centre).  The assignment (losses.py:43, scipy on the host upstream) runs on
+    the device (p2c_hungarian): no host sync anywhere in the step."""
     B, N, twoK = W_raw.shape
     K = twoK // 2
     _lib.set_tag("loss")
     from . import autograd as ag
     losses, match, n_gt, E_AX, centers, per_seg, per_cloud, stats = ag.fused_loss(
-        X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig, matcher)
+        X_raw, W_raw, pcs, gt_normals, gt_inst, gt_bb, gt_axes, gt_centers, weights, norm_eig)
     mask = torch.arange(K, device=pcs.device)[None, :] < n_gt[:, None]
     return dict(total=losses[0], normal=losses[1], miou=losses[2], bb=losses[3], axis=losses[4],
                 center=losses[5], losses=losses, matching_indices=match, mask=mask, E_AX=E_AX,
@@ -282,11 +266,10 @@ def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, 
 
 
 def forward_loss(net, batch: Dict[str, Tensor], fps_start=None, weights=(1.0,) * 5,
-                 norm_eig: bool = False, precision: Optional[str] = None,
-                 matcher: str = "device") -> Dict[str, Tensor]:
+                 norm_eig: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
     """One forward+loss pass: the unit BASELINE.json's clouds/s metric counts."""
     X_raw, W_raw = backbone_forward(net, batch["pcs"], fps_start, precision=precision)
     out = loss_forward(batch["pcs"], X_raw, W_raw, batch["normals"], batch["inst"], batch["bb"],
-                       batch["axes"], batch["centers"], weights, norm_eig, matcher)
+                       batch["axes"], batch["centers"], weights, norm_eig)
     out.update(X_raw=X_raw, W_raw=W_raw)
     return out

@@ -322,6 +322,18 @@ def test_hungarian_matches_scipy(K):
             assert got[b, :n].tolist() == cols.tolist()                # generic scores: same assignment
 
 
+def scipy_match(cost, n_gt, K):
+    """losses.py:43-45 as the reference runs it: scipy on the host, first n_gt slots filled, rest 0."""
+    from scipy.optimize import linear_sum_assignment
+    cost_h, n_h = cost.cpu().numpy(), n_gt.cpu().numpy()
+    match = np.zeros((cost_h.shape[0], K), dtype=np.int64)
+    for b in range(cost_h.shape[0]):
+        n = int(n_h[b])
+        if n > 0:
+            match[b, :n] = linear_sum_assignment(-cost_h[b, :n, :])[1]
+    return torch.from_numpy(match)
+
+
 def test_graph_replay_matches_eager(monkeypatch):
     from point2cyl_b200.graph import GraphedForwardLoss
     monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: x)
@@ -334,8 +346,9 @@ def test_graph_replay_matches_eager(monkeypatch):
     got = {k: out[k].clone() for k in ("losses", "matching_indices", "E_AX")}
     torch.manual_seed(5)
     with torch.no_grad():
-        ref = pipeline.forward_loss(net, data, matcher="scipy")
+        ref = pipeline.forward_loss(net, data)
     assert torch.equal(got["matching_indices"], ref["matching_indices"])
+    assert torch.equal(ref["matching_indices"].cpu(), scipy_match(*ops.segfit_cost(ref["stats"], K), K))
     assert rel_err(got["losses"], ref["losses"]) <= 1e-6
     # a DIFFERENT batch arriving from pinned host memory: the coordinates gate the backbone graph, labels / normals are
     # copied on the side stream and the loss graph waits for them - results must belong to the new batch
