@@ -12,23 +12,27 @@ from point2cyl_b200.dropin.models.pointnet_util import (PointNetFeaturePropagati
 class backbone(nn.Module):
     """reference models/pointnet_extrusion.py:8-66.  forward(x (B,N,3[+3])) -> [ (B,N,o_i) ]."""
 
+    # (attribute, npoint, radius, nsample, feature channels in, widths); sa3 groups all points (reference :21-23)
+    _LEVELS = (("sa1", 512, 0.2, 64, 0, (64, 64, 128)),
+               ("sa2", 128, 0.4, 64, 128, (128, 128, 256)),
+               ("sa3", None, None, None, 256, (256, 512, 1024)))
+    # (attribute, skip channels, coarse channels, widths) (reference :25-27); fp1's skip input is the raw extra channels
+    _UPS = (("fp3", 256, 1024, (256, 256)), ("fp2", 128, 256, (256, 128)), ("fp1", 0, 128, (128, 128, 128)))
+
     def __init__(self, normal_channel=False, output_sizes=[3]):
         super().__init__()
-        additional_channel = 3 if normal_channel else 0
-        self.normal_channel = normal_channel
-        self.dim_pos = 3
-        self.sa1 = PointNetSetAbstraction(npoint=512, radius=0.2, nsample=64,
-                                          in_channel=3 + additional_channel, mlp=[64, 64, 128], group_all=False)
-        self.sa2 = PointNetSetAbstraction(npoint=128, radius=0.4, nsample=64, in_channel=128 + 3,
-                                          mlp=[128, 128, 256], group_all=False)
-        self.sa3 = PointNetSetAbstraction(npoint=None, radius=None, nsample=None, in_channel=256 + 3,
-                                          mlp=[256, 512, 1024], group_all=True)
-        self.fp3 = PointNetFeaturePropagation(in_channel=1024 + 256, mlp=[256, 256])
-        self.fp2 = PointNetFeaturePropagation(in_channel=256 + 128, mlp=[256, 128])
-        self.fp1 = PointNetFeaturePropagation(in_channel=128 + additional_channel, mlp=[128, 128, 128])
-        self.fc1 = nn.Conv1d(128, 128, 1)
-        self.bn1 = nn.BatchNorm1d(128)
-        self.fc2 = nn.ModuleList(nn.Conv1d(128, o, 1) for o in output_sizes)
+        extra = 3 if normal_channel else 0
+        self.normal_channel, self.dim_pos = normal_channel, 3
+        for name, npoint, radius, nsample, c_in, widths in self._LEVELS:
+            c_feat = extra if name == "sa1" else c_in
+            setattr(self, name, PointNetSetAbstraction(npoint, radius, nsample, self.dim_pos + c_feat, list(widths),
+                                                       group_all=npoint is None))
+        for name, c_skip, c_coarse, widths in self._UPS:
+            c_skip = extra if name == "fp1" else c_skip
+            setattr(self, name, PointNetFeaturePropagation(c_coarse + c_skip, list(widths)))
+        width = self._UPS[-1][3][-1]
+        self.fc1, self.bn1 = nn.Conv1d(width, width, 1), nn.BatchNorm1d(width)
+        self.fc2 = nn.ModuleList([nn.Conv1d(width, int(o), 1) for o in output_sizes])
 
     def forward(self, x, fps_start=None):
         """fps_start: optional ((B,) int64, (B,) int64) first FPS centroids for sa1/sa2; default draws
