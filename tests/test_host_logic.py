@@ -123,3 +123,31 @@ def test_bn_decay_schedule_values():
     def decay(step, bs=32, every=200000):
         return max(0.5 * 0.5 ** int(np.floor(step * bs / every)), 0.01)
     assert decay(0) == 0.5 and decay(6250) == 0.25 and decay(10 ** 7) == 0.01
+
+
+@pytest.mark.timeout(300)
+def test_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference` launched like the driver launches it for N=2: rank 0 alone times the CPU port and
+    prints ONE JSON line with the contract's keys; the other rank exits 0 without work."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0"]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=280)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["metric"].startswith("point-clouds/sec") and d["unit"] == "clouds/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] >= 1 and "clouds" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("forward+loss") and d["gpu_launches"] == 0
