@@ -49,12 +49,14 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_oracle():
-    """The oracle is test infrastructure: nothing under point2cyl_b200/ may import it."""
+    """The oracle is test infrastructure: nothing under point2cyl_b200/ or tools/ may import it (only tests/,
+    __graft_entry__.smoke() and bench.py's CPU legs do)."""
     bad = []
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "point2cyl_b200")):
-        for f in files:
-            if f.endswith(".py"):
-                txt = open(os.path.join(dirpath, f)).read()
-                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
-                    bad.append(os.path.join(dirpath, f))
+    for top in ("point2cyl_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith(".py"):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
+                        bad.append(os.path.join(dirpath, f))
     assert not bad, bad

@@ -138,7 +138,7 @@ def test_eig3x3_backward_matches_eigh():
 
 # ---- backbone backward -------------------------------------------------------------------------------------------
 #
-# Conditioning (measured with the CPU oracle, tools/grad_sensitivity.py): with TRAIN-mode BatchNorm a relative
+# Conditioning (measured with the CPU oracle, tests/tools/grad_sensitivity.py): with TRAIN-mode BatchNorm a relative
 # perturbation of 1e-6 of the weights changes the reference's own parameter gradients by 1-2 % in L2 (every layer
 # upstream of the heads); with BatchNorm on running statistics the same perturbation moves them by <= 5e-4 (isolated
 # ReLU / arg-max flips, median 0).  No implementation with a different summation order can therefore match the

@@ -165,7 +165,7 @@ def identity_dropout(monkeypatch):
     monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: x)
 
 
-# Conditioning of the train-mode forward (tools/grad_sensitivity.py, CPU oracle): with batch-statistics BatchNorm on
+# Conditioning of the train-mode forward (tests/tools/grad_sensitivity.py, CPU oracle): with batch-statistics BatchNorm on
 # these tiny batches (B <= 2, sa3 / fp3 normalise over 128*B rows) a relative perturbation of 1e-6 of the weights - ten
 # float32 ulps - already moves the reference's own outputs by 8e-5 (B=2) / 5e-5 (B=1); with running statistics by 2e-6.
 # Our BatchNorm sums are fp64 (more exact than the reference's fp32 reduction order), so train-mode outputs differ

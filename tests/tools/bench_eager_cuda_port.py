@@ -3,7 +3,7 @@ on one B200 (what the unmodified reference does on a GPU: (B,S,N) distance tenso
 host-side scipy assignment, dense (B,N,N) axis fit), same workload as bench.py's headline (B=32, N=8192, K=8,
 forward+loss, no_grad).  This is a measurement tool: it executes oracle/ only as the thing timed BESIDE the product."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import p2c_oracle as orc
 from point2cyl_b200 import synthetic

@@ -1,6 +1,6 @@
 """Per-parameter gradient error of one training step against the reference golden (debug helper)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import p2c_oracle as orc
 from point2cyl_b200 import pipeline, synthetic

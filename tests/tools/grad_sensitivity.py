@@ -4,14 +4,14 @@ Perturbs every weight by a relative 1e-6 and reports how far the gradients of on
 train-mode BatchNorm and with BatchNorm on running statistics.  This is the bound on how tightly ANY implementation
 with a different summation order can reproduce the reference's gradients (tests/test_gpu_backward.py cites it).
 
-    python tools/grad_sensitivity.py
+    python tests/tools/grad_sensitivity.py
 """
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import p2c_oracle as orc  # noqa: E402
 from point2cyl_b200 import synthetic  # noqa: E402
 
