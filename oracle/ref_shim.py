@@ -96,3 +96,34 @@ def load():
         sys.path[:] = saved_path
     _loaded.update(util=util, net=net, losses=losses, data_utils=data_utils)
     return types.SimpleNamespace(**_loaded)
+
+
+_loaded_igr = {}
+
+
+def load_igr():
+    """The reference's implicit sketch network: namespace with .network (IGR/network.py) and .sampler (IGR/sampler.py).
+    Both resolve `general` through sys.path (train_Point2Cyl.py:17-21 appends IGR/); general.py imports trimesh at
+    module scope only for mesh I/O helpers, so the stub suffices."""
+    if _loaded_igr:
+        return types.SimpleNamespace(**_loaded_igr)
+    if not available():
+        raise FileNotFoundError(f"reference tree not found at {REF_ROOT}")
+    _install_stubs()
+    saved_path = list(sys.path)
+    names = ("general", "network", "sampler")
+    saved_mods = {k: sys.modules.get(k) for k in names}
+    for k in names:
+        sys.modules.pop(k, None)
+    sys.path.insert(0, os.path.join(REF_ROOT, "IGR"))
+    try:
+        network = importlib.import_module("network")
+        sampler = importlib.import_module("sampler")
+    finally:
+        for k in names:
+            sys.modules.pop(k, None)
+            if saved_mods[k] is not None:
+                sys.modules[k] = saved_mods[k]
+        sys.path[:] = saved_path
+    _loaded_igr.update(network=network, sampler=sampler)
+    return types.SimpleNamespace(**_loaded_igr)

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
 from oracle import p2c_oracle as orc  # noqa: E402
+from oracle import igr_oracle as igr  # noqa: E402
 from point2cyl_b200 import synthetic  # noqa: E402
 
 
@@ -261,6 +262,88 @@ def projection_case(ref, name, B, N, K, S, seed):
     print("wrote", name)
 
 
+def _sketch_loss_source():
+    """The implicit-sketch loss lines of the with-sketch trainer (train_Point2Cyl.py:608-672), dedented: from
+    `if WITH_IM_LOSS:` to `im_loss += latent_loss`.  Not an importable function, so the reference's own lines are
+    exec'd (same approach as the inline bb loss)."""
+    path = os.path.join(ref_shim.REF_ROOT, "train_Point2Cyl.py")
+    with open(path) as f:
+        lines = f.readlines()
+    block = lines[607:672]
+    src = textwrap.dedent("".join(l.replace("\t", "    ") for l in block))
+    assert src.startswith("if WITH_IM_LOSS:") and src.rstrip().endswith("im_loss += latent_loss"), src[:200]
+    assert "nonmnfld_pnts = sampler.get_points(sk_pnts)" in src and "torch.min(values, dim=-1)" in src
+    return src
+
+
+def igr_inputs(B, K, S, seed):
+    """Synthetic sketches: per (cloud, segment) S points on an ellipse with outward unit normals (the 'gt sketch'),
+    and a jittered, rotated copy standing for the projected prediction.  -> gt_sketches (B,K,S,4), global_pc
+    (B*K,S,4), mask_gt (B,K) bool (cloud b has 1 + (b % K) instances)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.rand(B, K, S, generator=g) * (2 * np.pi)
+    a = 0.3 + 0.6 * torch.rand(B, K, 1, generator=g)
+    b = 0.3 + 0.6 * torch.rand(B, K, 1, generator=g)
+    pts = torch.stack([a * torch.cos(t), b * torch.sin(t)], dim=-1)
+    nrm = F.normalize(torch.stack([b * torch.cos(t), a * torch.sin(t)], dim=-1), dim=-1)
+    gt_sketches = torch.cat([pts, nrm], dim=-1)
+    ang = torch.rand(B, K, 1, 1, generator=g) * 0.3
+    rot = torch.cat([torch.cat([torch.cos(ang), -torch.sin(ang)], -1), torch.cat([torch.sin(ang), torch.cos(ang)], -1)], -2)
+    p2 = pts @ rot.transpose(-1, -2) + 0.01 * torch.randn(B, K, S, 2, generator=g)
+    n2 = F.normalize(nrm @ rot.transpose(-1, -2) + 0.05 * torch.randn(B, K, S, 2, generator=g), dim=-1)
+    global_pc = torch.cat([p2, n2], dim=-1).reshape(B * K, S, 4)
+    n_inst = torch.tensor([1 + (i % K) for i in range(B)])
+    mask_gt = torch.arange(K)[None, :] < n_inst[:, None]
+    return gt_sketches, global_pc, mask_gt
+
+
+def igr_case(ref, name, B, K, S, seed, is_l2):
+    """latent codes, the implicit network's prediction and input gradient, the four loss terms
+    and every parameter gradient, by the reference's own modules (IGR/network.py, IGR/sampler.py) and loss lines."""
+    net_ref = ref_shim.load_igr()
+    nw, sm = net_ref.network, net_ref.sampler
+    gt_sketches, global_pc, mask_gt = igr_inputs(B, K, S, seed)
+    implicit_net = nw.ImplicitNet(d_in=igr.D_IN + igr.LATENT_SIZE, dims=list(igr.IMPLICIT_DIMS), skip_in=list(igr.IMPLICIT_SKIP),
+                                  geometric_init=True, radius_init=1, beta=100)
+    implicit_net.load_state_dict(igr.implicit_init(seed=seed), strict=True)
+    pn_encoder = nw.PointNetEncoder(igr.LATENT_SIZE, igr.D_IN, with_normals=True)
+    pn_encoder.load_state_dict(igr.encoder_init(seed=seed + 1), strict=True)
+    loaded_pn_encoder = nw.PointNetEncoder(igr.LATENT_SIZE, igr.D_IN, with_normals=True)
+    loaded_pn_encoder.load_state_dict(igr.encoder_init(seed=seed + 2), strict=True)
+    pn_encoder.train()
+    loaded_pn_encoder.train()
+    # train_Point2Cyl.py:598-605
+    batch_size, NUM_SK_POINT = B, S
+    latent_codes = pn_encoder(global_pc)
+    sk_pnts = gt_sketches[:, :, :, :2].view(batch_size * K, NUM_SK_POINT, 2)
+    sk_normals = gt_sketches[:, :, :, -2:].view(batch_size * K, NUM_SK_POINT, 2)
+    global_pc_gt = torch.cat((sk_pnts, sk_normals), dim=-1)
+    latent_codes_gt = loaded_pn_encoder(global_pc_gt)
+    latent_codes.retain_grad()
+    ns = dict(torch=torch, sampler=sm.NormalPerPoint(1.8, 0.01), add_latent=nw.add_latent, gradient=nw.gradient,
+              implicit_net=implicit_net, reduce_mean_masked_instance=ref_shim.load().losses.reduce_mean_masked_instance,
+              mask_gt=mask_gt, sk_pnts=sk_pnts, sk_normals=sk_normals, latent_codes=latent_codes,
+              latent_codes_gt=latent_codes_gt, batch_size=batch_size, K=K, WITH_IM_LOSS=True, IS_L2=is_l2,
+              pcs=global_pc)
+    torch.manual_seed(seed + 3)                      # the sampler draws randn_like then rand from the global generator
+    exec(_sketch_loss_source(), ns)
+    ns["im_loss"].backward()
+    out = dict(meta=np.array([B, K, S, seed, int(is_l2)]), gt_sketches=np32(gt_sketches), global_pc=np32(global_pc),
+               mask_gt=mask_gt.numpy(), latent=np32(latent_codes), latent_gt=np32(latent_codes_gt),
+               d_latent=np32(latent_codes.grad),
+               nonmnfld_pnts=np32(ns["nonmnfld_pnts"][:, -2:]), sk_pred=np32(ns["sk_pred"].reshape(-1, 1)),
+               mnfld_grad=np32(ns["mnfld_grad"].reshape(-1, 2)), nonmnfld_grad=np32(ns["nonmnfld_grad"].reshape(-1, 2)))
+    for k in ("im_loss", "mnfld_loss", "grad_loss", "normals_loss", "latent_loss"):
+        out[k] = np32(ns[k])
+    for prefix, mod in (("net", implicit_net), ("enc", pn_encoder), ("encgt", loaded_pn_encoder)):
+        for pname, p in mod.named_parameters():
+            smp, nrm_ = sample_grad(p.grad)
+            out[f"grad_{prefix}.{pname}"] = smp
+            out[f"gradnorm_{prefix}.{pname}"] = nrm_
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: float(out[k]) for k in ("im_loss", "mnfld_loss", "grad_loss", "normals_loss", "latent_loss")})
+
+
 def main():
     assert ref_shim.available(), "reference tree not present"
     torch.set_num_threads(8)
@@ -276,6 +359,8 @@ def main():
     projection_case(ref, "projection_b3_n512_k4.npz", 3, 512, 4, 128, seed=2)
     train_case(ref, "train_b2_n1024_k4.npz", 2, 1024, 4, seed=0)
     train_case(ref, "train_bneval_b2_n1024_k4.npz", 2, 1024, 4, seed=0, bn_eval=True)
+    igr_case(ref, "igr_b3_k2_s64.npz", 3, 2, 64, seed=0, is_l2=False)
+    igr_case(ref, "igr_b2_k4_s128_l2.npz", 2, 4, 128, seed=4, is_l2=True)
 
 
 if __name__ == "__main__":
