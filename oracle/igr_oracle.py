@@ -6,7 +6,7 @@ imported only by tests/ (and tests/golden/make_golden.py), never by the product 
 
 Parity status: PINNED by tests/golden/igr_*.npz, produced by the reference's own IGR/network.py + IGR/sampler.py and
 the loss lines of train_Point2Cyl.py run through oracle/ref_shim.load_igr() (tests/golden/make_golden.py), checked
-in tests/test_oracle_golden.py.
+in tests/test_oracle_igr.py.
 
 Reference (paths relative to the upstream root):
   IGR/network.py:8-17      gradient(): d out / d in by autograd with create_graph, last two columns
@@ -116,6 +116,85 @@ def implicit_forward_with_input_grad(sd: Dict[str, Tensor], x: Tensor, skip_in: 
             g = g[:, :-d_in]
     gx = gx + g
     return zs[-1], gx[:, -2:]
+
+
+def implicit_backward_closed_form(sd: Dict[str, Tensor], x: Tensor, f_bar: Tensor, g_bar: Tensor,
+                                  skip_in: Sequence[int] = IMPLICIT_SKIP, beta: float = 100.0):
+    """Backward of (f, g = df/dx[:, -2:]) WITHOUT autograd: the four sweeps a kernel implementation runs.
+    Given the upstream gradients f_bar (R,1) = dL/df and g_bar (R,2) = dL/dg, returns ({name: grad} for every weight
+    and bias, dL/dx (R, d_in)).  Notation (row vectors): p_i input of layer i (h_i, or cat(h_i, x)/sqrt 2 at a skip
+    layer), z_i = p_i W_i^T + b_i, h_{i+1} = softplus(z_i), s_i = softplus'(z_i) = sigmoid(beta z_i),
+    t_i = softplus''(z_i) = beta s_i (1 - s_i) (s = 1, t = 0 where beta z > 20, torch's threshold).
+      1. forward            keep p_i, z_i
+      2. reverse (for g)    a_L = 1, r_i = a_i W_i, q_i = d f / d h_i (r_i, or its leading part / sqrt 2 at a skip),
+                            a_{i-1} = s_{i-1} * q_i,  g_x = r_0 + sum_skip r_s[:, n_h:] / sqrt 2
+      3. adjoint of 2.      r_bar_0 = g_bar (+ g_bar / sqrt 2 into the trailing columns of r_bar_s); going up:
+                            a_bar_i = r_bar_i W_i^T, dW_i += a_i^T r_bar_i, q_bar_{i+1} = a_bar_i * s_i,
+                            z_extra_i = a_bar_i * q_{i+1} * t_i
+      4. backward of 1.     delta_L = f_bar, dW_i += delta_i^T p_i, db_i += sum delta_i, p_bar_i = delta_i W_i,
+                            delta_{i-1} = z_extra_{i-1} + s_{i-1} * h_bar_i,  dx collects p_bar_0 and the skip parts.
+    This is what torch.autograd does for `gradient(..., create_graph=True)` followed by backward(); checked against it
+    in tests/test_oracle_igr.py."""
+    L = len([k for k in sd if k.endswith(".weight")]) - 1          # index of the last layer
+    d_in = x.shape[1]
+    rt2 = math.sqrt(2.0)
+    W = [sd[f"lin{i}.weight"] for i in range(L + 1)]
+    # 1. forward
+    p, z, h = [], [], x
+    for i in range(L + 1):
+        pi = torch.cat([h, x], dim=-1) / rt2 if i in skip_in else h
+        zi = pi @ W[i].t() + sd[f"lin{i}.bias"]
+        p.append(pi)
+        z.append(zi)
+        h = softplus(zi, beta) if i < L else zi
+    s, t = [], []
+    for i in range(L):
+        bz = beta * z[i]
+        sg = torch.sigmoid(bz)
+        lin = bz > 20.0
+        s.append(torch.where(lin, torch.ones_like(sg), sg))
+        t.append(torch.where(lin, torch.zeros_like(sg), beta * sg * (1.0 - sg)))
+    # 2. reverse sweep
+    a = [None] * (L + 1)
+    q = [None] * (L + 1)                                          # q[i] = d f / d h_i, i >= 1
+    a[L] = torch.ones_like(z[L])
+    for i in range(L, 0, -1):
+        r = a[i] @ W[i]
+        q[i] = r[:, :r.shape[1] - d_in] / rt2 if i in skip_in else r
+        a[i - 1] = s[i - 1] * q[i]
+    # 3. adjoint of the reverse sweep
+    gx_bar = torch.zeros_like(x)
+    gx_bar[:, -2:] = g_bar
+    grads = {f"lin{i}.weight": torch.zeros_like(W[i]) for i in range(L + 1)}
+    z_extra = [None] * L
+    r_bar = gx_bar
+    for i in range(L + 1):
+        if i in skip_in and i > 0:                                # trailing columns of r_i feed g_x directly
+            r_bar = torch.cat([r_bar, gx_bar / rt2], dim=-1)
+        grads[f"lin{i}.weight"] += a[i].t() @ r_bar
+        if i == L:
+            break
+        a_bar = r_bar @ W[i].t()
+        z_extra[i] = a_bar * q[i + 1] * t[i]
+        q_bar = a_bar * s[i]
+        r_bar = q_bar / rt2 if (i + 1) in skip_in else q_bar      # leading (h) part of r_bar_{i+1}
+    # 4. backward of the forward, with the extra pre-activation gradients injected
+    dx = torch.zeros_like(x)
+    delta = f_bar
+    for i in range(L, -1, -1):
+        grads[f"lin{i}.weight"] += delta.t() @ p[i]
+        grads[f"lin{i}.bias"] = delta.sum(dim=0)
+        p_bar = delta @ W[i]
+        if i in skip_in:
+            dx += p_bar[:, -d_in:] / rt2
+            h_bar = p_bar[:, :-d_in] / rt2
+        else:
+            h_bar = p_bar
+        if i == 0:
+            dx += h_bar
+        else:
+            delta = z_extra[i - 1] + s[i - 1] * h_bar
+    return grads, dx
 
 
 # ---- PointNetEncoder ---------------------------------------------------------------------------------------------

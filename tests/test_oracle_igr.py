@@ -107,3 +107,26 @@ def test_sketch_training_gradients(golden_dir, name):
             assert float((got[:ref.numel()] - ref).abs().max()) <= 2e-4 * scale + 1e-9, key
             checked += 1
     assert checked == 18 + 22 + 22          # 9 Linear (w,b) + 2 x (5 conv (w,b) + 5 BN (w,b) + fc (w,b))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-4)])
+def test_closed_form_second_order_backward_matches_autograd(dtype, tol):
+    """The four-sweep backward of (f, df/dx) written out without autograd - the blueprint for the kernels - equals
+    torch's double backward, including rows on the linear branch of softplus (beta z > 20) and the skip layer."""
+    sd = {k: v.to(dtype) for k, v in igr.implicit_init(seed=3).items()}
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(200, 258, generator=g) * 0.3).to(dtype)
+    x[:40] *= 4.0
+    f_bar = torch.randn(200, 1, generator=g).to(dtype)
+    g_bar = torch.randn(200, 2, generator=g).to(dtype)
+    P = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    xa = x.clone().requires_grad_()
+    f = igr.implicit_forward(P, xa)
+    gx = igr.gradient(xa, f)
+    ((f * f_bar).sum() + (gx * g_bar).sum()).backward()
+    grads, dx = igr.implicit_backward_closed_form(sd, x, f_bar, g_bar)
+    assert set(grads) == set(sd)
+    for k in sd:
+        ref = P[k].grad
+        assert float((grads[k] - ref).abs().max() / ref.abs().max().clamp_min(1e-30)) <= tol, k
+    assert float((dx - xa.grad).abs().max() / xa.grad.abs().max()) <= tol
