@@ -13,13 +13,14 @@ from point2cyl_b200 import ops
 from point2cyl_b200.dropin.global_variables import *  # noqa: F401,F403
 
 
-def add_noise(pcs, normals, sigma=0.01):
-    """data_utils.py:84-96: host-side jitter along the normals (numpy RNG, before the device copy)."""
-    pcs_np = pcs.numpy() if torch.is_tensor(pcs) else np.asarray(pcs)
-    nrm_np = normals.numpy() if torch.is_tensor(normals) else np.asarray(normals)
-    noise = np.random.normal(0.0, sigma, size=pcs_np.shape[:-1] + (1,)).astype(pcs_np.dtype)
-    out = pcs_np + noise * nrm_np
-    return torch.from_numpy(out) if torch.is_tensor(pcs) else out
+def add_noise(batch_xyz, batch_normal, sigma=0.01):
+    """data_utils.py:84-96: host-side jitter of every point along its normal, before the device copy.  Same numpy
+    RNG call and shape as the reference (one N(0, sigma) draw per point, (B, N)), same float64 promotion of the
+    result (the training script casts to float32 when it moves the batch to the device)."""
+    batch_xyz, batch_normal = torch.as_tensor(batch_xyz), torch.as_tensor(batch_normal)
+    B, N, _ = batch_xyz.shape
+    noise = torch.from_numpy(np.random.normal(0.0, sigma, (B, N)))
+    return batch_xyz + noise[:, :, None] * batch_normal
 
 
 def _sym3(m6):

@@ -1,0 +1,99 @@
+"""The reference-side binding of INTEGRATION.md, exercised on CPU: with the drop-in directories first on sys.path the
+reference's own import statements (train_Point2Cyl_without_sketch.py:14-23,180) resolve to this repo's modules, every
+name the scripts use from them exists, and - when the reference checkout is present - each function / constructor has
+the reference's parameter names, order and defaults."""
+import inspect
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+LOSSES = ["compute_all_losses", "hungarian_matching", "compute_miou_loss", "compute_normal_loss", "get_mask_gt",
+          "reduce_mean_masked_instance", "hard_W_encoding", "compute_segmentation_iou", "compute_normal_difference",
+          "sequence_mask", "acos_safe"]
+DATA_UTILS = ["estimate_extrusion_axis", "estimate_extrusion_centers", "add_noise", "sketch_implicit_projection",
+              "sketch_implicit_projection2", "sketch_implicit_projection3", "get_extrusion_extents"]
+UTIL = ["PointNetSetAbstraction", "PointNetSetAbstractionMsg", "PointNetFeaturePropagation", "farthest_point_sample",
+        "query_ball_point", "index_points", "square_distance", "sample_and_group", "sample_and_group_all"]
+
+
+def test_reference_import_statements_resolve_to_the_dropin():
+    code = textwrap.dedent(f"""
+        import sys, importlib
+        sys.path.insert(0, {ROOT!r})
+        sys.path.insert(0, {os.path.join(ROOT, 'point2cyl_b200', 'dropin')!r})
+        sys.path.insert(0, {os.path.join(ROOT, 'point2cyl_b200', 'dropin', 'models')!r})
+        MODEL_IMPORTED = importlib.import_module('pointnet_extrusion')      # train_...without_sketch.py:180
+        from losses import *                                                # :23
+        from data_utils import *                                            # :21
+        from models.pointnet_util import PointNetSetAbstractionMsg, PointNetSetAbstraction, PointNetFeaturePropagation
+        import losses, data_utils, models.pointnet_util as pu
+        for m in (MODEL_IMPORTED, losses, data_utils, pu):
+            assert 'point2cyl_b200' in m.__file__, m.__file__
+        for n in {LOSSES!r}: assert callable(globals()[n]), n
+        for n in {DATA_UTILS!r}: assert callable(globals()[n]), n
+        for n in {UTIL!r}: assert hasattr(pu, n), n
+        model = MODEL_IMPORTED.backbone(output_sizes=[3, 16])               # :197
+        assert len(model.state_dict()) == 123
+        print('OK', g_zero_tol)
+    """)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=200)
+    assert res.returncode == 0 and res.stdout.startswith("OK"), res.stderr[-2000:]
+
+
+def _params(fn):
+    return [(p.name, p.default if p.default is not inspect.Parameter.empty else "<required>")
+            for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+
+
+def test_signatures_equal_the_reference():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("the reference checkout is not here")
+    ref = ref_shim.load()
+    from point2cyl_b200.dropin import data_utils as du, losses as ls
+    from point2cyl_b200.dropin.models import pointnet_extrusion as pe, pointnet_util as pu
+    checked = 0
+    for names, ours, theirs in ((LOSSES, ls, ref.losses), (DATA_UTILS, du, ref.data_utils), (UTIL, pu, ref.util)):
+        for n in names:
+            a, b = getattr(ours, n), getattr(theirs, n)
+            if inspect.isclass(a):
+                assert _params(a.__init__) == _params(b.__init__), n
+                assert [p for p, _ in _params(a.forward)] == [p for p, _ in _params(b.forward)], n
+            else:
+                pa, pb = _params(a), _params(b)
+                assert [p for p, _ in pa] == [p for p, _ in pb], (n, pa, pb)
+                assert [d for _, d in pa] == [d for _, d in pb], (n, pa, pb)
+            checked += 1
+    assert _params(pe.backbone.__init__) == _params(ref.net.backbone.__init__)
+    # our forward adds one OPTIONAL trailing argument (explicit FPS start indices); the reference call forward(x) is unchanged
+    ours_fwd = _params(pe.backbone.forward)
+    assert ours_fwd[0] == ("x", "<required>") and all(d != "<required>" for _, d in ours_fwd[1:])
+    assert checked == len(LOSSES) + len(DATA_UTILS) + len(UTIL)
+
+
+def test_add_noise_equals_the_reference():
+    """Host-side augmentation (data_utils.py:84-96): same numpy random stream, same values and dtype."""
+    import numpy as np
+    import torch
+    from oracle import ref_shim
+    from point2cyl_b200.dropin import data_utils as du
+    g = torch.Generator().manual_seed(0)
+    pcs = torch.rand(3, 50, 3, generator=g)
+    nrm = torch.nn.functional.normalize(torch.randn(3, 50, 3, generator=g), dim=-1)
+    np.random.seed(7)
+    out = du.add_noise(pcs, nrm, sigma=0.02)
+    assert out.shape == pcs.shape and out.dtype == torch.float64
+    off = out - pcs.double()
+    along = (off * nrm.double()).sum(-1)
+    assert float((off - along[..., None] * nrm.double()).abs().max()) <= 1e-7     # displaced along the normal only
+    assert 0.005 < float(along.std()) < 0.04
+    if not ref_shim.available():
+        return
+    np.random.seed(7)
+    ref = ref_shim.load().data_utils.add_noise(pcs, nrm, sigma=0.02)
+    assert ref.dtype == out.dtype and torch.equal(ref, out)
