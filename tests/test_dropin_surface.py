@@ -97,3 +97,38 @@ def test_add_noise_equals_the_reference():
     np.random.seed(7)
     ref = ref_shim.load().data_utils.add_noise(pcs, nrm, sigma=0.02)
     assert ref.dtype == out.dtype and torch.equal(ref, out)
+
+
+def test_mask_helpers_equal_the_reference():
+    """The torch-only helpers of losses.py (:70-88, :123-124) - no kernel behind them - give the reference's results,
+    including clouds with a single instance and the all-masked row."""
+    import torch
+    from oracle import ref_shim
+    from point2cyl_b200.dropin import losses as ls
+    g = torch.Generator().manual_seed(2)
+    K = 6
+    I_gt = torch.stack([torch.randint(0, n, (40,), generator=g) for n in (1, 3, 6, 2)])
+    I_gt[:, 0] = torch.tensor([0, 2, 5, 1])                              # make the maximum label present
+    mask = ls.get_mask_gt(I_gt, K)
+    assert mask.dtype == torch.bool and mask.sum(dim=1).tolist() == [1, 3, 6, 2]
+    loss = torch.rand(4, K, generator=g)
+    red = ls.reduce_mean_masked_instance(loss, mask)
+    assert torch.allclose(red, torch.stack([loss[b, :n].mean() for b, n in enumerate((1, 3, 6, 2))]))
+    none = torch.zeros(2, K, dtype=torch.bool)
+    assert torch.equal(ls.reduce_mean_masked_instance(loss[:2], none), torch.zeros(2))
+    x = torch.tensor([-2.0, -1.0, 0.0, 0.3, 1.0, 2.0])
+    assert torch.isfinite(ls.acos_safe(x)).all()
+    if not ref_shim.available():
+        return
+    rl = ref_shim.load().losses
+    assert torch.equal(rl.get_mask_gt(I_gt, K), mask)
+    assert torch.equal(rl.sequence_mask(torch.tensor([0, 2, 5]), maxlen=5), ls.sequence_mask(torch.tensor([0, 2, 5]), maxlen=5))
+    assert torch.equal(rl.sequence_mask(torch.tensor([1, 4])), ls.sequence_mask(torch.tensor([1, 4])))
+    assert torch.allclose(rl.reduce_mean_masked_instance(loss, mask), red, atol=1e-7)
+    assert torch.equal(rl.acos_safe(x), ls.acos_safe(x))
+    n1 = torch.nn.functional.normalize(torch.randn(2, 30, 3, generator=g), dim=-1)
+    n2 = torch.nn.functional.normalize(torch.randn(2, 30, 3, generator=g), dim=-1)
+    for angle_diff in (False, True):
+        for collapse in (False, True):
+            assert torch.allclose(rl.compute_normal_loss(n1, n2, angle_diff, collapse),
+                                  ls.compute_normal_loss(n1, n2, angle_diff, collapse), atol=1e-7)
