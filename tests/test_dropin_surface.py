@@ -132,3 +132,22 @@ def test_mask_helpers_equal_the_reference():
         for collapse in (False, True):
             assert torch.allclose(rl.compute_normal_loss(n1, n2, angle_diff, collapse),
                                   ls.compute_normal_loss(n1, n2, angle_diff, collapse), atol=1e-7)
+
+
+def test_module_state_dicts_equal_the_reference():
+    """Stand-alone modules of models/pointnet_util.py: same parameter / buffer names and shapes as the reference for
+    the single-scale, multi-scale (defined upstream, never instantiated) and feature-propagation classes."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("the reference checkout is not here")
+    ru = ref_shim.load().util
+    from point2cyl_b200.dropin.models import pointnet_util as pu
+    cases = [("PointNetSetAbstraction", dict(npoint=128, radius=0.4, nsample=64, in_channel=131, mlp=[128, 128, 256], group_all=False)),
+             ("PointNetSetAbstraction", dict(npoint=None, radius=None, nsample=None, in_channel=259, mlp=[256, 512, 1024], group_all=True)),
+             ("PointNetSetAbstractionMsg", dict(npoint=512, radius_list=[0.1, 0.2, 0.4], nsample_list=[32, 64, 128], in_channel=3,
+                                                mlp_list=[[32, 32, 64], [64, 64, 128], [64, 96, 128]])),
+             ("PointNetFeaturePropagation", dict(in_channel=384, mlp=[256, 128]))]
+    for cls, kw in cases:
+        a = {k: tuple(v.shape) for k, v in getattr(pu, cls)(**kw).state_dict().items()}
+        b = {k: tuple(v.shape) for k, v in getattr(ru, cls)(**kw).state_dict().items()}
+        assert a == b, cls
