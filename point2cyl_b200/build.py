@@ -30,11 +30,17 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + ["-lcuda"]
+    # link into a private name, then rename: a concurrent reader (another rank of a torchrun launch) never maps a
+    # half-written library, and two concurrent builders cannot interleave their output
+    tmp = f"{LIB}.{os.getpid()}.tmp"
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources() + ["-lcuda"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libp2c.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(res.stderr)
     return LIB
