@@ -20,7 +20,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import BATCH_KEYS, pipeline
+from . import BATCH_KEYS, _lib, pipeline
 
 
 class GraphedForwardLoss:
@@ -81,6 +81,10 @@ class GraphedForwardLoss:
             raise RuntimeError("GraphedForwardLoss: mode or BatchNorm momentum changed since capture; build a new one")
         cur = torch.cuda.current_stream(self.device)
         if batch is not None:
+            for k in BATCH_KEYS:                                           # copy_ would silently broadcast a short batch
+                if tuple(batch[k].shape) != tuple(self.static[k].shape):
+                    raise _lib.P2CError(f"GraphedForwardLoss was captured for {k} of shape "
+                                        f"{tuple(self.static[k].shape)}, got {tuple(batch[k].shape)}: build a new one")
             self.static["pcs"].copy_(batch["pcs"], non_blocking=True)      # the backbone needs only the coordinates
             self.copy_stream.wait_stream(cur)                              # (the previous step's loss has read the labels)
             with torch.cuda.stream(self.copy_stream):

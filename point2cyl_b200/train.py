@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import backward as bw
-from . import ops, pipeline
+from . import _lib, ops, pipeline
 
 Tensor = torch.Tensor
 
@@ -161,6 +161,10 @@ class GraphedTrainer(Trainer):
         cur = torch.cuda.current_stream(self.flat_param.device)
         copying = batch is not None and batch["pcs"] is not self.static["pcs"]
         if copying:
+            for k in self.keys:                                  # copy_ would silently broadcast e.g. a short last batch
+                if tuple(batch[k].shape) != tuple(self.static[k].shape):
+                    raise _lib.P2CError(f"GraphedTrainer was captured for {k} of shape {tuple(self.static[k].shape)}, "
+                                        f"got {tuple(batch[k].shape)}: build a new one (or use Trainer) for this batch")
             self.static["pcs"].copy_(batch["pcs"], non_blocking=True)
             self.copy_stream.wait_stream(cur)
             with torch.cuda.stream(self.copy_stream):
