@@ -137,13 +137,19 @@ def query_ball_point(radius: float, nsample: int, xyz: Tensor, new_xyz: Tensor) 
 
 
 def sample_and_group(npoint: int, radius: float, nsample: int, xyz: Tensor,
-                     points: Optional[Tensor], start: Optional[Tensor] = None):
+                     points: Optional[Tensor], start: Optional[Tensor] = None, forced=None):
     """FPS -> centres -> ball query -> centred neighbourhoods [+ features],
-    models/pointnet_util.py:110-143.  Returns (new_xyz, new_points, fps_idx, group_idx)."""
+    models/pointnet_util.py:110-143.  Returns (new_xyz, new_points, fps_idx, group_idx).
+    forced = (fps_idx, group_idx): use these index tensors instead of computing them (float64 adjudication runs
+    take the float32 run's discrete choices so that only the arithmetic differs)."""
     B = xyz.shape[0]
-    fps_idx = farthest_point_sample(xyz, npoint, start)
-    new_xyz = gather_points(xyz, fps_idx)
-    group_idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    if forced is not None:
+        fps_idx, group_idx = forced
+        new_xyz = gather_points(xyz, fps_idx)
+    else:
+        fps_idx = farthest_point_sample(xyz, npoint, start)
+        new_xyz = gather_points(xyz, fps_idx)
+        group_idx = query_ball_point(radius, nsample, xyz, new_xyz)
     local = gather_points(xyz, group_idx) - new_xyz.reshape(B, npoint, 1, 3)
     if points is not None:
         local = torch.cat([local, gather_points(points, group_idx)], dim=-1)  # xyz first (:137)
@@ -160,20 +166,24 @@ def sample_and_group_all(xyz: Tensor, points: Optional[Tensor]):
     return new_xyz, grouped
 
 
-def three_nn_interpolate(xyz1: Tensor, xyz2: Tensor, points2: Tensor):
+def three_nn_interpolate(xyz1: Tensor, xyz2: Tensor, points2: Tensor, forced=None):
     """Inverse-distance 3-NN interpolation, models/pointnet_util.py:298-308.
 
     Uses the expanded-form distance (it can be slightly negative; the reference does not clamp)
     and a full sort whose first three entries are the neighbours.  Returns (interp, idx, weight).
+    forced = (idx, weight): take the neighbours and weights of another (float32) run.
     """
     B, N, _ = xyz1.shape
     S = xyz2.shape[1]
     if S == 1:
         return points2.repeat(1, N, 1), None, None
-    d, order = square_distance(xyz1, xyz2).sort(dim=-1)
-    d, order = d[:, :, :3], order[:, :, :3]
-    recip = 1.0 / (d + 1e-8)
-    w = recip / recip.sum(dim=2, keepdim=True)
+    if forced is not None:
+        order, w = forced[0], forced[1].to(points2.dtype)
+    else:
+        d, order = square_distance(xyz1, xyz2).sort(dim=-1)
+        d, order = d[:, :, :3], order[:, :, :3]
+        recip = 1.0 / (d + 1e-8)
+        w = recip / recip.sum(dim=2, keepdim=True)
     interp = (gather_points(points2, order) * w.reshape(B, N, 3, 1)).sum(dim=2)
     return interp, order, w
 
@@ -252,7 +262,7 @@ def _bn(x: Tensor, sd: Dict[str, Tensor], prefix: str, training: bool, momentum:
 
 def set_abstraction(sd, spec, xyz_cf: Tensor, feats_cf: Optional[Tensor], training: bool,
                     momentum: float = 0.1, start: Optional[Tensor] = None, new_stats=None,
-                    trace: Optional[dict] = None):
+                    trace: Optional[dict] = None, forced: Optional[dict] = None):
     """PointNetSetAbstraction.forward, models/pointnet_util.py:181-207 (channel-first I/O)."""
     name = spec["name"]
     xyz = xyz_cf.permute(0, 2, 1)
@@ -260,8 +270,9 @@ def set_abstraction(sd, spec, xyz_cf: Tensor, feats_cf: Optional[Tensor], traini
     if spec["group_all"]:
         new_xyz, grouped = sample_and_group_all(xyz, feats)
     else:
+        f = None if forced is None else (forced[name + ".fps_idx"], forced[name + ".group_idx"])
         new_xyz, grouped, fps_idx, group_idx = sample_and_group(
-            spec["npoint"], spec["radius"], spec["nsample"], xyz, feats, start)
+            spec["npoint"], spec["radius"], spec["nsample"], xyz, feats, start, forced=f)
         if trace is not None:
             trace[name + ".fps_idx"] = fps_idx
             trace[name + ".group_idx"] = group_idx
@@ -274,12 +285,19 @@ def set_abstraction(sd, spec, xyz_cf: Tensor, feats_cf: Optional[Tensor], traini
 
 
 def feature_propagation(sd, spec, xyz1_cf, xyz2_cf, points1_cf, points2_cf, training: bool,
-                        momentum: float = 0.1, new_stats=None):
+                        momentum: float = 0.1, new_stats=None, trace: Optional[dict] = None,
+                        forced: Optional[dict] = None):
     """PointNetFeaturePropagation.forward, models/pointnet_util.py:283-320."""
     name = spec["name"]
     xyz1 = xyz1_cf.permute(0, 2, 1)
     xyz2 = xyz2_cf.permute(0, 2, 1)
-    interp, _, _ = three_nn_interpolate(xyz1, xyz2, points2_cf.permute(0, 2, 1))
+    f = None
+    if forced is not None and xyz2.shape[1] > 1:
+        f = (forced[name + ".nn_idx"], forced[name + ".nn_w"])
+    interp, nn_idx, nn_w = three_nn_interpolate(xyz1, xyz2, points2_cf.permute(0, 2, 1), forced=f)
+    if trace is not None and nn_idx is not None:
+        trace[name + ".nn_idx"] = nn_idx
+        trace[name + ".nn_w"] = nn_w
     if points1_cf is not None:
         interp = torch.cat([points1_cf.permute(0, 2, 1), interp], dim=-1)  # skip feats first (:312)
     h = interp.permute(0, 2, 1)
@@ -292,25 +310,28 @@ def feature_propagation(sd, spec, xyz1_cf, xyz2_cf, points1_cf, points2_cf, trai
 def backbone_forward(sd: Dict[str, Tensor], x: Tensor, training: bool = True,
                      momentum: float = 0.1, fps_start: Optional[Sequence[Tensor]] = None,
                      dropout_mask: Optional[Tensor] = None, new_stats: Optional[dict] = None,
-                     trace: Optional[dict] = None) -> List[Tensor]:
+                     trace: Optional[dict] = None, forced: Optional[dict] = None) -> List[Tensor]:
     """backbone.forward, models/pointnet_extrusion.py:37-66.
 
     fps_start: (start_sa1 (B,), start_sa2 (B,)) or None to draw them like the reference does
     (one CPU randint per level, sa1 first).  dropout_mask: (B,128,N) multiplicative mask that
     already contains the 1/(1-p) scale (what F.dropout(ones) returns), or None for identity —
     the reference applies F.dropout(p=0.5) unconditionally (:60).
+    forced: the `trace` of another run - its FPS / ball-query / 3-NN indices and 3-NN weights are used instead of
+    being recomputed.  With sd and x in float64 this gives the exact-arithmetic value of the same discrete
+    computation (tests: float64 adjudication of the float32 tolerances).
     """
     xc = x.transpose(2, 1)
     pos = xc[:, :3, :]
     feats = xc[:, 3:, :] if xc.shape[1] > 3 else None
     s1 = fps_start[0] if fps_start is not None else None
     s2 = fps_start[1] if fps_start is not None else None
-    l1_xyz, l1 = set_abstraction(sd, SA_SPECS[0], pos, feats, training, momentum, s1, new_stats, trace)
-    l2_xyz, l2 = set_abstraction(sd, SA_SPECS[1], l1_xyz, l1, training, momentum, s2, new_stats, trace)
-    l3_xyz, l3 = set_abstraction(sd, SA_SPECS[2], l2_xyz, l2, training, momentum, None, new_stats, trace)
-    l4 = feature_propagation(sd, FP_SPECS[0], l2_xyz, l3_xyz, l2, l3, training, momentum, new_stats)
-    l5 = feature_propagation(sd, FP_SPECS[1], l1_xyz, l2_xyz, l1, l4, training, momentum, new_stats)
-    l6 = feature_propagation(sd, FP_SPECS[2], pos, l1_xyz, feats, l5, training, momentum, new_stats)
+    l1_xyz, l1 = set_abstraction(sd, SA_SPECS[0], pos, feats, training, momentum, s1, new_stats, trace, forced)
+    l2_xyz, l2 = set_abstraction(sd, SA_SPECS[1], l1_xyz, l1, training, momentum, s2, new_stats, trace, forced)
+    l3_xyz, l3 = set_abstraction(sd, SA_SPECS[2], l2_xyz, l2, training, momentum, None, new_stats, trace, forced)
+    l4 = feature_propagation(sd, FP_SPECS[0], l2_xyz, l3_xyz, l2, l3, training, momentum, new_stats, trace, forced)
+    l5 = feature_propagation(sd, FP_SPECS[1], l1_xyz, l2_xyz, l1, l4, training, momentum, new_stats, trace, forced)
+    l6 = feature_propagation(sd, FP_SPECS[2], pos, l1_xyz, feats, l5, training, momentum, new_stats, trace, forced)
     h = F.conv1d(l6, sd["fc1.weight"], sd["fc1.bias"])
     h = F.relu(_bn(h, sd, "bn1", training, momentum, new_stats))
     if dropout_mask is not None:
@@ -345,7 +366,7 @@ def get_mask_gt(I_gt: Tensor, n_max_instances: int) -> Tensor:
 def reduce_mean_masked_instance(loss: Tensor, mask_gt: Tensor) -> Tensor:
     """losses.py:83-88: per-sample mean over existing instances (0 where there are none)."""
     kept = torch.where(mask_gt, loss, torch.zeros_like(loss)).sum(dim=1)
-    cnt = mask_gt.float().sum(dim=1)
+    cnt = mask_gt.to(loss.dtype).sum(dim=1)
     return torch.where(cnt > 0, kept / cnt, torch.zeros_like(kept))
 
 
@@ -358,7 +379,7 @@ def hungarian_matching(W_pred: Tensor, I_gt: Tensor):
     mask = torch.zeros(B, K, dtype=torch.bool)
     for b in range(B):
         n_gt = int(I_gt[b].max()) + 1
-        onehot = torch.eye(n_gt + 1)[I_gt[b]]                  # label -1 -> last row (:38)
+        onehot = torch.eye(n_gt + 1, dtype=W_pred.dtype)[I_gt[b]]   # label -1 -> last row (:38)
         inter = onehot.t() @ W_pred[b]
         union = onehot.sum(0)[:, None] + W_pred[b].sum(0)[None, :] - inter
         score = (inter / union.clamp(min=1e-10))[:n_gt]
@@ -373,7 +394,7 @@ def compute_miou_loss(W: Tensor, I_gt: Tensor, matching_indices: Tensor, div_eps
     B, N, K = W.shape
     L = matching_indices.shape[1]
     Wr = torch.gather(W, 2, matching_indices[:, None, :].expand(B, N, L))
-    onehot = torch.eye(L + 2)[I_gt][:, :, :L]
+    onehot = torch.eye(L + 2, dtype=W.dtype)[I_gt][:, :, :L]
     inter = (onehot * Wr).sum(dim=1)
     union = onehot.sum(dim=1) + Wr.sum(dim=1) - inter
     return 1.0 - inter / (union + div_eps), 1 - inter / N, Wr
@@ -446,7 +467,7 @@ def estimate_extrusion_axis(X, W_barrel, W_base, gt_bb=None, gt_inst=None, norma
     if not dense:
         M = axis_scatter_matrices(X, W_barrel, W_base, gt_bb, gt_inst, normalize)
         _, v = torch.linalg.eigh(M, UPLO="U")
-        return v[..., 0].float()
+        return v[..., 0].to(X.dtype)
     out = torch.zeros(B, K, 3)
     for k in range(K):
         Db = torch.diag_embed(W_barrel[:, :, k])
@@ -505,10 +526,10 @@ def loss_block(pcs, X_raw, W_raw, gt_normals, gt_inst, gt_bb, gt_axes, gt_center
 
 def forward_loss(sd, batch: Dict[str, Tensor], training=True, momentum=0.1, fps_start=None,
                  dropout_mask=None, weights=(1.0,) * 5, norm_eig=False, dense_axis=False,
-                 trace=None) -> Dict[str, Tensor]:
+                 trace=None, forced=None, new_stats=None) -> Dict[str, Tensor]:
     """One forward+loss pass (the unit BASELINE.json's metric counts clouds over)."""
     X_raw, W_raw = backbone_forward(sd, batch["pcs"], training, momentum, fps_start, dropout_mask,
-                                    trace=trace)
+                                    new_stats=new_stats, trace=trace, forced=forced)
     out = loss_block(batch["pcs"], X_raw, W_raw, batch["normals"], batch["inst"], batch["bb"],
                      batch["axes"], batch["centers"], weights, norm_eig, dense_axis)
     out.update(X_raw=X_raw, W_raw=W_raw)
