@@ -87,37 +87,67 @@ def make_net(device):
     return net.to(device).train()
 
 
+def _quiet_reference_timing(**kw):
+    """baseline.ref_arm.time_reference with the reference's import-time prints kept off stdout (one JSON line only)."""
+    import contextlib
+    from baseline import ref_arm
+    with contextlib.redirect_stdout(sys.stderr):
+        return ref_arm.time_reference(**kw)
+
+
+def reference_available():
+    from baseline import make_ref
+    return make_ref.root() is not None
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement of the reference algorithm (oracle/, dense axis fit like
-    data_utils.py:118-172), all host threads, bounded sample of the same workload.  Rank 0 only."""
+    """--impl reference: the UNMODIFIED reference (baseline/_ref, staged by baseline/make_ref.py: stock backbone
+    module + the training script's own loop-body lines exec'd, dense (B,N,N) axis fit) on the host cores, all
+    threads, no_grad, a bounded sample of the same workload per step.  Falls back to the oracle port only when the
+    reference files did not travel.  Rank 0 only."""
     if rank != 0:
         return
-    from oracle import p2c_oracle as orc
-    from point2cyl_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
-    data = synthetic.s_cyl(CPU_SAMPLE_B, N_POINTS, K_INST, seed=1234)
-    sd = orc.init_state_dict((3, 2 * K_INST), seed=0)
-    starts = (torch.zeros(CPU_SAMPLE_B, dtype=torch.long), torch.zeros(CPU_SAMPLE_B, dtype=torch.long))
-    mask = torch.nn.functional.dropout(torch.ones(CPU_SAMPLE_B, 128, N_POINTS), p=0.5)
-    times = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            orc.forward_loss(sd, data, training=True, fps_start=starts, dropout_mask=mask, dense_axis=True)
-            if i >= args.warmup:
-                times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    v = CPU_SAMPLE_B / sec
     cores = torch.get_num_threads()
-    sample = f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST} per step, {len(times)} steps, torch CPU no_grad"
+    extra = {}
+    if reference_available():
+        r = _quiet_reference_timing(B=CPU_SAMPLE_B, N=N_POINTS, K=K_INST, steps=args.steps, warmup=args.warmup)
+        sec, kind = r["sec_per_step"], "reference"
+        sample = (f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST} per step, {r['steps']} steps after {args.warmup} "
+                  f"warm-up, the reference's own modules and loop body ({r['root']}), torch CPU, no_grad")
+        try:   # the reference's default batch (4) with autograd recording, as its training loop runs forward+loss
+            d = _quiet_reference_timing(B=4, N=N_POINTS, K=K_INST, steps=1, warmup=0, grad=True)
+            extra["reference_default_b4_autograd"] = {"value": d["clouds_per_s"], "unit": UNIT,
+                                                      "ms_per_step": d["sec_per_step"] * 1e3, "clouds_per_step": 4}
+        except (RuntimeError, MemoryError) as e:
+            extra["reference_default_b4_autograd"] = {"value": None, "error": str(e)[:120]}
+    else:
+        from oracle import p2c_oracle as orc
+        from point2cyl_b200 import synthetic
+        data = synthetic.s_cyl(CPU_SAMPLE_B, N_POINTS, K_INST, seed=1234)
+        sd = orc.init_state_dict((3, 2 * K_INST), seed=0)
+        starts = (torch.zeros(CPU_SAMPLE_B, dtype=torch.long), torch.zeros(CPU_SAMPLE_B, dtype=torch.long))
+        mask = torch.nn.functional.dropout(torch.ones(CPU_SAMPLE_B, 128, N_POINTS), p=0.5)
+        times = []
+        with torch.no_grad():
+            for i in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                orc.forward_loss(sd, data, training=True, fps_start=starts, dropout_mask=mask, dense_axis=True)
+                if i >= args.warmup:
+                    times.append(time.perf_counter() - t0)
+        sec, kind = sum(times) / len(times), "port"
+        sample = (f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST} per step, {len(times)} steps, oracle port "
+                  "(reference files absent), torch CPU no_grad")
+    v = CPU_SAMPLE_B / sec
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * B_PER_GPU / CPU_SAMPLE_B,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "ms_per_step_extrapolated_to_b32": sec * 1e3 * B_PER_GPU / CPU_SAMPLE_B, "clouds_per_step": CPU_SAMPLE_B,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args.gpus, "cpu"),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, args.precision),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0, **extra}), flush=True)
 
 
 def workload_config(n_gpus, precision):
@@ -129,9 +159,15 @@ def workload_config(n_gpus, precision):
 
 
 def cpu_baseline_sample():
+    """rank 0, N=1: the reference's own forward+loss on the host cores (bounded sample); oracle port if absent."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    if reference_available():
+        r = _quiet_reference_timing(B=CPU_SAMPLE_B, N=N_POINTS, K=K_INST, steps=2, warmup=1)
+        return {"value": r["clouds_per_s"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST}, mean of 2 steps after 1 warm-up, the reference's "
+                          f"own modules and loop body ({r['root']}), torch CPU no_grad"}
     from oracle import p2c_oracle as orc
     from point2cyl_b200 import synthetic
-    torch.set_num_threads(os.cpu_count() or 1)
     data = synthetic.s_cyl(CPU_SAMPLE_B, N_POINTS, K_INST, seed=1234)
     sd = orc.init_state_dict((3, 2 * K_INST), seed=0)
     starts = (torch.zeros(CPU_SAMPLE_B, dtype=torch.long), torch.zeros(CPU_SAMPLE_B, dtype=torch.long))
@@ -143,8 +179,23 @@ def cpu_baseline_sample():
             ts.append(time.perf_counter() - t0)
     sec = min(ts[1:])
     return {"value": CPU_SAMPLE_B / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST}, best of 2 after 1 warm-up, torch CPU no_grad, "
-                      "dense (B,N,N) axis fit as the reference"}
+            "sample": f"{CPU_SAMPLE_B} clouds x N={N_POINTS} K={K_INST}, best of 2 after 1 warm-up, oracle port (reference "
+                      "files absent), torch CPU no_grad, dense (B,N,N) axis fit as the reference"}
+
+
+def gpu_eager_reference(dev):
+    """The reference's own modules as eager torch-CUDA ops on this GPU at the headline batch (the only 'GPU path' the
+    reference has): forward+loss, no_grad, B=32.  Context for the speed-up, not the product."""
+    if not reference_available():
+        return None
+    try:
+        r = _quiet_reference_timing(B=B_PER_GPU, N=N_POINTS, K=K_INST, steps=3, warmup=1, device=str(dev))
+    except RuntimeError as e:
+        return {"value": None, "error": str(e)[:160]}
+    finally:
+        torch.cuda.empty_cache()
+    return {"value": r["clouds_per_s"], "unit": UNIT, "ms_per_step": r["sec_per_step"] * 1e3, "clouds_per_step": r["B"],
+            "what": f"unmodified reference ({r['root']}) on torch-CUDA eager ops, no_grad, wall clock incl. its host syncs"}
 
 
 # algorithmic work per launch for the roofline (SURVEY.md 8d formulas; B clouds)
@@ -469,9 +520,10 @@ def main():
             roof["tensor_frac_of_bf16_peak"] = tf / pk["bf16"]
     # ---- the training step of configs[3] on the same batch (all ranks: it contains the gradient all-reduce) ----
     train = train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps=10, warmup=3)
-    cpu = None
+    cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample()
+        eager = gpu_eager_reference(dev)
 
     if rank == 0:
         print(json.dumps({
@@ -482,7 +534,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host),
                     "d2h_bytes_per_step": 24 + (0 if graphed is not None else B_PER_GPU * K_INST * K_INST * 4 + B_PER_GPU * 4), "ms_per_step": total_ms_e2e / args.steps},
             "gpu_launches": launches, "launch_mode": "eager" if graphed is None else "cuda_graph", "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "stages": stages, "train_step": train}), flush=True)
+            "gpu_eager_reference": eager, "stages": stages, "train_step": train}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -101,15 +101,35 @@ def kernel_pass(sd, data, training, starts, mask, grads=False, K=None):
         pipeline.F.dropout = real
 
 
-def run_case(B, N, K, seed, training, starts, mask=None, grads=False, sd=None, want64=True) -> Dict[str, dict]:
+def kernel_choices(data, ktrace) -> Dict[str, torch.Tensor]:
+    """The discrete choices of a kernel forward (FPS / ball-query indices from its trace, 3-NN neighbours and weights
+    recomputed with the same kernel on the same centres) in the oracle's `forced` format."""
+    from point2cyl_b200 import ops
+    f = {"sa1.fps_idx": ktrace["sa1"]["fps_idx"].cpu(), "sa1.group_idx": ktrace["sa1"]["group_idx"].cpu(),
+         "sa2.fps_idx": ktrace["sa2"]["fps_idx"].cpu(), "sa2.group_idx": ktrace["sa2"]["group_idx"].cpu()}
+    xyz = data["pcs"].to(DEV)
+    for name, q, s in (("fp1", xyz, ktrace["l1_xyz"]), ("fp2", ktrace["l1_xyz"], ktrace["l2_xyz"])):
+        z = torch.zeros(q.shape[0] * s.shape[1], 4, device=DEV)
+        _, nidx, w = ops.three_nn_interp(q, s, z, want_idx=True)
+        f[name + ".nn_idx"] = nidx.cpu().reshape(q.shape[0], q.shape[1], 3)
+        f[name + ".nn_w"] = w.cpu().reshape(q.shape[0], q.shape[1], 3)
+    return f
+
+
+def run_case(B, N, K, seed, training, starts, mask=None, grads=False, sd=None, want64=True,
+             force_kernel_choices=False) -> Dict[str, dict]:
+    """force_kernel_choices: both oracle runs take the kernel's discrete choices (checked separately, bit for bit),
+    so exact distance ties - where the reference's unstable sort is implementation-defined - cannot leak into the
+    float comparison."""
     data = synthetic.s_cyl(B, N, K, seed)
     sd = sd if sd is not None else orc.init_state_dict((3, 2 * K), seed)
     kern = kernel_pass(sd, data, training, starts, mask, grads)
-    ref32 = oracle_pass(sd, data, training, starts, mask, None, grads)
+    forced = kernel_choices(data, kern[1]) if force_kernel_choices else None
+    ref32 = oracle_pass(sd, data, training, starts, mask, forced, grads)
     ref64 = None
     if want64:
         ref64 = oracle_pass(to64(sd), data, training, starts, mask, ref32[1], grads, dtype=torch.float64)
-    return dict(data=data, sd=sd, kern=kern, ref32=ref32, ref64=ref64)
+    return dict(data=data, sd=sd, kern=kern, ref32=ref32, ref64=ref64, forced=forced)
 
 
 def axis_err(a, b, mask) -> float:

@@ -89,26 +89,43 @@ def test_config2_full_batch_vs_oracle(training):
               torch.randint(0, 512, (B,), generator=torch.Generator().manual_seed(2)))
     mask = (torch.rand(B, 128, N, generator=torch.Generator().manual_seed(9)) > 0.5).float() * 2.0
     sd = orc.init_state_dict((3, 2 * K), 0)
-    case = adj.run_case(B, N, K, 1234, training, starts, mask, grads=False, sd=sd, want64=True)
+    case = adj.run_case(B, N, K, 1234, training, starts, mask, grads=False, sd=sd, want64=True,
+                        force_kernel_choices=True)
     ko, kt, net, _ = case["kern"]
-    r32, rt, _, _ = case["ref32"]
-    # discrete choices
-    assert torch.equal(kt["sa1"]["fps_idx"].cpu(), rt["sa1.fps_idx"])
-    assert torch.equal(kt["sa1"]["group_idx"].cpu(), rt["sa1.group_idx"])
-    assert torch.equal(kt["sa2"]["fps_idx"].cpu(), rt["sa2.fps_idx"])
-    assert torch.equal(kt["sa2"]["group_idx"].cpu(), rt["sa2.group_idx"])
-    xyz = case["data"]["pcs"].to(DEV)
-    for name, q, s in (("fp1", xyz, kt["l1_xyz"]), ("fp2", kt["l1_xyz"], kt["l2_xyz"])):
-        f = torch.zeros(q.shape[0] * s.shape[1], 4, device=DEV)
-        _, nidx, w = ops.three_nn_interp(q, s, f, want_idx=True)
-        assert torch.equal(nidx.cpu().reshape(rt[name + ".nn_idx"].shape), rt[name + ".nn_idx"]), name
-        assert torch.equal(w.cpu().reshape(rt[name + ".nn_w"].shape), rt[name + ".nn_w"]), name
+    r32 = case["ref32"][0]
+    # ---- discrete choices against the reference algorithm run on the same inputs, all 32 clouds ----
+    ch, pcs = case["forced"], case["data"]["pcs"]
+    f1 = orc.farthest_point_sample(pcs, 512, starts[0])
+    assert torch.equal(ch["sa1.fps_idx"], f1)
+    l1_xyz = orc.gather_points(pcs, f1)
+    assert torch.equal(kt["l1_xyz"].cpu(), l1_xyz)
+    assert torch.equal(ch["sa1.group_idx"], orc.query_ball_point(0.2, 64, pcs, l1_xyz))
+    f2 = orc.farthest_point_sample(l1_xyz, 128, starts[1])
+    assert torch.equal(ch["sa2.fps_idx"], f2)
+    l2_xyz = orc.gather_points(l1_xyz, f2)
+    assert torch.equal(ch["sa2.group_idx"], orc.query_ball_point(0.4, 64, l1_xyz, l2_xyz))
+    ties = {}
+    for name, q, s_ in (("fp1", pcs, l1_xyz), ("fp2", l1_xyz, l2_xyz)):
+        d, order = orc.square_distance(q, s_).sort(dim=-1)
+        diff = (order[:, :, :3] != ch[name + ".nn_idx"]).nonzero()
+        # The reference takes the first three entries of an UNSTABLE sort (pointnet_util.py:301-303): at exactly equal
+        # distances its pick is implementation-defined; the kernels (and the C oracle) take the lowest index.  Any
+        # difference must be such a tie, and the neighbour DISTANCES must still agree bit for bit.
+        for bb, n, j in diff.tolist():
+            mine = int(ch[name + ".nn_idx"][bb, n, j])
+            dm = float(orc.square_distance(q[bb:bb + 1, n:n + 1], s_[bb:bb + 1, mine:mine + 1]))
+            assert dm == float(d[bb, n, j]), (name, bb, n, j)
+        ties[name] = len(diff)
+        assert len(diff) <= 16, (name, len(diff))
+        w_ref = 1.0 / (d[:, :, :3] + 1e-8)
+        w_ref = w_ref / w_ref.sum(dim=2, keepdim=True)
+        assert torch.equal(ch[name + ".nn_w"], w_ref), name      # weights depend on the distances only: exact
     assert torch.equal(ko["matching_indices"].cpu(), r32["matching_indices"])
     assert torch.equal(ko["mask"].cpu(), r32["mask"])
     b = adj.bars(case)
     w = adj.worst(b)
     report(f"config2_full_batch[{'train' if training else 'eval'}]",
-           {"worst": w, "bars": {k: v for k, v in b.items() if not k.startswith("stat:")},
+           {"worst": w, "nn_ties_resolved_differently_by_torch_sort": ties, "bars": {k: v for k, v in b.items() if not k.startswith("stat:")},
             "worst_stat": adj.worst(b, "stat:")})
     # the bar north_star states, against the float32 oracle directly
     direct_bad = {k: v["e_direct"] for k, v in b.items() if v["e_direct"] > TOL}

@@ -127,7 +127,7 @@ def test_bn_decay_schedule_values():
 
 @pytest.mark.timeout(300)
 def test_reference_arm_under_torchrun_prints_one_line():
-    """`bench.py --impl reference` launched like the driver launches it for N=2: rank 0 alone times the CPU port and
+    """`bench.py --impl reference` launched like the driver launches it for N=2: rank 0 alone times the CPU reference and
     prints ONE JSON line with the contract's keys; the other rank exits 0 without work."""
     import json
     import socket
@@ -147,7 +147,11 @@ def test_reference_arm_under_torchrun_prints_one_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 0
     assert d["metric"].startswith("point-clouds/sec") and d["unit"] == "clouds/s" and d["higher_is_better"] is True
-    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
+    from baseline import make_ref
+    kind = "reference" if make_ref.root() else "port"      # the reference's own files when staged (baseline/_ref)
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == kind
+    assert abs(d["ms_per_step"] * 1e-3 * d["value"] - d["clouds_per_step"]) < 1e-6      # measured time of the sample
+    assert res.stdout.count("\n") == 1                     # nothing but the line on stdout (import-time prints)
     assert d["cpu_baseline"]["cores"] >= 1 and "clouds" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("forward+loss") and d["gpu_launches"] == 0
