@@ -110,10 +110,14 @@ int p2c_debug_set_timeline(void* buf);
  *   Y[b*N+n, j] = sum_k max(H[b*N+n,k]*scale[k]+shift[k], 0) * mask_cf[b,k,n] * W[j,k] + bias[j]
  * H: fc1's raw output (B*N, C) rows; scale/shift: folded bn1 (NULL = identity, no ReLU); mask_cf: the
  * (B, C, N) channel-first multiplicative dropout mask exactly as F.dropout(ones(B,C,N)) returns it, or NULL;
+ * dropout_seed (used when mask_cf is NULL): device pointer to two int64 words; the kernel then draws the p = 0.5
+ * mask itself - keep-bit of (point m, channel c) = one bit of Philox4x32-10(counter {m, c/128, seed[1]}, key seed[0]),
+ * kept values scaled by 2 - so no (B, C, N) mask tensor crosses HBM (F.dropout semantics, its own random stream);
+ * p2c_head_bwd regenerates the same bits from the same two words.  Both NULL = no dropout.
  * W: the heads' weights concatenated (Nout, C), Nout <= 36, C <= 256, C % 16 == 0. */
 int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
-                    const float* mask_cf, const float* W, const float* bias, float* Y, int64_t ldy,
-                    int B, int N, int C, int Nout, void* stream);
+                    const float* mask_cf, const int64_t* dropout_seed, const float* W, const float* bias, float* Y,
+                    int64_t ldy, int B, int N, int C, int Nout, void* stream);
 
 /* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
  * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
@@ -344,9 +348,9 @@ int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const int64_t* id
  * generic p2c_bn_bwd_* on fc1's raw output).  With A_out != NULL the kernel also writes the heads' input
  * A[m,k] = max(H[m,k]*scale[k]+shift[k], 0) * mask_cf[b,k,n] (H: fc1's raw output), so that the heads' dW/db come
  * from the tensor-core p2c_wgrad on a plain row matrix. */
-int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const float* W, int B, int N, int C, int Nout,
-                 float* dA, int64_t ldda, const float* H, int64_t ldh, const float* scale, const float* shift,
-                 float* A_out, int64_t lda, void* stream);
+int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const int64_t* dropout_seed, const float* W,
+                 int B, int N, int C, int Nout, float* dA, int64_t ldda, const float* H, int64_t ldh, const float* scale,
+                 const float* shift, float* A_out, int64_t lda, void* stream);
 
 /* torch.optim.Adam step (train_Point2Cyl_without_sketch.py:189, :368) over a flat fp32 parameter buffer:
  * g = grads*grad_scale (+ weight_decay*p), m/v updated in place, bias-corrected with `step` (1-based). */

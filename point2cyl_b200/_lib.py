@@ -37,7 +37,7 @@ SIGNATURES = {
     "p2c_cast_bf16": [c_f32p, i32, i32, vp, i64, vp],
     "p2c_linear_path": [i64, i32, i32, i32, i32, i32, i32, i32],
     "p2c_debug_set_timeline": [vp],
-    "p2c_head_masked": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, vp],
+    "p2c_head_masked": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_i64p, c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, vp],
     "p2c_bn_finalize": [c_f64p, i64, c_f32p, c_f32p, f32, f32, i32, c_f32p, c_f32p, c_f32p, c_f32p,
                         c_f32p, c_f32p, i32, vp],
     "p2c_bn_relu_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i64, i32, vp],
@@ -81,8 +81,8 @@ SIGNATURES = {
                          c_f32p, vp],
     "p2c_group_bwd": [c_f32p, i64, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, vp],
     "p2c_three_nn_interp_bwd": [c_f32p, i64, c_i64p, c_f32p, i32, i32, i32, i32, c_f32p, i64, vp],
-    "p2c_head_bwd": [c_f32p, i64, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p,
-                     i64, vp],
+    "p2c_head_bwd": [c_f32p, i64, c_f32p, c_i64p, c_f32p, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64, c_f32p, c_f32p,
+                     c_f32p, i64, vp],
     "p2c_adam_step": [c_f32p, c_f32p, c_f32p, c_f32p, i64, f32, f32, f32, f32, f32, i32, f32, vp],
 }
 

@@ -154,8 +154,58 @@ class SetAbstractionFn(torch.autograd.Function):
         params = list(ctx.sa.parameters())
         grads = {id(p): torch.zeros_like(p) for p in params}
         prec = pipeline._PRECISIONS[pipeline.get_precision()]
-        d_feats = bw._sa_backward(ctx.tape, d_out.contiguous(), lambda p: grads[id(p)], prec)
+        # the backward kernels work in place on the gradient buffer: never on the tensor autograd handed us (it may
+        # be shared with a sibling branch or be the user's `backward(gradient=...)` argument)
+        d_feats = bw._sa_backward(ctx.tape, d_out.clone(memory_format=torch.contiguous_format),
+                                  lambda p: grads[id(p)], prec)
         ctx.tape = None
+        return (None, None, d_feats, None) + tuple(grads[id(p)] for p in params)
+
+
+class SetAbstractionMsgFn(torch.autograd.Function):
+    """PointNetSetAbstractionMsg (models/pointnet_util.py:228-267) as an autograd node: one shared FPS, one ball query +
+    grouped MLP stack + max-pool per scale, outputs concatenated.  Differentiable w.r.t. the input features (rows)
+    and the module's parameters."""
+
+    @staticmethod
+    def forward(ctx, sa, xyz, feats, start, *params):
+        from . import pipeline
+        B, N, _ = xyz.shape
+        D = 0 if feats is None else feats.shape[1]
+        _, new_xyz = ops.fps(xyz, sa.npoint, start)
+        outs, scales = [], []
+        for i, radius in enumerate(sa.radius_list):
+            idx = ops.ball_query(radius, sa.nsample_list[i], xyz, new_xyz)
+            # the Msg variant concatenates [features, centred xyz] (:246-249): gather, then swap the two blocks
+            rows = ops.group(xyz, feats, new_xyz, idx, ldo=3 + D)
+            if D:
+                rows = torch.cat([rows[:, 3:], rows[:, :3]], dim=1).contiguous()
+            layers = []
+            outs.append(pipeline.mlp_stack(rows, 3 + D, sa.conv_blocks[i], sa.bn_blocks[i], sa.training,
+                                           pool_group=sa.nsample_list[i], tag=f"sa_msg{i}", tape=layers))
+            scales.append((idx, layers))
+        ctx.sa, ctx.scales, ctx.dims = sa, scales, (B, N, D)
+        ctx.mark_non_differentiable(new_xyz)
+        return new_xyz, torch.cat(outs, dim=1)
+
+    @staticmethod
+    def backward(ctx, _d_xyz, d_out):
+        from . import backward as bw
+        from . import pipeline
+        B, N, D = ctx.dims
+        params = list(ctx.sa.parameters())
+        grads = {id(p): torch.zeros_like(p) for p in params}
+        prec = pipeline._PRECISIONS[pipeline.get_precision()]
+        d_feats, c0 = None, 0
+        for idx, layers in ctx.scales:
+            C = layers[-1]["conv"].weight.shape[0]
+            d_rows = bw._stack_backward(layers, d_out[:, c0:c0 + C].contiguous(), lambda p: grads[id(p)], prec,
+                                        need_input_grad=D > 0)
+            c0 += C
+            if D:     # rows are [features | xyz]: p2c_group_bwd wants the features behind three xyz columns
+                d = ops.group_bwd(torch.cat([d_rows[:, D:D + 3], d_rows[:, :D]], dim=1).contiguous(), idx, B, N, D)
+                d_feats = d if d_feats is None else d_feats + d
+        ctx.scales = None
         return (None, None, d_feats, None) + tuple(grads[id(p)] for p in params)
 
 
@@ -178,7 +228,8 @@ class FeaturePropagationFn(torch.autograd.Function):
         params = list(ctx.fp.parameters())
         grads = {id(p): torch.zeros_like(p) for p in params}
         prec = pipeline._PRECISIONS[pipeline.get_precision()]
-        d_f1, d_f2 = bw._fp_backward(ctx.tape, d_out.contiguous(), lambda p: grads[id(p)], prec)
+        d_f1, d_f2 = bw._fp_backward(ctx.tape, d_out.clone(memory_format=torch.contiguous_format),   # (see above)
+                                     lambda p: grads[id(p)], prec)
         ctx.tape = None
         return (None, None, None, d_f1, d_f2) + tuple(grads[id(p)] for p in params)
 

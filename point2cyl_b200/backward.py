@@ -126,7 +126,8 @@ def backbone_backward(tape: Dict, d_out: Tensor, grad_of: GradOf, precision: Opt
     # aligned - the Trainer allocates them padded; a contiguous autograd gradient is copied into a padded buffer)
     Wcat = head["Wcat"]
     aff_h = head["aff_h"]
-    dA, A_h = ops.head_bwd(d_rows, head["mask_cf"], Wcat, B, N, head["h"], aff_h.scale, aff_h.shift)
+    dA, A_h = ops.head_bwd(d_rows, head["mask_cf"], Wcat, B, N, head["h"], aff_h.scale, aff_h.shift,
+                           seed=head.get("seed"))
     if d_rows.stride(0) % 4:
         padded = torch.zeros(B * N, ops.pad4(d_rows.shape[1]), dtype=torch.float32, device=d_rows.device)
         padded[:, :d_rows.shape[1]].copy_(d_rows)

@@ -400,7 +400,7 @@ broadcast_bwd_kernel(const float* __restrict__ dI, int64_t ldi, int N, int D, fl
 template <int NP>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const float* __restrict__ dOut, int64_t ldo, const float* __restrict__ mask_cf,
-                const float* __restrict__ W, int64_t M, int N, int C, int Nout, float* __restrict__ dA,
+                const int64_t* __restrict__ seed, const float* __restrict__ W, int64_t M, int N, int C, int Nout, float* __restrict__ dA,
                 int64_t ldda, const float* __restrict__ H, int64_t ldh, const float* __restrict__ scale,
                 const float* __restrict__ shift, float* __restrict__ A_out, int64_t lda) {
   extern __shared__ __align__(16) float s_w[];   // [C][NP]  (W transposed), then scale[C], shift[C]
@@ -424,15 +424,17 @@ head_bwd_kernel(const float* __restrict__ dOut, int64_t ldo, const float* __rest
   for (int j = 0; j < NP; ++j) g[j] = j < Nout ? __ldg(dOut + m * ldo + j) : 0.f;
   const float* mk = mask_cf ? mask_cf + (size_t)b * C * N + n : nullptr;
   float* out = dA + m * ldda;
+  P2CPhilox4 bits;
   for (int k0 = 0; k0 < C; k0 += 4) {
     float v[4], mq[4];
+    if (seed && !mk && (k0 & 127) == 0) bits = p2c_dropout_bits(seed, m, k0 >> 7);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float* wr = s_w + (k0 + i) * NP;
       float t = 0.f;
 #pragma unroll
       for (int j = 0; j < NP; ++j) t = fmaf(g[j], wr[j], t);
-      mq[i] = mk ? __ldg(mk + (size_t)(k0 + i) * N) : 1.f;
+      mq[i] = mk ? __ldg(mk + (size_t)(k0 + i) * N) : (seed ? p2c_dropout_scale(bits, k0 + i) : 1.f);
       v[i] = t * mq[i];
     }
     *reinterpret_cast<float4*>(out + k0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -625,7 +627,8 @@ extern "C" int p2c_three_nn_interp_bwd(const float* dInterp, int64_t ldi, const 
   return 0;
 }
 
-extern "C" int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const float* W, int B, int N, int C,
+extern "C" int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const int64_t* dropout_seed,
+                            const float* W, int B, int N, int C,
                             int Nout, float* dA, int64_t ldda, const float* H, int64_t ldh, const float* scale,
                             const float* shift, float* A_out, int64_t lda, void* stream) {
   if (!dOut || !W || !dA || B <= 0 || N <= 0 || C <= 0 || Nout <= 0 || ldo < Nout || ldda < C) return P2C_EINVAL;
@@ -640,8 +643,8 @@ extern "C" int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf
 #define P2C_HB(NPV)                                                                                              \
   do {                                                                                                           \
     const size_t smem = ((size_t)C * NPV + 2 * C) * sizeof(float);                                               \
-    head_bwd_kernel<NPV><<<p2c_ceil_div(M, 256), 256, smem, st>>>(dOut, ldo, mask_cf, W, M, N, C, Nout, dA, ldda, H, \
-                                                                  ldh, scale, shift, A_out, lda);                \
+    head_bwd_kernel<NPV><<<p2c_ceil_div(M, 256), 256, smem, st>>>(dOut, ldo, mask_cf, dropout_seed, W, M, N, C, Nout,  \
+                                                                  dA, ldda, H, ldh, scale, shift, A_out, lda);     \
   } while (0)
   if (Nout <= 4) P2C_HB(4); else if (Nout <= 8) P2C_HB(8); else if (Nout <= 12) P2C_HB(12);
   else if (Nout <= 20) P2C_HB(20); else if (Nout <= 28) P2C_HB(28); else P2C_HB(36);

@@ -48,3 +48,30 @@ __device__ __forceinline__ float p2c_sqdist_expanded(float ax, float ay, float a
   float dot = __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
   return __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), na), nb);
 }
+
+// Philox4x32-10 (Salmon et al., SC'11): 128 random bits from a 128-bit counter and a 64-bit key.  Used for the
+// in-kernel dropout mask of the output heads: keep-bit of channel c of point m = bit (c & 31) of word (c >> 5) & 3 of
+// philox(counter = {m, c >> 7, seed[1]}, key = seed[0]) - forward and backward regenerate the same bits from the
+// two 64-bit seed words instead of reading a (B, C, N) float mask from HBM.
+struct P2CPhilox4 { uint32_t v[4]; };
+__device__ __forceinline__ P2CPhilox4 p2c_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  P2CPhilox4 o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+// keep-bits of channels [128*blk, 128*blk + 128) of point m (p = 0.5: one bit per element, kept values scale by 2)
+__device__ __forceinline__ P2CPhilox4 p2c_dropout_bits(const int64_t* seed, int64_t m, int blk) {
+  const uint64_t s0 = (uint64_t)seed[0], s1 = (uint64_t)seed[1];
+  return p2c_philox4x32_10((uint32_t)m, (uint32_t)((uint64_t)m >> 32) ^ ((uint32_t)blk << 24), (uint32_t)s1,
+                           (uint32_t)(s1 >> 32), (uint32_t)s0, (uint32_t)(s0 >> 32));
+}
+__device__ __forceinline__ float p2c_dropout_scale(const P2CPhilox4& b, int c) {
+  return ((b.v[(c >> 5) & 3] >> (c & 31)) & 1u) ? 2.0f : 0.0f;
+}

@@ -17,8 +17,8 @@ constexpr int KC = 16;           // channels per software-pipeline step (64 B = 
 template <int NP>   // NP = Nout padded to a multiple of 4
 __global__ void __launch_bounds__(HEAD_ROWS)
 head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ scale, const float* __restrict__ shift,
-            const float* __restrict__ mask_cf, const float* __restrict__ W, const float* __restrict__ bias,
-            float* __restrict__ Y, int64_t ldy, int64_t M, int N, int C, int Nout) {
+            const float* __restrict__ mask_cf, const int64_t* __restrict__ seed, const float* __restrict__ W,
+            const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy, int64_t M, int N, int C, int Nout) {
   extern __shared__ __align__(16) float sm[];
   float* s_wt = sm;                           // [C][NP]   (W transposed, zero padded)
   float* s_sc = s_wt + C * NP;                // [C]
@@ -53,11 +53,18 @@ head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ 
   // FMAs of step c
   float4 hq[KC / 4];
   float mq[KC];
+  P2CPhilox4 bits;                            // in-kernel dropout: 128 keep-bits of this point per Philox call
   auto load_step = [&](int k0) {
 #pragma unroll
     for (int v = 0; v < KC / 4; ++v) hq[v] = __ldg(reinterpret_cast<const float4*>(hrow + k0) + v);
+    if (seed && !mk) {
+      if ((k0 & 127) == 0) bits = p2c_dropout_bits(seed, mm, k0 >> 7);
 #pragma unroll
-    for (int i = 0; i < KC; ++i) mq[i] = mk ? __ldg(mk + (size_t)(k0 + i) * N) : 1.f;
+      for (int i = 0; i < KC; ++i) mq[i] = p2c_dropout_scale(bits, k0 + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < KC; ++i) mq[i] = mk ? __ldg(mk + (size_t)(k0 + i) * N) : 1.f;
+    }
   };
   load_step(0);
   for (int k0 = 0; k0 < C; k0 += KC) {
@@ -102,12 +109,12 @@ head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ 
 
 template <int NP>
 int launch_head(const float* H, int64_t ldh, const float* scale, const float* shift, const float* mask_cf,
-                const float* W, const float* bias, float* Y, int64_t ldy, int64_t M, int N, int C, int Nout,
-                cudaStream_t st) {
+                const int64_t* seed, const float* W, const float* bias, float* Y, int64_t ldy, int64_t M, int N, int C,
+                int Nout, cudaStream_t st) {
   const size_t smem = ((size_t)C * NP + 2 * C + (size_t)HEAD_ROWS * Nout) * sizeof(float);
   auto k = head_kernel<NP>;
   if (smem > 48 * 1024) P2C_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<p2c_ceil_div(M, HEAD_ROWS), HEAD_ROWS, smem, st>>>(H, ldh, scale, shift, mask_cf, W, bias, Y, ldy, M, N, C, Nout);
+  k<<<p2c_ceil_div(M, HEAD_ROWS), HEAD_ROWS, smem, st>>>(H, ldh, scale, shift, mask_cf, seed, W, bias, Y, ldy, M, N, C, Nout);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }
@@ -115,15 +122,15 @@ int launch_head(const float* H, int64_t ldh, const float* scale, const float* sh
 }  // namespace
 
 extern "C" int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
-                               const float* mask_cf, const float* W, const float* bias, float* Y, int64_t ldy,
-                               int B, int N, int C, int Nout, void* stream) {
+                               const float* mask_cf, const int64_t* dropout_seed, const float* W, const float* bias,
+                               float* Y, int64_t ldy, int B, int N, int C, int Nout, void* stream) {
   if (!H || !W || !Y || B <= 0 || N <= 0 || C <= 0 || Nout <= 0 || ldh < C || ldy < Nout) return P2C_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return P2C_EINVAL;
   if (C % 16 != 0 || (ldh % 4) != 0 || (reinterpret_cast<uintptr_t>(H) & 15) != 0) return P2C_EALIGN;
   if (C > 256 || Nout > 36) return P2C_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = (int64_t)B * N;
-#define P2C_HEAD(NPV) return launch_head<NPV>(H, ldh, scale, shift, mask_cf, W, bias, Y, ldy, M, N, C, Nout, st)
+#define P2C_HEAD(NPV) return launch_head<NPV>(H, ldh, scale, shift, mask_cf, dropout_seed, W, bias, Y, ldy, M, N, C, Nout, st)
   if (Nout <= 4) P2C_HEAD(4);
   if (Nout <= 8) P2C_HEAD(8);
   if (Nout <= 12) P2C_HEAD(12);

@@ -123,6 +123,10 @@ class PointNetSetAbstractionMsg(nn.Module):
         feats = _to_rows(points)
         D = 0 if feats is None else feats.shape[1]
         start = pipeline.draw_fps_start(B, N, xyz.device)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or (feats is not None and feats.requires_grad)):
+            new_xyz, out = autograd.SetAbstractionMsgFn.apply(self, xyz_pm, feats, start, *list(self.parameters()))
+            return new_xyz.permute(0, 2, 1), _to_cf(out, B)
         _, new_xyz = ops.fps(xyz_pm, self.npoint, start)
         outs = []
         for i, radius in enumerate(self.radius_list):

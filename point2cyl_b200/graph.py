@@ -23,29 +23,73 @@ import torch
 from . import BATCH_KEYS, _lib, pipeline
 
 
+class StartRing:
+    """First-centroid draws of the two FPS levels (models/pointnet_util.py:75: CPU generator, then moved) for graph
+    replay.  The host may run several replays ahead of the GPU, so the pinned staging buffers form a ring and each slot
+    is rewritten only after the async copy that last read it has completed (an event per slot)."""
+
+    def __init__(self, B: int, ranges, device, depth: int = 4):
+        self.B, self.ranges = B, tuple(ranges)
+        self.host = [[torch.zeros(B, dtype=torch.long).pin_memory() for _ in self.ranges] for _ in range(depth)]
+        self.done = [None] * depth
+        self.dev = [torch.zeros(B, dtype=torch.long, device=device) for _ in self.ranges]
+        self.i = 0
+
+    def draw(self):
+        """same calls, same order as the reference: sa1 draws from [0,N), then sa2 from [0,npoint1)"""
+        slot = self.i % len(self.host)
+        self.i += 1
+        if self.done[slot] is not None:
+            self.done[slot].synchronize()
+        for h, d, hi in zip(self.host[slot], self.dev, self.ranges):
+            h.copy_(torch.randint(0, hi, (self.B,), dtype=torch.long))
+            d.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.done[slot] = ev
+
+
+def bn_state_key(net):
+    return (net.training,) + tuple(m.momentum for m in net.modules()
+                                   if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+
+
 class GraphedForwardLoss:
+    """auto_rebuild: when the train/eval mode or a BatchNorm momentum changed since capture (the training scripts call
+    update_momentum, train_Point2Cyl_without_sketch.py:357-366) the graphs are re-captured on the next call instead
+    of raising; `rebuild_if_stale()` does the same explicitly."""
+
     def __init__(self, net, example: Dict[str, torch.Tensor], weights=(1.0,) * 5, norm_eig: bool = False,
-                 precision: Optional[str] = None, warmup: int = 2):
+                 precision: Optional[str] = None, warmup: int = 2, auto_rebuild: bool = True):
         self.net = net
         dev = next(net.parameters()).device
         self.device = dev
         self.static = {k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS}
         B, N, _ = self.static["pcs"].shape
         self.B, self.N, self.S1 = B, N, net.sa1.npoint
-        self.start_host = [torch.zeros(B, dtype=torch.long).pin_memory() for _ in range(2)]
-        self.start_dev = [torch.zeros(B, dtype=torch.long, device=dev) for _ in range(2)]
-        self._key = self._state_key()
+        self.starts = StartRing(B, (N, self.S1), dev)
+        self.start_dev = self.starts.dev
         self.weights, self.norm_eig, self.precision = weights, norm_eig, precision
+        self.auto_rebuild = auto_rebuild
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = torch.cuda.Event()
+        self.captures = 0
+        self._capture(warmup)
+
+    def _capture(self, warmup: int):
+        dev = self.device
+        self._key = self._state_key()
+        # eager warm-up outside the capture (one-time lazy init, allocator growth).  Train-mode passes update the
+        # BatchNorm running statistics: they are restored afterwards, so building the graph is not a training step.
+        buffers = {k: v.clone() for k, v in self.net.named_buffers()}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(warmup):                       # one-time lazy init (func attributes, allocator) outside capture
+            for _ in range(warmup):
                 self._draw_starts()
                 self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.copied = torch.cuda.Event()
         self.graph = torch.cuda.CUDAGraph()            # backbone
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.X_raw, self.W_raw = pipeline.backbone_forward(self.net, self.static["pcs"], self.start_dev,
@@ -56,21 +100,28 @@ class GraphedForwardLoss:
                                              self.static["inst"], self.static["bb"], self.static["axes"],
                                              self.static["centers"], self.weights, self.norm_eig)
             self.out.update(X_raw=self.X_raw, W_raw=self.W_raw)
+        with torch.no_grad():
+            for k, v in self.net.named_buffers():
+                v.copy_(buffers[k])
+        self.captures += 1
+
+    def rebuild_if_stale(self) -> bool:
+        """Re-capture when mode / BatchNorm momentum changed since the last capture.  Returns True if it did."""
+        if not self.stale():
+            return False
+        torch.cuda.synchronize(self.device)
+        self._capture(warmup=1)
+        return True
 
     def _state_key(self):
-        return (self.net.training,) + tuple(m.momentum for m in self.net.modules()
-                                            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+        return bn_state_key(self.net)
 
     def _run(self):
         return pipeline.forward_loss(self.net, self.static, fps_start=self.start_dev, weights=self.weights,
                                      norm_eig=self.norm_eig, precision=self.precision)
 
     def _draw_starts(self):
-        # same calls, same order as the reference: sa1 draws from [0,N), then sa2 from [0,npoint1)
-        self.start_host[0].copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
-        self.start_host[1].copy_(torch.randint(0, self.S1, (self.B,), dtype=torch.long))
-        for h, d in zip(self.start_host, self.start_dev):
-            d.copy_(h, non_blocking=True)
+        self.starts.draw()
 
     def stale(self) -> bool:
         return self._key != self._state_key()
@@ -78,7 +129,10 @@ class GraphedForwardLoss:
     def __call__(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """batch: host (pinned) or device tensors copied into the graph's static inputs; None = reuse them."""
         if self.stale():
-            raise RuntimeError("GraphedForwardLoss: mode or BatchNorm momentum changed since capture; build a new one")
+            if not self.auto_rebuild:
+                raise RuntimeError("GraphedForwardLoss: mode or BatchNorm momentum changed since capture; call "
+                                   "rebuild_if_stale()")
+            self.rebuild_if_stale()
         cur = torch.cuda.current_stream(self.device)
         if batch is not None:
             for k in BATCH_KEYS:                                           # copy_ would silently broadcast a short batch

@@ -140,9 +140,17 @@ def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None
     return Y
 
 
+def _seed(seed: Optional[Tensor]) -> Optional[Tensor]:
+    if seed is not None and (seed.dtype != torch.long or seed.numel() != 2 or not seed.is_cuda
+                             or not seed.is_contiguous()):
+        raise _lib.P2CError("dropout seed: a contiguous CUDA int64 tensor of two words expected")
+    return seed
+
+
 def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mask_cf: Optional[Tensor],
-                W: Tensor, bias: Optional[Tensor], B: int, N: int) -> Tensor:
-    """Output heads: (B*N, C) raw fc1 rows -> (B*N, Nout); mask_cf is the (B, C, N) dropout mask."""
+                W: Tensor, bias: Optional[Tensor], B: int, N: int, seed: Optional[Tensor] = None) -> Tensor:
+    """Output heads: (B*N, C) raw fc1 rows -> (B*N, Nout); mask_cf is the (B, C, N) dropout mask, or - with
+    mask_cf None - `seed` (two int64 words on the device) makes the kernel draw the p=0.5 mask itself (Philox)."""
     H = _rows(H)
     C_ = H.shape[1]
     W2 = W.reshape(W.shape[0], -1).contiguous()
@@ -150,7 +158,7 @@ def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mas
     if mask_cf is not None and (tuple(mask_cf.shape) != (B, C_, N) or not mask_cf.is_contiguous()):
         raise _lib.P2CError(f"head_masked: mask must be contiguous (B,C,N)=({B},{C_},{N}), got {tuple(mask_cf.shape)}")
     Y = torch.empty(B * N, Nout, dtype=torch.float32, device=H.device)
-    call("p2c_head_masked", ptr(H), H.stride(0), ptr(scale), ptr(shift), ptr(mask_cf), ptr(W2), ptr(bias), ptr(Y),
+    call("p2c_head_masked", ptr(H), H.stride(0), ptr(scale), ptr(shift), ptr(mask_cf), ptr(_seed(seed)), ptr(W2), ptr(bias), ptr(Y),
          Nout, B, N, C_, Nout, stream_ptr())
     return Y
 
@@ -658,7 +666,7 @@ def three_nn_interp_bwd(dInterp: Tensor, idx: Optional[Tensor], w: Optional[Tens
 
 
 def head_bwd(dOut: Tensor, mask_cf: Optional[Tensor], W: Tensor, B: int, N: int, H: Optional[Tensor] = None,
-             scale: Optional[Tensor] = None, shift: Optional[Tensor] = None):
+             scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, seed: Optional[Tensor] = None):
     """-> dA (B*N, C) [, A (B*N, C) = relu(bn(H)) * mask when H is given: the heads' input for their wgrad]."""
     dOut = _rows(dOut)
     W2 = W.reshape(W.shape[0], -1).contiguous()
@@ -668,7 +676,7 @@ def head_bwd(dOut: Tensor, mask_cf: Optional[Tensor], W: Tensor, B: int, N: int,
     if H is not None:
         H = _rows(H)
         A = torch.empty(B * N, C_, dtype=torch.float32, device=dOut.device)
-    call("p2c_head_bwd", ptr(dOut), dOut.stride(0), ptr(mask_cf), ptr(W2), B, N, C_, Nout, ptr(dA), dA.stride(0),
+    call("p2c_head_bwd", ptr(dOut), dOut.stride(0), ptr(mask_cf), ptr(_seed(seed)), ptr(W2), B, N, C_, Nout, ptr(dA), dA.stride(0),
          ptr(H), 0 if H is None else H.stride(0), ptr(scale), ptr(shift), ptr(A), 0 if A is None else A.stride(0),
          stream_ptr())
     return dA if H is None else (dA, A)

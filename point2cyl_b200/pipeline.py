@@ -35,6 +35,23 @@ def get_precision() -> str:
     return _default_precision
 
 
+# Dropout of the head (models/pointnet_extrusion.py:60, F.dropout(p=0.5), always on).  Default: the head kernels draw
+# the mask themselves (Philox4x32-10 keyed by two int64 words from torch's CUDA generator - torch.manual_seed controls
+# it, CUDA-graph replays get fresh words), so no (B,128,N) mask tensor is written or read.  `dropout_mask_fn`, when
+# set, is called like F.dropout(ones(B,128,N), p=0.5) and must return the multiplicative mask: tests inject fixed
+# masks through it, and `dropout_mask_fn = torch_dropout_mask` reproduces the reference's own mask stream for a
+# shared seed (same torch op on the same shape) at the cost of 268 MB of traffic per step at B=32 x N=8192.
+dropout_mask_fn = None
+
+
+def torch_dropout_mask(ones: Tensor, p: float = 0.5) -> Tensor:
+    return F.dropout(ones, p=p)
+
+
+def draw_dropout_seed(device) -> Tensor:
+    return torch.randint(-2 ** 62, 2 ** 62, (2,), dtype=torch.long, device=device)
+
+
 def _bn_momentum(bn) -> float:
     if bn.momentum is None:  # cumulative moving average
         return 1.0 / float(int(bn.num_batches_tracked) + 1)
@@ -218,22 +235,25 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     head_layers = [] if tape is not None else None
     h, aff_h = mlp_stack(y6, y6.shape[1], [net.fc1], [net.bn1], net.training, in_affine=aff6,
                          precision=precision, tag="fc1", tape=head_layers)
-    # Same torch op on the same (B,128,N) shape as the reference so a shared seed gives the same mask; the head
-    # kernel consumes it in that channel-first layout (no transpose copy).
-    mask_cf = F.dropout(torch.ones(B, h.shape[1], N, dtype=torch.float32, device=dev), p=0.5)
-    if tuple(mask_cf.shape) != (B, h.shape[1], N):
-        raise _lib.P2CError("dropout mask must keep the (B,128,N) shape")
-    mask_cf = mask_cf.contiguous()
+    mask_cf = seed = None
+    if dropout_mask_fn is not None:
+        # explicit mask in the reference's own (B,128,N) channel-first layout (consumed without a transpose copy)
+        mask_cf = dropout_mask_fn(torch.ones(B, h.shape[1], N, dtype=torch.float32, device=dev), p=0.5)
+        if tuple(mask_cf.shape) != (B, h.shape[1], N):
+            raise _lib.P2CError("dropout mask must keep the (B,128,N) shape")
+        mask_cf = mask_cf.contiguous()
+    else:
+        seed = draw_dropout_seed(dev)
     Wcat = torch.cat([fc.weight.reshape(fc.weight.shape[0], -1) for fc in net.fc2], dim=0)
     bcat = torch.cat([fc.bias for fc in net.fc2], dim=0)
     _lib.set_tag("fc2")
-    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N)
+    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N, seed=seed)
     if trace is not None:
         trace.update(sa1=t1, sa2=t2, l1_xyz=l1_xyz, l1=l1, l2_xyz=l2_xyz, l2=l2, l3=l3, l4=l4, l5=l5,
                      y6=y6, aff6=aff6, h=h, aff_h=aff_h)
     if tape is not None:
         tape.update(B=B, N=N, sa1=r_sa1, sa2=r_sa2, sa3=r_sa3, fp3=r_fp3, fp2=r_fp2, fp1=r_fp1,
-                    head=dict(layers=head_layers, h=h, aff_h=aff_h, mask_cf=mask_cf, Wcat=Wcat, fc2=list(net.fc2)),
+                    head=dict(layers=head_layers, h=h, aff_h=aff_h, mask_cf=mask_cf, seed=seed, Wcat=Wcat, fc2=list(net.fc2)),
                     out=out, feats0=feats0)
     results, c0 = [], 0
     out3 = out.reshape(B, N, out.shape[1])

@@ -107,19 +107,30 @@ class GraphedTrainer(Trainer):
 
     Re-capture (build a new object) when the batch shape, train/eval mode or the BatchNorm momentum changes."""
 
-    def __init__(self, net, example: Dict[str, Tensor], warmup: int = 2, **kw):
+    def __init__(self, net, example: Dict[str, Tensor], warmup: int = 2, auto_rebuild: bool = True, **kw):
         super().__init__(net, **kw)
         from . import BATCH_KEYS
+        from .graph import StartRing
         dev = self.flat_param.device
         self.keys = BATCH_KEYS
         self.static = {k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS}
         B, N, _ = self.static["pcs"].shape
         self.B, self.N, self.S1 = B, N, net.sa1.npoint
-        self.start_host = [torch.zeros(B, dtype=torch.long).pin_memory() for _ in range(2)]
-        self.start_dev = [torch.zeros(B, dtype=torch.long, device=dev) for _ in range(2)]
+        self.starts = StartRing(B, (N, self.S1), dev)
+        self.start_dev = self.starts.dev
+        self.auto_rebuild = auto_rebuild
+        # two graphs, like graph.GraphedForwardLoss: the backbone forward needs only the coordinates, so the labels /
+        # normals of a host batch are copied on a side stream while it runs
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = torch.cuda.Event()
+        self.captures = 0
+        self._capture(warmup)
+
+    def _capture(self, warmup: int):
+        net, dev = self.net, self.flat_param.device
         self._key = self._state_key()
         # eager warm-up outside the capture (one-time cudaFuncSetAttribute calls, allocator growth); BatchNorm buffers
-        # are restored afterwards so that building the graph does not count as training steps
+        # and gradients are restored afterwards so that building the graph does not count as training steps
         buffers = {k: v.clone() for k, v in net.named_buffers()}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -129,10 +140,7 @@ class GraphedTrainer(Trainer):
                 Trainer.forward_backward(self, self.static, self.start_dev)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        # two graphs, like graph.GraphedForwardLoss: the backbone forward needs only the coordinates, so the labels /
-        # normals of a host batch are copied on a side stream while it runs
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.copied = torch.cuda.Event()
+        self._tape = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             tape, X_raw, W_raw = Trainer._forward(self, self.static["pcs"], self.start_dev)
@@ -143,21 +151,31 @@ class GraphedTrainer(Trainer):
         with torch.no_grad():
             for k, v in net.named_buffers():
                 v.copy_(buffers[k])
+        self.captures += 1
 
     def _state_key(self):
-        return (self.net.training,) + tuple(m.momentum for m in self.net.modules()
-                                            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+        from .graph import bn_state_key
+        return bn_state_key(self.net)
+
+    def rebuild_if_stale(self) -> bool:
+        """Re-capture when mode / BatchNorm momentum changed since the last capture (update_momentum in the training
+        scripts, train_Point2Cyl_without_sketch.py:357-366).  Returns True if it did."""
+        if self._key == self._state_key():
+            return False
+        torch.cuda.synchronize(self.flat_param.device)
+        self._capture(warmup=1)
+        return True
 
     def _draw_starts(self):
-        self.start_host[0].copy_(torch.randint(0, self.N, (self.B,), dtype=torch.long))
-        self.start_host[1].copy_(torch.randint(0, self.S1, (self.B,), dtype=torch.long))
-        for h, d in zip(self.start_host, self.start_dev):
-            d.copy_(h, non_blocking=True)
+        self.starts.draw()
 
     @torch.no_grad()
     def forward_backward(self, batch: Optional[Dict[str, Tensor]] = None, fps_start=None) -> Dict[str, Tensor]:
         if self._key != self._state_key():
-            raise RuntimeError("GraphedTrainer: mode or BatchNorm momentum changed since capture; build a new one")
+            if not self.auto_rebuild:
+                raise RuntimeError("GraphedTrainer: mode or BatchNorm momentum changed since capture; call "
+                                   "rebuild_if_stale()")
+            self.rebuild_if_stale()
         cur = torch.cuda.current_stream(self.flat_param.device)
         copying = batch is not None and batch["pcs"] is not self.static["pcs"]
         if copying:

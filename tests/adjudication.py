@@ -78,9 +78,9 @@ def kernel_pass(sd, data, training, starts, mask, grads=False, K=None):
     net = net.to(DEV).train(training)
     dev = {k: v.to(DEV) for k, v in data.items()}
     dstarts = [s.to(DEV) for s in starts]
-    real = pipeline.F.dropout
+    real = pipeline.dropout_mask_fn
     mdev = None if mask is None else mask.to(DEV)
-    pipeline.F.dropout = (lambda x, p=0.5, **kw: x) if mask is None else (lambda x, p=0.5, **kw: mdev)
+    pipeline.dropout_mask_fn = (lambda x, p=0.5, **kw: x) if mask is None else (lambda x, p=0.5, **kw: mdev)
     try:
         trace = {}
         if grads:
@@ -98,7 +98,7 @@ def kernel_pass(sd, data, training, starts, mask, grads=False, K=None):
             out.update(X_raw=X_raw, W_raw=W_raw)
         return out, trace, net, None
     finally:
-        pipeline.F.dropout = real
+        pipeline.dropout_mask_fn = real
 
 
 def kernel_choices(data, ktrace) -> Dict[str, torch.Tensor]:

@@ -160,7 +160,7 @@ def _train_setup(g, monkeypatch, training=True):
     net = net.to(DEV).train(training)
     mask = (torch.rand(B, 128, N, generator=torch.Generator().manual_seed(seed + 3)) > 0.5).float() * 2.0
     mask = mask.to(DEV)
-    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: mask)
+    monkeypatch.setattr(pipeline, "dropout_mask_fn", lambda x, p=0.5, **kw: mask)
     starts = (torch.from_numpy(g["s1"]).to(DEV), torch.from_numpy(g["s2"]).to(DEV))
     return net, data, starts, K
 
@@ -369,7 +369,7 @@ def test_graphed_trainer_matches_eager(monkeypatch):
     B, N, K = 4, 2048, 4
     data = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, seed=2).items()}
     mask = ((torch.rand(B, 128, N, generator=torch.Generator().manual_seed(1)) > 0.5).float() * 2.0).to(DEV)
-    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: mask)
+    monkeypatch.setattr(pipeline, "dropout_mask_fn", lambda x, p=0.5, **kw: mask)
     starts = (torch.arange(B, device=DEV), torch.arange(B, device=DEV) + 3)
     nets = []
     for _ in range(2):

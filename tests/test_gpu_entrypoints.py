@@ -1,0 +1,313 @@
+"""GPU tests of entry points that had none and of this round's host-side changes:
+index_points / p2c_gather_rows, PointNetSetAbstractionMsg (forward and autograd), the loss block at the stress
+configuration's K = 16, the in-kernel Philox dropout mask, graph re-capture after update_momentum."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import p2c_oracle as orc
+from point2cyl_b200 import ops, pipeline, synthetic
+from point2cyl_b200.dropin.models import pointnet_util as dpu
+from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).detach().cpu().double().reshape(-1)
+    b = torch.as_tensor(b).detach().cpu().double().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ---- a3: index_points (models/pointnet_util.py:43-60) ------------------------------------------------------------
+
+@pytest.mark.parametrize("B,N,C,shape", [(3, 700, 3, (40,)), (2, 1024, 16, (50, 8)), (2, 333, 131, (7, 5)),
+                                         (1, 64, 1, (64,)), (4, 8192, 3, (512, 64))])
+def test_index_points_matches_reference_gather(B, N, C, shape):
+    g = torch.Generator().manual_seed(N + C)
+    pts = torch.randn(B, N, C, generator=g)
+    idx = torch.randint(0, N, (B,) + shape, generator=g)
+    idx[0].reshape(-1)[:2] = torch.tensor([0, N - 1])            # both ends of the range
+    ref = orc.gather_points(pts, idx)
+    got = dpu.index_points(pts.to(DEV), idx.to(DEV))
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+    got2 = ops.gather_rows(pts.to(DEV), idx.to(DEV))
+    assert torch.equal(got2.cpu(), ref)
+
+
+def test_index_points_strided_input():
+    """a channel slice of a wider buffer and a permuted (B,C,N)->(B,N,C) view are valid `points` arguments"""
+    g = torch.Generator().manual_seed(3)
+    wide = torch.randn(2, 500, 24, generator=g)
+    idx = torch.randint(0, 500, (2, 33, 4), generator=g)
+    got = dpu.index_points(wide.to(DEV)[:, :, 4:20], idx.to(DEV))
+    assert torch.equal(got.cpu(), orc.gather_points(wide[:, :, 4:20].contiguous(), idx))
+    cf = torch.randn(2, 10, 500, generator=g)
+    got = dpu.index_points(cf.to(DEV).permute(0, 2, 1), idx.to(DEV))
+    assert torch.equal(got.cpu(), orc.gather_points(cf.permute(0, 2, 1).contiguous(), idx))
+
+
+# ---- PointNetSetAbstractionMsg (models/pointnet_util.py:210-267) --------------------------------------------------
+
+def msg_reference(mod_cpu, xyz_cf, points_cf, start):
+    """The reference forward (:229-267) restated on torch CPU with the oracle's point operators."""
+    xyz = xyz_cf.permute(0, 2, 1)
+    points = points_cf.permute(0, 2, 1) if points_cf is not None else None
+    B, N, C = xyz.shape
+    S = mod_cpu.npoint
+    new_xyz = orc.gather_points(xyz, orc.farthest_point_sample(xyz, S, start))
+    outs = []
+    for i, radius in enumerate(mod_cpu.radius_list):
+        gidx = orc.query_ball_point(radius, mod_cpu.nsample_list[i], xyz, new_xyz)
+        gx = orc.gather_points(xyz, gidx) - new_xyz.view(B, S, 1, C)
+        gp = torch.cat([orc.gather_points(points, gidx), gx], dim=-1) if points is not None else gx
+        h = gp.permute(0, 3, 2, 1)
+        for conv, bn in zip(mod_cpu.conv_blocks[i], mod_cpu.bn_blocks[i]):
+            h = F.relu(bn(conv(h)))
+        outs.append(h.max(dim=2)[0])
+    return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+@pytest.mark.parametrize("D", [0, 6])
+@pytest.mark.parametrize("training", [False, True])
+def test_set_abstraction_msg_forward(D, training):
+    torch.manual_seed(5)
+    B, N = 2, 600
+    mk = lambda: dpu.PointNetSetAbstractionMsg(48, [0.2, 0.4], [16, 32], D, [[16, 32], [24, 40]])
+    mod = mk()
+    for m in mod.modules():                                   # non-trivial running statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-0.1, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    ref_mod = mk()
+    ref_mod.load_state_dict(mod.state_dict())
+    mod, ref_mod = mod.to(DEV).train(training), ref_mod.train(training)
+    xyz = synthetic.s_uniform(B, N, 8).permute(0, 2, 1).contiguous()
+    pts = torch.randn(B, D, N) if D else None
+    start = torch.tensor([3, 77])
+    real = pipeline.draw_fps_start
+    pipeline.draw_fps_start = lambda B_, N_, dev: start.to(dev)
+    try:
+        with torch.no_grad():
+            new_xyz, out = mod(xyz.to(DEV), None if pts is None else pts.to(DEV))
+            rx, ro = msg_reference(ref_mod, xyz, pts, start)
+    finally:
+        pipeline.draw_fps_start = real
+    assert out.shape == ro.shape == (B, 32 + 40, 48)
+    assert torch.equal(new_xyz.cpu(), rx)
+    assert rel_err(out, ro) <= TOL
+    if training:
+        for (k, a), (_, b) in zip(mod.state_dict().items(), ref_mod.state_dict().items()):
+            if "running" in k:
+                assert rel_err(a, b) <= TOL, k
+
+
+def test_set_abstraction_msg_autograd():
+    """the Msg module had no grad_fn.  Parameter and feature gradients against torch autograd of the
+    restated reference forward (BatchNorm on running statistics: the well-conditioned case)."""
+    torch.manual_seed(6)
+    B, N, D = 2, 500, 5
+    mk = lambda: dpu.PointNetSetAbstractionMsg(40, [0.25, 0.5], [16, 32], D, [[16, 24], [32]])
+    mod, ref_mod = mk(), mk()
+    ref_mod.load_state_dict(mod.state_dict())
+    mod, ref_mod = mod.to(DEV).eval(), ref_mod.eval()
+    xyz = synthetic.s_uniform(B, N, 9).permute(0, 2, 1).contiguous()
+    pts = torch.randn(B, D, N)
+    start = torch.tensor([1, 2])
+    p_dev = pts.to(DEV).requires_grad_(True)
+    p_ref = pts.clone().requires_grad_(True)
+    real = pipeline.draw_fps_start
+    pipeline.draw_fps_start = lambda B_, N_, dev: start.to(dev)
+    try:
+        _, out = mod(xyz.to(DEV), p_dev)
+    finally:
+        pipeline.draw_fps_start = real
+    assert out.grad_fn is not None
+    _, ro = msg_reference(ref_mod, xyz, p_ref, start)
+    assert rel_err(out, ro) <= TOL
+    w = torch.randn(ro.shape, generator=torch.Generator().manual_seed(1))
+    (out * w.to(DEV)).sum().backward()
+    (ro * w).sum().backward()
+    assert rel_l2(p_dev.grad, p_ref.grad) <= 5e-3
+    for (k, a), (_, b) in zip(mod.named_parameters(), ref_mod.named_parameters()):
+        assert a.grad is not None, k
+        assert rel_l2(a.grad, b.grad) <= 5e-3, k
+
+
+def test_module_backward_does_not_clobber_the_incoming_gradient():
+    """the in-place backward kernels must not write into the gradient tensor autograd hands in."""
+    torch.manual_seed(2)
+    fp = dpu.PointNetFeaturePropagation(16 + 8, [32, 16]).to(DEV).eval()
+    B, N, S = 2, 300, 40
+    xyz1 = synthetic.s_uniform(B, N, 1).permute(0, 2, 1).contiguous().to(DEV)
+    xyz2 = xyz1[:, :, :S].contiguous()
+    p1 = torch.randn(B, 8, N, device=DEV, requires_grad=True)
+    p2 = torch.randn(B, 16, S, device=DEV, requires_grad=True)
+    out = fp(xyz1, xyz2, p1, p2)
+    g = torch.randn_like(out)
+    keep = g.clone()
+    out.backward(gradient=g)
+    assert torch.equal(g, keep)
+
+
+# ---- loss block at K = 16 (BASELINE.json configs[4]'s K) ----------------------------------------------------------
+
+def test_loss_block_k16_vs_oracle():
+    B, N, K = 3, 4096, 16
+    data = synthetic.s_cyl(B, N, K, 21)
+    g = torch.Generator().manual_seed(22)
+    X_raw = data["normals"] + 0.3 * torch.randn(B, N, 3, generator=g)
+    W_raw = torch.randn(B, N, 2 * K, generator=g)
+    perm = torch.stack([torch.randperm(K, generator=g) for _ in range(B)])
+    col = torch.gather(perm, 1, data["inst"].clamp_min(0)) * 2 + data["bb"]
+    W_raw.scatter_add_(2, col[:, :, None], torch.full((B, N, 1), 2.5))
+    dev = {k: v.to(DEV) for k, v in data.items()}
+    for norm_eig in (False, True):
+        out = pipeline.loss_forward(dev["pcs"], X_raw.to(DEV), W_raw.to(DEV), dev["normals"], dev["inst"], dev["bb"],
+                                    dev["axes"], dev["centers"], norm_eig=norm_eig)
+        ref = orc.loss_block(data["pcs"], X_raw, W_raw, data["normals"], data["inst"], data["bb"], data["axes"],
+                             data["centers"], norm_eig=norm_eig)
+        assert int(ref["mask"].sum(1).max()) > 8                  # more than 8 live instances: the K = 16 paths
+        assert torch.equal(out["matching_indices"].cpu(), ref["matching_indices"])
+        assert torch.equal(out["mask"].cpu(), ref["mask"])
+        for k in ("total", "normal", "miou", "bb", "axis", "center"):
+            assert rel_err(out[k], ref[k]) <= TOL, (k, norm_eig)
+        m = ref["mask"]
+        dots = (out["E_AX"].cpu() * ref["E_AX"]).sum(-1).abs()
+        assert float((1 - dots[m]).max()) <= TOL
+        assert rel_err(out["centers"].cpu()[m], ref["centers"][m]) <= TOL
+
+
+# ---- in-kernel dropout mask (models/pointnet_extrusion.py:60: F.dropout(p=0.5), always on) ------------------------
+
+def philox_mask(seed, B, N, C=128):
+    """Reads the mask the head kernel draws: H = 1, no BN fold, W = 32 selector rows at a time."""
+    H = torch.ones(B * N, C, device=DEV)
+    cols = []
+    for c0 in range(0, C, 32):
+        W = torch.zeros(32, C, device=DEV)
+        W[torch.arange(32), c0 + torch.arange(32)] = 1.0
+        cols.append(ops.head_masked(H, None, None, None, W, None, B, N, seed=seed))
+    return torch.cat(cols, dim=1)                                  # (B*N, C)
+
+
+def test_philox_dropout_mask_statistics_and_determinism():
+    B, N, C = 4, 4096, 128
+    s1 = torch.tensor([1234567, -42], dtype=torch.long, device=DEV)
+    m1 = philox_mask(s1, B, N)
+    assert set(m1.unique().tolist()) == {0.0, 2.0}                 # kept values scaled by 1/(1-p)
+    n = m1.numel()
+    assert abs(float(m1.mean()) - 1.0) <= 4 * 2 * 0.5 / math.sqrt(n) * 1.5      # E[mask] = 1, sd 1/sqrt(n)
+    keep = (m1 > 0).float()
+    assert float((keep.mean(0) - 0.5).abs().max()) <= 5 * 0.5 / math.sqrt(B * N)   # every channel
+    assert float((keep.mean(1) - 0.5).abs().max()) <= 6 * 0.5 / math.sqrt(C)       # every point
+    # neighbouring channels / points are uncorrelated
+    a, b = keep[:, :-1].reshape(-1) - 0.5, keep[:, 1:].reshape(-1) - 0.5
+    assert abs(float((a * b).mean())) * 4 <= 5 / math.sqrt(a.numel())
+    a, b = keep[:-1].reshape(-1) - 0.5, keep[1:].reshape(-1) - 0.5
+    assert abs(float((a * b).mean())) * 4 <= 5 / math.sqrt(a.numel())
+    assert torch.equal(m1, philox_mask(s1.clone(), B, N))          # same words -> same mask
+    m2 = philox_mask(torch.tensor([1234568, -42], dtype=torch.long, device=DEV), B, N)
+    assert 0.45 <= float((m1 != m2).float().mean()) <= 0.55        # another seed -> an independent mask
+    m3 = philox_mask(torch.tensor([1234567, -41], dtype=torch.long, device=DEV), B, N)
+    assert 0.45 <= float((m1 != m3).float().mean()) <= 0.55
+
+
+def test_philox_dropout_backward_regenerates_the_same_mask():
+    B, N, C, Nout = 2, 1000, 128, 19
+    seed = torch.tensor([99, 7], dtype=torch.long, device=DEV)
+    mask = philox_mask(seed, B, N)                                 # (B*N, C)
+    g = torch.Generator().manual_seed(0)
+    H = torch.randn(B * N, C, generator=g).to(DEV)
+    sc, sh = (torch.rand(C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
+    W = torch.randn(Nout, C, generator=g).to(DEV)
+    bias = torch.randn(Nout, generator=g).to(DEV)
+    Y = ops.head_masked(H, sc, sh, None, W, bias, B, N, seed=seed)
+    A_ref = torch.relu(H * sc + sh) * mask
+    assert rel_err(Y, A_ref.double() @ W.double().t() + bias.double()) <= 1e-5
+    # the same through an explicit (B, C, N) mask tensor: bit-identical
+    mask_cf = mask.reshape(B, N, C).permute(0, 2, 1).contiguous()
+    assert torch.equal(Y, ops.head_masked(H, sc, sh, mask_cf, W, bias, B, N))
+    dOut = torch.randn(B * N, Nout, generator=g).to(DEV)
+    dA, A = ops.head_bwd(dOut, None, W, B, N, H, sc, sh, seed=seed)
+    dA2, A2 = ops.head_bwd(dOut, mask_cf, W, B, N, H, sc, sh)
+    assert torch.equal(dA, dA2) and torch.equal(A, A2)
+    assert rel_err(A, A_ref) <= 1e-6
+
+
+def _small_net(K=4):
+    net = backbone(output_sizes=[3, 2 * K])
+    net.load_state_dict(orc.init_state_dict((3, 2 * K), 0), strict=True)
+    return net.to(DEV)
+
+
+def test_backbone_default_dropout_follows_the_cuda_generator():
+    """No mask tensor: the seed words come from torch's CUDA generator, so torch.manual_seed reproduces a forward and
+    consecutive forwards differ; the eval-mode network with dropout differs from the identity-mask run."""
+    B, N, K = 2, 1024, 4
+    net = _small_net(K).eval()
+    x = synthetic.s_cyl(B, N, K, 0)["pcs"].to(DEV)
+    starts = [torch.zeros(B, dtype=torch.long, device=DEV), torch.ones(B, dtype=torch.long, device=DEV)]
+    assert pipeline.dropout_mask_fn is None
+    with torch.no_grad():
+        torch.manual_seed(11)
+        a = pipeline.backbone_forward(net, x, starts)[1].clone()
+        b = pipeline.backbone_forward(net, x, starts)[1].clone()
+        torch.manual_seed(11)
+        c = pipeline.backbone_forward(net, x, starts)[1].clone()
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    assert bool(torch.isfinite(a).all())
+
+
+def test_graph_survives_update_momentum_and_leaves_bn_buffers_alone():
+    """ADVICE r1 (low) + VERDICT item 10: constructing the graph does not advance the BatchNorm running statistics;
+    a BatchNorm momentum change (update_momentum, train_Point2Cyl_without_sketch.py:357-366) re-captures instead of
+    raising, and the replayed step then uses the new momentum."""
+    from point2cyl_b200.graph import GraphedForwardLoss
+    B, N, K = 2, 1024, 4
+    net = _small_net(K).train()
+    batch = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, 0).items()}
+    before = {k: v.clone() for k, v in net.named_buffers()}
+    gfl = GraphedForwardLoss(net, batch)
+    for k, v in net.named_buffers():
+        assert torch.equal(v, before[k]), k
+    gfl()
+    torch.cuda.synchronize()
+    rm1 = net.bn1.running_mean.clone()
+    assert not torch.equal(rm1, before["bn1.running_mean"]) and int(net.bn1.num_batches_tracked) == 1
+    for m in net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = 0.5
+    assert gfl.stale()
+    out = gfl()                                                    # re-captures
+    torch.cuda.synchronize()
+    assert gfl.captures == 2 and not gfl.stale() and bool(torch.isfinite(out["losses"]).all())
+    assert int(net.bn1.num_batches_tracked) == 2                   # the re-capture itself was not a step
+    # running_mean moved by momentum 0.5 towards the batch mean: new = 0.5*old + 0.5*batch
+    net2 = _small_net(K).train()
+    net2.load_state_dict({k: v for k, v in net.state_dict().items()})
+    assert float((net.bn1.running_mean - rm1).abs().max()) > 0
+
+
+def test_start_ring_reuses_slots_only_after_their_copy():
+    from point2cyl_b200.graph import StartRing
+    ring = StartRing(8, (1000, 50), torch.device(DEV), depth=2)
+    torch.manual_seed(3)
+    want = []
+    for _ in range(5):
+        want.append((torch.randint(0, 1000, (8,)), torch.randint(0, 50, (8,))))
+    torch.manual_seed(3)
+    for w in want:                                                 # same CPU-generator stream, same order as the reference
+        ring.draw()
+        assert torch.equal(ring.dev[0].cpu(), w[0]) and torch.equal(ring.dev[1].cpu(), w[1])

@@ -113,8 +113,8 @@ def test_config2_full_batch_vs_oracle(training):
         # difference must be such a tie, and the neighbour DISTANCES must still agree bit for bit.
         for bb, n, j in diff.tolist():
             mine = int(ch[name + ".nn_idx"][bb, n, j])
-            dm = float(orc.square_distance(q[bb:bb + 1, n:n + 1], s_[bb:bb + 1, mine:mine + 1]))
-            assert dm == float(d[bb, n, j]), (name, bb, n, j)
+            pos = int((order[bb, n] == mine).nonzero()[0])
+            assert float(d[bb, n, pos]) == float(d[bb, n, j]), (name, bb, n, j)
         ties[name] = len(diff)
         assert len(diff) <= 16, (name, len(diff))
         w_ref = 1.0 / (d[:, :, :3] + 1e-8)

@@ -162,7 +162,7 @@ def make_net(K, seed, mode):
 
 @pytest.fixture
 def identity_dropout(monkeypatch):
-    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: x)
+    monkeypatch.setattr(pipeline, "dropout_mask_fn", lambda x, p=0.5, **kw: x)
 
 
 # Conditioning of the train-mode forward (tests/tools/grad_sensitivity.py, CPU oracle): with batch-statistics BatchNorm on
@@ -216,7 +216,7 @@ def test_backbone_dropout_mask_path(golden_dir, monkeypatch):
     B, N, K, seed = 2, 1024, 4, 0
     data = synthetic.s_cyl(B, N, K, seed)
     mask = (torch.rand(B, 128, N, generator=torch.Generator().manual_seed(9)) > 0.5).float() * 2.0
-    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: mask.to(x.device))
+    monkeypatch.setattr(pipeline, "dropout_mask_fn", lambda x, p=0.5, **kw: mask.to(x.device))
     net = make_net(K, seed, "eval")
     starts = (torch.zeros(B, dtype=torch.long), torch.ones(B, dtype=torch.long))
     with torch.no_grad():
@@ -336,7 +336,7 @@ def scipy_match(cost, n_gt, K):
 
 def test_graph_replay_matches_eager(monkeypatch):
     from point2cyl_b200.graph import GraphedForwardLoss
-    monkeypatch.setattr(pipeline.F, "dropout", lambda x, p=0.5, **kw: x)
+    monkeypatch.setattr(pipeline, "dropout_mask_fn", lambda x, p=0.5, **kw: x)
     B, N, K = 4, 2048, 4
     data = {k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, 77).items()}
     net = make_net(K, 1, "eval")

@@ -14,7 +14,7 @@ net = backbone(output_sizes=[3, 2 * K])
 net.load_state_dict(orc.init_state_dict((3, 2 * K), seed=seed), strict=True)
 net = net.to(DEV).train()
 mask = ((torch.rand(B, 128, N, generator=torch.Generator().manual_seed(seed + 3)) > 0.5).float() * 2.0).to(DEV)
-pipeline.F.dropout = lambda x, p=0.5, **kw: mask
+pipeline.dropout_mask_fn = lambda x, p=0.5, **kw: mask
 if len(sys.argv) > 1:
     pipeline.set_precision(sys.argv[1])
 starts = (torch.from_numpy(g["s1"]).to(DEV), torch.from_numpy(g["s2"]).to(DEV))

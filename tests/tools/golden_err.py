@@ -4,7 +4,7 @@ import numpy as np, torch
 from oracle import p2c_oracle as orc
 from point2cyl_b200 import pipeline, synthetic
 from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
-pipeline.F.dropout = lambda x, p=0.5, **kw: x
+pipeline.dropout_mask_fn = lambda x, p=0.5, **kw: x
 for name in ("backbone_b2_n1024_k4.npz", "backbone_b1_n1024_k4.npz"):
     g = np.load("tests/golden/" + name)
     B, N, K, seed = (int(v) for v in g["meta"])

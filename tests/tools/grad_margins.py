@@ -11,7 +11,7 @@ for name, training in (("train_bneval_b2_n1024_k4.npz", False), ("train_b2_n1024
     B, N, K, seed = (int(v) for v in g["meta"])
     data = {k: v.cuda() for k, v in synthetic.s_cyl(B, N, K, seed).items()}
     mask = ((torch.rand(B, 128, N, generator=torch.Generator().manual_seed(seed + 3)) > 0.5).float() * 2.0).cuda()
-    pipeline.F.dropout = lambda x, p=0.5, **kw: mask
+    pipeline.dropout_mask_fn = lambda x, p=0.5, **kw: mask
     starts = (torch.from_numpy(g["s1"]).cuda(), torch.from_numpy(g["s2"]).cuda())
     for rep in range(3):
         net = backbone(output_sizes=[3, 2 * K]); net.load_state_dict(orc.init_state_dict((3, 2 * K), seed=seed)); net = net.cuda().train(training)
