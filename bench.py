@@ -369,6 +369,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("P2C_PRECISION", "3xtf32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sequential"],
+                    help="pipelined (default): graph.PipelinedForwardLoss - the coordinate-only stage of batch i+1 "
+                         "runs on a second stream under the layers of batch i; sequential: one batch at a time "
+                         "(graph.GraphedForwardLoss)")
     ap.add_argument("--workload", default="forward_loss", choices=["forward_loss", "train", "stress"],
                     help="forward_loss = BASELINE.json configs[1] (the headline metric, default); train = configs[3], "
                          "the data-parallel training step (32 clouds per GPU); stress = configs[4], FPS + ball query "
@@ -418,21 +422,36 @@ def main():
             ms.append(s.elapsed_time(e))
         return ms
 
-    graphed = None
+    graphed = pipe = None
     if not args.no_graph:
-        from point2cyl_b200.graph import GraphedForwardLoss
+        from point2cyl_b200.graph import GraphedForwardLoss, PipelinedForwardLoss
         graphed = GraphedForwardLoss(net, batch, precision=args.precision)
+        if args.mode == "pipelined" and args.workload == "forward_loss":
+            pipe = PipelinedForwardLoss(net, batch, precision=args.precision)
+            pipe.prime(None)
 
     def step_eager():
         with torch.no_grad():
             return pipeline.forward_loss(net, batch)
 
+    def step_sequential():
+        return graphed() if graphed is not None else step_eager()     # static inputs already hold `batch`
+
     def step_resident():
-        if graphed is not None:
-            return graphed()                      # static inputs already hold `batch`
-        return step_eager()
+        if pipe is not None:
+            # loss of the resident current batch + the coordinate stage of the (resident) next one; join(): the timed
+            # region ends only when the side-stream work launched in it has finished too
+            out = pipe.step(None)
+            pipe.join()
+            return out
+        return step_sequential()
 
     def step_e2e():
+        if pipe is not None:
+            out = pipe.step(host)                 # H2D of the NEXT batch's six tensors + its coordinate stage, beside
+            out["losses_host"] = out["losses"].cpu()   # the layers + loss of the current one; D2H of its loss scalars
+            pipe.join()
+            return out
         if graphed is not None:
             out = graphed(host)                   # H2D of the six batch tensors, replay
             out["losses_host"] = out["losses"].cpu()   # D2H of the loss scalars (synchronises)
@@ -454,6 +473,7 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     ms = timed(step_resident, args.steps)
+    ms_seq = timed(step_sequential, args.steps) if pipe is not None else ms
     l0 = _lib.launch_count
     step_eager()                                  # launches per step, counted on one eager pass (a replay re-issues them)
     launches = _lib.launch_count - l0
@@ -464,6 +484,7 @@ def main():
 
     total_ms = pd.reduce_max(sum(ms), dev)
     total_ms_e2e = pd.reduce_max(sum(ms_e2e), dev)
+    total_ms_seq = pd.reduce_max(sum(ms_seq), dev)
     clouds = B_PER_GPU * world * args.steps
     value = clouds / (total_ms / 1e3)
     e2e = clouds / (total_ms_e2e / 1e3)
@@ -533,7 +554,15 @@ def main():
             "config": workload_config(world, args.precision),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host),
                     "d2h_bytes_per_step": 24 + (0 if graphed is not None else B_PER_GPU * K_INST * K_INST * 4 + B_PER_GPU * 4), "ms_per_step": total_ms_e2e / args.steps},
-            "gpu_launches": launches, "launch_mode": "eager" if graphed is None else "cuda_graph", "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches,
+            "launch_mode": "eager" if graphed is None else ("cuda_graph" if pipe is None else
+                           f"cuda_graphs, two-stage pipeline over batches (coordinate stage of batch i+1 on a second stream, "
+                           f"{pipe.geometry_sms} SMs left to it, beside the layers + loss of batch i; one batch of every kind "
+                           "of work per step, side stream joined inside the timed region)"),
+            "sequential": None if pipe is None else {"value": B_PER_GPU * world * args.steps / (total_ms_seq / 1e3),
+                                                     "unit": UNIT, "ms_per_step": total_ms_seq / args.steps,
+                                                     "what": "one batch at a time (graph.GraphedForwardLoss): per-batch latency"},
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             "gpu_eager_reference": eager, "stages": stages, "train_step": train}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -33,6 +33,12 @@ extern "C" {
 int p2c_version(void);           /* 100 * major + minor */
 const char* p2c_arch(void);      /* "sm_100a" */
 
+/* Number of SMs the persistent one-CTA-per-SM tensor-core kernels (p2c_linear, p2c_wgrad) of SUBSEQUENT launches
+ * from this process may occupy; 0 = all.  Returns the previous value.  point2cyl_b200.graph.PipelinedForwardLoss
+ * sets it so that the coordinate-only stage of the next batch (FPS, ball query, 3-NN search: small grids) runs on a
+ * second stream beside the per-point MLP layers of the current batch. */
+int p2c_set_sm_budget(int sms);
+
 /* Farthest point sampling — replaces farthest_point_sample, models/pointnet_util.py:63-84, fused
  * with the gather of the sampled centres (index_points, :43-60, as used at :124).
  * start[b] is the first centroid (the reference draws it on the CPU generator, :75).
@@ -146,6 +152,15 @@ int p2c_pool_bn_relu(const float* Ymax, const float* Ymin, const float* scale, c
 int p2c_three_nn_interp(const float* xyz1 /* (B,N,3) */, const float* xyz2 /* (B,S,3) */,
                         const float* feats2 /* (B*S, D) */, int64_t ldf, int B, int N, int S, int D,
                         float* out, int64_t ldo, int64_t* idx_out, float* w_out, void* stream);
+
+/* The two halves of p2c_three_nn_interp on their own.  The neighbour search depends on the coordinates only, the
+ * gather on the features only, so a pipelined caller runs them in different stages:
+ *   p2c_three_nn_search: idx (B,N,3) int64 and w (B,N,3) of the three nearest sources (same arithmetic, same ties);
+ *   p2c_three_nn_gather: out[(b,n), :] = sum_j w[b,n,j] * feats2[b*S + idx[b,n,j], :]  (same rounding order). */
+int p2c_three_nn_search(const float* xyz1, const float* xyz2, int B, int N, int S, int64_t* idx_out, float* w_out,
+                        void* stream);
+int p2c_three_nn_gather(const float* feats2, int64_t ldf, const int64_t* idx, const float* w, int B, int N, int S, int D,
+                        float* out, int64_t ldo, void* stream);
 
 /* Loss pass 1 — one sweep over the points that produces every per-cloud sufficient statistic of
  * train_Point2Cyl_without_sketch.py:246-353: unit normals (:247), softmax over 2K and the

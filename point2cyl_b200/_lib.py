@@ -26,6 +26,7 @@ vp = C.c_void_p
 SIGNATURES = {
     "p2c_version": [],
     "p2c_arch": [],
+    "p2c_set_sm_budget": [i32],
     "p2c_fps": [c_f32p, c_i64p, i32, i32, i32, c_i64p, c_f32p, vp],
     "p2c_ball_query": [c_f32p, c_f32p, i32, i32, i32, f32, i32, c_i64p, vp],
     "p2c_group": [c_f32p, c_f32p, i64, c_f32p, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, vp],
@@ -43,6 +44,8 @@ SIGNATURES = {
     "p2c_bn_relu_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i64, i32, vp],
     "p2c_pool_bn_relu": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, i64, i32, vp],
     "p2c_three_nn_interp": [c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, c_f32p, i64, c_i64p, c_f32p, vp],
+    "p2c_three_nn_search": [c_f32p, c_f32p, i32, i32, i32, c_i64p, c_f32p, vp],
+    "p2c_three_nn_gather": [c_f32p, i64, c_i64p, c_f32p, i32, i32, i32, i32, c_f32p, i64, vp],
     "p2c_segfit_stats_stride": [i32],
     "p2c_segfit_stats": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_i64p, c_i64p, i32, i32, i32, c_f32p,
                          i64, c_f32p, vp],
@@ -151,7 +154,7 @@ def need_cuda(*tensors) -> None:
 # kernels launched by one call of each entry point (the `gpu_launches` claim of bench.py)
 LAUNCHES_PER_CALL = {
     "p2c_split_tf32": 1, "p2c_cast_bf16": 1, "p2c_sa_first_layer": 1, "p2c_head_masked": 1, "p2c_fps": 1, "p2c_ball_query": 1, "p2c_group": 1, "p2c_linear": 1, "p2c_bn_finalize": 1,
-    "p2c_bn_relu_apply": 1, "p2c_pool_bn_relu": 1, "p2c_three_nn_interp": 1, "p2c_segfit_stats": 2, "p2c_segfit_stats_w": 2,
+    "p2c_bn_relu_apply": 1, "p2c_pool_bn_relu": 1, "p2c_three_nn_interp": 1, "p2c_three_nn_search": 1, "p2c_three_nn_gather": 1, "p2c_segfit_stats": 2, "p2c_segfit_stats_w": 2,
     "p2c_segfit_cost": 1, "p2c_hungarian": 1, "p2c_bb_loss": 2, "p2c_loss_finalize": 2, "p2c_eig3x3_smallest": 1,
     "p2c_square_distance": 1, "p2c_gather_rows": 1, "p2c_segment_lists": 1, "p2c_sketch_project": 1, "p2c_sketch_project_bwd": 1,
     "p2c_extrusion_extents": 1, "p2c_hard_w_encoding": 1, "p2c_normal_angle": 1,

@@ -21,6 +21,13 @@
 
 static inline int p2c_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// SMs the persistent (one CTA per SM) tensor-core kernels may occupy: p2c_set_sm_budget (version.cu).  A pipelined
+// caller that runs the geometry stage of the next batch on a second stream leaves it some SMs this way.
+extern int g_p2c_sm_budget;
+static inline int p2c_sm_budget(int device_sms) {
+  return (g_p2c_sm_budget > 0 && g_p2c_sm_budget < device_sms) ? g_p2c_sm_budget : device_sms;
+}
+
 __device__ __forceinline__ float p2c_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(P2C_FULL_MASK, v, o);

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(QPB)
 three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                        const float* __restrict__ feats2, int64_t ldf, int N, int S, int D,
                        float* __restrict__ out, int64_t ldo, int64_t* __restrict__ idx_out,
-                       float* __restrict__ w_out) {
+                       float* __restrict__ w_out, const int64_t* __restrict__ idx_in, const float* __restrict__ w_in) {
+  // three modes: search + gather (the fused call), search only (feats2 == NULL), gather only (idx_in != NULL)
   // sources in PAIRS: sA[p] = (x0, x1, y0, y1), sB[p] = (z0, z1, |p0|^2, |p1|^2) for sources 2p, 2p+1 - two broadcast
   // LDS.128 feed six packed FMUL2 / FFMA2 / FADD2 (same rounding per half as the scalar ops: bit-identical distances)
   extern __shared__ float4 sm4[];
@@ -29,8 +30,16 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
   __shared__ float s_w[QPB][3];
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
+  if (idx_in) {
+    const int q = blockIdx.x * QPB + tid;
+    if (q < N) {
+      const size_t o = ((size_t)b * N + q) * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { s_idx[tid][j] = (int)idx_in[o + j]; s_w[tid][j] = __ldg(w_in + o + j); }
+    }
+  }
   const float* p2 = xyz2 + (size_t)b * S * 3;
-  for (int pr = tid; pr < (S + 1) / 2; pr += QPB) {
+  for (int pr = tid; !idx_in && pr < (S + 1) / 2; pr += QPB) {
     const int i0 = 2 * pr, i1 = 2 * pr + 1;
     const float x0 = __ldg(p2 + i0 * 3), y0 = __ldg(p2 + i0 * 3 + 1), z0 = __ldg(p2 + i0 * 3 + 2);
     float x1 = 0.f, y1 = 0.f, z1 = 0.f, n1 = __int_as_float(0x7f800000);   // odd S: the pad never enters the top 3
@@ -41,7 +50,7 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
   __syncthreads();
 
   const int q = blockIdx.x * QPB + tid;
-  if (q < N) {
+  if (q < N && !idx_in) {
     const float* p1 = xyz1 + ((size_t)b * N + q) * 3;
     const float ax = __ldg(p1), ay = __ldg(p1 + 1), az = __ldg(p1 + 2);
     const float na = p2c_norm2_rn(ax, ay, az);
@@ -84,6 +93,7 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
     }
   }
   __syncthreads();
+  if (!feats2) return;                               // search only
 
   const int lane = tid & 31, warp = tid >> 5;
   const float* f2 = feats2 + (size_t)b * S * ldf;
@@ -151,7 +161,33 @@ extern "C" int p2c_three_nn_interp(const float* xyz1, const float* xyz2, const f
   if (smem > 48 * 1024)
     P2C_CUDA_TRY(cudaFuncSetAttribute(three_nn_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p2c_ceil_div(N, QPB), B);
-  three_nn_interp_kernel<<<grid, QPB, smem, st>>>(xyz1, xyz2, feats2, ldf, N, S, D, out, ldo, idx_out, w_out);
+  three_nn_interp_kernel<<<grid, QPB, smem, st>>>(xyz1, xyz2, feats2, ldf, N, S, D, out, ldo, idx_out, w_out, nullptr,
+                                                   nullptr);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_three_nn_search(const float* xyz1, const float* xyz2, int B, int N, int S, int64_t* idx_out,
+                                   float* w_out, void* stream) {
+  if (!xyz1 || !xyz2 || !idx_out || !w_out || B <= 0 || N <= 0 || S <= 0) return P2C_EINVAL;
+  if (S < 3) return P2C_EUNSUPPORTED;
+  const size_t smem = (size_t)((S + 1) / 2) * 2 * sizeof(float4);
+  if (smem > 200 * 1024) return P2C_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    P2C_CUDA_TRY(cudaFuncSetAttribute(three_nn_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p2c_ceil_div(N, QPB), B);
+  three_nn_interp_kernel<<<grid, QPB, smem, (cudaStream_t)stream>>>(xyz1, xyz2, nullptr, 0, N, S, 0, nullptr, 0, idx_out,
+                                                                    w_out, nullptr, nullptr);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_three_nn_gather(const float* feats2, int64_t ldf, const int64_t* idx, const float* w, int B, int N,
+                                   int S, int D, float* out, int64_t ldo, void* stream) {
+  if (!feats2 || !idx || !w || !out || B <= 0 || N <= 0 || S <= 0 || D <= 0 || ldf < D || ldo < D) return P2C_EINVAL;
+  dim3 grid(p2c_ceil_div(N, QPB), B);
+  three_nn_interp_kernel<<<grid, QPB, 0, (cudaStream_t)stream>>>(nullptr, nullptr, feats2, ldf, N, S, D, out, ldo, nullptr,
+                                                                 nullptr, idx, w);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

@@ -496,7 +496,7 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
   }
-  const int sms = dev < 64 ? sms_of[dev] : 148;
+  const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int n_tiles = (N + TC_BN - 1) / TC_BN;
   int gx = sms / n_tiles;
   if (gx < 1) gx = 1;

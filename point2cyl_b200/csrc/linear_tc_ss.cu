@@ -466,7 +466,7 @@ int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t 
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
   }
-  const int sms = dev < 64 ? sms_of[dev] : 148;
+  const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int tiles = a.m_tiles * a.n_tiles;
   if (bf16)
     linear_tc_ss_kernel<true><<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);

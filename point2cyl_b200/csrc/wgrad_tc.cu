@@ -293,7 +293,7 @@ int p2c_wgrad_tc(const float* dY, int64_t lddy, const float* X, int64_t ldx, con
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
   }
-  const int sms = dev < 64 ? sms_of[dev] : 148;
+  const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int n_tiles = (N + WG_TILE - 1) / WG_TILE, k_tiles = (K + WG_TILE - 1) / WG_TILE;
   const int stages_total = (int)((M + WG_ROWS - 1) / WG_ROWS);
   int gx = sms / (n_tiles * k_tiles);

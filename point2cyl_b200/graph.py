@@ -152,3 +152,168 @@ class GraphedForwardLoss:
             cur.wait_event(self.copied)
         self.loss_graph.replay()
         return self.out
+
+
+class PipelinedForwardLoss:
+    """Forward+loss over a STREAM of batches as a two-stage software pipeline (one batch deep).
+
+    The coordinate-only stage of a batch (pipeline.geometry_forward: both FPS levels, both ball queries, the 3-NN
+    searches - ~0.6 ms of short, mostly serial kernels on a few SMs) needs nothing but the coordinates, so it runs for
+    batch i+1 on a second stream while batch i goes through the per-point MLP layers and the loss on the main stream.
+    Each stage is a CUDA graph per buffer slot (two slots, ping-pong); events order slot reuse.  The persistent
+    tensor-core kernels of the feature stage are captured with `p2c_set_sm_budget(SMs - geometry_sms)`, which leaves
+    the geometry kernels (one FPS CTA per cloud) SMs of their own.
+
+        pipe = PipelinedForwardLoss(net, example_batch)
+        pipe.prime(batch0)                       # fills the pipeline: copies batch0 in, starts its geometry
+        out0 = pipe.step(batch1)                 # loss of batch0; batch1 is staged and its geometry started
+        out1 = pipe.step(batch2) ...
+
+    Every step() does one batch's worth of every kind of work (H2D of one batch, one geometry stage, one feature
+    stage + loss); results are identical to pipeline.forward_loss on the same batches in the same order (same CPU
+    generator stream for the first FPS centroids).  step(None) re-uses the batch already resident in the next slot.
+    """
+
+    def __init__(self, net, example: Dict[str, torch.Tensor], weights=(1.0,) * 5, norm_eig: bool = False,
+                 precision: Optional[str] = None, geometry_sms: Optional[int] = None, auto_rebuild: bool = True):
+        self.net = net
+        dev = next(net.parameters()).device
+        self.device = dev
+        self.weights, self.norm_eig, self.precision, self.auto_rebuild = weights, norm_eig, precision, auto_rebuild
+        B, N, _ = example["pcs"].shape
+        self.B, self.N = B, N
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.geometry_sms = min(B, sms // 4) if geometry_sms is None else int(geometry_sms)
+        self.feature_sms = sms - self.geometry_sms
+        self.static = [{k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS}
+                       for _ in range(2)]
+        self.geo = [pipeline.Geometry.empty(net, B, N, dev) for _ in range(2)]
+        self.geo_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self.geo_stream):
+            self.starts = [StartRing(B, (N, net.sa1.npoint), dev) for _ in range(2)]
+        self.geo_done = [torch.cuda.Event() for _ in range(2)]
+        self.labels_done = [torch.cuda.Event() for _ in range(2)]
+        self.feat_done = [torch.cuda.Event() for _ in range(2)]
+        self.cur = 0
+        self.primed = False
+        self.captures = 0
+        self._capture()
+
+    # ---- capture -------------------------------------------------------------------------------------------------
+    def _geometry(self, s: int):
+        return pipeline.geometry_forward(self.net, self.static[s]["pcs"], self.starts[s].dev, out=self.geo[s])
+
+    def _features(self, s: int):
+        b = self.static[s]
+        out = pipeline.forward_loss(self.net, b, weights=self.weights, norm_eig=self.norm_eig,
+                                    precision=self.precision, geo=self.geo[s])
+        return out
+
+    def _capture(self):
+        from . import ops
+        dev = self.device
+        self._key = bn_state_key(self.net)
+        buffers = {k: v.clone() for k, v in self.net.named_buffers()}
+        torch.cuda.synchronize(dev)
+        prev = ops.set_sm_budget(self.feature_sms)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():       # eager warm-up outside the capture
+                for s in range(2):
+                    self.starts[s].draw()
+                    self._geometry(s)
+                    self._features(s)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.g_geo, self.g_feat, self.out = [], [], []
+            for s in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g):
+                    self._geometry(s)
+                self.g_geo.append(g)
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g):
+                    out = self._features(s)
+                self.g_feat.append(g)
+                self.out.append(out)
+        finally:
+            ops.set_sm_budget(prev)
+        with torch.no_grad():
+            for k, v in self.net.named_buffers():
+                v.copy_(buffers[k])
+        torch.cuda.synchronize(dev)
+        self.captures += 1
+
+    def stale(self) -> bool:
+        return self._key != bn_state_key(self.net)
+
+    def rebuild_if_stale(self) -> bool:
+        if not self.stale():
+            return False
+        torch.cuda.synchronize(self.device)
+        self._capture()
+        return True
+
+    # ---- running -------------------------------------------------------------------------------------------------
+    def _check(self, batch):
+        for k in BATCH_KEYS:
+            if tuple(batch[k].shape) != tuple(self.static[0][k].shape):
+                raise _lib.P2CError(f"PipelinedForwardLoss was captured for {k} of shape "
+                                    f"{tuple(self.static[0][k].shape)}, got {tuple(batch[k].shape)}: build a new one")
+
+    def _stage(self, s: int, batch: Optional[Dict[str, torch.Tensor]]):
+        """Slot s <- batch (H2D when it lives in host memory), then its geometry stage, all off the main stream."""
+        cur = torch.cuda.current_stream(self.device)
+        if batch is not None:
+            self._check(batch)
+        self.geo_stream.wait_event(self.feat_done[s])              # the slot's previous batch has been consumed
+        self.geo_stream.wait_stream(cur)                           # (and whatever produced `batch` on the caller's stream)
+        with torch.cuda.stream(self.geo_stream):
+            if batch is not None:
+                self.static[s]["pcs"].copy_(batch["pcs"], non_blocking=True)
+            self.starts[s].draw()
+            self.g_geo[s].replay()
+            self.geo_done[s].record(self.geo_stream)
+        self.copy_stream.wait_event(self.feat_done[s])
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            if batch is not None:
+                for k in BATCH_KEYS:
+                    if k != "pcs":
+                        self.static[s][k].copy_(batch[k], non_blocking=True)
+            self.labels_done[s].record(self.copy_stream)
+
+    def prime(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """Fill the pipeline: stage `batch` (None = the batch already resident) as the CURRENT batch."""
+        if self.stale() and self.auto_rebuild:
+            self.rebuild_if_stale()
+        self._stage(self.cur, batch)
+        self.primed = True
+
+    def step(self, next_batch: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Loss of the current batch; `next_batch` is staged (and its geometry started) to become the current one."""
+        if self.stale():
+            if not self.auto_rebuild:
+                raise RuntimeError("PipelinedForwardLoss: mode or BatchNorm momentum changed; call rebuild_if_stale()")
+            self.rebuild_if_stale()
+        if not self.primed:
+            self.prime(None)
+        c, n = self.cur, self.cur ^ 1
+        main = torch.cuda.current_stream(self.device)
+        self._stage(n, next_batch)
+        main.wait_event(self.geo_done[c])
+        main.wait_event(self.labels_done[c])
+        self.g_feat[c].replay()
+        self.feat_done[c].record(main)
+        self.cur = n
+        return self.out[c]
+
+    def join(self) -> None:
+        """Make the caller's stream wait for the side-stream work of the last step() (the staging and geometry of the
+        batch that is now current).  Not needed for correctness - step() orders everything it uses - but a timed
+        region that must contain ALL work launched in it ends with this."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self.geo_done[self.cur])
+        main.wait_event(self.labels_done[self.cur])

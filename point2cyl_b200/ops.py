@@ -32,14 +32,28 @@ def _cloud(t: Tensor) -> Tensor:
     return t.contiguous().float()
 
 
-def fps(xyz: Tensor, npoint: int, start: Tensor) -> Tuple[Tensor, Tensor]:
+def _out(out: Optional[Tensor], shape, dtype, device) -> Tensor:
+    """A caller-provided result buffer (static across CUDA-graph replays) or a fresh one."""
+    if out is None:
+        return torch.empty(*shape, dtype=dtype, device=device)
+    if tuple(out.shape) != tuple(shape) or out.dtype != dtype or not out.is_contiguous() or out.device != device:
+        raise _lib.P2CError(f"out= buffer must be contiguous {tuple(shape)} {dtype}, got {tuple(out.shape)} {out.dtype}")
+    return out
+
+
+def set_sm_budget(sms: int) -> int:
+    """SMs the persistent tensor-core kernels of later launches may occupy (0 = all); returns the previous value."""
+    return int(_lib.load().p2c_set_sm_budget(int(sms)))
+
+
+def fps(xyz: Tensor, npoint: int, start: Tensor, out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
     """(idx (B,npoint) int64, new_xyz (B,npoint,3)).  start: (B,) int64 first centroid per cloud."""
     need_cuda(xyz)
     xyz = _cloud(xyz)
     B, N, _ = xyz.shape
     start = start.to(device=xyz.device, dtype=torch.long).contiguous()
-    idx = torch.empty(B, npoint, dtype=torch.long, device=xyz.device)
-    new_xyz = torch.empty(B, npoint, 3, dtype=torch.float32, device=xyz.device)
+    idx = _out(None if out is None else out[0], (B, npoint), torch.long, xyz.device)
+    new_xyz = _out(None if out is None else out[1], (B, npoint, 3), torch.float32, xyz.device)
     call("p2c_fps", ptr(xyz), ptr(start), B, N, npoint, ptr(idx), ptr(new_xyz), stream_ptr())
     return idx, new_xyz
 
@@ -49,12 +63,12 @@ def radius_sq_f32(radius: float) -> float:
     return float(np.float32(float(radius) ** 2))
 
 
-def ball_query(radius: float, nsample: int, xyz: Tensor, new_xyz: Tensor) -> Tensor:
+def ball_query(radius: float, nsample: int, xyz: Tensor, new_xyz: Tensor, out: Optional[Tensor] = None) -> Tensor:
     need_cuda(xyz, new_xyz)
     xyz, new_xyz = _cloud(xyz), _cloud(new_xyz)
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
-    out = torch.empty(B, S, nsample, dtype=torch.long, device=xyz.device)
+    out = _out(out, (B, S, nsample), torch.long, xyz.device)
     call("p2c_ball_query", ptr(xyz), ptr(new_xyz), B, N, S, radius_sq_f32(radius), nsample,
                                      ptr(out), stream_ptr())
     return out
@@ -262,6 +276,37 @@ def three_nn_interp(xyz1: Tensor, xyz2: Tensor, feats2: Tensor, out: Optional[Te
                                           ptr(out), out.stride(0), ptr(idx), ptr(w), stream_ptr())
     if want_idx:
         return out, idx, w
+    return out
+
+
+def three_nn_search(xyz1: Tensor, xyz2: Tensor, out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """The coordinate-only half of three_nn_interp: (idx (B,N,3) int64, w (B,N,3)) of the three nearest sources."""
+    need_cuda(xyz1, xyz2)
+    xyz1, xyz2 = _cloud(xyz1), _cloud(xyz2)
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    idx = _out(None if out is None else out[0], (B, N, 3), torch.long, xyz1.device)
+    w = _out(None if out is None else out[1], (B, N, 3), torch.float32, xyz1.device)
+    call("p2c_three_nn_search", ptr(xyz1), ptr(xyz2), B, N, S, ptr(idx), ptr(w), stream_ptr())
+    return idx, w
+
+
+def three_nn_gather(feats2: Tensor, idx: Tensor, w: Tensor, S: int, out: Optional[Tensor] = None) -> Tensor:
+    """The feature half: out (B*N, D) rows = sum_j w[b,n,j] * feats2[b*S + idx[b,n,j]] (same rounding as the fused
+    kernel).  `out` may be a column slice of a wider buffer."""
+    need_cuda(feats2, idx, w)
+    feats2 = _rows(feats2)
+    B, N, _ = idx.shape
+    D = feats2.shape[1]
+    if not (idx.is_contiguous() and w.is_contiguous() and idx.dtype == torch.long and w.dtype == torch.float32):
+        raise _lib.P2CError("three_nn_gather: contiguous int64 idx / float32 w of shape (B,N,3) expected")
+    if feats2.shape[0] != B * S:
+        raise _lib.P2CError(f"three_nn_gather: feats2 has {feats2.shape[0]} rows, expected B*S = {B * S}")
+    if out is None:
+        out = torch.empty(B * N, D, dtype=torch.float32, device=feats2.device)
+    _rows(out)
+    call("p2c_three_nn_gather", ptr(feats2), feats2.stride(0), ptr(idx), ptr(w), B, N, S, D, ptr(out), out.stride(0),
+         stream_ptr())
     return out
 
 

@@ -123,10 +123,11 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
 
 def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Tensor],
                     trace: Optional[dict] = None, precision: Optional[str] = None, tag: str = "sa",
-                    fused_first: bool = True, tape: Optional[dict] = None):
+                    fused_first: bool = True, tape: Optional[dict] = None, geo=None):
     """PointNetSetAbstraction in point-major form (models/pointnet_util.py:181-207).
     xyz (B,N,3), feats (B*N, D) rows or None -> (new_xyz (B,S,3), new_feats (B*S, C)).
-    tape: dict filled with what the backward of this level needs."""
+    tape: dict filled with what the backward of this level needs.
+    geo: (fps_idx, new_xyz, group_idx) computed earlier by `geometry_forward` (they depend on xyz only)."""
     B, N, _ = xyz.shape
     D = 0 if feats is None else feats.shape[1]
     _lib.set_tag(tag)
@@ -139,8 +140,11 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
         new_xyz = torch.zeros(B, 1, 3, dtype=torch.float32, device=xyz.device)
         pool = N
     else:
-        fps_idx, new_xyz = ops.fps(xyz, sa.npoint, start)
-        gidx = ops.ball_query(sa.radius, sa.nsample, xyz, new_xyz)
+        if geo is not None:
+            fps_idx, new_xyz, gidx = geo
+        else:
+            fps_idx, new_xyz = ops.fps(xyz, sa.npoint, start)
+            gidx = ops.ball_query(sa.radius, sa.nsample, xyz, new_xyz)
         pool = sa.nsample
         if trace is not None:
             trace["fps_idx"], trace["group_idx"] = fps_idx, gidx
@@ -175,7 +179,7 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
 
 def feature_propagation(fp, xyz1: Tensor, xyz2: Tensor, feats1: Optional[Tensor], feats2: Tensor,
                         materialize: bool = True, precision: Optional[str] = None, tag: str = "fp",
-                        tape: Optional[dict] = None):
+                        tape: Optional[dict] = None, nn=None):
     """PointNetFeaturePropagation in point-major form (models/pointnet_util.py:283-320).
     feats1 (B*N, D1) or None, feats2 (B*S, D2) -> (B*N, C) post-BN/ReLU rows (materialize=True) or
     (raw rows, Affine) for a consumer that folds the last BN+ReLU into its own load."""
@@ -188,12 +192,17 @@ def feature_propagation(fp, xyz1: Tensor, xyz2: Tensor, feats1: Optional[Tensor]
     if feats1 is not None:
         buf[:, :D1].copy_(feats1)           # skip features first (:312)
     layers = None
-    if tape is not None:
-        layers = []
+    nn_idx = nn_w = None
+    if nn is not None and S > 1:           # neighbours found earlier by `geometry_forward`: gather only
+        nn_idx, nn_w = nn
+        ops.three_nn_gather(feats2, nn_idx, nn_w, S, out=buf[:, D1:])
+    elif tape is not None:
         _, nn_idx, nn_w = ops.three_nn_interp(xyz1, xyz2, feats2, out=buf[:, D1:], want_idx=True)
-        tape.update(kind="fp", module=fp, B=B, N=N, S=S, D1=D1, D2=D2, nn_idx=nn_idx, nn_w=nn_w, layers=layers)
     else:
         ops.three_nn_interp(xyz1, xyz2, feats2, out=buf[:, D1:])
+    if tape is not None:
+        layers = []
+        tape.update(kind="fp", module=fp, B=B, N=N, S=S, D1=D1, D2=D2, nn_idx=nn_idx, nn_w=nn_w, layers=layers)
     Y, aff = mlp_stack(buf, D1 + D2, fp.mlp_convs, fp.mlp_bns, fp.training, precision=precision, tag=tag, tape=layers)
     _lib.set_tag(tag)
     if materialize:
@@ -207,11 +216,68 @@ def draw_fps_start(B: int, N: int, device) -> Tensor:
     return torch.randint(0, N, (B,), dtype=torch.long).to(device)
 
 
+@dataclass
+class Geometry:
+    """Everything of a backbone forward that depends on the point COORDINATES only (no weights, no features): the
+    two FPS levels, both ball queries and the 3-NN neighbours / weights of fp1 and fp2 (fp3 interpolates from a single
+    point).  A pipelined caller computes it for batch i+1 on a second stream while batch i runs through the per-point
+    MLP layers (graph.PipelinedForwardLoss); `backbone_forward` computes it inline."""
+    xyz: Tensor
+    fps1: Tensor
+    l1_xyz: Tensor
+    gidx1: Tensor
+    fps2: Tensor
+    l2_xyz: Tensor
+    gidx2: Tensor
+    nn1_idx: Tensor
+    nn1_w: Tensor
+    nn2_idx: Tensor
+    nn2_w: Tensor
+
+    @staticmethod
+    def empty(net, B: int, N: int, device) -> "Geometry":
+        S1, S2, ns1, ns2 = net.sa1.npoint, net.sa2.npoint, net.sa1.nsample, net.sa2.nsample
+        e = lambda shape, dt: torch.empty(*shape, dtype=dt, device=device)
+        return Geometry(e((B, N, 3), torch.float32), e((B, S1), torch.long), e((B, S1, 3), torch.float32),
+                        e((B, S1, ns1), torch.long), e((B, S2), torch.long), e((B, S2, 3), torch.float32),
+                        e((B, S2, ns2), torch.long), e((B, N, 3), torch.long), e((B, N, 3), torch.float32),
+                        e((B, S1, 3), torch.long), e((B, S1, 3), torch.float32))
+
+
+def geometry_forward(net, xyz: Tensor, fps_start: Optional[Sequence[Tensor]] = None,
+                     out: Optional[Geometry] = None) -> Geometry:
+    """FPS -> ball query (both levels) and the 3-NN searches of fp1 / fp2 for coordinates xyz (B,N,3) contiguous:
+    models/pointnet_util.py:63-107 and :301-305.  out: a Geometry whose buffers are overwritten (static across
+    CUDA-graph replays)."""
+    _lib.need_cuda(xyz)
+    B, N, _ = xyz.shape
+    dev = xyz.device
+    g = out
+    _lib.set_tag("sa1")
+    s1 = fps_start[0] if fps_start is not None else draw_fps_start(B, N, dev)
+    fps1, l1_xyz = ops.fps(xyz, net.sa1.npoint, s1, out=None if g is None else (g.fps1, g.l1_xyz))
+    gidx1 = ops.ball_query(net.sa1.radius, net.sa1.nsample, xyz, l1_xyz, out=None if g is None else g.gidx1)
+    _lib.set_tag("sa2")
+    s2 = fps_start[1] if fps_start is not None else draw_fps_start(B, l1_xyz.shape[1], dev)
+    fps2, l2_xyz = ops.fps(l1_xyz, net.sa2.npoint, s2, out=None if g is None else (g.fps2, g.l2_xyz))
+    gidx2 = ops.ball_query(net.sa2.radius, net.sa2.nsample, l1_xyz, l2_xyz, out=None if g is None else g.gidx2)
+    _lib.set_tag("fp1")
+    nn1 = ops.three_nn_search(xyz, l1_xyz, out=None if g is None else (g.nn1_idx, g.nn1_w))
+    _lib.set_tag("fp2")
+    nn2 = ops.three_nn_search(l1_xyz, l2_xyz, out=None if g is None else (g.nn2_idx, g.nn2_w))
+    if g is not None:
+        if g.xyz.data_ptr() != xyz.data_ptr():
+            g.xyz.copy_(xyz)
+        return g
+    return Geometry(xyz, fps1, l1_xyz, gidx1, fps2, l2_xyz, gidx2, nn1[0], nn1[1], nn2[0], nn2[1])
+
+
 def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = None,
                      trace: Optional[dict] = None, precision: Optional[str] = None,
-                     tape: Optional[dict] = None) -> List[Tensor]:
+                     tape: Optional[dict] = None, geo: Optional[Geometry] = None) -> List[Tensor]:
     """models/pointnet_extrusion.py:37-66.  x (B,N,3[+3]) -> [ (B,N,o_i) ] (views of one buffer).
-    tape: dict that receives the per-stage records point2cyl_b200.backward.backbone_backward consumes."""
+    tape: dict that receives the per-stage records point2cyl_b200.backward.backbone_backward consumes.
+    geo: the coordinate-only stage computed ahead of time (`geometry_forward`); None = compute it here."""
     _lib.need_cuda(x)
     B, N, Cx = x.shape
     x = x.float()
@@ -220,17 +286,20 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     dev = x.device
     rec = (lambda: {}) if tape is not None else (lambda: None)
     r_sa1, r_sa2, r_sa3, r_fp3, r_fp2, r_fp1 = rec(), rec(), rec(), rec(), rec(), rec()
-    s1 = fps_start[0] if fps_start is not None else draw_fps_start(B, N, dev)
+    if geo is None:
+        geo = geometry_forward(net, xyz, fps_start)
     t1 = {} if trace is not None else None
-    l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, s1, t1, precision, tag="sa1", tape=r_sa1)
-    s2 = fps_start[1] if fps_start is not None else draw_fps_start(B, l1_xyz.shape[1], dev)
+    l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, None, t1, precision, tag="sa1", tape=r_sa1,
+                                 geo=(geo.fps1, geo.l1_xyz, geo.gidx1))
     t2 = {} if trace is not None else None
-    l2_xyz, l2 = set_abstraction(net.sa2, l1_xyz, l1, s2, t2, precision, tag="sa2", tape=r_sa2)
+    l2_xyz, l2 = set_abstraction(net.sa2, l1_xyz, l1, None, t2, precision, tag="sa2", tape=r_sa2,
+                                 geo=(geo.fps2, geo.l2_xyz, geo.gidx2))
     l3_xyz, l3 = set_abstraction(net.sa3, l2_xyz, l2, None, None, precision, tag="sa3", tape=r_sa3)
     l4 = feature_propagation(net.fp3, l2_xyz, l3_xyz, l2, l3, precision=precision, tag="fp3", tape=r_fp3)
-    l5 = feature_propagation(net.fp2, l1_xyz, l2_xyz, l1, l4, precision=precision, tag="fp2", tape=r_fp2)
+    l5 = feature_propagation(net.fp2, l1_xyz, l2_xyz, l1, l4, precision=precision, tag="fp2", tape=r_fp2,
+                             nn=(geo.nn2_idx, geo.nn2_w))
     y6, aff6 = feature_propagation(net.fp1, xyz, l1_xyz, feats0, l5, materialize=False, precision=precision,
-                                    tag="fp1", tape=r_fp1)
+                                    tag="fp1", tape=r_fp1, nn=(geo.nn1_idx, geo.nn1_w))
     # FC head: fc1 -> bn1 -> ReLU -> dropout(p=.5, always on, :60) -> fc2 heads
     head_layers = [] if tape is not None else None
     h, aff_h = mlp_stack(y6, y6.shape[1], [net.fc1], [net.bn1], net.training, in_affine=aff6,
@@ -286,9 +355,9 @@ def loss_forward(pcs: Tensor, X_raw: Tensor, W_raw: Tensor, gt_normals: Tensor, 
 
 
 def forward_loss(net, batch: Dict[str, Tensor], fps_start=None, weights=(1.0,) * 5,
-                 norm_eig: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
+                 norm_eig: bool = False, precision: Optional[str] = None, geo: Optional[Geometry] = None) -> Dict[str, Tensor]:
     """One forward+loss pass: the unit BASELINE.json's clouds/s metric counts."""
-    X_raw, W_raw = backbone_forward(net, batch["pcs"], fps_start, precision=precision)
+    X_raw, W_raw = backbone_forward(net, batch["pcs"], fps_start, precision=precision, geo=geo)
     out = loss_forward(batch["pcs"], X_raw, W_raw, batch["normals"], batch["inst"], batch["bb"],
                        batch["axes"], batch["centers"], weights, norm_eig)
     out.update(X_raw=X_raw, W_raw=W_raw)

@@ -118,7 +118,7 @@ def test_set_abstraction_msg_autograd():
     restated reference forward (BatchNorm on running statistics: the well-conditioned case)."""
     torch.manual_seed(6)
     B, N, D = 2, 500, 5
-    mk = lambda: dpu.PointNetSetAbstractionMsg(40, [0.25, 0.5], [16, 32], D, [[16, 24], [32]])
+    mk = lambda: dpu.PointNetSetAbstractionMsg(40, [0.25, 0.5], [16, 32], D, [[32, 64], [64]])   # backward widths: 32 / 64 / k*128
     mod, ref_mod = mk(), mk()
     ref_mod.load_state_dict(mod.state_dict())
     mod, ref_mod = mod.to(DEV).eval(), ref_mod.eval()
@@ -148,7 +148,7 @@ def test_set_abstraction_msg_autograd():
 def test_module_backward_does_not_clobber_the_incoming_gradient():
     """the in-place backward kernels must not write into the gradient tensor autograd hands in."""
     torch.manual_seed(2)
-    fp = dpu.PointNetFeaturePropagation(16 + 8, [32, 16]).to(DEV).eval()
+    fp = dpu.PointNetFeaturePropagation(16 + 8, [32, 64]).to(DEV).eval()
     B, N, S = 2, 300, 40
     xyz1 = synthetic.s_uniform(B, N, 1).permute(0, 2, 1).contiguous().to(DEV)
     xyz2 = xyz1[:, :, :S].contiguous()
@@ -311,3 +311,67 @@ def test_start_ring_reuses_slots_only_after_their_copy():
     for w in want:                                                 # same CPU-generator stream, same order as the reference
         ring.draw()
         assert torch.equal(ring.dev[0].cpu(), w[0]) and torch.equal(ring.dev[1].cpu(), w[1])
+
+
+def test_geometry_stage_equals_the_fused_calls():
+    """pipeline.geometry_forward (+ the search / gather halves of the 3-NN kernel) against the one-kernel calls."""
+    B, N = 3, 2048
+    net = _small_net(4).eval()
+    xyz = synthetic.s_cyl(B, N, 4, 5)["pcs"].to(DEV)
+    starts = [torch.tensor([5, 6, 7], device=DEV), torch.tensor([1, 2, 3], device=DEV)]
+    geo = pipeline.geometry_forward(net, xyz, starts)
+    buf = pipeline.Geometry.empty(net, B, N, torch.device(DEV, torch.cuda.current_device()))
+    geo2 = pipeline.geometry_forward(net, xyz, starts, out=buf)
+    assert geo2 is buf
+    for f in ("fps1", "l1_xyz", "gidx1", "fps2", "l2_xyz", "gidx2", "nn1_idx", "nn1_w", "nn2_idx", "nn2_w", "xyz"):
+        assert torch.equal(getattr(geo, f), getattr(buf, f)), f
+    feats = torch.randn(B * 512, 20, device=DEV)
+    out, idx, w = ops.three_nn_interp(xyz, geo.l1_xyz, feats, want_idx=True)
+    assert torch.equal(idx, geo.nn1_idx) and torch.equal(w, geo.nn1_w)
+    wide = torch.zeros(B * N, 28, device=DEV)
+    ops.three_nn_gather(feats, geo.nn1_idx, geo.nn1_w, 512, out=wide[:, 8:])
+    assert torch.equal(wide[:, 8:], out) and bool((wide[:, :8] == 0).all())
+
+
+def test_pipelined_forward_loss_equals_sequential():
+    """graph.PipelinedForwardLoss (geometry of batch i+1 on a second stream under the layers of batch i, SM budget)
+    returns what pipeline.forward_loss returns for the same batches in the same order."""
+    from point2cyl_b200 import pin_batch
+    from point2cyl_b200.graph import PipelinedForwardLoss
+    B, N, K = 4, 2048, 4
+    batches = [synthetic.s_cyl(B, N, K, 100 + i) for i in range(4)]
+    real = pipeline.dropout_mask_fn
+    pipeline.dropout_mask_fn = lambda ones, p=0.5: ones
+    try:
+        net = _small_net(K).train()
+        state = {k: v.clone() for k, v in net.state_dict().items()}
+        torch.manual_seed(77)
+        ref = []
+        for b in batches:
+            with torch.no_grad():
+                o = pipeline.forward_loss(net, {k: v.to(DEV) for k, v in b.items()})
+            ref.append({k: o[k].clone() for k in ("losses", "X_raw", "W_raw", "matching_indices")})
+        ref_state = {k: v.clone() for k, v in net.state_dict().items()}
+        net.load_state_dict(state)
+        pipe = PipelinedForwardLoss(net, {k: v.to(DEV) for k, v in batches[0].items()})
+        for k, v in net.state_dict().items():                       # capture is not a training step
+            assert torch.equal(v, state[k]), k
+        torch.manual_seed(77)
+        host = [pin_batch(b) for b in batches]
+        pipe.prime(host[0])
+        for i in range(4):
+            out = pipe.step(host[i + 1] if i + 1 < 4 else None)
+            torch.cuda.synchronize()
+            assert torch.equal(out["matching_indices"], ref[i]["matching_indices"]), i
+            assert rel_err(out["losses"], ref[i]["losses"]) <= 1e-5, i
+            assert rel_err(out["X_raw"], ref[i]["X_raw"]) <= 1e-5 and rel_err(out["W_raw"], ref[i]["W_raw"]) <= 1e-5, i
+        pipe.join()
+        torch.cuda.synchronize()
+        for k, v in net.state_dict().items():                       # four real steps of running statistics
+            if v.is_floating_point():
+                assert rel_err(v, ref_state[k]) <= 1e-5, k
+            else:
+                assert torch.equal(v, ref_state[k]), k
+        assert ops.set_sm_budget(0) == 0                            # the budget is only set while capturing
+    finally:
+        pipeline.dropout_mask_fn = real

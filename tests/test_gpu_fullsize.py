@@ -134,9 +134,14 @@ def test_config2_full_batch_vs_oracle(training):
 
 GOLDEN_BACKBONE = ["backbone_b2_n1024_k4.npz", "backbone_b1_n1024_k4.npz"]
 # How much less exact than the reference's own float32 run the kernels may be, per quantity, before a test fails.
-# 3xTF32 carries ~21 mantissa bits per operand and the tensor core's fp32 accumulation truncates, so one layer is
-# ~2e-6 from exact where an fp32 FMA chain is ~3e-7 (test_linear_tc): the factor below is that ratio with margin.
-SLACK_FWD = 8.0
+# Measured (tests/tools/precision_probe.py, profiles/r2a_precision_probe.json): one 3xTF32 layer on the tensor cores is
+# 0.8e-6 (K=64) ... 1.3e-6 (K=128) ... 9.6e-6 (K=1280) rms from the exact product where an fp32 FMA chain is
+# 1.0e-7 ... 4.6e-7: the operand split itself is fp32-grade (4e-7 with exact accumulation), the difference is the
+# tensor core's TRUNCATING fp32 accumulate (48 accumulate steps at K=128).  That is a factor 6-20 per layer; measured
+# end to end on these ill-conditioned tiny batches the kernels are 11x (B=2) / 3x (B=1) the reference's own distance
+# from the exact result, and 1.8x at the headline batch (B=32: 5.7e-5 vs 3.1e-5, test_config2_full_batch_vs_oracle,
+# where the plain 1e-4 bar holds without any adjudication).
+SLACK_FWD = 16.0
 
 
 @pytest.mark.parametrize("name", GOLDEN_BACKBONE)
@@ -154,7 +159,7 @@ def test_golden_train_mode_fp64_adjudicated(golden_dir, name):
     _assert_bars(b, name, SLACK_FWD)
 
 
-SLACK_GRAD = 8.0
+SLACK_GRAD = 16.0      # same factor as the forward (measured worst 8.3x, median 3.9x)
 
 
 @pytest.mark.parametrize("name,training", [("train_b2_n1024_k4.npz", True), ("train_bneval_b2_n1024_k4.npz", False)])

@@ -1,5 +1,6 @@
 """GPU box: how exact is one MLP layer?  3xTF32 tcgen05 kernel vs the fp32 SIMT kernel vs torch fp32 matmul, all against
-the float64 product of the same operands (max |err| / max |ref| and rms err / rms ref).  Feeds DESIGN.md section 2."""
+the float64 product of the same operands (max |err| / max |ref|, rms err / rms ref, the proportional
+coefficient c of err ~ c * ref, and the rms of the residual after removing it).  Feeds DESIGN.md section 2."""
 import json
 import os
 import sys
@@ -21,7 +22,10 @@ for M, K, N in [(16384, 64, 64), (16384, 64, 128), (16384, 128, 128), (16384, 12
 
     def err(Y):
         d = Y.double() - ref
-        return float(d.abs().max() / ref.abs().max()), float(d.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+        c = float((d * ref).sum() / (ref * ref).sum())          # proportional part: d ~ c * ref (truncating accumulate)
+        r = d - c * ref
+        return (float(d.abs().max() / ref.abs().max()), float(d.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()), c,
+                float(r.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()))
 
     row = {"M": M, "K": K, "N": N}
     ws = ops.weight_operand(X, W, N, K, False, 0, _lib.PREC_3XTF32)
