@@ -85,16 +85,46 @@ int p2c_sa_first_layer(const float* xyz, const float* new_xyz, const int64_t* id
  * Y may be NULL when only the pooled output is wanted.  precision: P2C_PREC_*. */
 #define P2C_PREC_FP32 0      /* SIMT fp32 FMA */
 #define P2C_PREC_3XTF32 1    /* tcgen05 kind::tf32, error-compensated split (fp32-faithful) */
-#define P2C_PREC_BF16 2      /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate */
+#define P2C_PREC_BF16 2      /* A BatchNorm whose finalisation is DEFERRED to the kernel that consumes the normalised values (p2c_linear,
+ * p2c_pool_bn_relu, p2c_bn_relu_apply, p2c_head_masked take one as `in_bn` / `bn` in place of ready scale / shift
+ * arrays): the consumer folds  scale = gamma / sqrt(var + eps),  shift = beta - mean * scale  per channel in its
+ * prologue (same arithmetic as p2c_bn_finalize) and ONE of its CTAs writes scale_out / shift_out (required),
+ * mean_out / invstd_out (optional, for the backward) and updates running_mean / running_var with `momentum`
+ * (optional).  stats: float64 (2C) sum | sum of squares over `count` rows = batch statistics (train mode); NULL = use
+ * running_mean / running_var (eval mode, nothing is updated).  Replaces nn.BatchNorm{1,2}d.forward,
+ * models/pointnet_util.py:203, :318, without a launch of its own.  All pointers are device pointers. */
+typedef struct p2c_bn_fold {
+  const double* stats;
+  int64_t count;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float momentum;
+  float* running_mean;
+  float* running_var;
+  float* scale_out;
+  float* shift_out;
+  float* mean_out;
+  float* invstd_out;
+  int C;
+} p2c_bn_fold;
+
+/* tcgen05 kind::f16 with bf16 operands, fp32 accumulate */
 int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                const float* in_scale, const float* in_shift, const float* in_mask, int64_t ldmask,
                float* Y, int64_t ldy, int M, int N, int K, double* stats, int pool_group,
-               float* Ymax, float* Ymin, int precision, const float* w_split, int64_t ldws, void* stream);
+               float* Ymax, float* Ymin, int precision, const float* w_split, int64_t ldws,
+               const p2c_bn_fold* in_bn /* NULL, or the pending BatchNorm of X (in_scale / in_shift then unused) */,
+               void* stream);
 
 /* hi/lo tf32 split of a weight matrix for the large-K tensor-core kernel: out[0][n][k] = w with the low 13
  * mantissa bits cleared, out[1][n][k] = w - hi; rows padded with zeros to ldw (multiple of 4) floats.
  * Pass the result as w_split/ldws to p2c_linear; NULL keeps large-K layers on the fp32 SIMT kernel. */
 int p2c_split_tf32(const float* W, int N, int K, float* out /* (2,N,ldw) */, int64_t ldw, void* stream);
+/* The same for up to 16 weight matrices in ONE launch (host arrays of `count` device pointers / sizes): every
+ * streamed-weight layer of a forward pass is split by a single kernel. */
+int p2c_split_tf32_multi(const float* const* W, const int* N, const int* K, float* const* out, const int64_t* ldw,
+                         int count, void* stream);
 
 /* bf16 copy of a weight matrix for P2C_PREC_BF16: out (N, ldw) bf16 (round-to-nearest), rows zero padded to ldw
  * (multiple of 8) elements.  Pass it as w_split (ldws = ldw) to p2c_linear with precision P2C_PREC_BF16: the layer then
@@ -123,7 +153,7 @@ int p2c_debug_set_timeline(void* buf);
  * W: the heads' weights concatenated (Nout, C), Nout <= 36, C <= 256, C % 16 == 0. */
 int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
                     const float* mask_cf, const int64_t* dropout_seed, const float* W, const float* bias, float* Y,
-                    int64_t ldy, int B, int N, int C, int Nout, void* stream);
+                    int64_t ldy, int B, int N, int C, int Nout, const p2c_bn_fold* bn /* or NULL */, void* stream);
 
 /* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
  * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
@@ -137,13 +167,13 @@ int p2c_bn_finalize(const double* stats, int64_t count, const float* gamma, cons
 /* out[m,c] = max(Y[m,c]*scale[c]+shift[c], 0) — the BN+ReLU application where a layer's output
  * has to exist in memory (module outputs). */
 int p2c_bn_relu_apply(const float* Y, int64_t ldy, const float* scale, const float* shift,
-                      float* out, int64_t ldo, int64_t M, int C, void* stream);
+                      float* out, int64_t ldo, int64_t M, int C, const p2c_bn_fold* bn /* or NULL */, void* stream);
 
 /* Pooled BN+ReLU: out[g,c] = max(v*scale[c]+shift[c], 0) with v = scale[c] >= 0 ? Ymax : Ymin —
  * equals max over the group of relu(bn(y)) (models/pointnet_util.py:203-205) by monotonicity.
  * Also emits nothing else; arg-max routing for backward is recomputed there. */
 int p2c_pool_bn_relu(const float* Ymax, const float* Ymin, const float* scale, const float* shift,
-                     float* out, int64_t ldo, int64_t G, int C, void* stream);
+                     float* out, int64_t ldo, int64_t G, int C, const p2c_bn_fold* bn /* or NULL */, void* stream);
 
 /* 3-NN inverse-distance interpolation — replaces PointNetFeaturePropagation's
  * square_distance + sort + gather + weighted sum, models/pointnet_util.py:301-308.

@@ -22,6 +22,16 @@ i32 = C.c_int
 f32 = C.c_float
 vp = C.c_void_p
 
+class BnFold(C.Structure):
+    """include/point2cyl.h: p2c_bn_fold (a BatchNorm whose finalisation is deferred to the consuming kernel)."""
+    _fields_ = [("stats", C.c_void_p), ("count", C.c_int64), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("eps", C.c_float), ("momentum", C.c_float), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("scale_out", C.c_void_p), ("shift_out", C.c_void_p),
+                ("mean_out", C.c_void_p), ("invstd_out", C.c_void_p), ("C", C.c_int)]
+
+
+bnp = C.POINTER(BnFold)
+
 # name -> argtypes; restype is int unless noted.  Kept in the same order as include/point2cyl.h.
 SIGNATURES = {
     "p2c_version": [],
@@ -33,16 +43,18 @@ SIGNATURES = {
     "p2c_sa_first_layer": [c_f32p, c_f32p, c_i64p, c_f32p, i64, c_f32p, i64, c_f32p, i32, i32, i32, i32, i32, c_f32p,
                            i64, c_f64p, vp],
     "p2c_linear": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, c_f32p, i64, i32, i32, i32,
-                   c_f64p, i32, c_f32p, c_f32p, i32, c_f32p, i64, vp],
+                   c_f64p, i32, c_f32p, c_f32p, i32, c_f32p, i64, bnp, vp],
     "p2c_split_tf32": [c_f32p, i32, i32, c_f32p, i64, vp],
+    "p2c_split_tf32_multi": [vp, vp, vp, vp, vp, i32, vp],
     "p2c_cast_bf16": [c_f32p, i32, i32, vp, i64, vp],
     "p2c_linear_path": [i64, i32, i32, i32, i32, i32, i32, i32],
     "p2c_debug_set_timeline": [vp],
-    "p2c_head_masked": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_i64p, c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, vp],
+    "p2c_head_masked": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_i64p, c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32,
+                        bnp, vp],
     "p2c_bn_finalize": [c_f64p, i64, c_f32p, c_f32p, f32, f32, i32, c_f32p, c_f32p, c_f32p, c_f32p,
                         c_f32p, c_f32p, i32, vp],
-    "p2c_bn_relu_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i64, i32, vp],
-    "p2c_pool_bn_relu": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, i64, i32, vp],
+    "p2c_bn_relu_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i64, i32, bnp, vp],
+    "p2c_pool_bn_relu": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, i64, i32, bnp, vp],
     "p2c_three_nn_interp": [c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32, c_f32p, i64, c_i64p, c_f32p, vp],
     "p2c_three_nn_search": [c_f32p, c_f32p, i32, i32, i32, c_i64p, c_f32p, vp],
     "p2c_three_nn_gather": [c_f32p, i64, c_i64p, c_f32p, i32, i32, i32, i32, c_f32p, i64, vp],
@@ -153,7 +165,7 @@ def need_cuda(*tensors) -> None:
 
 # kernels launched by one call of each entry point (the `gpu_launches` claim of bench.py)
 LAUNCHES_PER_CALL = {
-    "p2c_split_tf32": 1, "p2c_cast_bf16": 1, "p2c_sa_first_layer": 1, "p2c_head_masked": 1, "p2c_fps": 1, "p2c_ball_query": 1, "p2c_group": 1, "p2c_linear": 1, "p2c_bn_finalize": 1,
+    "p2c_split_tf32": 1, "p2c_split_tf32_multi": 1, "p2c_cast_bf16": 1, "p2c_sa_first_layer": 1, "p2c_head_masked": 1, "p2c_fps": 1, "p2c_ball_query": 1, "p2c_group": 1, "p2c_linear": 1, "p2c_bn_finalize": 1,
     "p2c_bn_relu_apply": 1, "p2c_pool_bn_relu": 1, "p2c_three_nn_interp": 1, "p2c_three_nn_search": 1, "p2c_three_nn_gather": 1, "p2c_segfit_stats": 2, "p2c_segfit_stats_w": 2,
     "p2c_segfit_cost": 1, "p2c_hungarian": 1, "p2c_bb_loss": 2, "p2c_loss_finalize": 2, "p2c_eig3x3_smallest": 1,
     "p2c_square_distance": 1, "p2c_gather_rows": 1, "p2c_segment_lists": 1, "p2c_sketch_project": 1, "p2c_sketch_project_bwd": 1,

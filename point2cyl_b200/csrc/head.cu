@@ -7,7 +7,7 @@
 // Each thread streams its own H row 64 bytes (two full sectors) at a time, software-pipelined one step ahead;
 // W^T lives in shared memory and is read as broadcast float4; the Y tile is staged through shared memory so
 // the (rows x Nout) block leaves as one contiguous run.
-#include "common.cuh"
+#include "bn_fold.cuh"
 
 namespace {
 
@@ -18,7 +18,8 @@ template <int NP>   // NP = Nout padded to a multiple of 4
 __global__ void __launch_bounds__(HEAD_ROWS)
 head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ scale, const float* __restrict__ shift,
             const float* __restrict__ mask_cf, const int64_t* __restrict__ seed, const float* __restrict__ W,
-            const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy, int64_t M, int N, int C, int Nout) {
+            const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy, int64_t M, int N, int C, int Nout,
+            const BnFoldDev bn) {
   extern __shared__ __align__(16) float sm[];
   float* s_wt = sm;                           // [C][NP]   (W transposed, zero padded)
   float* s_sc = s_wt + C * NP;                // [C]
@@ -32,10 +33,15 @@ head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ 
     s_wt[e] = j < Nout ? __ldg(W + (size_t)j * C + k) : 0.f;
   }
   for (int k = tid; k < C; k += HEAD_ROWS) {
-    s_sc[k] = scale ? __ldg(scale + k) : 1.f;
-    s_sh[k] = shift ? __ldg(shift + k) : 0.f;
+    if (bn.active) {                          // pending bn1: folded here, CTA 0 publishes it
+      p2c_bn_fold_channel(bn, k, blockIdx.x == 0, s_sc[k], s_sh[k]);
+    } else {
+      s_sc[k] = scale ? __ldg(scale + k) : 1.f;
+      s_sh[k] = shift ? __ldg(shift + k) : 0.f;
+    }
   }
   __syncthreads();
+  const bool affine = scale != nullptr || bn.active;
 
   const int64_t m = m0 + tid;
   const bool ok = m < M;
@@ -78,7 +84,7 @@ head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < KC; ++i) {
       float xi = x[i];
-      if (scale) xi = fmaxf(fmaf(xi, s_sc[k0 + i], s_sh[k0 + i]), 0.f);
+      if (affine) xi = fmaxf(fmaf(xi, s_sc[k0 + i], s_sh[k0 + i]), 0.f);
       xi *= mcur[i];
       const float* wr = s_wt + (k0 + i) * NP;
 #pragma unroll
@@ -110,11 +116,11 @@ head_kernel(const float* __restrict__ H, int64_t ldh, const float* __restrict__ 
 template <int NP>
 int launch_head(const float* H, int64_t ldh, const float* scale, const float* shift, const float* mask_cf,
                 const int64_t* seed, const float* W, const float* bias, float* Y, int64_t ldy, int64_t M, int N, int C,
-                int Nout, cudaStream_t st) {
+                int Nout, const BnFoldDev& bn, cudaStream_t st) {
   const size_t smem = ((size_t)C * NP + 2 * C + (size_t)HEAD_ROWS * Nout) * sizeof(float);
   auto k = head_kernel<NP>;
   if (smem > 48 * 1024) P2C_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<p2c_ceil_div(M, HEAD_ROWS), HEAD_ROWS, smem, st>>>(H, ldh, scale, shift, mask_cf, seed, W, bias, Y, ldy, M, N, C, Nout);
+  k<<<p2c_ceil_div(M, HEAD_ROWS), HEAD_ROWS, smem, st>>>(H, ldh, scale, shift, mask_cf, seed, W, bias, Y, ldy, M, N, C, Nout, bn);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }
@@ -123,14 +129,17 @@ int launch_head(const float* H, int64_t ldh, const float* scale, const float* sh
 
 extern "C" int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
                                const float* mask_cf, const int64_t* dropout_seed, const float* W, const float* bias,
-                               float* Y, int64_t ldy, int B, int N, int C, int Nout, void* stream) {
+                               float* Y, int64_t ldy, int B, int N, int C, int Nout, const p2c_bn_fold* bn,
+                               void* stream) {
   if (!H || !W || !Y || B <= 0 || N <= 0 || C <= 0 || Nout <= 0 || ldh < C || ldy < Nout) return P2C_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return P2C_EINVAL;
+  if (int e = p2c_bn_fold_check(bn, C)) return e;
+  const BnFoldDev bnd = p2c_bn_fold_dev(bn);
   if (C % 16 != 0 || (ldh % 4) != 0 || (reinterpret_cast<uintptr_t>(H) & 15) != 0) return P2C_EALIGN;
   if (C > 256 || Nout > 36) return P2C_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = (int64_t)B * N;
-#define P2C_HEAD(NPV) return launch_head<NPV>(H, ldh, scale, shift, mask_cf, dropout_seed, W, bias, Y, ldy, M, N, C, Nout, st)
+#define P2C_HEAD(NPV) return launch_head<NPV>(H, ldh, scale, shift, mask_cf, dropout_seed, W, bias, Y, ldy, M, N, C, Nout, bnd, st)
   if (Nout <= 4) P2C_HEAD(4);
   if (Nout <= 8) P2C_HEAD(8);
   if (Nout <= 12) P2C_HEAD(12);

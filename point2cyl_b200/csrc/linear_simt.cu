@@ -9,7 +9,7 @@
 // one is the full-fp32 fallback for shapes they do not take and the in-library cross-check.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "bn_fold.cuh"
 
 #include <math_constants.h>
 
@@ -328,6 +328,46 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
   if (save_invstd) save_invstd[c] = (float)invstd;
 }
 
+// the pending BatchNorm folded by every CTA into shared memory (CTA 0 publishes it)
+__device__ __forceinline__ void fold_to_smem(const BnFoldDev& bn, float* s_sc, float* s_sh, int C) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) p2c_bn_fold_channel(bn, c, blockIdx.x == 0, s_sc[c], s_sh[c]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_apply_fold_kernel(const float* __restrict__ Y, int64_t ldy, const BnFoldDev bn, float* __restrict__ out,
+                          int64_t ldo, int64_t M, int C) {
+  extern __shared__ float s_fold[];
+  float* s_sc = s_fold;
+  float* s_sh = s_fold + C;
+  fold_to_smem(bn, s_sc, s_sh, C);
+  const int64_t total = M * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / C;
+    const int c = (int)(e - m * C);
+    out[m * ldo + c] = fmaxf(fmaf(__ldg(Y + m * ldy + c), s_sc[c], s_sh[c]), 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pool_bn_relu_fold_kernel(const float* __restrict__ Ymax, const float* __restrict__ Ymin, const BnFoldDev bn,
+                         float* __restrict__ out, int64_t ldo, int64_t G, int C) {
+  extern __shared__ float s_fold[];
+  float* s_sc = s_fold;
+  float* s_sh = s_fold + C;
+  fold_to_smem(bn, s_sc, s_sh, C);
+  const int64_t total = G * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = e / C;
+    const int c = (int)(e - g * C);
+    const float s = s_sc[c];
+    const float v = s >= 0.f ? __ldg(Ymax + e) : __ldg(Ymin + e);
+    out[g * ldo + c] = fmaxf(fmaf(v, s, s_sh[c]), 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 bn_relu_apply_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ scale,
                      const float* __restrict__ shift, float* __restrict__ out, int64_t ldo,
@@ -362,19 +402,31 @@ pool_bn_relu_kernel(const float* __restrict__ Ymax, const float* __restrict__ Ym
 int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias,
                   const float* in_scale, const float* in_shift, const float* in_mask,
                   int64_t ldmask, float* Y, int64_t ldy, int M, int N, int K, double* stats,
-                  int pool_group, float* Ymax, float* Ymin, int precision, cudaStream_t st);
+                  int pool_group, float* Ymax, float* Ymin, int precision, const p2c_bn_fold* in_bn, cudaStream_t st);
 int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int pool_group, int precision);
 int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                      const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
-                     double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, cudaStream_t st);
+                     double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, const p2c_bn_fold* in_bn,
+                     cudaStream_t st);
+
+// the stand-alone finalisation of a pending BatchNorm (kernels that do not fold it themselves)
+static int resolve_bn_fold(const p2c_bn_fold* f, cudaStream_t st) {
+  bn_finalize_kernel<<<p2c_ceil_div(f->C, 128), 128, 0, st>>>(f->stats, (double)f->count, f->gamma, f->beta, f->eps,
+                                                            f->momentum, f->stats != nullptr, f->running_mean,
+                                                            f->running_var, f->scale_out, f->shift_out, f->mean_out,
+                                                            f->invstd_out, f->C);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
 
 extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                           const float* in_scale, const float* in_shift, const float* in_mask,
                           int64_t ldmask, float* Y, int64_t ldy, int M, int N, int K, double* stats,
                           int pool_group, float* Ymax, float* Ymin, int precision, const float* w_split,
-                          int64_t ldws, void* stream) {
+                          int64_t ldws, const p2c_bn_fold* in_bn, void* stream) {
   if (!X || !W || M <= 0 || N <= 0 || K <= 0 || ldx < K) return P2C_EINVAL;
   if ((in_scale == nullptr) != (in_shift == nullptr)) return P2C_EINVAL;
+  if (int e = p2c_bn_fold_check(in_bn, K)) return e;
   if (!Y && !pool_group && !stats) return P2C_EINVAL;
   if (Y && ldy < N) return P2C_EINVAL;
   if (pool_group) {
@@ -387,15 +439,20 @@ extern "C" int p2c_linear(const float* X, int64_t ldx, const float* W, const flo
     int rc = P2C_EUNSUPPORTED;
     if (!(force_ss && w_split) && precision != P2C_PREC_BF16)
       rc = p2c_linear_tc(X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
-                         stats, pool_group, Ymax, Ymin, precision, st);
+                         stats, pool_group, Ymax, Ymin, precision, in_bn, st);
     if (rc != P2C_EUNSUPPORTED) return rc;
     if (w_split && p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, in_mask != nullptr,
                                          pool_group, precision)) {
       rc = p2c_linear_tc_ss(X, ldx, w_split, ldws, bias, in_scale, in_shift, Y, ldy, M, N, K, stats, pool_group,
-                            Ymax, Ymin, precision == P2C_PREC_BF16 ? 1 : 0, st);
+                            Ymax, Ymin, precision == P2C_PREC_BF16 ? 1 : 0, in_bn, st);
       if (rc != P2C_EUNSUPPORTED) return rc;
     }
     // shapes the tensor-core kernels do not take fall through to the fp32 SIMT kernel (still CUDA)
+  }
+  if (in_bn) {   // the SIMT kernel reads scale / shift from global memory: finalise first
+    if (int e = resolve_bn_fold(in_bn, st)) return e;
+    in_scale = in_bn->scale_out;
+    in_shift = in_bn->shift_out;
   }
   LinearArgs a{X, ldx, W, bias, in_scale, in_shift, in_mask, ldmask, Y, ldy, M, N, K,
                stats, pool_group, Ymax, Ymin};
@@ -419,10 +476,21 @@ extern "C" int p2c_bn_finalize(const double* stats, int64_t count, const float* 
 }
 
 extern "C" int p2c_bn_relu_apply(const float* Y, int64_t ldy, const float* scale, const float* shift,
-                                 float* out, int64_t ldo, int64_t M, int C, void* stream) {
-  if (!Y || !scale || !shift || !out || M <= 0 || C <= 0) return P2C_EINVAL;
+                                 float* out, int64_t ldo, int64_t M, int C, const p2c_bn_fold* bn, void* stream) {
+  if (!Y || !out || M <= 0 || C <= 0 || (!bn && (!scale || !shift))) return P2C_EINVAL;
+  if (int e = p2c_bn_fold_check(bn, C)) return e;
   const int64_t total = M * C;
   const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
+  if (bn && C <= 4096) {
+    bn_relu_apply_fold_kernel<<<blocks, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(Y, ldy, p2c_bn_fold_dev(bn),
+                                                                                           out, ldo, M, C);
+    P2C_RETURN_IF_CUDA_ERROR();
+    return 0;
+  }
+  if (bn) {
+    if (int e = resolve_bn_fold(bn, (cudaStream_t)stream)) return e;
+    scale = bn->scale_out; shift = bn->shift_out;
+  }
   bn_relu_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y, ldy, scale, shift, out, ldo, M, C);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
@@ -430,10 +498,21 @@ extern "C" int p2c_bn_relu_apply(const float* Y, int64_t ldy, const float* scale
 
 extern "C" int p2c_pool_bn_relu(const float* Ymax, const float* Ymin, const float* scale,
                                 const float* shift, float* out, int64_t ldo, int64_t G, int C,
-                                void* stream) {
-  if (!Ymax || !Ymin || !scale || !shift || !out || G <= 0 || C <= 0) return P2C_EINVAL;
+                                const p2c_bn_fold* bn, void* stream) {
+  if (!Ymax || !Ymin || !out || G <= 0 || C <= 0 || (!bn && (!scale || !shift))) return P2C_EINVAL;
+  if (int e = p2c_bn_fold_check(bn, C)) return e;
   const int64_t total = G * C;
   const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
+  if (bn && C <= 4096) {
+    pool_bn_relu_fold_kernel<<<blocks, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(Ymax, Ymin, p2c_bn_fold_dev(bn),
+                                                                                          out, ldo, G, C);
+    P2C_RETURN_IF_CUDA_ERROR();
+    return 0;
+  }
+  if (bn) {
+    if (int e = resolve_bn_fold(bn, (cudaStream_t)stream)) return e;
+    scale = bn->scale_out; shift = bn->shift_out;
+  }
   pool_bn_relu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Ymax, Ymin, scale, shift, out, ldo, G, C);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;

@@ -31,6 +31,7 @@
 // TMEM columns: [0, 128*ACC) accumulators (ACC = 2 when K <= 128, else 1), then W_hi [KPAD] | W_lo [KPAD].
 #include <cstdlib>
 
+#include "bn_fold.cuh"
 #include "tc_common.cuh"
 
 using namespace p2c_tc;
@@ -52,6 +53,7 @@ struct TcArgs {
   int y_tma;        // Y rows are 16-byte aligned: per-warp TMA stores of [32 rows x 32 channels] boxes
   long long* dbg;   // optional timeline buffer (tools/tc_timeline.py); NULL in production
   int dbg_mode;     // tools only (env P2C_TC_DBG): bit0 skip transform math, bit1 skip epilogue body
+  BnFoldDev bn;     // pending BatchNorm of X, folded in the prologue (bn.active) instead of in_scale / in_shift
 };
 
 struct SmemLayout {
@@ -117,9 +119,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   for (int k = tid; k < KPAD; k += LTC_THREADS) {
-    const bool ok = a.in_scale != nullptr && k < a.K;
-    s_scale[k] = ok ? __ldg(a.in_scale + k) : 0.f;
-    s_shift[k] = ok ? __ldg(a.in_shift + k) : 0.f;
+    float sc = 0.f, sh = 0.f;
+    if (k < a.K) {
+      if (a.bn.active) p2c_bn_fold_channel(a.bn, k, blockIdx.x == 0 && blockIdx.y == 0, sc, sh);
+      else if (a.in_scale) { sc = __ldg(a.in_scale + k); sh = __ldg(a.in_shift + k); }
+    }
+    s_scale[k] = sc;
+    s_shift[k] = sh;
   }
   tc_fence_before();
   __syncthreads();
@@ -226,7 +232,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // BatchNorm scale/shift are 8 registers per k-block instead of shared-memory loads per element
     const int tt = tid - 256;
     const int cj = tt & 7, rg = tt >> 3;
-    const bool has_affine = a.in_scale != nullptr && !(a.dbg_mode & 1);
+    const bool has_affine = (a.in_scale != nullptr || a.bn.active) && !(a.dbg_mode & 1);
     int s = 0; uint32_t ph = 0;
     int xs = 0; uint32_t xph = 0;
     int dbg_n = 0;
@@ -452,7 +458,8 @@ extern "C" int p2c_linear_path(int64_t ldx, int M, int N, int K, int has_mask, i
 
 int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias, const float* in_scale,
                   const float* in_shift, const float* in_mask, int64_t ldmask, float* Y, int64_t ldy, int M, int N,
-                  int K, double* stats, int pool_group, float* Ymax, float* Ymin, int precision, cudaStream_t st) {
+                  int K, double* stats, int pool_group, float* Ymax, float* Ymin, int precision,
+                  const p2c_bn_fold* in_bn, cudaStream_t st) {
   (void)ldmask;
   TcPlan p;
   if (!tc_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, M, N, K, in_mask != nullptr, pool_group, precision, &p))
@@ -485,7 +492,8 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
   const char* dm = getenv("P2C_TC_DBG");
   p.raw_stages = tc_raw_stages(p.KB, p.xt_stages, y_tma);
   TcArgs a{W, bias, in_scale, in_shift, Y, ldy, M, N, K, p.KB, stats, pool_group, Ymax, Ymin,
-           p.raw_stages, p.xt_stages, p.acc_bufs, (M + TC_BM - 1) / TC_BM, y_tma, g_tc_dbg, dm ? atoi(dm) : 0};
+           p.raw_stages, p.xt_stages, p.acc_bufs, (M + TC_BM - 1) / TC_BM, y_tma, g_tc_dbg, dm ? atoi(dm) : 0,
+           p2c_bn_fold_dev(in_bn)};
   const SmemLayout L = tc_smem_layout(p.KB, p.raw_stages, p.xt_stages, y_tma);
   int dev = 0;
   cudaGetDevice(&dev);

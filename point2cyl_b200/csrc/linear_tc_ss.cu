@@ -8,6 +8,7 @@
 // round-robin to a persistent grid; consecutive CTAs share a row tile (L2 reuse of X).
 #include <cstdlib>
 
+#include "bn_fold.cuh"
 #include "tc_common.cuh"
 
 using namespace p2c_tc;
@@ -28,6 +29,7 @@ struct SsArgs {
   int raw_stages, xt_stages;
   int m_tiles, n_tiles;
   int y_tma;
+  BnFoldDev bn;     // pending BatchNorm of X, folded in the prologue (bn.active) instead of in_scale / in_shift
 };
 
 // ---- bf16 mode (P2C_PREC_BF16): one kind::f16 MMA pass on bf16 operands instead of the three tf32 passes ----
@@ -137,9 +139,13 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
   for (int k = tid; k < KPAD; k += SS_THREADS) {
-    const bool ok = a.in_scale != nullptr && k < a.K;
-    s_scale[k] = ok ? __ldg(a.in_scale + k) : 0.f;
-    s_shift[k] = ok ? __ldg(a.in_shift + k) : 0.f;
+    float sc = 0.f, sh = 0.f;
+    if (k < a.K) {
+      if (a.bn.active) p2c_bn_fold_channel(a.bn, k, blockIdx.x == 0, sc, sh);
+      else if (a.in_scale) { sc = __ldg(a.in_scale + k); sh = __ldg(a.in_shift + k); }
+    }
+    s_scale[k] = sc;
+    s_shift[k] = sh;
   }
   tc_fence_before();
   __syncthreads();
@@ -217,7 +223,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // ===== operand transform (see linear_tc.cu) =====
     const int tt = tid - 256;
     const int cj = tt & 7, rg = tt >> 3;
-    const bool has_affine = a.in_scale != nullptr;
+    const bool has_affine = a.in_scale != nullptr || a.bn.active;
     int s = 0; uint32_t ph = 0;
     int xs = 0; uint32_t xph = 0;
     for (int t = 0; t < my_tiles; ++t) {
@@ -373,6 +379,30 @@ split_tf32_kernel(const float* __restrict__ W, int N, int K, float* __restrict__
   }
 }
 
+// All streamed-weight layers of a forward in ONE launch: blockIdx.y = matrix (descriptors passed by value)
+constexpr int SPLIT_MULTI_MAX = 16;
+struct SplitMulti {
+  const float* W[SPLIT_MULTI_MAX];
+  float* out[SPLIT_MULTI_MAX];
+  int N[SPLIT_MULTI_MAX], K[SPLIT_MULTI_MAX], ldw[SPLIT_MULTI_MAX];
+};
+__global__ void __launch_bounds__(256)
+split_tf32_multi_kernel(const SplitMulti d) {
+  const int m = blockIdx.y;
+  const float* __restrict__ W = d.W[m];
+  float* __restrict__ out = d.out[m];
+  const int K = d.K[m];
+  const int64_t ldw = d.ldw[m], total = (int64_t)d.N[m] * ldw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e / ldw;
+    const int k = (int)(e - n * ldw);
+    const float w = k < K ? __ldg(W + n * K + k) : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    out[e] = hi;
+    out[total + e] = w - hi;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ W, int N, int K, uint16_t* __restrict__ out, int64_t ldw) {
   const int64_t total = (int64_t)N * ldw;
@@ -405,6 +435,24 @@ extern "C" int p2c_split_tf32(const float* W, int N, int K, float* out, int64_t 
   return 0;
 }
 
+extern "C" int p2c_split_tf32_multi(const float* const* W, const int* N, const int* K, float* const* out,
+                                    const int64_t* ldw, int count, void* stream) {
+  if (!W || !N || !K || !out || !ldw || count <= 0) return P2C_EINVAL;
+  if (count > SPLIT_MULTI_MAX) return P2C_EUNSUPPORTED;
+  SplitMulti d;
+  int64_t biggest = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!W[i] || !out[i] || N[i] <= 0 || K[i] <= 0 || ldw[i] < K[i] || (ldw[i] % 4) != 0) return P2C_EINVAL;
+    d.W[i] = W[i]; d.out[i] = out[i]; d.N[i] = N[i]; d.K[i] = K[i]; d.ldw[i] = (int)ldw[i];
+    biggest = max(biggest, (int64_t)N[i] * ldw[i]);
+  }
+  for (int i = count; i < SPLIT_MULTI_MAX; ++i) { d.W[i] = nullptr; d.out[i] = nullptr; d.N[i] = d.K[i] = d.ldw[i] = 0; }
+  dim3 grid((unsigned)min((int64_t)64, (biggest + 255) / 256), (unsigned)count);
+  split_tf32_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
 extern "C" int p2c_cast_bf16(const float* W, int N, int K, void* out, int64_t ldw, void* stream) {
   if (!W || !out || N <= 0 || K <= 0 || ldw < K || (ldw % 8) != 0) return P2C_EINVAL;
   const int64_t total = (int64_t)N * ldw;
@@ -425,7 +473,8 @@ int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int
 
 int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                      const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
-                     double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, cudaStream_t st) {
+                     double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, const p2c_bn_fold* in_bn,
+                     cudaStream_t st) {
   const int KB = (K + TC_BK - 1) / TC_BK;
   const int y_tma = (Y && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
   int raw, xt;
@@ -454,7 +503,7 @@ int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t 
   tmY = tmX;
   if (y_tma && (rc = make_map_2d(&tmY, Y, N, M, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
-           (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma};
+           (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn)};
   const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma);
   int dev = 0;
   cudaGetDevice(&dev);

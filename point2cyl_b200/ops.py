@@ -121,7 +121,7 @@ def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None
            in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
            in_mask: Optional[Tensor] = None, stats: Optional[Tensor] = None, pool_group: int = 0,
            out: Optional[Tensor] = None, want_y: bool = True, precision: int = _lib.PREC_FP32,
-           w_split: Optional[Tensor] = None):
+           w_split: Optional[Tensor] = None, in_bn: Optional["PendingBN"] = None):
     """One MLP layer.  X (M, >=K) rows, W (N, K) (any trailing singleton dims), returns Y (M,N) or,
     with pool_group, (Y or None, Ymax, Ymin).  stats: float64 (2N,) accumulator (pre-zeroed)."""
     need_cuda(X, W)
@@ -144,11 +144,12 @@ def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None
         Ymin = torch.empty_like(Ymax)
     if in_mask is not None:
         _rows(in_mask)
-    call("p2c_linear", 
-        ptr(X), X.stride(0), ptr(W2), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(in_mask),
+    ps, ph, d = _fold_args(in_bn, in_scale, in_shift)
+    call("p2c_linear",
+        ptr(X), X.stride(0), ptr(W2), ptr(bias), ps, ph, ptr(in_mask),
         0 if in_mask is None else in_mask.stride(0), ptr(Y), 0 if Y is None else Y.stride(0), M, N, K,
         ptr(stats), pool_group, ptr(Ymax), ptr(Ymin), precision, ptr(w_split),
-        0 if w_split is None else w_split.shape[-1], stream_ptr())
+        0 if w_split is None else w_split.shape[-1], d, stream_ptr())
     if pool_group:
         return Y, Ymax, Ymin
     return Y
@@ -162,7 +163,8 @@ def _seed(seed: Optional[Tensor]) -> Optional[Tensor]:
 
 
 def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mask_cf: Optional[Tensor],
-                W: Tensor, bias: Optional[Tensor], B: int, N: int, seed: Optional[Tensor] = None) -> Tensor:
+                W: Tensor, bias: Optional[Tensor], B: int, N: int, seed: Optional[Tensor] = None,
+                bn: Optional["PendingBN"] = None) -> Tensor:
     """Output heads: (B*N, C) raw fc1 rows -> (B*N, Nout); mask_cf is the (B, C, N) dropout mask, or - with
     mask_cf None - `seed` (two int64 words on the device) makes the kernel draw the p=0.5 mask itself (Philox)."""
     H = _rows(H)
@@ -172,8 +174,9 @@ def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mas
     if mask_cf is not None and (tuple(mask_cf.shape) != (B, C_, N) or not mask_cf.is_contiguous()):
         raise _lib.P2CError(f"head_masked: mask must be contiguous (B,C,N)=({B},{C_},{N}), got {tuple(mask_cf.shape)}")
     Y = torch.empty(B * N, Nout, dtype=torch.float32, device=H.device)
-    call("p2c_head_masked", ptr(H), H.stride(0), ptr(scale), ptr(shift), ptr(mask_cf), ptr(_seed(seed)), ptr(W2), ptr(bias), ptr(Y),
-         Nout, B, N, C_, Nout, stream_ptr())
+    ps, ph, d = _fold_args(bn, scale, shift)
+    call("p2c_head_masked", ptr(H), H.stride(0), ps, ph, ptr(mask_cf), ptr(_seed(seed)), ptr(W2), ptr(bias), ptr(Y),
+         Nout, B, N, C_, Nout, d, stream_ptr())
     return Y
 
 
@@ -186,6 +189,28 @@ def split_tf32(W: Tensor) -> Tensor:
     out = torch.empty(2, N, pad4(K), dtype=torch.float32, device=W.device)
     call("p2c_split_tf32", ptr(W2), N, K, ptr(out), out.shape[2], stream_ptr())
     return out
+
+
+def split_tf32_multi(weights, outs=None):
+    """hi/lo split of several weight matrices in ONE launch.  weights: list of (N, K[,1[,1]]) tensors; outs: matching
+    list of (2, N, pad4(K)) buffers to refresh (allocated when None).  Returns the list of split buffers."""
+    Ws = []
+    for W in weights:
+        W2 = W.reshape(W.shape[0], -1)
+        Ws.append(W2 if W2.is_contiguous() else W2.contiguous())
+    if outs is None:
+        outs = [torch.empty(2, W2.shape[0], pad4(W2.shape[1]), dtype=torch.float32, device=W2.device) for W2 in Ws]
+    res = list(outs)
+    for c0 in range(0, len(Ws), 16):
+        ws, os_ = Ws[c0:c0 + 16], outs[c0:c0 + 16]
+        n = len(ws)
+        pW = (C.c_void_p * n)(*[ptr(w) for w in ws])
+        pO = (C.c_void_p * n)(*[ptr(o) for o in os_])
+        aN = (C.c_int * n)(*[w.shape[0] for w in ws])
+        aK = (C.c_int * n)(*[w.shape[1] for w in ws])
+        aL = (C.c_int64 * n)(*[o.shape[2] for o in os_])
+        call("p2c_split_tf32_multi", pW, aN, aK, pO, aL, n, stream_ptr())
+    return res
 
 
 def cast_bf16(W: Tensor) -> Tensor:
@@ -216,6 +241,57 @@ def needs_split(X: Tensor, N: int, K: int, has_mask: bool, pool_group: int, prec
     return _lib.load().p2c_linear_path(X.stride(0), X.shape[0], N, K, int(has_mask), pool_group, precision, 1) == 2
 
 
+class PendingBN:
+    """A BatchNorm whose finalisation is deferred to the kernel that consumes it (include/point2cyl.h: p2c_bn_fold).
+    scale / shift (/ mean / invstd) are its output tensors: valid - in stream order - after the first consumer
+    (`fold()` hands the descriptor to that kernel, once) or after `resolve()` (the stand-alone p2c_bn_finalize)."""
+
+    def __init__(self, stats: Optional[Tensor], count: int, gamma: Tensor, beta: Tensor, eps: float, momentum: float,
+                 training: bool, running_mean: Optional[Tensor], running_var: Optional[Tensor], save: bool = False,
+                 out: Optional[Tensor] = None):
+        C_ = gamma.shape[0]
+        buf = out if out is not None else torch.empty(4 * C_, dtype=torch.float32, device=gamma.device)
+        self.scale, self.shift = buf[:C_], buf[C_:2 * C_]
+        self.mean = buf[2 * C_:3 * C_] if save else None
+        self.invstd = buf[3 * C_:4 * C_] if save else None
+        self.training, self.count, self.C = training, int(count), C_
+        self._keep = (stats, gamma, beta, running_mean, running_var, buf)
+        self._desc = _lib.BnFold(
+            stats=ptr(stats) if training else None, count=int(count), gamma=ptr(gamma), beta=ptr(beta), eps=float(eps),
+            momentum=float(momentum), running_mean=ptr(running_mean), running_var=ptr(running_var),
+            scale_out=ptr(self.scale), shift_out=ptr(self.shift), mean_out=ptr(self.mean),
+            invstd_out=ptr(self.invstd), C=C_)
+        self.pending = True
+
+    def fold(self):
+        """ctypes pointer to the descriptor for the ONE kernel that folds it (None once it has been consumed)."""
+        if not self.pending:
+            return None
+        self.pending = False
+        return C.byref(self._desc)
+
+    def resolve(self) -> None:
+        """Finalise with the stand-alone kernel if no consumer has folded it yet."""
+        if not self.pending:
+            return
+        self.pending = False
+        stats, gamma, beta, rm, rv, _ = self._keep
+        call("p2c_bn_finalize", ptr(stats), self.count, ptr(gamma), ptr(beta), self._desc.eps, self._desc.momentum,
+             1 if self.training else 0, ptr(rm), ptr(rv), ptr(self.scale), ptr(self.shift), ptr(self.mean),
+             ptr(self.invstd), self.C, stream_ptr())
+
+
+def _fold_args(bn: Optional["PendingBN"], scale: Optional[Tensor], shift: Optional[Tensor]):
+    """(scale ptr, shift ptr, descriptor or None) for a consumer call: a still-pending BatchNorm goes in as the
+    descriptor, an already finalised one (or plain arrays) as pointers."""
+    d = bn.fold() if bn is not None else None
+    if bn is not None and d is None:
+        scale, shift = bn.scale, bn.shift
+    if d is not None:
+        return None, None, d
+    return ptr(scale), ptr(shift), None
+
+
 def bn_finalize(stats: Optional[Tensor], count: int, gamma: Tensor, beta: Tensor, eps: float,
                 momentum: float, training: bool, running_mean: Optional[Tensor],
                 running_var: Optional[Tensor], save: bool = False):
@@ -234,25 +310,26 @@ def bn_finalize(stats: Optional[Tensor], count: int, gamma: Tensor, beta: Tensor
     return scale, shift
 
 
-def bn_relu_apply(Y: Tensor, scale: Tensor, shift: Tensor, out: Optional[Tensor] = None) -> Tensor:
+def bn_relu_apply(Y: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], out: Optional[Tensor] = None,
+                  bn: Optional[PendingBN] = None) -> Tensor:
     Y = _rows(Y)
     M, C_ = Y.shape
     if out is None:
         out = torch.empty(M, C_, dtype=torch.float32, device=Y.device)
     _rows(out)
-    call("p2c_bn_relu_apply", ptr(Y), Y.stride(0), ptr(scale), ptr(shift), ptr(out),
-                                        out.stride(0), M, C_, stream_ptr())
+    ps, ph, d = _fold_args(bn, scale, shift)
+    call("p2c_bn_relu_apply", ptr(Y), Y.stride(0), ps, ph, ptr(out), out.stride(0), M, C_, d, stream_ptr())
     return out
 
 
-def pool_bn_relu(Ymax: Tensor, Ymin: Tensor, scale: Tensor, shift: Tensor,
-                 out: Optional[Tensor] = None) -> Tensor:
+def pool_bn_relu(Ymax: Tensor, Ymin: Tensor, scale: Optional[Tensor], shift: Optional[Tensor],
+                 out: Optional[Tensor] = None, bn: Optional[PendingBN] = None) -> Tensor:
     G, C_ = Ymax.shape
     if out is None:
         out = torch.empty(G, C_, dtype=torch.float32, device=Ymax.device)
     _rows(out)
-    call("p2c_pool_bn_relu", ptr(Ymax), ptr(Ymin), ptr(scale), ptr(shift), ptr(out),
-                                       out.stride(0), G, C_, stream_ptr())
+    ps, ph, d = _fold_args(bn, scale, shift)
+    call("p2c_pool_bn_relu", ptr(Ymax), ptr(Ymin), ps, ph, ptr(out), out.stride(0), G, C_, d, stream_ptr())
     return out
 
 

