@@ -122,9 +122,23 @@ int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
  * Pass the result as w_split/ldws to p2c_linear; NULL keeps large-K layers on the fp32 SIMT kernel. */
 int p2c_split_tf32(const float* W, int N, int K, float* out /* (2,N,ldw) */, int64_t ldw, void* stream);
 /* The same for up to 16 weight matrices in ONE launch (host arrays of `count` device pointers / sizes): every
- * streamed-weight layer of a forward pass is split by a single kernel. */
+ * streamed-weight layer of a forward pass is split by a single kernel.  transposed (NULL = all 0): entry i != 0 means
+ * W[i] is stored as (K, N) and the split of its TRANSPOSE (N, K) is written (the reverse sweeps multiply by W^T).
+ * src_ld (NULL = dense): row stride of W[i] as stored, so a column block of a wider matrix can be the source. */
 int p2c_split_tf32_multi(const float* const* W, const int* N, const int* K, float* const* out, const int64_t* ldw,
-                         int count, void* stream);
+                         const int* transposed, const int64_t* src_ld, int count, void* stream);
+
+/* One hidden layer of the implicit sketch network (IGR/network.py:8-92: ImplicitNet.forward and gradient()) on the
+ * tensor cores, 3xTF32, weights pre-split (p2c_split_tf32[_multi]):
+ *   op 1 (forward sweep):  Z = X W^T + bias;  Y = softplus_beta(Z) * oscale  (nn.Softplus(beta), threshold 20);
+ *                          S = sigmoid(beta Z) (1 above the threshold) when S != NULL - softplus'(Z), kept for the
+ *                          closed-form input gradient;
+ *   op 2 (reverse sweep):  Y = (X W^T + bias) * Mul * oscale, Mul (M, N) read element-wise: a_{i-1} = s_{i-1} * (a_i W_i);
+ *   op 0:                  Y = X W^T + bias.
+ * X (M, K) rows with stride ldx (16-byte aligned rows), Y / S / Mul (M, N) rows; channels >= N are not written. */
+int p2c_linear_act(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias, int M, int N,
+                   int K, int op, float beta, float oscale, float* Y, int64_t ldy, float* S, int64_t lds,
+                   const float* Mul, int64_t ldmul, void* stream);
 
 /* bf16 copy of a weight matrix for P2C_PREC_BF16: out (N, ldw) bf16 (round-to-nearest), rows zero padded to ldw
  * (multiple of 8) elements.  Pass it as w_split (ldws = ldw) to p2c_linear with precision P2C_PREC_BF16: the layer then
@@ -401,6 +415,25 @@ int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf, const int
  * g = grads*grad_scale (+ weight_decay*p), m/v updated in place, bias-corrected with `step` (1-based). */
 int p2c_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* ---- implicit sketch network of the with-sketch trainer -------------------------------------------
+ * add_latent (IGR/network.py:200-206): X0[r] = [latent[r / S] (E) | pts[r] (2)], zero padded to ldx columns; when P is
+ * given the same row, times pscale, is also written at column colp of P (the skip concatenation, network.py:80-81). */
+int p2c_igr_add_latent(const float* latent /* (R/S, E) */, const float* pts /* (R, 2) */, int64_t R, int S, int E,
+                       float* X0, int64_t ldx, float* P, int64_t ldp, int colp, float pscale, void* stream);
+/* out[m, c] = A[m, c] * w[c]: seed of the closed-form input-gradient sweep, a = softplus'(z) * W_last. */
+int p2c_igr_scale_cols(const float* A, int64_t lda, const float* w, int64_t M, int C, float* out, int64_t ldo,
+                       void* stream);
+/* out[m, j] (+)= scale * <A[m, :C], V[j, :C]> + bias[j], NV in {1, 2}: the 512 -> 1 output layer (network.py:88-91) and
+ * the two columns of d f / d x that gradient() keeps (network.py:17). */
+int p2c_igr_rowdots(const float* A, int64_t lda, int64_t M, int C, const float* V, int64_t v_stride_j,
+                    int64_t v_stride_c /* V[j, c] = V[j * v_stride_j + c * v_stride_c] */, int NV, const float* bias,
+                    float scale, float* out, int64_t ldo, int accumulate, void* stream);
+/* Per sketch instance i (S on-surface rows, S_off off-surface rows): out[i] = { mean |f_on|, mean min(|g_on - n|,
+ * |g_on + n|), mean (|g_off| - 1)^2 } - the manifold, SALD-normal and eikonal terms before the masked instance mean,
+ * train_Point2Cyl.py:627-647. */
+int p2c_igr_loss_terms(const float* f_on, const float* g_on, const float* normals, const float* g_off, int instances,
+                       int S, int S_off, float* out /* (instances, 3) */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,11 @@ struct SsArgs {
   int m_tiles, n_tiles;
   int y_tma;
   BnFoldDev bn;     // pending BatchNorm of X, folded in the prologue (bn.active) instead of in_scale / in_shift
+  // activation / multiplier epilogues of the implicit-network layers (template parameter EPI, p2c_linear_act):
+  //   EPI 1: Y = softplus_beta(acc + bias) * oscale, S = sigmoid(beta (acc + bias));  EPI 2: Y = (acc + bias) * Mul * oscale
+  float beta, oscale;
+  int s_tma;                     // the second output S leaves through TMA stores too
+  const float* mul; int64_t ldmul;
 };
 
 // ---- bf16 mode (P2C_PREC_BF16): one kind::f16 MMA pass on bf16 operands instead of the three tf32 passes ----
@@ -86,7 +91,7 @@ __host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_
   L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES;
   L.xt_off = o;     o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
   L.w_off = o;      o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
-  L.ystage_off = o; o += y_stage ? 4u * 2u * 4096u : 0u;
+  L.ystage_off = o; o += (uint32_t)y_stage * 4u * 2u * 4096u;   // y_stage staging tiles of 4 KB per epilogue warp
   L.scale_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.shift_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.bar_off = o;    o += 512u;
@@ -94,14 +99,14 @@ __host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_
   return L;
 }
 
-template <bool BF16>
+template <bool BF16, int EPI>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmY,
-                    const SsArgs a) {
+                    const __grid_constant__ CUtensorMap tmS, const SsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma);
+  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma + a.s_tma);
   uint8_t* raw_sm = smem + L.raw_off;
   uint8_t* xt_sm = smem + L.xt_off;
   uint8_t* w_sm = smem + L.w_off;
@@ -324,6 +329,44 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
           __syncwarp();
         }
+        if (EPI != 0) {
+          // implicit-network epilogues (p2c_linear_act): both outputs leave through [32 rows x 32 channels] staging
+          // tiles and TMA stores (rows >= M and channels >= N are clipped by the tensor maps)
+          float* st2 = ystg + 8 * 1024;               // second tile of this warp: 8 warps x 4 KB further on
+          if (EPI == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float z = __uint_as_float(raw[j]) + bias;
+              const float bz = a.beta * z;
+              float h = z, sg = 1.f;                  // nn.Softplus(beta, threshold 20): identity above the threshold
+              if (!(bz > 20.f)) {
+                const float e = expf(bz);
+                h = __fdiv_rn(log1pf(e), a.beta);
+                sg = __fdiv_rn(e, 1.f + e);
+              }
+              st[j * 32 + lane] = h * a.oscale;
+              if (a.s_tma) st2[j * 32 + lane] = sg;
+            }
+          } else {
+            const float* mp = a.mul + (size_t)mrow * a.ldmul + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float m = (n_ok && j < jmax) ? __ldg(mp + (size_t)j * a.ldmul) : 0.f;   // warp = 128 B of row mrow+j
+              st[j * 32 + lane] = (__uint_as_float(raw[j]) + bias) * m * a.oscale;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+            if (EPI == 1 && a.s_tma)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmS)), "r"(smem_u32(st2)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          continue;
+        }
         float* yp = (a.Y && !y_tma && n_ok) ? a.Y + (size_t)mrow * a.ldy + n : nullptr;
         float mx = NEG_INF, mn = POS_INF;
         if (jmax == 32) epi_chunk<true>(raw, bias, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
@@ -385,6 +428,7 @@ struct SplitMulti {
   const float* W[SPLIT_MULTI_MAX];
   float* out[SPLIT_MULTI_MAX];
   int N[SPLIT_MULTI_MAX], K[SPLIT_MULTI_MAX], ldw[SPLIT_MULTI_MAX];
+  int sn[SPLIT_MULTI_MAX], sk[SPLIT_MULTI_MAX];   // element strides of W: (K, 1) as stored, (1, N) = its transpose
 };
 __global__ void __launch_bounds__(256)
 split_tf32_multi_kernel(const SplitMulti d) {
@@ -392,11 +436,12 @@ split_tf32_multi_kernel(const SplitMulti d) {
   const float* __restrict__ W = d.W[m];
   float* __restrict__ out = d.out[m];
   const int K = d.K[m];
+  const int64_t sn = d.sn[m], sk = d.sk[m];
   const int64_t ldw = d.ldw[m], total = (int64_t)d.N[m] * ldw;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = e / ldw;
     const int k = (int)(e - n * ldw);
-    const float w = k < K ? __ldg(W + n * K + k) : 0.f;
+    const float w = k < K ? __ldg(W + n * sn + k * sk) : 0.f;
     const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
     out[e] = hi;
     out[total + e] = w - hi;
@@ -436,7 +481,8 @@ extern "C" int p2c_split_tf32(const float* W, int N, int K, float* out, int64_t 
 }
 
 extern "C" int p2c_split_tf32_multi(const float* const* W, const int* N, const int* K, float* const* out,
-                                    const int64_t* ldw, int count, void* stream) {
+                                    const int64_t* ldw, const int* transposed, const int64_t* src_ld, int count,
+                                    void* stream) {
   if (!W || !N || !K || !out || !ldw || count <= 0) return P2C_EINVAL;
   if (count > SPLIT_MULTI_MAX) return P2C_EUNSUPPORTED;
   SplitMulti d;
@@ -444,10 +490,15 @@ extern "C" int p2c_split_tf32_multi(const float* const* W, const int* N, const i
   for (int i = 0; i < count; ++i) {
     if (!W[i] || !out[i] || N[i] <= 0 || K[i] <= 0 || ldw[i] < K[i] || (ldw[i] % 4) != 0) return P2C_EINVAL;
     d.W[i] = W[i]; d.out[i] = out[i]; d.N[i] = N[i]; d.K[i] = K[i]; d.ldw[i] = (int)ldw[i];
+    const bool tr = transposed && transposed[i];     // source stored as (K, N): the split of its transpose is written
+    const int ld = src_ld ? (int)src_ld[i] : (tr ? N[i] : K[i]);   // row stride of the source as stored
+    if (ld < (tr ? N[i] : K[i])) return P2C_EINVAL;
+    d.sn[i] = tr ? 1 : ld;
+    d.sk[i] = tr ? ld : 1;
     biggest = max(biggest, (int64_t)N[i] * ldw[i]);
   }
-  for (int i = count; i < SPLIT_MULTI_MAX; ++i) { d.W[i] = nullptr; d.out[i] = nullptr; d.N[i] = d.K[i] = d.ldw[i] = 0; }
-  dim3 grid((unsigned)min((int64_t)64, (biggest + 255) / 256), (unsigned)count);
+  for (int i = count; i < SPLIT_MULTI_MAX; ++i) { d.W[i] = nullptr; d.out[i] = nullptr; d.N[i] = d.K[i] = d.ldw[i] = d.sn[i] = d.sk[i] = 0; }
+  dim3 grid((unsigned)min((int64_t)296, (biggest + 255) / 256), (unsigned)count);
   split_tf32_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
@@ -471,14 +522,33 @@ int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int
   return ss_stages((K + TC_BK - 1) / TC_BK, 1, &raw, &xt);
 }
 
+struct SsEpiHost { int op; float beta, oscale; float* S; int64_t lds; const float* mul; int64_t ldmul; };
+
+static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
+                               const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
+                               double* stats, int pool_group, float* Ymax, float* Ymin, int bf16,
+                               const p2c_bn_fold* in_bn, const SsEpiHost& epi, cudaStream_t st);
+
 int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                      const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
                      double* stats, int pool_group, float* Ymax, float* Ymin, int bf16, const p2c_bn_fold* in_bn,
                      cudaStream_t st) {
+  const SsEpiHost none{0, 0.f, 1.f, nullptr, 0, nullptr, 0};
+  return linear_tc_ss_launch(X, ldx, w_split, ldws, bias, in_scale, in_shift, Y, ldy, M, N, K, stats, pool_group, Ymax,
+                             Ymin, bf16, in_bn, none, st);
+}
+
+static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
+                               const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
+                               double* stats, int pool_group, float* Ymax, float* Ymin, int bf16,
+                               const p2c_bn_fold* in_bn, const SsEpiHost& epi, cudaStream_t st) {
   const int KB = (K + TC_BK - 1) / TC_BK;
   const int y_tma = (Y && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
+  const int s_tma = (epi.op == 1 && epi.S) ? 1 : 0;
+  if (epi.op != 0 && !y_tma) return P2C_EALIGN;
+  if (s_tma && ((epi.lds % 4) != 0 || (reinterpret_cast<uintptr_t>(epi.S) & 15) != 0)) return P2C_EALIGN;
   int raw, xt;
-  if (!ss_stages(KB, y_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
+  if (!ss_stages(KB, y_tma + s_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
   if ((ldws % (bf16 ? 8 : 4)) != 0 || (reinterpret_cast<uintptr_t>(w_split) & 15) != 0) return P2C_EALIGN;
   CUtensorMap tmX, tmWhi, tmWlo, tmY;
   int rc;
@@ -502,25 +572,51 @@ int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t 
   }
   tmY = tmX;
   if (y_tma && (rc = make_map_2d(&tmY, Y, N, M, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  CUtensorMap tmS = tmY;
+  if (s_tma && (rc = make_map_2d(&tmS, epi.S, N, M, epi.lds, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
-           (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn)};
-  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma);
+           (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn),
+           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul};
+  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma + s_tma);
   int dev = 0;
   cudaGetDevice(&dev);
   static int sms_of[64] = {0};
   if (dev < 64 && sms_of[dev] == 0) {
-    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
   }
   const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
   if (bf16)
-    linear_tc_ss_kernel<true><<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);
+    linear_tc_ss_kernel<true, 0><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
+  else if (epi.op == 1)
+    linear_tc_ss_kernel<false, 1><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
+  else if (epi.op == 2)
+    linear_tc_ss_kernel<false, 2><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
   else
-    linear_tc_ss_kernel<false><<<tiles < sms ? tiles : sms, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, a);
+    linear_tc_ss_kernel<false, 0><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
+}
+
+// One hidden layer of the implicit sketch network on the tensor cores (3xTF32): see include/point2cyl.h
+extern "C" int p2c_linear_act(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias, int M,
+                              int N, int K, int op, float beta, float oscale, float* Y, int64_t ldy, float* S,
+                              int64_t lds, const float* Mul, int64_t ldmul, void* stream) {
+  if (!X || !w_split || !Y || M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || ldws < K) return P2C_EINVAL;
+  if (op < 0 || op > 2 || (op == 2 && (!Mul || ldmul < N)) || (S && (op != 1 || lds < N))) return P2C_EINVAL;
+  if (!p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, 0, 0, P2C_PREC_3XTF32))
+    return P2C_EUNSUPPORTED;
+  const SsEpiHost epi{op, beta, oscale, S, lds, Mul, ldmul};
+  if (op == 0) {   // plain scaled layer: the multiplier epilogue needs a matrix, so scale through EPI 1? no: use EPI 0
+    if (oscale != 1.f) return P2C_EUNSUPPORTED;
+  }
+  return linear_tc_ss_launch(X, ldx, w_split, ldws, bias, nullptr, nullptr, Y, ldy, M, N, K, nullptr, 0, nullptr, nullptr,
+                             0, nullptr, epi, (cudaStream_t)stream);
 }

@@ -191,26 +191,52 @@ def split_tf32(W: Tensor) -> Tensor:
     return out
 
 
-def split_tf32_multi(weights, outs=None):
+def split_tf32_multi(weights, outs=None, transposed=None):
     """hi/lo split of several weight matrices in ONE launch.  weights: list of (N, K[,1[,1]]) tensors; outs: matching
-    list of (2, N, pad4(K)) buffers to refresh (allocated when None).  Returns the list of split buffers."""
+    list of (2, N, pad4(K)) buffers to refresh (allocated when None).  transposed[i]: weights[i] is stored as (K, N) and
+    the split of its transpose is produced (no transposed copy is made).  Returns the list of split buffers."""
     Ws = []
     for W in weights:
-        W2 = W.reshape(W.shape[0], -1)
-        Ws.append(W2 if W2.is_contiguous() else W2.contiguous())
+        W2 = W.reshape(W.shape[0], -1) if W.dim() != 2 else W
+        Ws.append(W2 if W2.stride(1) == 1 else W2.contiguous())       # a column block of a wider matrix is fine
+    tr = [bool(t) for t in transposed] if transposed is not None else [False] * len(Ws)
+    shape = [(w.shape[1], w.shape[0]) if t else (w.shape[0], w.shape[1]) for w, t in zip(Ws, tr)]   # (N, K) of the result
     if outs is None:
-        outs = [torch.empty(2, W2.shape[0], pad4(W2.shape[1]), dtype=torch.float32, device=W2.device) for W2 in Ws]
+        outs = [torch.empty(2, n, pad4(k), dtype=torch.float32, device=w.device) for w, (n, k) in zip(Ws, shape)]
     res = list(outs)
     for c0 in range(0, len(Ws), 16):
-        ws, os_ = Ws[c0:c0 + 16], outs[c0:c0 + 16]
+        ws, os_, sh, ts = Ws[c0:c0 + 16], outs[c0:c0 + 16], shape[c0:c0 + 16], tr[c0:c0 + 16]
         n = len(ws)
         pW = (C.c_void_p * n)(*[ptr(w) for w in ws])
         pO = (C.c_void_p * n)(*[ptr(o) for o in os_])
-        aN = (C.c_int * n)(*[w.shape[0] for w in ws])
-        aK = (C.c_int * n)(*[w.shape[1] for w in ws])
+        aN = (C.c_int * n)(*[x[0] for x in sh])
+        aK = (C.c_int * n)(*[x[1] for x in sh])
         aL = (C.c_int64 * n)(*[o.shape[2] for o in os_])
-        call("p2c_split_tf32_multi", pW, aN, aK, pO, aL, n, stream_ptr())
+        aT = (C.c_int * n)(*[1 if t else 0 for t in ts])
+        aS = (C.c_int64 * n)(*[w.stride(0) for w in ws])
+        call("p2c_split_tf32_multi", pW, aN, aK, pO, aL, aT, aS, n, stream_ptr())
     return res
+
+
+def linear_act(X: Tensor, w_split: Tensor, bias: Optional[Tensor], N: int, K: int, op: int, beta: float = 100.0,
+               oscale: float = 1.0, out: Optional[Tensor] = None, S: Optional[Tensor] = None,
+               mul: Optional[Tensor] = None) -> Tensor:
+    """One implicit-network layer on the tensor cores (p2c_linear_act): op 1 = softplus (+ sigmoid into S),
+    op 2 = multiply by `mul`, op 0 = plain.  w_split: (2, N, pad4(K)) from split_tf32[_multi]."""
+    need_cuda(X, w_split)
+    X = _rows(X)
+    M = X.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=X.device)
+    _rows(out)
+    if S is not None:
+        _rows(S)
+    if mul is not None:
+        _rows(mul)
+    call("p2c_linear_act", ptr(X), X.stride(0), ptr(w_split), w_split.shape[-1], ptr(bias), M, N, K, op, float(beta),
+         float(oscale), ptr(out), out.stride(0), ptr(S), 0 if S is None else S.stride(0), ptr(mul),
+         0 if mul is None else mul.stride(0), stream_ptr())
+    return out
 
 
 def cast_bf16(W: Tensor) -> Tensor:
