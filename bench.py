@@ -42,8 +42,27 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         p = json.load(open(path))
-        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops_sustained"], bf16_burst=p["bf16_tflops"], src="measured")
-    return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, src="fallback")
+        pk = dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops_sustained"], bf16_burst=p["bf16_tflops"], src="measured")
+    else:
+        pk = dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, src="fallback")
+    # MEASURED_PEAKS has no TF32 figure: tools/tf32_peak_probe.py measures cuBLAS TF32 8192^3 on the box
+    # (profiles/tf32_peak.json); without it the bf16 peak / 2 (the nominal tf32 : bf16 ratio) stands in, and says so
+    tpath = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    if os.path.isfile(tpath):
+        pk.update(tf32=json.load(open(tpath))["tf32_tflops_sustained"], tf32_src="measured (profiles/tf32_peak.json)")
+    else:
+        pk.update(tf32=pk["bf16"] / 2, tf32_src="bf16 sustained / 2 (nominal ratio)")
+    return pk
+
+
+def kernel_source_sha():
+    """sha256 over the CUDA sources: ties profiles/linear_traffic.json (an ncu pass) to the kernels it measured."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "point2cyl_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -360,6 +379,96 @@ def run_stress(args, rank, world, dev, pd):
         dist.destroy_process_group()
 
 
+def run_igr(args, rank, world, dev, pd):
+    """--workload igr: the implicit sketch network of the with-sketch trainer at its training shape -
+    B=32 clouds x K=8 sketch instances x (1024 on-surface + 1152 off-surface) points = 557,056 rows per GPU through the
+    8 x 512 softplus network: forward sweep, closed-form input gradient, the four loss terms, PointNetEncoder latents
+    (train_Point2Cyl.py:598-672).  Tensor bound: reported against the TF32 peak (3 tf32 MMA passes per product)."""
+    import torch.distributed as dist
+    from point2cyl_b200 import igr
+    from point2cyl_b200.dropin.IGR import network as dnet
+    from point2cyl_b200.dropin.IGR.sampler import NormalPerPoint
+    B, K, S = B_PER_GPU, K_INST, 1024
+    I = B * K
+    torch.manual_seed(0)
+    net = dnet.ImplicitNet(d_in=258, dims=[512] * 8, skip_in=[4], geometric_init=True, radius_init=1, beta=100).to(dev)
+    enc = dnet.PointNetEncoder(256, 2, with_normals=True).to(dev).train()
+    enc_gt = dnet.PointNetEncoder(256, 2, with_normals=True).to(dev).train()
+    g = torch.Generator().manual_seed(1 + rank)
+    ang = torch.rand(I, S, generator=g) * 6.2831853
+    rad = 0.5 + 0.3 * torch.rand(I, 1, generator=g)
+    pts = torch.stack([rad * torch.cos(ang), rad * torch.sin(ang)], -1)
+    nrm = torch.stack([torch.cos(ang), torch.sin(ang)], -1)
+    sk = torch.cat([pts, nrm], -1).to(dev)                       # (I, S, 4) circles: synthetic sketches
+    mask_gt = torch.ones(B, K, dtype=torch.bool, device=dev)
+    sampler = NormalPerPoint(1.8, 0.01)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        latent = enc(sk)
+        latent_gt = enc_gt(sk)
+        off = sampler.get_points(sk[:, :, :2])
+        return igr.sketch_loss_block(net, latent, latent_gt, sk[:, :, :2], sk[:, :, 2:], off, mask_gt)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = step()
+    pd.barrier()
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    ms = []
+    with torch.no_grad():
+        for _ in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = step()
+            e.record()
+            e.synchronize()
+            ms.append(s.elapsed_time(e))
+        # per entry point
+        _lib_mod = __import__("point2cyl_b200._lib", fromlist=["x"])
+        _lib_mod.profile_start()
+        step()
+        prof = _lib_mod.profile_stop()
+    pd.barrier()
+    clk = clocks.stop()
+    tot = pd.reduce_max(sum(ms), dev)
+    if rank == 0:
+        pk = peaks()
+        R = I * (S + S + S // 8)
+        fwd = 2.0 * (258 * 512 + 2 * 512 * 512 + 512 * 254 + 4 * 512 * 512 + 512)
+        rev = 2.0 * (5 * 512 * 512 + 2 * 512 * 254)
+        flops = R * (fwd + rev)
+        act_ms = sum(t for n, tag, t in prof if n == "p2c_linear_act")
+        n_act = sum(1 for n, tag, t in prof if n == "p2c_linear_act")
+        tf = flops / (act_ms / 1e3) / 1e12
+        stages = {}
+        for n, tag, t in prof:
+            d = stages.setdefault(n, {"ms": 0.0, "launches": 0})
+            d["ms"] = round(d["ms"] + t, 4)
+            d["launches"] += 1
+        print(json.dumps({
+            "metric": "sketch instances/sec, implicit network forward + input gradient + loss (with-sketch trainer block)",
+            "value": I * world * args.steps / (tot / 1e3), "unit": "instances/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 (3xTF32 on tcgen05)", "data": "synthetic",
+            "config": {"workload": f"IGR block: B={B}/GPU x K={K} instances x ({S} + {S + S // 8}) points = {R} rows through "
+                                   "ImplicitNet 8x512 softplus(100) skip@4, PointNetEncoder latents, 4 loss terms "
+                                   "(train_Point2Cyl.py:598-672), forward values", "rows": R,
+                       "parallelism": f"dp{world} (instances sharded)", "l2": "flushed between timed steps (512 MiB write)"},
+            "roofline": {"kernel": "p2c_linear_act", "bound": "tensor", "achieved": 3.0 * tf, "peak": pk["tf32"],
+                         "unit": "TFLOP/s", "frac": 3.0 * tf / pk["tf32"], "traffic": None,
+                         "algorithmic_tflops": tf, "launches": n_act, "ms": act_ms, "tf32_peak_source": pk["tf32_src"],
+                         "note": "achieved = 3 x algorithmic FLOP (three tf32 MMA passes per fp32-faithful product: hi*hi + "
+                                 "lo*hi + hi*lo) / summed CUDA-event time of the 15 layer launches; algorithmic work per row "
+                                 f"{fwd + rev:.0f} FLOP (forward {fwd:.0f}, input-gradient sweep {rev:.0f})"},
+            "losses": {k: float(out[k]) for k in ("im_loss", "mnfld_loss", "grad_loss", "normals_loss", "latent_loss")},
+            "gpu_launches": len(prof), "stages": stages, "clocks": clk}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,7 +482,7 @@ def main():
                     help="pipelined (default): graph.PipelinedForwardLoss - the coordinate-only stage of batch i+1 "
                          "runs on a second stream under the layers of batch i; sequential: one batch at a time "
                          "(graph.GraphedForwardLoss)")
-    ap.add_argument("--workload", default="forward_loss", choices=["forward_loss", "train", "stress"],
+    ap.add_argument("--workload", default="forward_loss", choices=["forward_loss", "train", "stress", "igr"],
                     help="forward_loss = BASELINE.json configs[1] (the headline metric, default); train = configs[3], "
                          "the data-parallel training step (32 clouds per GPU); stress = configs[4], FPS + ball query "
                          "at B=128 x N=32768")
@@ -400,6 +509,9 @@ def main():
 
     if args.workload == "stress":
         run_stress(args, rank, world, dev, pd)
+        return
+    if args.workload == "igr":
+        run_igr(args, rank, world, dev, pd)
         return
 
     net = make_net(dev)
@@ -523,22 +635,48 @@ def main():
             if v["flops"]:
                 e["tflops"] = round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)
             stages[k] = e
+        # per MLP layer: both floors and which one binds (3xTF32 = three tf32 MMA passes per product)
+        layers, floor_us, meas_us = {}, 0.0, 0.0
+        for (name, tag), (t, n) in sorted(agg.items(), key=lambda kv: kv[0][1]):
+            if name != "p2c_linear":
+                continue
+            _, (fl, by) = algorithmic_work(name, tag, B_PER_GPU)
+            us = t / reps * 1e3
+            hbm_floor = by / (pk["hbm"] * 1e9) * 1e6
+            tc_floor = 3.0 * fl / (pk["tf32"] * 1e12) * 1e6
+            fl_us = max(hbm_floor, tc_floor)
+            layers[tag] = {"us": round(us, 1), "hbm_floor_us": round(hbm_floor, 1), "tensor_floor_us": round(tc_floor, 1),
+                           "bound": "hbm" if hbm_floor >= tc_floor else "tensor", "frac_of_floor": round(fl_us / us, 3)}
+            floor_us += fl_us
+            meas_us += us
+        stages["p2c_linear"]["layers"] = layers
         top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
         d = per_kernel[top]
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "linear_traffic.json")   # ncu dram bytes of the same launches
         if top == "p2c_linear" and os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+            tj = json.load(open(tpath))
+            if tj.get("kernel_source_sha") == kernel_source_sha():
+                traffic = tj.get("dram_bytes_per_step")
+                traffic_note = tj.get("source")
+            else:
+                traffic_note = "profiles/linear_traffic.json was measured on other kernel sources: not reported"
         ach = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["bytes"] else 0.0
         roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": ach / pk["hbm"], "traffic": traffic,
+                "frac": ach / pk["hbm"], "traffic": traffic, "traffic_source": traffic_note,
                 "note": f"the {d['launches']} {top} launches of one step taken together: compulsory bytes "
-                        f"(4*rows*(K+N) per layer) / summed CUDA-event time, peak = {pk['src']} copy bandwidth. "
-                        "These per-point MLP layers are HBM bound on this network (K, N <= 128 on the big row counts)"}
+                        f"(4*rows*(K+N) per layer) / summed CUDA-event time, peak = {pk['src']} copy bandwidth.  Per "
+                        "layer (stages.p2c_linear.layers) the binding floor is HBM for the K, N <= 128 layers on the big "
+                        "row counts and the tensor pipe (3 tf32 passes) for the pooled 64->128 / 128->256 layers and the "
+                        "coarse levels"}
         if d["flops"]:
             tf = d["flops"] / (d["ms"] / 1e3) / 1e12
             roof["tensor_tflops"] = tf
             roof["tensor_frac_of_bf16_peak"] = tf / pk["bf16"]
+            roof["tf32_mma_tflops"] = 3.0 * tf
+            roof["tf32_mma_frac_of_tf32_peak"] = 3.0 * tf / pk["tf32"]
+            roof["tf32_peak"] = {"tflops": pk["tf32"], "source": pk["tf32_src"]}
+            roof["frac_of_per_layer_floor"] = floor_us / meas_us if meas_us else None
     # ---- the training step of configs[3] on the same batch (all ranks: it contains the gradient all-reduce) ----
     train = train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps=10, warmup=3)
     cpu = eager = None

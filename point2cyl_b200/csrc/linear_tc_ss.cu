@@ -91,7 +91,7 @@ __host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_
   L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES;
   L.xt_off = o;     o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
   L.w_off = o;      o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
-  L.ystage_off = o; o += (uint32_t)y_stage * 4u * 2u * 4096u;   // y_stage staging tiles of 4 KB per epilogue warp
+  L.ystage_off = o; o += y_stage ? 4u * 2u * 4096u : 0u;        // one 4 KB staging tile per epilogue warp
   L.scale_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.shift_off = o;  o += (uint32_t)KB * TC_BK * 4u;
   L.bar_off = o;    o += 512u;
@@ -106,7 +106,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const __grid_constant__ CUtensorMap tmS, const SsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma + a.s_tma);
+  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma);
   uint8_t* raw_sm = smem + L.raw_off;
   uint8_t* xt_sm = smem + L.xt_off;
   uint8_t* w_sm = smem + L.w_off;
@@ -332,8 +332,8 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (EPI != 0) {
           // implicit-network epilogues (p2c_linear_act): both outputs leave through [32 rows x 32 channels] staging
           // tiles and TMA stores (rows >= M and channels >= N are clipped by the tensor maps)
-          float* st2 = ystg + 8 * 1024;               // second tile of this warp: 8 warps x 4 KB further on
           if (EPI == 1) {
+            float sgv[32];                            // softplus'(z) of the 32 rows: second store through the same tile
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float z = __uint_as_float(raw[j]) + bias;
@@ -345,7 +345,27 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 sg = __fdiv_rn(e, 1.f + e);
               }
               st[j * 32 + lane] = h * a.oscale;
-              if (a.s_tma) st2[j * 32 + lane] = sg;
+              sgv[j] = sg;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (a.s_tma) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the Y store has read the tile
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) st[j * 32 + lane] = sgv[j];
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmS)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
             }
           } else {
             const float* mp = a.mul + (size_t)mrow * a.ldmul + n;
@@ -354,16 +374,13 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               const float m = (n_ok && j < jmax) ? __ldg(mp + (size_t)j * a.ldmul) : 0.f;   // warp = 128 B of row mrow+j
               st[j * 32 + lane] = (__uint_as_float(raw[j]) + bias) * m * a.oscale;
             }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
-            if (EPI == 1 && a.s_tma)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                           ::"l"(reinterpret_cast<uint64_t>(&tmS)), "r"(smem_u32(st2)), "r"(n0 + q * 32), "r"(mrow) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                           ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
           continue;
         }
@@ -548,7 +565,7 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   if (epi.op != 0 && !y_tma) return P2C_EALIGN;
   if (s_tma && ((epi.lds % 4) != 0 || (reinterpret_cast<uintptr_t>(epi.S) & 15) != 0)) return P2C_EALIGN;
   int raw, xt;
-  if (!ss_stages(KB, y_tma + s_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
+  if (!ss_stages(KB, y_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
   if ((ldws % (bf16 ? 8 : 4)) != 0 || (reinterpret_cast<uintptr_t>(w_split) & 15) != 0) return P2C_EALIGN;
   CUtensorMap tmX, tmWhi, tmWlo, tmY;
   int rc;
@@ -577,7 +594,7 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
            (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn),
            epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul};
-  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma + s_tma);
+  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma);
   int dev = 0;
   cudaGetDevice(&dev);
   static int sms_of[64] = {0};
