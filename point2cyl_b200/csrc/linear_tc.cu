@@ -307,7 +307,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int dbg_n = 0;
     int ybuf = 0;
     float* ystg = reinterpret_cast<float*>(ystage + (size_t)(grp * 4 + q) * 8192);   // this warp's two 4 KB staging tiles
-    const bool y_tma = a.Y != nullptr && a.y_tma;
+    // a [32 x 32] box sticking out over channel N is stored by the warp itself (TMA stores clip at 16-byte granularity)
+    const bool y_tma = a.Y != nullptr && a.y_tma && (n0 + q * 32 + 32 <= a.N);
     const bool warp_live = n0 + q * 32 < a.N;          // warp-uniform
     float f1 = 0.f, f2 = 0.f;                          // fp32 partial sums, flushed to fp64 every few tiles
     int since_flush = 0;

@@ -35,6 +35,7 @@ struct SsArgs {
   float beta, oscale;
   int s_tma;                     // the second output S leaves through TMA stores too
   const float* mul; int64_t ldmul;
+  float* S; int64_t lds;
 };
 
 // ---- bf16 mode (P2C_PREC_BF16): one kind::f16 MMA pass on bf16 operands instead of the three tf32 passes ----
@@ -299,13 +300,17 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int G = a.pool_group;
     const int gshift = G ? 31 - __clz(G) : 0;
     float* ystg = reinterpret_cast<float*>(ystage + (size_t)(grp * 4 + q) * 4096);   // one 4 KB staging tile per warp
-    const bool y_tma = a.Y != nullptr && a.y_tma;
+    const bool y_tma_all = a.Y != nullptr && a.y_tma;
     for (int t = grp; t < my_tiles; t += 2) {
       const int ab = t & 1;
       const uint32_t accph = (uint32_t)(t >> 1) & 1u;
       const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
       const int n = n0 + ch;
       const bool n_ok = n < a.N;
+      // A [32 x 32] box that sticks out over channel N is NOT left to the TMA unit (measured: its stores clip at
+      // 16-byte granularity, so with N % 4 != 0 up to three channels beyond N were written): this warp then stores its
+      // rows itself - lanes = consecutive channels, so each store instruction is still one coalesced line.
+      const bool y_tma = y_tma_all && (n0 + q * 32 + 32 <= a.N);
       const float bias = (a.bias && n_ok) ? __ldg(a.bias + n) : 0.f;
       float gmx = NEG_INF, gmn = POS_INF;
       float t1 = 0.f, t2 = 0.f;
@@ -329,9 +334,32 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
           __syncwarp();
         }
+        if (EPI != 0 && !y_tma) {
+          // a box that is partial in the channel direction: guarded direct stores (see above)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (!(n_ok && j < jmax)) continue;
+            const float z = __uint_as_float(raw[j]) + bias;
+            const size_t row = (size_t)(mrow + j);
+            if (EPI == 1) {
+              const float bz = a.beta * z;
+              float h = z, sg = 1.f;
+              if (!(bz > 20.f)) {
+                const float e = expf(bz);
+                h = __fdiv_rn(log1pf(e), a.beta);
+                sg = __fdiv_rn(e, 1.f + e);
+              }
+              a.Y[row * a.ldy + n] = h * a.oscale;
+              if (a.s_tma) a.S[row * a.lds + n] = sg;
+            } else {
+              a.Y[row * a.ldy + n] = z * __ldg(a.mul + row * a.ldmul + n) * a.oscale;
+            }
+          }
+          continue;
+        }
         if (EPI != 0) {
           // implicit-network epilogues (p2c_linear_act): both outputs leave through [32 rows x 32 channels] staging
-          // tiles and TMA stores (rows >= M and channels >= N are clipped by the tensor maps)
+          // tiles and TMA stores (rows >= M are clipped by the tensor maps)
           if (EPI == 1) {
             float sgv[32];                            // softplus'(z) of the 32 rows: second store through the same tile
 #pragma unroll
@@ -415,7 +443,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         atomicAdd(a.stats + a.N + n, (double)t2);
       }
     }
-    if (y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (y_tma_all && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -593,7 +621,7 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   if (s_tma && (rc = make_map_2d(&tmS, epi.S, N, M, epi.lds, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
            (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn),
-           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul};
+           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds};
   const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma);
   int dev = 0;
   cudaGetDevice(&dev);

@@ -33,6 +33,7 @@ from ._lib import call, ptr, stream_ptr
 
 Tensor = torch.Tensor
 RT2 = math.sqrt(2.0)
+_debug_layers = None          # tests/tools/igr_debug.py: list that receives every hidden layer's output buffer
 
 
 def _layers(net) -> List[torch.nn.Linear]:
@@ -128,6 +129,8 @@ def implicit_forward(net, x: Optional[Tensor] = None, latent: Optional[Tensor] =
         ops.linear_act(h, wsplit[i], lins[i].bias, out_i, in_i, op=1, beta=beta, oscale=osc, out=Y[:, :out_i],
                        S=None if Si is None else Si[:, :out_i])
         h = Y
+        if _debug_layers is not None:
+            _debug_layers.append(Y)
     f = torch.empty(R, 1, dtype=torch.float32, device=dev)
     wl = lins[L].weight
     _lib.set_tag("igr.out")

@@ -53,7 +53,8 @@ def test_linear_act_epilogues_against_fp64():
                        S=S[:, :N])
         got = wide[:, 4:4 + N] if N % 4 == 0 else wide[:, :N]
         assert rel_err(got, 0.5 * torch.nn.functional.softplus(Z, beta=100.0)) <= 1e-5
-        assert rel_err(S[:, :N], torch.where(100 * Z > 20, torch.ones_like(Z), torch.sigmoid(100 * Z))) <= 1e-5
+        # (sigmoid(100 z) amplifies the 3xTF32 error of z by up to 25)
+        assert rel_err(S[:, :N], torch.where(100 * Z > 20, torch.ones_like(Z), torch.sigmoid(100 * Z))) <= 5e-5
         untouched = wide[:, 4 + N:] if N % 4 == 0 else wide[:, ops.pad4(N):]
         assert bool((untouched == 7.0).all())                      # channels >= N are clipped, neighbours untouched
         mul = torch.randn(M, N, generator=g)

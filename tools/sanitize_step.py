@@ -56,4 +56,26 @@ odd = torch.rand(3, 777, 3, device="cuda")                        # ragged tail:
 idx2, _ = ops.fps(odd, 33, torch.tensor([0, 776, 100]))
 torch.cuda.synchronize()
 print("fps ok", int(idx.max()), int(idx2.max()))
+# the implicit sketch network (p2c_linear_act epilogues, reverse sweep, encoder, loss terms) on a small instance set
+from point2cyl_b200 import igr
+from point2cyl_b200.dropin.IGR import network as dnet
+inet = dnet.ImplicitNet(d_in=258, dims=[512] * 8, skip_in=[4], geometric_init=True, radius_init=1, beta=100).cuda()
+ienc = dnet.PointNetEncoder(256, 2, with_normals=True).cuda().train()
+sk = torch.rand(4, 64, 4, device="cuda")
+with torch.no_grad():
+    lat = ienc(sk)
+    out = igr.sketch_loss_block(inet, lat, lat, sk[:, :, :2], sk[:, :, 2:], torch.rand(4, 72, 2, device="cuda"),
+                                torch.ones(2, 2, dtype=torch.bool, device="cuda"))
+torch.cuda.synchronize()
+print("igr ok", float(out["im_loss"]))
+# the two-stage pipeline (second stream, SM budget, CUDA graphs)
+from point2cyl_b200.graph import PipelinedForwardLoss
+net.train()
+pipe = PipelinedForwardLoss(net, batch)
+pipe.prime(None)
+for _ in range(2):
+    o = pipe.step(None)
+pipe.join()
+torch.cuda.synchronize()
+print("pipelined ok", float(o["losses"][0]))
 print("DONE")
