@@ -143,7 +143,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);      // 2 x (main accumulator | correction accumulator), 128 columns each
   for (int k = tid; k < KPAD; k += SS_THREADS) {
     float sc = 0.f, sh = 0.f;
     if (k < a.K) {
@@ -210,12 +210,16 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                            TC_IDESC_BF16, (kb | ks) != 0);
           } else {
 #pragma unroll
+          // The tensor core's fp32 accumulate TRUNCATES (measured: a relative shrink of ~2.3e-8 per accumulate step,
+          // tests/tools/precision_probe.py).  The two correction products are 2^-11 of the main one, so they go to
+          // their own accumulator (columns 256..511) where that truncation is negligible, and the main accumulator sees
+          // K/8 accumulate steps instead of 3K/8; the epilogue adds the two in round-to-nearest fp32.
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u), blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
             const uint64_t ahi = make_kmajor_sw128_desc(w_hi + ks * 32u), alo = make_kmajor_sw128_desc(w_lo + ks * 32u);
             umma_tf32_ss(d, ahi, bhi, TC_IDESC, (kb | ks) != 0);
-            umma_tf32_ss(d, alo, bhi, TC_IDESC, 1u);
-            umma_tf32_ss(d, ahi, blo, TC_IDESC, 1u);
+            umma_tf32_ss(d + 256u, alo, bhi, TC_IDESC, (kb | ks) != 0);
+            umma_tf32_ss(d + 256u, ahi, blo, TC_IDESC, 1u);
           }
           }
           umma_commit(&xt_empty[xs]);
@@ -320,6 +324,13 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
+        if (!BF16) {                                   // + the correction accumulator (see the MMA issuer)
+          uint32_t cor[32];
+          tmem_ld32(tmem_base + 256u + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, cor);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(cor[j]));
+        }
         tmem_wait_ld();
         if (c == 3) {
           tc_fence_before();
@@ -450,7 +461,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

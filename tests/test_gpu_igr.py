@@ -58,15 +58,20 @@ def test_linear_act_epilogues_against_fp64():
         untouched = wide[:, 4 + N:] if N % 4 == 0 else wide[:, ops.pad4(N):]
         assert bool((untouched == 7.0).all())                      # channels >= N are clipped, neighbours untouched
         mul = torch.randn(M, N, generator=g)
-        out = ops.linear_act(Xd, ws, None, N, K, op=2, oscale=2.0 ** -0.5, mul=mul.to(DEV))
+        obuf = torch.zeros(M, ops.pad4(N), device=DEV)
+        mbuf = torch.zeros(M, ops.pad4(N), device=DEV)
+        mbuf[:, :N] = mul.to(DEV)
+        out = ops.linear_act(Xd, ws, None, N, K, op=2, oscale=2.0 ** -0.5, out=obuf[:, :N], mul=mbuf[:, :N])
         assert rel_err(out, (X[:, :K].double() @ W.double().t()) * mul.double() * 2.0 ** -0.5) <= 1e-5
+        assert bool((obuf[:, N:] == 0).all())
         # the transposed split used by the reverse sweep: (a W)[:, :n_h]
         n_h = K - 4
         wt = ops.split_tf32_multi([Wd[:, :n_h]], transposed=[True])[0]
         A = torch.randn(M, N, generator=g) * 0.1
         Ap = torch.zeros(M, ops.pad4(N))
         Ap[:, :N] = A
-        r = ops.linear_act(Ap.to(DEV)[:, :N], wt, None, n_h, N, op=0)
+        rbuf = torch.zeros(M, ops.pad4(n_h), device=DEV)
+        r = ops.linear_act(Ap.to(DEV)[:, :N], wt, None, n_h, N, op=0, out=rbuf[:, :n_h])
         assert rel_err(r, A.double() @ W[:, :n_h].double()) <= 1e-5
 
 
