@@ -214,10 +214,16 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           // tests/tools/precision_probe.py).  The two correction products are 2^-11 of the main one, so they go to
           // their own accumulator (columns 256..511) where that truncation is negligible, and the main accumulator sees
           // K/8 accumulate steps instead of 3K/8; the epilogue adds the two in round-to-nearest fp32.
+          // (the four main products back to back, then the eight correction products: the tensor pipe chains
+          // accumulations into one accumulator better than it alternates between two)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32_ss(d, make_kmajor_sw128_desc(w_hi + ks * 32u), make_kmajor_sw128_desc(x_hi + ks * 32u), TC_IDESC,
+                         (kb | ks) != 0);
+#pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u), blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
             const uint64_t ahi = make_kmajor_sw128_desc(w_hi + ks * 32u), alo = make_kmajor_sw128_desc(w_lo + ks * 32u);
-            umma_tf32_ss(d, ahi, bhi, TC_IDESC, (kb | ks) != 0);
             umma_tf32_ss(d + 256u, alo, bhi, TC_IDESC, (kb | ks) != 0);
             umma_tf32_ss(d + 256u, ahi, blo, TC_IDESC, 1u);
           }

@@ -33,5 +33,7 @@ out = {"dram_bytes_per_step": total, "launches": len(launches), "kernel_source_s
        "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the {len(launches)} tensor-core MLP-layer launches of "
                  f"one forward+loss step ({os.path.basename(path)}), same kernel sources as this build",
        "per_launch": launches}
-json.dump(out, open(os.path.join(ROOT, "profiles", "linear_traffic.json"), "w"), indent=1)
+for d in ("profiles", "gpurun_out"):
+    os.makedirs(os.path.join(ROOT, d), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, d, "linear_traffic.json"), "w"), indent=1)
 print(json.dumps({k: out[k] for k in ("dram_bytes_per_step", "launches", "kernel_source_sha")}))
