@@ -36,6 +36,9 @@ struct SsArgs {
   int s_tma;                     // the second output S leaves through TMA stores too
   const float* mul; int64_t ldmul;
   float* S; int64_t lds;
+  int raw_hi;                    // RAW tile = hi operand, XT ring holds lo only (no operand transform needed)
+  int dbg_mode;                  // tools only (env P2C_SS_DBG): 1 skip the epilogue body, 2 skip the correction read,
+                                 // 4 skip the correction MMAs, 8 transform copies hi only (timing experiments)
 };
 
 // ---- bf16 mode (P2C_PREC_BF16): one kind::f16 MMA pass on bf16 operands instead of the three tf32 passes ----
@@ -86,15 +89,18 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
 struct SsSmem {
   uint32_t raw_off, xt_off, w_off, ystage_off, scale_off, shift_off, bar_off, total;
 };
-__host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_stages, int y_stage) {
+// raw_hi: the activation needs no operand transform (no BatchNorm fold), so the RAW fp32 tile itself is the tf32 "hi"
+// operand (the tensor core ignores the low 13 mantissa bits) and the XT ring holds only the lo tiles: 64 KB instead
+// of 80 KB per pipeline stage, i.e. three stages in flight instead of two for K = 512.
+__host__ __device__ inline SsSmem ss_smem_layout(int KB, int raw_stages, int xt_stages, int y_stage, int raw_hi = 0) {
   SsSmem L;
   uint32_t o = 0;
   L.raw_off = o;    o += (uint32_t)raw_stages * RAW_BYTES;
-  L.xt_off = o;     o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
+  L.xt_off = o;     o += (uint32_t)xt_stages * (raw_hi ? 1u : 2u) * RAW_BYTES;   // [stage][hi|lo] or [stage][lo]
   L.w_off = o;      o += (uint32_t)xt_stages * 2u * RAW_BYTES;   // [stage][hi|lo]
   L.ystage_off = o; o += y_stage ? 4u * 2u * 4096u : 0u;        // one 4 KB staging tile per epilogue warp
-  L.scale_off = o;  o += (uint32_t)KB * TC_BK * 4u;
-  L.shift_off = o;  o += (uint32_t)KB * TC_BK * 4u;
+  L.scale_off = o;  o += raw_hi ? 0u : (uint32_t)KB * TC_BK * 4u;
+  L.shift_off = o;  o += raw_hi ? 0u : (uint32_t)KB * TC_BK * 4u;
   L.bar_off = o;    o += 512u;
   L.total = o;
   return L;
@@ -107,7 +113,9 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const __grid_constant__ CUtensorMap tmS, const SsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma);
+  const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma, a.raw_hi);
+  const bool raw_hi = !BF16 && a.raw_hi;
+  const uint32_t xt_stage_bytes = raw_hi ? RAW_BYTES : 2u * RAW_BYTES;
   uint8_t* raw_sm = smem + L.raw_off;
   uint8_t* xt_sm = smem + L.xt_off;
   uint8_t* w_sm = smem + L.w_off;
@@ -135,7 +143,8 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
-    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    // raw_hi: a RAW stage is released by the MMAs that read it (one tcgen05.commit), else by the 4 transform warps
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], raw_hi ? 1 : 4); }
     for (int s = 0; s < XS; ++s) {
       mbar_init(&xt_full[s], 4); mbar_init(&xt_empty[s], 1);
       mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1);
@@ -144,7 +153,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);      // 2 x (main accumulator | correction accumulator), 128 columns each
-  for (int k = tid; k < KPAD; k += SS_THREADS) {
+  for (int k = tid; !raw_hi && k < KPAD; k += SS_THREADS) {
     float sc = 0.f, sh = 0.f;
     if (k < a.K) {
       if (a.bn.active) p2c_bn_fold_channel(a.bn, k, blockIdx.x == 0, sc, sh);
@@ -191,6 +200,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // ===== MMA issuer =====
     if (lane == 0) {
       int xs = 0; uint32_t xph = 0;
+      int rs = 0;                                      // RAW stage of this k-block (raw_hi mode: the hi operand)
       for (int t = 0; t < my_tiles; ++t) {
         const int ab = t & 1;
         const uint32_t accph = (uint32_t)(t >> 1) & 1u;
@@ -201,7 +211,9 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           mbar_wait(&w_full[xs], xph);
           mbar_wait(&xt_full[xs], xph);
           tc_fence_after();
-          const uint32_t x_hi = smem_u32(xt_sm + (size_t)xs * 2 * RAW_BYTES), x_lo = x_hi + RAW_BYTES;
+          const uint32_t xt0 = smem_u32(xt_sm + (size_t)xs * xt_stage_bytes);
+          const uint32_t x_hi = raw_hi ? smem_u32(raw_sm + (size_t)rs * RAW_BYTES) : xt0;
+          const uint32_t x_lo = raw_hi ? xt0 : xt0 + RAW_BYTES;
           const uint32_t w_hi = smem_u32(w_sm + (size_t)xs * 2 * RAW_BYTES), w_lo = w_hi + RAW_BYTES;
           if (BF16) {
 #pragma unroll
@@ -222,6 +234,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                          (kb | ks) != 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            if (a.dbg_mode & 4) break;
             const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u), blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
             const uint64_t ahi = make_kmajor_sw128_desc(w_hi + ks * 32u), alo = make_kmajor_sw128_desc(w_lo + ks * 32u);
             umma_tf32_ss(d + 256u, alo, bhi, TC_IDESC, (kb | ks) != 0);
@@ -230,8 +243,10 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
           umma_commit(&xt_empty[xs]);
           umma_commit(&w_empty[xs]);
+          if (raw_hi) umma_commit(&raw_empty[rs]);     // the RAW tile was an MMA operand: free it when they retire
           if (kb == KB - 1) umma_commit(&acc_full[ab]);
           if (++xs == XS) { xs = 0; xph ^= 1; }
+          if (++rs == RS) rs = 0;
         }
       }
     }
@@ -239,7 +254,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // ===== operand transform (see linear_tc.cu) =====
     const int tt = tid - 256;
     const int cj = tt & 7, rg = tt >> 3;
-    const bool has_affine = a.in_scale != nullptr || a.bn.active;
+    const bool has_affine = !raw_hi && (a.in_scale != nullptr || a.bn.active);
     int s = 0; uint32_t ph = 0;
     int xs = 0; uint32_t xph = 0;
     for (int t = 0; t < my_tiles; ++t) {
@@ -258,7 +273,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           x[i] = *reinterpret_cast<const float4*>(rawp + (size_t)r * 128 + ((cj ^ (r & 7)) << 4));
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[s]);
+        if (lane == 0 && !raw_hi) mbar_arrive(&raw_empty[s]);
         if (++s == RS) { s = 0; ph ^= 1; }
         if (has_affine) {
 #pragma unroll
@@ -270,8 +285,19 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
         }
         mbar_wait(&xt_empty[xs], xph ^ 1);
-        uint8_t* hip = xt_sm + (size_t)xs * 2 * RAW_BYTES;
-        if (BF16) {
+        uint8_t* hip = xt_sm + (size_t)xs * xt_stage_bytes;
+        if (raw_hi) {                                  // lo tile only: x - trunc_tf32(x), same swizzled position
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rg * 8 + i;
+            float4 l;
+            l.x = x[i].x - __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u);
+            l.y = x[i].y - __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u);
+            l.z = x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u);
+            l.w = x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u);
+            *reinterpret_cast<float4*>(hip + (size_t)r * 128 + ((cj ^ (r & 7)) << 4)) = l;
+          }
+        } else if (BF16) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = rg * 8 + i;
@@ -330,7 +356,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
-        if (!BF16) {                                   // + the correction accumulator (see the MMA issuer)
+        if (!BF16 && !(a.dbg_mode & 2)) {              // + the correction accumulator (see the MMA issuer)
           uint32_t cor[32];
           tmem_ld32(tmem_base + 256u + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, cor);
           tmem_wait_ld();
@@ -345,7 +371,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         const int mrow = m0 + c * 32;
         const int jmax = min(32, a.M - mrow);
-        if (jmax <= 0) continue;
+        if (jmax <= 0 || (a.dbg_mode & 1)) continue;
         float* st = ystg;
         if (y_tma) {
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
@@ -378,19 +404,24 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           // implicit-network epilogues (p2c_linear_act): both outputs leave through [32 rows x 32 channels] staging
           // tiles and TMA stores (rows >= M are clipped by the tensor maps)
           if (EPI == 1) {
-            float sgv[32];                            // softplus'(z) of the 32 rows: second store through the same tile
+            // H through the staging tile + TMA store; S = softplus'(Z) straight from registers (lanes = consecutive
+            // channels of one row: a coalesced line per store instruction) - no second pass over the staging tile
+            float* sp = a.s_tma ? a.S + (size_t)mrow * a.lds + n : nullptr;
+            const float bl2e = a.beta * 1.4426950408889634f, inv_b = 0.6931471805599453f / a.beta;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float z = __uint_as_float(raw[j]) + bias;
-              const float bz = a.beta * z;
               float h = z, sg = 1.f;                  // nn.Softplus(beta, threshold 20): identity above the threshold
-              if (!(bz > 20.f)) {
-                const float e = expf(bz);
-                h = __fdiv_rn(log1pf(e), a.beta);
-                sg = __fdiv_rn(e, 1.f + e);
+              if (!(a.beta * z > 20.f)) {
+                // e = exp(beta z) <= e^20; softplus = ln(1 + e) / beta, sigmoid = e / (1 + e): MUFU ex2 / lg2 / rcp
+                // (absolute error of h < 1e-9, relative error of sg < 1e-6 - below the 3xTF32 error of z itself)
+                const float e = exp2f(bl2e * z);
+                const float p = 1.f + e;
+                h = (e < 1e-4f) ? (e - 0.5f * e * e) * (1.f / a.beta) : __log2f(p) * inv_b;
+                sg = __fdividef(e, p);
               }
               st[j * 32 + lane] = h * a.oscale;
-              sgv[j] = sg;
+              if (sp && j < jmax) sp[(size_t)j * a.lds] = sg;
             }
             fence_proxy_async();
             __syncwarp();
@@ -398,19 +429,6 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            if (a.s_tma) {
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the Y store has read the tile
-              __syncwarp();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) st[j * 32 + lane] = sgv[j];
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmS)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
             }
           } else {
             const float* mp = a.mul + (size_t)mrow * a.ldmul + n;
@@ -521,10 +539,12 @@ cast_bf16_kernel(const float* __restrict__ W, int N, int K, uint16_t* __restrict
   }
 }
 
-int ss_stages(int KB, int y_tma, int* raw, int* xt) {
-  const int tries[4][2] = {{4, 3}, {2, 3}, {4, 2}, {2, 2}};
+int ss_stages(int KB, int y_tma, int* raw, int* xt, int raw_hi = 0) {
+  const int tries_t[4][2] = {{4, 3}, {2, 3}, {4, 2}, {2, 2}};
+  const int tries_r[4][2] = {{3, 3}, {3, 2}, {2, 2}, {2, 2}};   // raw_hi: a RAW stage lives as long as its XT / W stage
+  const int (*tries)[2] = raw_hi ? tries_r : tries_t;
   for (int i = 0; i < 4; ++i)
-    if (ss_smem_layout(KB, tries[i][0], tries[i][1], y_tma).total + 1024 <= 227 * 1024) {
+    if (ss_smem_layout(KB, tries[i][0], tries[i][1], y_tma, raw_hi).total + 1024 <= 227 * 1024) {
       *raw = tries[i][0]; *xt = tries[i][1];
       return 1;
     }
@@ -610,7 +630,8 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   if (epi.op != 0 && !y_tma) return P2C_EALIGN;
   if (s_tma && ((epi.lds % 4) != 0 || (reinterpret_cast<uintptr_t>(epi.S) & 15) != 0)) return P2C_EALIGN;
   int raw, xt;
-  if (!ss_stages(KB, y_tma, &raw, &xt)) return P2C_EUNSUPPORTED;
+  const int raw_hi = (!bf16 && !in_scale && !in_bn) ? 1 : 0;   // nothing to fold into the operand: RAW = hi operand
+  if (!ss_stages(KB, y_tma, &raw, &xt, raw_hi)) return P2C_EUNSUPPORTED;
   if ((ldws % (bf16 ? 8 : 4)) != 0 || (reinterpret_cast<uintptr_t>(w_split) & 15) != 0) return P2C_EALIGN;
   CUtensorMap tmX, tmWhi, tmWlo, tmY;
   int rc;
@@ -638,8 +659,8 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   if (s_tma && (rc = make_map_2d(&tmS, epi.S, N, M, epi.lds, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
            (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn),
-           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds};
-  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma);
+           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds, raw_hi, getenv("P2C_SS_DBG") ? atoi(getenv("P2C_SS_DBG")) : 0};
+  const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma, raw_hi);
   int dev = 0;
   cudaGetDevice(&dev);
   static int sms_of[64] = {0};
