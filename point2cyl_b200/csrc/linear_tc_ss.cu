@@ -149,7 +149,8 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_init(&xt_full[s], 4); mbar_init(&xt_empty[s], 1);
       mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    // EPI != 0: both epilogue groups drain every tile (two 32-row chunks each), so 8 warps release an accumulator
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI != 0 ? 8 : 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);      // 2 x (main accumulator | correction accumulator), 128 columns each
@@ -337,12 +338,27 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int gshift = G ? 31 - __clz(G) : 0;
     float* ystg = reinterpret_cast<float*>(ystage + (size_t)(grp * 4 + q) * 4096);   // one 4 KB staging tile per warp
     const bool y_tma_all = a.Y != nullptr && a.y_tma;
-    for (int t = grp; t < my_tiles; t += 2) {
+    // EPI == 0: group g drains the tiles t = g (mod 2) whole (the BatchNorm / pool reductions run over a tile's rows).
+    // EPI != 0 (element-wise epilogues): BOTH groups drain every tile, chunks {0,1} and {2,3} - an accumulator is held
+    // for a quarter of a tile's epilogue instead of three quarters, which is what lets the MMAs of tile t+2 start on
+    // time (measured: the multiplier epilogue's dependent global loads made the old scheme epilogue-bound).
+    const int t_step = EPI != 0 ? 1 : 2;
+    const int c_lo = EPI != 0 ? 2 * grp : 0, c_hi = EPI != 0 ? 2 * grp + 2 : 4;
+    for (int t = (EPI != 0 ? 0 : grp); t < my_tiles; t += t_step) {
       const int ab = t & 1;
       const uint32_t accph = (uint32_t)(t >> 1) & 1u;
       const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
       const int n = n0 + ch;
       const bool n_ok = n < a.N;
+      if (EPI == 2 && n_ok) {
+        // the multiplier rows this warp will read in its two chunks: pull them into L2 while the MMAs of the tile run
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = m0 + c_lo * 32 + j * 32 + lane;
+          if (row < a.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mul + (size_t)row * a.ldmul + n0 + q * 32));
+        }
+      }
       // A [32 x 32] box that sticks out over channel N is NOT left to the TMA unit (measured: its stores clip at
       // 16-byte granularity, so with N % 4 != 0 up to three channels beyond N were written): this warp then stores its
       // rows itself - lanes = consecutive channels, so each store instruction is still one coalesced line.
@@ -353,7 +369,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       mbar_wait(&acc_full[ab], accph);
       tc_fence_after();
 #pragma unroll 1                                       // rolled on purpose: instruction-cache footprint (see linear_tc.cu)
-      for (int c = 0; c < 4; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
         if (!BF16 && !(a.dbg_mode & 2)) {              // + the correction accumulator (see the MMA issuer)
@@ -364,7 +380,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(cor[j]));
         }
         tmem_wait_ld();
-        if (c == 3) {
+        if (c == c_hi - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[ab]);
@@ -412,7 +428,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int j = 0; j < 32; ++j) {
               const float z = __uint_as_float(raw[j]) + bias;
               float h = z, sg = 1.f;                  // nn.Softplus(beta, threshold 20): identity above the threshold
-              if (!(a.beta * z > 20.f)) {
+              if (!(a.beta * z > 20.f) && !(a.dbg_mode & 16)) {
                 // e = exp(beta z) <= e^20; softplus = ln(1 + e) / beta, sigmoid = e / (1 + e): MUFU ex2 / lg2 / rcp
                 // (absolute error of h < 1e-9, relative error of sg < 1e-6 - below the 3xTF32 error of z itself)
                 const float e = exp2f(bl2e * z);
@@ -421,11 +437,11 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 sg = __fdividef(e, p);
               }
               st[j * 32 + lane] = h * a.oscale;
-              if (sp && j < jmax) sp[(size_t)j * a.lds] = sg;
+              if (sp && j < jmax && !(a.dbg_mode & 8)) sp[(size_t)j * a.lds] = sg;
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(a.dbg_mode & 32)) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
