@@ -117,6 +117,46 @@ int p2c_linear(const float* X, int64_t ldx, const float* W, const float* bias,
                const p2c_bn_fold* in_bn /* NULL, or the pending BatchNorm of X (in_scale / in_shift then unused) */,
                void* stream);
 
+/* A layer whose input is a concatenation [X | V broadcast over groups of rows] - PointNetFeaturePropagation with a
+ * single source point per cloud (models/pointnet_util.py:298-299: `points2.repeat(1, N, 1)`, then the concat at :312
+ * and the first Conv1d): by linearity  [X | V[g]] W^T + b = X W[:, :K]^T + (V W[:, K:]^T + b)[g],  g = row / group,
+ * so the broadcast rows and the concat buffer never exist.
+ * p2c_linear_small: Y = X W^T + bias for a handful of rows (M <= 256, K <= 3072; fp32 SIMT) - the per-group term.
+ * p2c_linear_group_bias: the tcgen05 streamed-weight layer (3xTF32; w_split from p2c_split_tf32[_multi], which
+ * takes a column slice of the weight through its source row stride) with bias_rows[(row / group), n] in place of a
+ * per-channel bias; group % 32 == 0; in_scale / in_shift / in_bn and stats as in p2c_linear.
+ * P2C_EUNSUPPORTED: shapes the streamed-weight kernel does not take (the caller then builds the concat). */
+int p2c_linear_small(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* Y,
+                     int64_t ldy, int M, int N, int K, void* stream);
+int p2c_linear_group_bias(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias_rows,
+                          int group, const float* in_scale, const float* in_shift, const p2c_bn_fold* in_bn /* or NULL */,
+                          float* Y, int64_t ldy, int M, int N, int K, double* stats, void* stream);
+
+/* The same first layer WITHOUT its output, for levels with no input features (D = 0: sa1 of the backbone,
+ * models/pointnet_util.py:130-139, 200-203 and the layer after it).  The raw first-layer rows (B*S*nsample, C0) are
+ * neither written nor read back: p2c_sa_xyz_linear is the level's SECOND layer (p2c_linear semantics for W1 / b1 / Y /
+ * stats / pool_group / Ymax / Ymin, tensor cores, 3xTF32) whose operand transform recomputes row (b,s,j) of its input
+ * as max(scale0 * (W0 (xyz[b,idx] - new_xyz[b,s]) + b0) + shift0, 0) - with scale0 / shift0 folded into the conv's
+ * coefficients, three FMAs per element (within one rounding of the materialised p2c_sa_first_layer + BatchNorm).  Train-mode BatchNorm statistics of the first layer come in closed form from nine
+ * moments of the centred neighbour coordinates: p2c_group_moments (coordinates only; `moments` holds
+ * p2c_group_moments_size() doubles: per-CTA partials, the nine sums, and a launch counter in the last word that must
+ * be ZERO before the first launch and is left zero by every launch).  Given `moments` and a pending train-mode bn0,
+ * p2c_sa_xyz_linear derives the first layer's sum / sum-of-squares itself (and stores them into bn0->stats);
+ * p2c_sa_xyz_stats is the same closed form as a stand-alone kernel (writes the 2C sums where p2c_sa_first_layer
+ * would have accumulated them).  scale0 / shift0 or bn0 as in p2c_linear.
+ * Returns P2C_EUNSUPPORTED for shapes the tcgen05 kernel does not take (the caller then runs p2c_sa_first_layer). */
+int p2c_group_moments_size(void);
+int p2c_group_moments(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S, int nsample,
+                      double* moments, void* stream);
+int p2c_sa_xyz_stats(const double* moments, int64_t rows, const float* W, int64_t ldw, const float* bias, int C,
+                     double* stats, void* stream);
+int p2c_sa_xyz_linear(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S, int nsample,
+                      const float* W0, int64_t ldw0, const float* b0, int C0, const float* scale0, const float* shift0,
+                      const p2c_bn_fold* bn0 /* or NULL */, const double* moments /* or NULL */, const float* W1,
+                      const float* b1, int N1, float* Y,
+                      int64_t ldy, double* stats, int pool_group, float* Ymax, float* Ymin, void* stream);
+
+
 /* hi/lo tf32 split of a weight matrix for the large-K tensor-core kernel: out[0][n][k] = w with the low 13
  * mantissa bits cleared, out[1][n][k] = w - hi; rows padded with zeros to ldw (multiple of 4) floats.
  * Pass the result as w_split/ldws to p2c_linear; NULL keeps large-K layers on the fp32 SIMT kernel. */
@@ -164,10 +204,14 @@ int p2c_debug_set_timeline(void* buf);
  * mask itself - keep-bit of (point m, channel c) = one bit of Philox4x32-10(counter {m, c/128, seed[1]}, key seed[0]),
  * kept values scaled by 2 - so no (B, C, N) mask tensor crosses HBM (F.dropout semantics, its own random stream);
  * p2c_head_bwd regenerates the same bits from the same two words.  Both NULL = no dropout.
- * W: the heads' weights concatenated (Nout, C), Nout <= 36, C <= 256, C % 16 == 0. */
+ * W: the heads' weights concatenated (Nout, C), Nout <= 36, C <= 256, C % 16 == 0.
+ * precision: P2C_PREC_3XTF32 with a folded BatchNorm and no explicit mask runs on the tcgen05 layer kernel (the mask
+ * is drawn in its operand transform: same bits); otherwise (explicit mask, P2C_PREC_FP32, shapes the tensor-core
+ * kernel does not take) the fp32 SIMT kernel. */
 int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
                     const float* mask_cf, const int64_t* dropout_seed, const float* W, const float* bias, float* Y,
-                    int64_t ldy, int B, int N, int C, int Nout, const p2c_bn_fold* bn /* or NULL */, void* stream);
+                    int64_t ldy, int B, int N, int C, int Nout, const p2c_bn_fold* bn /* or NULL */, int precision,
+                    void* stream);
 
 /* BatchNorm bookkeeping — replaces the statistics half of nn.BatchNorm{1,2}d (eps, momentum,
  * unbiased running_var) used at models/pointnet_util.py:201-203, :317-319, pointnet_extrusion.py:59.
@@ -216,7 +260,7 @@ int p2c_segfit_stats_stride(int K);
 int p2c_segfit_stats(const float* X_raw, int64_t ldx, const float* W_raw, int64_t ldw,
                      const float* pcs, const float* gt_normals, const int64_t* inst,
                      const int64_t* bb, int B, int N, int K, float* partial /* scratch */,
-                     int64_t partial_elems /* >= B*ceil(N/1024)*stride */, float* stats, void* stream);
+                     int64_t partial_elems /* >= B*ceil(N/256)*stride */, float* stats, void* stream);
 
 /* Same statistics from soft assignments the caller already holds (function-level losses.py / data_utils.py
  * API: hungarian_matching, compute_miou_loss, estimate_extrusion_axis, estimate_extrusion_centers).
@@ -240,7 +284,7 @@ int p2c_hungarian(const float* score /* (B,K,K) */, const int32_t* n_gt /* (B) *
  * summed per cloud (the sort at :292 cancels out of the sum). bb_sum: (B). */
 int p2c_bb_loss(const float* W_raw, int64_t ldw, const int64_t* bb, const int64_t* match,
                 const int32_t* n_gt, int B, int N, int K, float* partial /* scratch */,
-                int64_t partial_elems /* >= B*ceil(N/1024) */, float* bb_sum, void* stream);
+                int64_t partial_elems /* >= B*ceil(N/256) */, float* bb_sum, void* stream);
 
 /* Loss finalisation — per (cloud, gt slot): relaxed IoU (losses.py:95-101), centre
  * (data_utils.py:253-266), axis = eigenvector of the smallest eigenvalue of the matched 3x3

@@ -42,6 +42,14 @@ SIGNATURES = {
     "p2c_group": [c_f32p, c_f32p, i64, c_f32p, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, vp],
     "p2c_sa_first_layer": [c_f32p, c_f32p, c_i64p, c_f32p, i64, c_f32p, i64, c_f32p, i32, i32, i32, i32, i32, c_f32p,
                            i64, c_f64p, vp],
+    "p2c_linear_small": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, i64, i32, i32, i32, vp],
+    "p2c_linear_group_bias": [c_f32p, i64, c_f32p, i64, c_f32p, i32, c_f32p, c_f32p, bnp, c_f32p, i64, i32, i32, i32,
+                              c_f64p, vp],
+    "p2c_group_moments_size": [],
+    "p2c_group_moments": [c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, c_f64p, vp],
+    "p2c_sa_xyz_stats": [c_f64p, i64, c_f32p, i64, c_f32p, i32, c_f64p, vp],
+    "p2c_sa_xyz_linear": [c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, c_f32p, i64, c_f32p, i32, c_f32p, c_f32p, bnp,
+                          c_f64p, c_f32p, c_f32p, i32, c_f32p, i64, c_f64p, i32, c_f32p, c_f32p, vp],
     "p2c_linear": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, c_f32p, i64, i32, i32, i32,
                    c_f64p, i32, c_f32p, c_f32p, i32, c_f32p, i64, bnp, vp],
     "p2c_split_tf32": [c_f32p, i32, i32, c_f32p, i64, vp],
@@ -52,7 +60,7 @@ SIGNATURES = {
     "p2c_linear_path": [i64, i32, i32, i32, i32, i32, i32, i32],
     "p2c_debug_set_timeline": [vp],
     "p2c_head_masked": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_i64p, c_f32p, c_f32p, c_f32p, i64, i32, i32, i32, i32,
-                        bnp, vp],
+                        bnp, i32, vp],
     "p2c_bn_finalize": [c_f64p, i64, c_f32p, c_f32p, f32, f32, i32, c_f32p, c_f32p, c_f32p, c_f32p,
                         c_f32p, c_f32p, i32, vp],
     "p2c_bn_relu_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i64, i32, bnp, vp],
@@ -178,6 +186,7 @@ LAUNCHES_PER_CALL = {
     "p2c_extrusion_extents": 1, "p2c_hard_w_encoding": 1, "p2c_normal_angle": 1,
     "p2c_bn_bwd_reduce": 1, "p2c_pool_bwd_reduce": 1, "p2c_bn_bwd_coef": 1, "p2c_bn_bwd_apply": 1,
     "p2c_pool_bwd_apply": 1, "p2c_wgrad": 1, "p2c_sa_first_bwd": 1, "p2c_group_bwd": 1, "p2c_three_nn_interp_bwd": 1, "p2c_head_bwd": 1,
+    "p2c_linear_small": 1, "p2c_linear_group_bias": 1, "p2c_group_moments": 1, "p2c_sa_xyz_stats": 1, "p2c_sa_xyz_linear": 1,
     "p2c_adam_step": 1, "p2c_loss_backward_coef": 1, "p2c_segfit_backward": 1, "p2c_segfit_backward_w": 1,
     "p2c_eig3x3_backward": 1,
 }

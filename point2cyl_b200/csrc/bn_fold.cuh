@@ -32,11 +32,13 @@ static inline int p2c_bn_fold_check(const p2c_bn_fold* f, int C) {
   return 0;
 }
 
-__device__ __forceinline__ void p2c_bn_fold_channel(const BnFoldDev& f, int c, bool writer, float& sc, float& sh) {
+// (sum, sumsq) = the float64 sum / sum of squares of channel c over f.count rows (ignored when f.stats is NULL)
+__device__ __forceinline__ void p2c_bn_fold_sums(const BnFoldDev& f, int c, bool writer, double sum, double sumsq,
+                                                 float& sc, float& sh) {
   double mean, var;
   if (f.stats) {
-    mean = f.stats[c] / f.count;
-    var = f.stats[f.C + c] / f.count - mean * mean;
+    mean = sum / f.count;
+    var = sumsq / f.count - mean * mean;
     if (var < 0.0) var = 0.0;
     if (writer && f.running_mean) {
       const double unbiased = f.count > 1.0 ? var * f.count / (f.count - 1.0) : var;
@@ -58,4 +60,18 @@ __device__ __forceinline__ void p2c_bn_fold_channel(const BnFoldDev& f, int c, b
     if (f.mean_out) f.mean_out[c] = (float)mean;
     if (f.invstd_out) f.invstd_out[c] = (float)invstd;
   }
+}
+
+__device__ __forceinline__ void p2c_bn_fold_channel(const BnFoldDev& f, int c, bool writer, float& sc, float& sh) {
+  p2c_bn_fold_sums(f, c, writer, f.stats ? f.stats[c] : 0.0, f.stats ? f.stats[f.C + c] : 0.0, sc, sh);
+}
+
+// BatchNorm sums of the xyz-only first SA conv y_c = w_c . d + b_c from the nine moments m of d over n rows
+// (sa_first.cu: m[0..2] = sum d, m[3..8] = sum d d^T as xx, xy, xz, yy, yz, zz)
+__device__ __forceinline__ void p2c_xyz_first_sums(const double* __restrict__ m, double n, double w0, double w1, double w2,
+                                                   double b, double& sum, double& sumsq) {
+  const double ws = w0 * m[0] + w1 * m[1] + w2 * m[2];
+  const double q = w0 * w0 * m[3] + w1 * w1 * m[6] + w2 * w2 * m[8] + 2.0 * (w0 * w1 * m[4] + w0 * w2 * m[5] + w1 * w2 * m[7]);
+  sum = n * b + ws;
+  sumsq = q + 2.0 * b * ws + n * b * b;
 }

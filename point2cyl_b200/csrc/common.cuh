@@ -28,6 +28,18 @@ static inline int p2c_sm_budget(int device_sms) {
   return (g_p2c_sm_budget > 0 && g_p2c_sm_budget < device_sms) ? g_p2c_sm_budget : device_sms;
 }
 
+// "xyz-first" operand of the tcgen05 layer kernel (linear_tc.cu, p2c_sa_xyz_linear): the layer's input rows are not
+// read from memory - row r = (b, s, j) is relu(bn0(W0 (xyz[b, idx[r]] - new_xyz[b, s]) + b0)), the first (xyz-only)
+// conv of a set-abstraction level recomputed in the operand transform (three FMAs per element) instead of written by
+// p2c_sa_first_layer and read back (2 x 268 MB per forward at B = 32 x N = 8192).
+struct P2cXyzFirst {
+  const float* xyz; const float* new_xyz; const int64_t* idx;
+  const float* W0; int64_t ldw0; const float* b0;
+  int N, S, ns;
+  const double* moments;   // nine moments of the centred coordinates (p2c_group_moments) or NULL: when set, a pending
+                           // train-mode BatchNorm of the first conv takes its sums from them in closed form
+};
+
 __device__ __forceinline__ float p2c_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(P2C_FULL_MASK, v, o);

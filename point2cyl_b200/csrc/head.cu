@@ -127,13 +127,28 @@ int launch_head(const float* H, int64_t ldh, const float* scale, const float* sh
 
 }  // namespace
 
+// linear_tc.cu: the tcgen05 layer kernel; drop_seed makes its operand transform draw the dropout mask
+int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias, const float* in_scale,
+                  const float* in_shift, const float* in_mask, int64_t ldmask, float* Y, int64_t ldy, int M, int N,
+                  int K, double* stats, int pool_group, float* Ymax, float* Ymin, int precision,
+                  const p2c_bn_fold* in_bn, cudaStream_t st, const int64_t* drop_seed, const P2cXyzFirst* xyz_first);
+
 extern "C" int p2c_head_masked(const float* H, int64_t ldh, const float* scale, const float* shift,
                                const float* mask_cf, const int64_t* dropout_seed, const float* W, const float* bias,
                                float* Y, int64_t ldy, int B, int N, int C, int Nout, const p2c_bn_fold* bn,
-                               void* stream) {
+                               int precision, void* stream) {
   if (!H || !W || !Y || B <= 0 || N <= 0 || C <= 0 || Nout <= 0 || ldh < C || ldy < Nout) return P2C_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return P2C_EINVAL;
   if (int e = p2c_bn_fold_check(bn, C)) return e;
+  if (precision == P2C_PREC_3XTF32 && !mask_cf && (int64_t)B * N < (1ll << 31) && (scale || bn)) {
+    // The heads are one more per-point layer: relu(bn1(fc1)) * dropout -> (3 + 2K) channels.  On the tcgen05 layer
+    // kernel (weights resident in tensor memory, the mask drawn in the operand transform from the same Philox counter
+    // this file and p2c_head_bwd use) the launch is bound by reading H once; the SIMT kernel below - one thread per
+    // point, 2560 FMAs and 640 shared-memory loads each - ran at a fifth of that.
+    const int rc = p2c_linear_tc(H, ldh, W, bias, scale, shift, nullptr, 0, Y, ldy, B * N, Nout, C, nullptr, 0, nullptr,
+                                 nullptr, precision, bn, (cudaStream_t)stream, dropout_seed, nullptr);
+    if (rc != P2C_EUNSUPPORTED) return rc;
+  }
   const BnFoldDev bnd = p2c_bn_fold_dev(bn);
   if (C % 16 != 0 || (ldh % 4) != 0 || (reinterpret_cast<uintptr_t>(H) & 15) != 0) return P2C_EALIGN;
   if (C > 256 || Nout > 36) return P2C_EUNSUPPORTED;

@@ -396,13 +396,65 @@ pool_bn_relu_kernel(const float* __restrict__ Ymax, const float* __restrict__ Ym
   }
 }
 
+// A layer over a handful of rows (one per cloud): four output channels per CTA with their weight rows in shared
+// memory, warp = row (blockIdx.y picks the group of eight rows), lanes stride over K with eight loads in flight.
+// The tiled kernels above would run it on one or two CTAs.
+__global__ void __launch_bounds__(256)
+linear_small_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw,
+                    const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy, int M, int N, int K) {
+  extern __shared__ float s_w4[];              // [4][K]
+  const int n0 = blockIdx.x * 4;
+  for (int e = threadIdx.x; e < 4 * K; e += 256) {
+    const int j = e / K, k = e - j * K;
+    s_w4[e] = (n0 + j < N) ? __ldg(W + (size_t)(n0 + j) * ldw + k) : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.y * 8 + warp;
+  if (m >= M) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* xr = X + (size_t)m * ldx;
+  for (int k0 = 0; k0 < K; k0 += 256) {
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * 32 + lane;
+      x[u] = k < K ? __ldg(xr + k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u * 32 + lane;
+      if (k < K) {
+        a0 = fmaf(x[u], s_w4[k], a0); a1 = fmaf(x[u], s_w4[K + k], a1);
+        a2 = fmaf(x[u], s_w4[2 * K + k], a2); a3 = fmaf(x[u], s_w4[3 * K + k], a3);
+      }
+    }
+  }
+  a0 = p2c_warp_sum(a0); a1 = p2c_warp_sum(a1); a2 = p2c_warp_sum(a2); a3 = p2c_warp_sum(a3);
+  if (lane < 4 && n0 + lane < N) {
+    const float v = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
+    Y[(size_t)m * ldy + n0 + lane] = v + (bias ? __ldg(bias + n0 + lane) : 0.f);
+  }
+}
+
 }  // namespace
+
+extern "C" int p2c_linear_small(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* Y,
+                                int64_t ldy, int M, int N, int K, void* stream) {
+  if (!X || !W || !Y || M <= 0 || N <= 0 || K <= 0 || ldx < K || ldw < K || ldy < N) return P2C_EINVAL;
+  if (M > 256 || K > 3072) return P2C_EUNSUPPORTED;
+  const dim3 grid(p2c_ceil_div(N, 4), p2c_ceil_div(M, 8));
+  linear_small_kernel<<<grid, 256, 4 * K * sizeof(float), (cudaStream_t)stream>>>(X, ldx, W, ldw, bias, Y, ldy, M, N, K);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
 
 // tensor-core paths, linear_tc.cu
 int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias,
                   const float* in_scale, const float* in_shift, const float* in_mask,
                   int64_t ldmask, float* Y, int64_t ldy, int M, int N, int K, double* stats,
-                  int pool_group, float* Ymax, float* Ymin, int precision, const p2c_bn_fold* in_bn, cudaStream_t st);
+                  int pool_group, float* Ymax, float* Ymin, int precision, const p2c_bn_fold* in_bn, cudaStream_t st,
+                  const int64_t* drop_seed = nullptr, const P2cXyzFirst* xyz_first = nullptr);
 int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int pool_group, int precision);
 int p2c_linear_tc_ss(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                      const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,

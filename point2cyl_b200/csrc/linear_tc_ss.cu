@@ -37,6 +37,7 @@ struct SsArgs {
   const float* mul; int64_t ldmul;
   float* S; int64_t lds;
   int raw_hi;                    // RAW tile = hi operand, XT ring holds lo only (no operand transform needed)
+  const float* bias_rows; int bias_group;   // EPI 0: bias[(row / bias_group), n] (N floats per group of rows) in place of bias[n]
   int dbg_mode;                  // tools only (env P2C_SS_DBG): 1 skip the epilogue body, 2 skip the correction read,
                                  // 4 skip the correction MMAs, 8 transform copies hi only (timing experiments)
 };
@@ -111,6 +112,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1)
 linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
                     const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmY,
                     const __grid_constant__ CUtensorMap tmS, const SsArgs a) {
+#ifdef P2C_SS_DEBUG      // timing toggles (tools/igr_exp.sh): build with NVCC_FLAGS=-DP2C_SS_DEBUG; compiled out otherwise
+  const int dbg_mode = a.dbg_mode;
+#else
+  constexpr int dbg_mode = 0;
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SsSmem L = ss_smem_layout(a.KB, a.raw_stages, a.xt_stages, a.y_tma, a.raw_hi);
@@ -173,35 +179,42 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   auto tile_nt = [&](int t) { return ((int)blockIdx.x + t * (int)gridDim.x) % a.n_tiles; };
 
   if (warp == 0) {
-    // ===== TMA producer: X k-block -> RAW ring, W_hi / W_lo k-blocks -> W ring =====
-    if (lane == 0) {
+    // ===== TMA producer: X k-block -> RAW ring, W_hi / W_lo k-blocks -> W ring (warp-uniform loop, elected issuer) =====
+    {
       int s = 0; uint32_t ph = 0;
       int ws = 0; uint32_t wph = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&w_empty[ws], wph ^ 1);
-          if (BF16) {
-            mbar_arrive_expect_tx(&w_full[ws], W_BF16_BYTES);
-            tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
-          } else {
-            mbar_arrive_expect_tx(&w_full[ws], 2 * RAW_BYTES);
-            tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
-            tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES + RAW_BYTES, &tmWlo, &w_full[ws], kb * TC_BK, n0);
+          if (elect_one_sync()) {
+            if (BF16) {
+              mbar_arrive_expect_tx(&w_full[ws], W_BF16_BYTES);
+              tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
+            } else {
+              mbar_arrive_expect_tx(&w_full[ws], 2 * RAW_BYTES);
+              tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES, &tmWhi, &w_full[ws], kb * TC_BK, n0);
+              tma_load_2d(w_sm + (size_t)ws * 2 * RAW_BYTES + RAW_BYTES, &tmWlo, &w_full[ws], kb * TC_BK, n0);
+            }
           }
+          __syncwarp();
           if (++ws == XS) { ws = 0; wph ^= 1; }
           mbar_wait(&raw_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
-          tma_load_2d(raw_sm + (size_t)s * RAW_BYTES, &tmX, &raw_full[s], kb * TC_BK, m0);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
+            tma_load_2d(raw_sm + (size_t)s * RAW_BYTES, &tmX, &raw_full[s], kb * TC_BK, m0);
+          }
+          __syncwarp();
           if (++s == RS) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (see tc_common.cuh: elect_one_sync) =====
+    {
       int xs = 0; uint32_t xph = 0;
       int rs = 0;                                      // RAW stage of this k-block (raw_hi mode: the hi operand)
+      const bool corr = !(dbg_mode & 4);
       for (int t = 0; t < my_tiles; ++t) {
         const int ab = t & 1;
         const uint32_t accph = (uint32_t)(t >> 1) & 1u;
@@ -216,45 +229,52 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           const uint32_t x_hi = raw_hi ? smem_u32(raw_sm + (size_t)rs * RAW_BYTES) : xt0;
           const uint32_t x_lo = raw_hi ? xt0 : xt0 + RAW_BYTES;
           const uint32_t w_hi = smem_u32(w_sm + (size_t)xs * 2 * RAW_BYTES), w_lo = w_hi + RAW_BYTES;
-          if (BF16) {
+          if (elect_one_sync()) {
+            if (BF16) {
+              const uint64_t a0 = make_kmajor_sw64_desc(w_hi), b0 = make_kmajor_sw64_desc(x_hi);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)           // 16 bf16 = 32 bytes per k-step
-              umma_bf16_ss(d, make_kmajor_sw64_desc(w_hi + ks * 32u), make_kmajor_sw64_desc(x_hi + ks * 32u),
-                           TC_IDESC_BF16, (kb | ks) != 0);
-          } else {
+              for (int ks = 0; ks < 2; ++ks)           // 16 bf16 = 32 bytes per k-step
+                umma_bf16_ss(d, a0 + (uint64_t)(ks * 2), b0 + (uint64_t)(ks * 2), TC_IDESC_BF16, (kb | ks) != 0);
+            } else {
+              // The tensor core's fp32 accumulate TRUNCATES (measured: a relative shrink of ~2.3e-8 per accumulate
+              // step, tests/tools/precision_probe.py).  The two correction products are 2^-11 of the main one, so
+              // they go to their own accumulator (columns 256..511) where that truncation is negligible, and the main
+              // accumulator sees K/8 accumulate steps instead of 3K/8; the epilogue adds the two in round-to-nearest
+              // fp32.  (Four main products back to back, then the eight corrections: the tensor pipe chains
+              // accumulations into one accumulator better than it alternates between two.)
+              // The four 8-column k-steps of a tile differ in the descriptor's start-address field only (+32 B = +2).
+              const uint64_t ahi = make_kmajor_sw128_desc(w_hi), alo = make_kmajor_sw128_desc(w_lo);
+              const uint64_t bhi = make_kmajor_sw128_desc(x_hi), blo = make_kmajor_sw128_desc(x_lo);
 #pragma unroll
-          // The tensor core's fp32 accumulate TRUNCATES (measured: a relative shrink of ~2.3e-8 per accumulate step,
-          // tests/tools/precision_probe.py).  The two correction products are 2^-11 of the main one, so they go to
-          // their own accumulator (columns 256..511) where that truncation is negligible, and the main accumulator sees
-          // K/8 accumulate steps instead of 3K/8; the epilogue adds the two in round-to-nearest fp32.
-          // (the four main products back to back, then the eight correction products: the tensor pipe chains
-          // accumulations into one accumulator better than it alternates between two)
+              for (int ks = 0; ks < 4; ++ks)
+                umma_tf32_ss(d, ahi + (uint64_t)(ks * 2), bhi + (uint64_t)(ks * 2), TC_IDESC, (kb | ks) != 0);
+              if (corr) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32_ss(d, make_kmajor_sw128_desc(w_hi + ks * 32u), make_kmajor_sw128_desc(x_hi + ks * 32u), TC_IDESC,
-                         (kb | ks) != 0);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (a.dbg_mode & 4) break;
-            const uint64_t bhi = make_kmajor_sw128_desc(x_hi + ks * 32u), blo = make_kmajor_sw128_desc(x_lo + ks * 32u);
-            const uint64_t ahi = make_kmajor_sw128_desc(w_hi + ks * 32u), alo = make_kmajor_sw128_desc(w_lo + ks * 32u);
-            umma_tf32_ss(d + 256u, alo, bhi, TC_IDESC, (kb | ks) != 0);
-            umma_tf32_ss(d + 256u, ahi, blo, TC_IDESC, 1u);
+                for (int ks = 0; ks < 4; ++ks) {
+                  umma_tf32_ss(d + 256u, alo + (uint64_t)(ks * 2), bhi + (uint64_t)(ks * 2), TC_IDESC, (kb | ks) != 0);
+                  umma_tf32_ss(d + 256u, ahi + (uint64_t)(ks * 2), blo + (uint64_t)(ks * 2), TC_IDESC, 1u);
+                }
+              }
+            }
+            umma_commit(&xt_empty[xs]);
+            umma_commit(&w_empty[xs]);
+            if (raw_hi) umma_commit(&raw_empty[rs]);     // the RAW tile was an MMA operand: free it when they retire
+            if (kb == KB - 1) umma_commit(&acc_full[ab]);
           }
-          }
-          umma_commit(&xt_empty[xs]);
-          umma_commit(&w_empty[xs]);
-          if (raw_hi) umma_commit(&raw_empty[rs]);     // the RAW tile was an MMA operand: free it when they retire
-          if (kb == KB - 1) umma_commit(&acc_full[ab]);
+          __syncwarp();
           if (++xs == XS) { xs = 0; xph ^= 1; }
           if (++rs == RS) rs = 0;
         }
       }
     }
   } else if (warp >= 8 && warp < 12) {
-    // ===== operand transform (see linear_tc.cu) =====
+    // ===== operand transform (see linear_tc.cu: thread = (16-byte chunk cj, row mod 8, half), its eight rows 1024 B
+    // apart, so the swizzled position is one per-thread constant and every access is [base + immediate]) =====
     const int tt = tid - 256;
-    const int cj = tt & 7, rg = tt >> 3;
+    const int cj = tt & 7, r7 = (tt >> 3) & 7, hf = tt >> 6;
+    const uint32_t toff = (uint32_t)(hf * 8192 + r7 * 128 + ((cj ^ r7) << 4));
+    // bf16 tile: rows of 64 bytes, SWIZZLE_64B (16-byte chunk cj >> 1 XOR (row >> 1) & 3), rows 8 apart = 512 B
+    const uint32_t toff16 = (uint32_t)((hf * 64 + r7) * 64 + ((((unsigned)cj >> 1) ^ (((unsigned)r7 >> 1) & 3u)) << 4) + ((cj & 1) << 3));
     const bool has_affine = !raw_hi && (a.in_scale != nullptr || a.bn.active);
     int s = 0; uint32_t ph = 0;
     int xs = 0; uint32_t xph = 0;
@@ -266,59 +286,45 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           sh = *reinterpret_cast<const float4*>(s_shift + kb * TC_BK + cj * 4);
         }
         mbar_wait(&raw_full[s], ph);
-        const uint8_t* rawp = raw_sm + (size_t)s * RAW_BYTES;
+        const uint8_t* rawp = raw_sm + (size_t)s * RAW_BYTES + toff;
         float4 x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rg * 8 + i;
-          x[i] = *reinterpret_cast<const float4*>(rawp + (size_t)r * 128 + ((cj ^ (r & 7)) << 4));
-        }
+        for (int i = 0; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(rawp + i * 1024);
         __syncwarp();
         if (lane == 0 && !raw_hi) mbar_arrive(&raw_empty[s]);
         if (++s == RS) { s = 0; ph ^= 1; }
         if (has_affine) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            x[i].x = fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f);
-            x[i].y = fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f);
-            x[i].z = fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f);
-            x[i].w = fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f);
+            const float2 p0 = __ffma2_rn(make_float2(x[i].x, x[i].y), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+            const float2 p1 = __ffma2_rn(make_float2(x[i].z, x[i].w), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+            x[i] = make_float4(fmaxf(p0.x, 0.f), fmaxf(p0.y, 0.f), fmaxf(p1.x, 0.f), fmaxf(p1.y, 0.f));
           }
         }
         mbar_wait(&xt_empty[xs], xph ^ 1);
         uint8_t* hip = xt_sm + (size_t)xs * xt_stage_bytes;
-        if (raw_hi) {                                  // lo tile only: x - trunc_tf32(x), same swizzled position
+        if (BF16) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rg * 8 + i;
-            float4 l;
-            l.x = x[i].x - __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u);
-            l.y = x[i].y - __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u);
-            l.z = x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u);
-            l.w = x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u);
-            *reinterpret_cast<float4*>(hip + (size_t)r * 128 + ((cj ^ (r & 7)) << 4)) = l;
-          }
-        } else if (BF16) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rg * 8 + i;
-            // fp32 chunk cj (columns 4cj..4cj+3) -> half (cj & 1) of 16-byte bf16 chunk cj >> 1, rows of 64 bytes
-            const size_t off = (size_t)r * 64 + ((((unsigned)cj >> 1) ^ (((unsigned)r >> 1) & 3u)) << 4) + ((cj & 1) << 3);
-            *reinterpret_cast<uint2*>(hip + off) = make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
-          }
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint2*>(hip + toff16 + i * 512) = make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
         } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rg * 8 + i;
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u); l.x = x[i].x - h.x;
-          h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u); l.y = x[i].y - h.y;
-          h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u); l.z = x[i].z - h.z;
-          h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u); l.w = x[i].w - h.w;
-          const size_t off = (size_t)r * 128 + ((cj ^ (r & 7)) << 4);
-          *reinterpret_cast<float4*>(hip + off) = h;
-          *reinterpret_cast<float4*>(hip + RAW_BYTES + off) = l;
-        }
+          for (int i = 0; i < 8; ++i) {
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xffffe000u);
+            h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u);
+            h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u);
+            const float2 l0 = __fadd2_rn(make_float2(x[i].x, x[i].y), make_float2(-h.x, -h.y));
+            const float2 l1 = __fadd2_rn(make_float2(x[i].z, x[i].w), make_float2(-h.z, -h.w));
+            const float4 l = make_float4(l0.x, l0.y, l1.x, l1.y);
+            if (raw_hi) {                                // lo tile only: the RAW tile itself is the hi operand
+              *reinterpret_cast<float4*>(hip + toff + i * 1024) = l;
+            } else {
+              *reinterpret_cast<float4*>(hip + toff + i * 1024) = h;
+              *reinterpret_cast<float4*>(hip + RAW_BYTES + toff + i * 1024) = l;
+            }
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -372,7 +378,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, raw);
-        if (!BF16 && !(a.dbg_mode & 2)) {              // + the correction accumulator (see the MMA issuer)
+        if (!BF16 && !(dbg_mode & 2)) {              // + the correction accumulator (see the MMA issuer)
           uint32_t cor[32];
           tmem_ld32(tmem_base + 256u + (uint32_t)ab * TC_BM + (uint32_t)c * 32u + lane_addr, cor);
           tmem_wait_ld();
@@ -387,10 +393,10 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         const int mrow = m0 + c * 32;
         const int jmax = min(32, a.M - mrow);
-        if (jmax <= 0 || (a.dbg_mode & 1)) continue;
+        if (jmax <= 0 || (dbg_mode & 1)) continue;
         float* st = ystg;
         if (y_tma) {
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
+          if (elect_one_sync()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read it
           __syncwarp();
         }
         if (EPI != 0 && !y_tma) {
@@ -428,7 +434,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int j = 0; j < 32; ++j) {
               const float z = __uint_as_float(raw[j]) + bias;
               float h = z, sg = 1.f;                  // nn.Softplus(beta, threshold 20): identity above the threshold
-              if (!(a.beta * z > 20.f) && !(a.dbg_mode & 16)) {
+              if (!(a.beta * z > 20.f) && !(dbg_mode & 16)) {
                 // e = exp(beta z) <= e^20; softplus = ln(1 + e) / beta, sigmoid = e / (1 + e): MUFU ex2 / lg2 / rcp
                 // (absolute error of h < 1e-9, relative error of sg < 1e-6 - below the 3xTF32 error of z itself)
                 const float e = exp2f(bl2e * z);
@@ -437,11 +443,11 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 sg = __fdividef(e, p);
               }
               st[j * 32 + lane] = h * a.oscale;
-              if (sp && j < jmax && !(a.dbg_mode & 8)) sp[(size_t)j * a.lds] = sg;
+              if (sp && j < jmax && !(dbg_mode & 8)) sp[(size_t)j * a.lds] = sg;
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && !(a.dbg_mode & 32)) {
+            if (!(dbg_mode & 32) && elect_one_sync()) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -455,7 +461,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one_sync()) {
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                            ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -465,12 +471,14 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         float* yp = (a.Y && !y_tma && n_ok) ? a.Y + (size_t)mrow * a.ldy + n : nullptr;
         float mx = NEG_INF, mn = POS_INF;
-        if (jmax == 32) epi_chunk<true>(raw, bias, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
-        else epi_chunk<false>(raw, bias, jmax, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        // per-row-group bias (p2c_linear_group_bias): the 32 rows of a chunk lie in one group (bias_group % 32 == 0)
+        const float bias_c = a.bias_rows ? (n_ok ? __ldg(a.bias_rows + (size_t)(mrow / a.bias_group) * a.N + n) : 0.f) : bias;
+        if (jmax == 32) epi_chunk<true>(raw, bias_c, 32, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
+        else epi_chunk<false>(raw, bias_c, jmax, y_tma ? st + lane : nullptr, yp, a.ldy, a.stats != nullptr, G != 0, t1, t2, mx, mn);
         if (y_tma) {
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                          ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(st)), "r"(n0 + q * 32), "r"(mrow) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -494,7 +502,8 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         atomicAdd(a.stats + a.N + n, (double)t2);
       }
     }
-    if (y_tma_all && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (y_tma_all && elect_one_sync()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -620,7 +629,8 @@ int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int
   return ss_stages((K + TC_BK - 1) / TC_BK, 1, &raw, &xt);
 }
 
-struct SsEpiHost { int op; float beta, oscale; float* S; int64_t lds; const float* mul; int64_t ldmul; };
+struct SsEpiHost { int op; float beta, oscale; float* S; int64_t lds; const float* mul; int64_t ldmul;
+                   const float* bias_rows = nullptr; int bias_group = 0; };
 
 static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                                const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
@@ -675,7 +685,8 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   if (s_tma && (rc = make_map_2d(&tmS, epi.S, N, M, epi.lds, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
            (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn),
-           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds, raw_hi, getenv("P2C_SS_DBG") ? atoi(getenv("P2C_SS_DBG")) : 0};
+           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds, raw_hi, epi.bias_rows, epi.bias_group,
+           getenv("P2C_SS_DBG") ? atoi(getenv("P2C_SS_DBG")) : 0};
   const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma, raw_hi);
   int dev = 0;
   cudaGetDevice(&dev);
@@ -702,6 +713,24 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
     linear_tc_ss_kernel<false, 0><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
+}
+
+// p2c_linear with a bias per GROUP of rows: Y[m, :] = f(X[m, :]) W^T + bias_rows[m / group, :] (see include/point2cyl.h)
+extern "C" int p2c_linear_group_bias(const float* X, int64_t ldx, const float* w_split, int64_t ldws,
+                                     const float* bias_rows, int group, const float* in_scale, const float* in_shift,
+                                     const p2c_bn_fold* in_bn, float* Y, int64_t ldy, int M, int N, int K, double* stats,
+                                     void* stream) {
+  if (!X || !w_split || !bias_rows || !Y || M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || ldws < K) return P2C_EINVAL;
+  if (group <= 0 || group % 32 != 0) return P2C_EUNSUPPORTED;
+  if ((in_scale == nullptr) != (in_shift == nullptr)) return P2C_EINVAL;
+  if (int e = p2c_bn_fold_check(in_bn, K)) return e;
+  if (!p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, 0, 0, P2C_PREC_3XTF32))
+    return P2C_EUNSUPPORTED;
+  SsEpiHost epi{0, 0.f, 1.f, nullptr, 0, nullptr, 0};
+  epi.bias_rows = bias_rows;
+  epi.bias_group = group;
+  return linear_tc_ss_launch(X, ldx, w_split, ldws, nullptr, in_scale, in_shift, Y, ldy, M, N, K, stats, 0, nullptr,
+                             nullptr, 0, in_bn, epi, (cudaStream_t)stream);
 }
 
 // One hidden layer of the implicit sketch network on the tensor cores (3xTF32): see include/point2cyl.h

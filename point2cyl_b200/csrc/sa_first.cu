@@ -11,7 +11,7 @@
 // coordinates.  The kernel is HBM bound on its only large stream, the raw output Y (4*C bytes per row);
 // Qf rows come from L2.  BatchNorm sum / sum-of-squares are accumulated per lane and folded once per CTA.
 // One warp per row, lane = C/32 consecutive channels.
-#include "common.cuh"
+#include "bn_fold.cuh"
 
 namespace {
 
@@ -104,7 +104,152 @@ sa_first_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz
   }
 }
 
+// ---- the first layer WITHOUT its output (p2c_sa_xyz_linear): BatchNorm statistics in closed form ----------------
+// With no point features the first conv sees only the centred neighbour coordinates d = xyz[idx] - centre, so its
+// raw output y_c = w_c . d + b_c never has to exist: the next layer recomputes it in its operand transform
+// (linear_tc.cu), and the train-mode BatchNorm statistics of y follow from nine moments of d over all rows:
+//   sum y_c   = n b_c + w_c . S1                      S1 = sum d      (3)
+//   sum y_c^2 = w_c^T S2 w_c + 2 b_c w_c . S1 + n b_c^2   S2 = sum d d^T  (6)
+// group_moments_kernel reduces (S1, S2) per CTA (coordinates only: it belongs to the geometry stage),
+// sa_xyz_stats_kernel sums the CTA partials and writes the 2 C sums where p2c_sa_first_layer would have accumulated them.
+constexpr int MOM_CTAS = 592;     // 4 per SM: the per-row work is a dependent index -> coordinate load chain
+
+__global__ void __launch_bounds__(256)
+group_moments_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, const int64_t* __restrict__ idx,
+                     int N, int S, int ns, int64_t rows, double* __restrict__ partials) {
+  __shared__ double s_red[8][9];
+  double m[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) m[q] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t r0 = (int64_t)blockIdx.x * 256 + threadIdx.x; r0 < rows; r0 += 4 * stride) {
+    // four independent rows per step: the loads of all four chains are in flight together
+    float d[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * stride;
+      d[u][0] = d[u][1] = d[u][2] = 0.f;
+      if (r < rows) {
+        const unsigned bs = (unsigned)r / (unsigned)ns, b = bs / (unsigned)S;
+        int64_t p = __ldg(idx + r);
+        p = (p < 0 || p >= N) ? 0 : p;
+        const float* pp = xyz + ((size_t)b * N + (size_t)p) * 3;
+        const float* cc = new_xyz + (size_t)bs * 3;
+        d[u][0] = __ldg(pp) - __ldg(cc); d[u][1] = __ldg(pp + 1) - __ldg(cc + 1); d[u][2] = __ldg(pp + 2) - __ldg(cc + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double d0 = (double)d[u][0], d1 = (double)d[u][1], d2 = (double)d[u][2];
+      m[0] += d0; m[1] += d1; m[2] += d2;
+      m[3] += d0 * d0; m[4] += d0 * d1; m[5] += d0 * d2; m[6] += d1 * d1; m[7] += d1 * d2; m[8] += d2 * d2;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const double v = p2c_warp_sum(m[q]);
+    if (lane == 0) s_red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 9 + threadIdx.x] = t;
+  }
+  // the last CTA to finish sums the partials in a fixed order (deterministic) into partials[9 P .. 9 P + 9) and
+  // re-arms the launch counter (the word after them) for the next launch
+  __shared__ bool s_last;
+  unsigned* counter = reinterpret_cast<unsigned*>(partials + (size_t)gridDim.x * 9 + 9);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int q = 0; q < 9; ++q) m[q] = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) m[q] += __ldcg(partials + (size_t)i * 9 + q);
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const double v = p2c_warp_sum(m[q]);
+    if (lane == 0) s_red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
+    partials[(size_t)gridDim.x * 9 + threadIdx.x] = t;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+__global__ void __launch_bounds__(128)
+sa_xyz_stats_kernel(const double* __restrict__ moments, double count, const float* __restrict__ W, int64_t ldw,
+                    const float* __restrict__ bias, int C, double* __restrict__ stats) {
+  for (int c = threadIdx.x; c < C; c += 128) {
+    double sum, sumsq;
+    p2c_xyz_first_sums(moments, count, (double)__ldg(W + (size_t)c * ldw), (double)__ldg(W + (size_t)c * ldw + 1),
+                       (double)__ldg(W + (size_t)c * ldw + 2), bias ? (double)__ldg(bias + c) : 0.0, sum, sumsq);
+    stats[c] = sum;
+    stats[C + c] = sumsq;
+  }
+}
+
 }  // namespace
+
+// linear_tc.cu
+int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias, const float* in_scale,
+                  const float* in_shift, const float* in_mask, int64_t ldmask, float* Y, int64_t ldy, int M, int N,
+                  int K, double* stats, int pool_group, float* Ymax, float* Ymin, int precision,
+                  const p2c_bn_fold* in_bn, cudaStream_t st, const int64_t* drop_seed, const P2cXyzFirst* xyz_first);
+
+extern "C" int p2c_group_moments_size(void) { return MOM_CTAS * 9 + 9 + 1; }
+
+extern "C" int p2c_group_moments(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S,
+                                 int nsample, double* partials, void* stream) {
+  if (!xyz || !new_xyz || !idx || !partials || B <= 0 || N <= 0 || S <= 0 || nsample <= 0) return P2C_EINVAL;
+  const int64_t rows = (int64_t)B * S * nsample;
+  if (rows >= ((int64_t)1 << 31) || (int64_t)B * N >= ((int64_t)1 << 32)) return P2C_EUNSUPPORTED;
+  group_moments_kernel<<<MOM_CTAS, 256, 0, (cudaStream_t)stream>>>(xyz, new_xyz, idx, N, S, nsample, rows, partials);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_sa_xyz_stats(const double* partials, int64_t rows, const float* W, int64_t ldw, const float* bias,
+                                int C, double* stats, void* stream) {
+  if (!partials || !W || !stats || rows <= 0 || C <= 0 || ldw < 3) return P2C_EINVAL;
+  sa_xyz_stats_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(partials + MOM_CTAS * 9, (double)rows, W, ldw, bias, C, stats);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_sa_xyz_linear(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S,
+                                 int nsample, const float* W0, int64_t ldw0, const float* b0, int C0,
+                                 const float* scale0, const float* shift0, const p2c_bn_fold* bn0,
+                                 const double* moments, const float* W1,
+                                 const float* b1, int N1, float* Y, int64_t ldy, double* stats, int pool_group,
+                                 float* Ymax, float* Ymin, void* stream) {
+  if (!xyz || !new_xyz || !idx || !W0 || !W1 || B <= 0 || N <= 0 || S <= 0 || nsample <= 0 || C0 <= 0 || N1 <= 0 ||
+      ldw0 < 3)
+    return P2C_EINVAL;
+  if ((scale0 == nullptr) != (shift0 == nullptr)) return P2C_EINVAL;
+  if (int e = p2c_bn_fold_check(bn0, C0)) return e;
+  if (!Y && !pool_group && !stats) return P2C_EINVAL;
+  if (Y && ldy < N1) return P2C_EINVAL;
+  const int64_t rows = (int64_t)B * S * nsample;
+  if (rows >= ((int64_t)1 << 31) || (int64_t)B * N >= ((int64_t)1 << 32)) return P2C_EUNSUPPORTED;
+  if (pool_group && (!Ymax || !Ymin || rows % pool_group != 0)) return P2C_EINVAL;
+  if (moments && bn0 && bn0->stats && bn0->count != rows) return P2C_EINVAL;
+  const P2cXyzFirst g{xyz, new_xyz, idx, W0, ldw0, b0, N, S, nsample, moments ? moments + MOM_CTAS * 9 : nullptr};
+  return p2c_linear_tc(nullptr, 0, W1, b1, scale0, shift0, nullptr, 0, Y, ldy, (int)rows, N1, C0, stats, pool_group,
+                       Ymax, Ymin, P2C_PREC_3XTF32, bn0, (cudaStream_t)stream, nullptr, &g);
+}
 
 extern "C" int p2c_sa_first_layer(const float* xyz, const float* new_xyz, const int64_t* idx, const float* Qf,
                                   int64_t ldq, const float* W, int64_t ldw, const float* bias, int B, int N, int S,

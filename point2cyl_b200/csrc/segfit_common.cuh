@@ -6,7 +6,7 @@
 namespace {
 
 constexpr int SEG_THREADS = 256;
-constexpr int SEG_CHUNK = 1024;  // points per CTA
+constexpr int SEG_CHUNK = 256;   // points per CTA (B=32 x N=8192: 1024 CTAs; with 1024 points per CTA the 256-CTA grid was latency bound)
 
 __host__ __device__ inline int seg_stride(int K) { return K * K + 19 * K + 2; }
 __host__ __device__ inline int off_cnt(int K) { return K * K; }

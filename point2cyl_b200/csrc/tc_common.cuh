@@ -59,6 +59,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a fully converged warp (elect.sync).  The MMA-issuing role runs WARP-UNIFORM code and elects the issuing
+// lane per instruction group: inside an `if (lane == 0)` region the compiler treats every operand of tcgen05.mma /
+// tcgen05.commit as potentially divergent and wraps each instruction in a waterfall loop (R2UR + ELECT + BRA.U.ANY,
+// ~100 issue cycles per MMA - measured: the issuing warp, not the tensor pipe, paced every layer).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {

@@ -117,24 +117,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   const uint32_t tm_acc = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer: 4 boxes of dY and 4 boxes of X per stage =====
-    if (lane == 0) {
+    // ===== TMA producer: 4 boxes of dY and 4 boxes of X per stage (warp-uniform loop, elected issuer) =====
+    {
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < my_stages; ++t) {
         const int m0 = (st0 + t) * WG_ROWS;
         mbar_wait(&raw_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&raw_full[s], WG_RAW_STAGE);
-        uint8_t* dst = raw_sm + (size_t)s * WG_RAW_STAGE;
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&raw_full[s], WG_RAW_STAGE);
+          uint8_t* dst = raw_sm + (size_t)s * WG_RAW_STAGE;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(dst + b * WG_BOX, &tmDY, &raw_full[s], n0 + b * 32, m0);
+          for (int b = 0; b < 4; ++b) tma_load_2d(dst + b * WG_BOX, &tmDY, &raw_full[s], n0 + b * 32, m0);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(dst + WG_OP + b * WG_BOX, &tmX, &raw_full[s], k0 + b * 32, m0);
+          for (int b = 0; b < 4; ++b) tma_load_2d(dst + WG_OP + b * WG_BOX, &tmX, &raw_full[s], k0 + b * 32, m0);
+        }
+        __syncwarp();
         if (++s == WG_RAW) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (tc_common.cuh: elect_one_sync) =====
+    {
       const bool affine = a.in_scale != nullptr;
       int xs = 0; uint32_t xph = 0;
       int rs = 0;
@@ -144,19 +147,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const uint32_t rawb = smem_u32(raw_sm + (size_t)rs * WG_RAW_STAGE);
         const uint32_t xtb = smem_u32(xt_sm + (size_t)xs * WG_XT_STAGE);
         const uint32_t ahib = affine ? xtb + 2 * WG_OP : rawb + WG_OP;
+        if (elect_one_sync()) {
+          // the four 8-row k-steps differ in the descriptors' start-address field only (+1024 B = +64 units)
+          const uint64_t dyhi = make_mnmajor_sw128_desc(rawb), dylo = make_mnmajor_sw128_desc(xtb);
+          const uint64_t ahi = make_mnmajor_sw128_desc(ahib), alo = make_mnmajor_sw128_desc(xtb + WG_OP);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t dyhi = make_mnmajor_sw128_desc(rawb + ks * 1024u);
-          const uint64_t dylo = make_mnmajor_sw128_desc(xtb + ks * 1024u);
-          const uint64_t ahi = make_mnmajor_sw128_desc(ahib + ks * 1024u);
-          const uint64_t alo = make_mnmajor_sw128_desc(xtb + WG_OP + ks * 1024u);
-          umma_tf32_ss(tm_acc, dyhi, ahi, WG_IDESC, (t | ks) != 0);
-          umma_tf32_ss(tm_acc, dylo, ahi, WG_IDESC, 1u);
-          umma_tf32_ss(tm_acc, dyhi, alo, WG_IDESC, 1u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t o = (uint64_t)(ks * 64);
+            umma_tf32_ss(tm_acc, dyhi + o, ahi + o, WG_IDESC, (t | ks) != 0);
+            umma_tf32_ss(tm_acc, dylo + o, ahi + o, WG_IDESC, 1u);
+            umma_tf32_ss(tm_acc, dyhi + o, alo + o, WG_IDESC, 1u);
+          }
+          umma_commit(&xt_empty[xs]);
+          umma_commit(&raw_empty[rs]);                // the tensor core has read the RAW stage: TMA may refill it
+          if (t == my_stages - 1) umma_commit(acc_full);
         }
-        umma_commit(&xt_empty[xs]);
-        umma_commit(&raw_empty[rs]);                // the tensor core has read the RAW stage: TMA may refill it
-        if (t == my_stages - 1) umma_commit(acc_full);
+        __syncwarp();
         if (++xs == WG_XT) { xs = 0; xph ^= 1; }
         if (++rs == WG_RAW) rs = 0;
       }

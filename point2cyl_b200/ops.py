@@ -117,6 +117,103 @@ def sa_first_layer(xyz: Tensor, new_xyz: Tensor, idx: Tensor, Qf: Optional[Tenso
     return Y
 
 
+def linear_small(X: Tensor, W: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """Y = X W^T + bias for a handful of rows (p2c_linear_small: M <= 256, K <= 3072, fp32).  W (N, K) may be a column
+    slice of a wider matrix."""
+    X = _rows(X)
+    W2 = W.reshape(W.shape[0], -1) if W.dim() != 2 else W
+    if W2.stride(1) != 1:
+        W2 = W2.contiguous()
+    M, K = X.shape
+    N = W2.shape[0]
+    if W2.shape[1] != K:
+        raise _lib.P2CError(f"linear_small: X {tuple(X.shape)} W {tuple(W2.shape)}")
+    Y = torch.empty(M, N, dtype=torch.float32, device=X.device)
+    call("p2c_linear_small", ptr(X), X.stride(0), ptr(W2), W2.stride(0), ptr(bias), ptr(Y), N, M, N, K, stream_ptr())
+    return Y
+
+
+def linear_group_bias(X: Tensor, w_split: Tensor, bias_rows: Tensor, group: int, N: int, K: int,
+                      in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
+                      in_bn: Optional["PendingBN"] = None, stats: Optional[Tensor] = None) -> Tensor:
+    """Y[m] = f(X[m]) W^T + bias_rows[m // group] on the streamed-weight tensor-core kernel (p2c_linear_group_bias).
+    w_split (2, N, pad4(K)) from split_tf32[_multi]; bias_rows (M / group, N) contiguous."""
+    X = _rows(X)
+    M = X.shape[0]
+    bias_rows = _rows(bias_rows)
+    if bias_rows.shape != (-(-M // group), N) or not bias_rows.is_contiguous():
+        raise _lib.P2CError(f"linear_group_bias: bias_rows {tuple(bias_rows.shape)} for M={M}, group={group}, N={N}")
+    Y = torch.empty(M, N, dtype=torch.float32, device=X.device)
+    ps, ph, d = _fold_args(in_bn, in_scale, in_shift)
+    call("p2c_linear_group_bias", ptr(X), X.stride(0), ptr(w_split), w_split.shape[-1], ptr(bias_rows), group, ps, ph, d,
+         ptr(Y), N, M, N, K, ptr(stats), stream_ptr())
+    return Y
+
+
+def group_moments(xyz: Tensor, new_xyz: Tensor, idx: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """Per-CTA partial sums of the nine first / second moments of the centred neighbour coordinates
+    xyz[b, idx[b,s,j]] - new_xyz[b,s] over all rows (coordinates only: geometry stage); input of `sa_xyz_stats`."""
+    xyz, new_xyz = _cloud(xyz), _cloud(new_xyz)
+    B, N, _ = xyz.shape
+    idx = idx.contiguous()
+    n = int(_lib.load().p2c_group_moments_size())
+    # (the last word is the kernel's launch counter: zero before the first launch, left zero by every launch)
+    out = torch.zeros(n, dtype=torch.float64, device=xyz.device) if out is None else _out(out, (n,), torch.float64, xyz.device)
+    call("p2c_group_moments", ptr(xyz), ptr(new_xyz), ptr(idx), B, N, idx.shape[1], idx.shape[2], ptr(out), stream_ptr())
+    return out
+
+
+def sa_xyz_stats(partials: Tensor, rows: int, W: Tensor, bias: Optional[Tensor], stats: Tensor) -> None:
+    """BatchNorm sum / sum-of-squares of the xyz-only first SA conv in closed form (p2c_sa_xyz_stats)."""
+    W2 = W.reshape(W.shape[0], -1)
+    if not W2.is_contiguous():
+        W2 = W2.contiguous()
+    call("p2c_sa_xyz_stats", ptr(partials), rows, ptr(W2), W2.stride(0), ptr(bias), W2.shape[0], ptr(stats), stream_ptr())
+
+
+def sa_xyz_linear(xyz: Tensor, new_xyz: Tensor, idx: Tensor, W0: Tensor, b0: Optional[Tensor], W1: Tensor,
+                  b1: Optional[Tensor], scale0: Optional[Tensor] = None, shift0: Optional[Tensor] = None,
+                  bn0: Optional["PendingBN"] = None, stats: Optional[Tensor] = None, pool_group: int = 0,
+                  want_y: bool = True, moments: Optional[Tensor] = None):
+    """Second layer of a feature-less SA level with the first (xyz-only) layer recomputed in its operand transform
+    (p2c_sa_xyz_linear).  Returns Y (rows, N1) or, with pool_group, (Y or None, Ymax, Ymin); None when the tensor-core
+    kernel does not take the shape (the caller then materialises the first layer)."""
+    xyz, new_xyz = _cloud(xyz), _cloud(new_xyz)
+    B, N, _ = xyz.shape
+    idx = idx.contiguous()
+    S, ns = idx.shape[1], idx.shape[2]
+    W0_ = W0.reshape(W0.shape[0], -1)
+    W1_ = W1.reshape(W1.shape[0], -1)
+    if not W0_.is_contiguous():
+        W0_ = W0_.contiguous()
+    if not W1_.is_contiguous():
+        W1_ = W1_.contiguous()
+    C0, N1 = W0_.shape[0], W1_.shape[0]
+    if W1_.shape[1] != C0 or W0_.shape[1] != 3:
+        raise _lib.P2CError(f"sa_xyz_linear: W0 {tuple(W0_.shape)} / W1 {tuple(W1_.shape)}")
+    rows = B * S * ns
+    Y = torch.empty(rows, N1, dtype=torch.float32, device=xyz.device) if want_y else None
+    Ymax = Ymin = None
+    if pool_group:
+        Ymax = torch.empty(rows // pool_group, N1, dtype=torch.float32, device=xyz.device)
+        Ymin = torch.empty_like(Ymax)
+    pending = bn0 is not None and bn0.pending
+    ps, ph, d = _fold_args(bn0, scale0, shift0)
+    try:
+        call("p2c_sa_xyz_linear", ptr(xyz), ptr(new_xyz), ptr(idx), B, N, S, ns, ptr(W0_), W0_.stride(0), ptr(b0), C0,
+             ps, ph, d, ptr(moments) if d is not None else None, ptr(W1_), ptr(b1), N1, ptr(Y), 0 if Y is None else Y.stride(0), ptr(stats), pool_group,
+             ptr(Ymax), ptr(Ymin), stream_ptr())
+    except _lib.P2CError as e:
+        if "P2C_EUNSUPPORTED" not in str(e):
+            raise
+        if pending:
+            bn0.pending = True
+        return None
+    if pool_group:
+        return Y, Ymax, Ymin
+    return Y
+
+
 def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None,
            in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
            in_mask: Optional[Tensor] = None, stats: Optional[Tensor] = None, pool_group: int = 0,
@@ -164,9 +261,11 @@ def _seed(seed: Optional[Tensor]) -> Optional[Tensor]:
 
 def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mask_cf: Optional[Tensor],
                 W: Tensor, bias: Optional[Tensor], B: int, N: int, seed: Optional[Tensor] = None,
-                bn: Optional["PendingBN"] = None) -> Tensor:
+                bn: Optional["PendingBN"] = None, precision: int = _lib.PREC_3XTF32) -> Tensor:
     """Output heads: (B*N, C) raw fc1 rows -> (B*N, Nout); mask_cf is the (B, C, N) dropout mask, or - with
-    mask_cf None - `seed` (two int64 words on the device) makes the kernel draw the p=0.5 mask itself (Philox)."""
+    mask_cf None - `seed` (two int64 words on the device) makes the kernel draw the p=0.5 mask itself (Philox).
+    precision 3xtf32 (default): the tcgen05 layer kernel when a BatchNorm is folded and no explicit mask is given;
+    fp32 / explicit mask: the SIMT kernel."""
     H = _rows(H)
     C_ = H.shape[1]
     W2 = W.reshape(W.shape[0], -1).contiguous()
@@ -176,7 +275,7 @@ def head_masked(H: Tensor, scale: Optional[Tensor], shift: Optional[Tensor], mas
     Y = torch.empty(B * N, Nout, dtype=torch.float32, device=H.device)
     ps, ph, d = _fold_args(bn, scale, shift)
     call("p2c_head_masked", ptr(H), H.stride(0), ps, ph, ptr(mask_cf), ptr(_seed(seed)), ptr(W2), ptr(bias), ptr(Y),
-         Nout, B, N, C_, Nout, d, stream_ptr())
+         Nout, B, N, C_, Nout, d, precision, stream_ptr())
     return Y
 
 
@@ -426,7 +525,7 @@ def segfit_stats(X_raw: Tensor, W_raw: Tensor, pcs: Tensor, gt_normals: Tensor, 
     pcs, gt_normals = _cloud(pcs), _cloud(gt_normals)
     inst, bb = inst.contiguous(), bb.contiguous()
     stride = segfit_stride(K)
-    nchunks = (N + 1023) // 1024
+    nchunks = (N + 255) // 256
     partial = torch.empty(B * nchunks * stride, dtype=torch.float32, device=pcs.device)
     stats = torch.empty(B, stride, dtype=torch.float32, device=pcs.device)
     call("p2c_segfit_stats", ptr(Xr), Xr.stride(0), ptr(Wr), Wr.stride(0), ptr(pcs),
@@ -461,7 +560,7 @@ def segfit_stats_w(Wb: Tensor, Wc: Optional[Tensor] = None, X: Optional[Tensor] 
     inst = None if inst is None else inst.contiguous().long()
     bb = None if bb is None else bb.contiguous().long()
     stride = segfit_stride(K)
-    nchunks = (N + 1023) // 1024
+    nchunks = (N + 255) // 256
     partial = torch.empty(B * nchunks * stride, dtype=torch.float32, device=Wb.device)
     stats = torch.empty(B, stride, dtype=torch.float32, device=Wb.device)
     call("p2c_segfit_stats_w", ptr(Xr), 0 if Xr is None else Xr.stride(0), 1 if normalize_x else 0, ptr(wb), ldb, sb,
@@ -503,7 +602,7 @@ def hungarian(cost: Tensor, n_gt: Tensor) -> Tensor:
 def bb_loss_sums(W_raw: Tensor, bb: Tensor, match: Tensor, n_gt: Tensor, K: int) -> Tensor:
     B, N = bb.shape
     Wr = _rows(_as_rows(W_raw))
-    nchunks = (N + 1023) // 1024
+    nchunks = (N + 255) // 256
     partial = torch.empty(B * nchunks, dtype=torch.float32, device=bb.device)
     out = torch.empty(B, dtype=torch.float32, device=bb.device)
     call("p2c_bb_loss", ptr(Wr), Wr.stride(0), ptr(bb.contiguous()), ptr(match.contiguous()),

@@ -43,6 +43,12 @@ def get_precision() -> str:
 # shared seed (same torch op on the same shape) at the cost of 268 MB of traffic per step at B=32 x N=8192.
 dropout_mask_fn = None
 
+# fp3 (one source point per cloud) through the linearity of its first conv (feature_propagation -> ops.linear_group_bias)
+group_bias_enabled = True
+
+# sa1 without its first layer's activations (set_abstraction -> ops.sa_xyz_linear); False = always materialise them
+xyz_first_enabled = True
+
 
 def torch_dropout_mask(ones: Tensor, p: float = 0.5) -> Tensor:
     return F.dropout(ones, p=p)
@@ -88,21 +94,26 @@ class _ForwardScratch:
         self.wsplit = {}
         if prec == _lib.PREC_3XTF32:
             convs = [m for m in net.modules() if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d))]
-            big = []
+            # column slices registered by feature_propagation's linearity path (split next to the full matrices)
+            slices = getattr(net, "_p2c_split_slices", {})
+            big = []          # (dict key, weight view)
             for c in convs:
                 N_, K_ = c.weight.shape[0], c.weight[0].numel()
                 # the layers p2c_linear sends to the streamed-weight kernel when given a split copy (pure function of
                 # the shape; row stride pad4(K) as mlp_stack / the concat buffers produce it)
                 if _lib.load().p2c_linear_path(ops.pad4(K_), 1 << 20, N_, K_, 0, 0, prec, 1) == 2:
-                    big.append(c)
+                    big.append((id(c), c.weight))
+                ks = slices.get(id(c))
+                if ks:
+                    big.append(((id(c), ks), c.weight.reshape(N_, -1)[:, :ks]))
             if big:
                 cache = getattr(net, "_p2c_wsplit_buffers", None)
-                key = tuple((id(c), c.weight.data_ptr()) for c in big)
+                key = tuple((k, w.data_ptr()) for k, w in big)
                 if cache is None or cache[0] != key:
                     cache = (key, None)
-                outs = ops.split_tf32_multi([c.weight for c in big], cache[1])
+                outs = ops.split_tf32_multi([w for _, w in big], cache[1])
                 net._p2c_wsplit_buffers = (key, outs)
-                self.wsplit = {id(c): o for c, o in zip(big, outs)}
+                self.wsplit = {k: o for (k, _), o in zip(big, outs)}
 
         self.floats = torch.empty(4 * sum(m.num_features for m in bns), dtype=torch.float32, device=dev)
         self._floats_off = 0
@@ -129,13 +140,17 @@ _scratch: Optional[_ForwardScratch] = None
 
 def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0,
               in_affine: Optional[Affine] = None, in_mask: Optional[Tensor] = None,
-              precision: Optional[str] = None, tag: str = "mlp", first_layer=None, tape: Optional[list] = None):
+              precision: Optional[str] = None, tag: str = "mlp", first_layer=None, tape: Optional[list] = None,
+              xyz_first: Optional[dict] = None):
     """Runs [conv1x1 -> BN -> ReLU] * L over the rows of X.
 
     Returns (Y_last_raw, Affine_last) — or, with pool_group, the pooled post-BN/ReLU features
     (rows/pool_group, C_last).  The BN of layer i is applied inside layer i+1's operand load.
     tape: when given, every layer appends what point2cyl_b200.backward needs (raw input/output, folded BN,
     batch mean / invstd, pooled extrema) and pooled layers keep their raw output.
+    xyz_first (dict xyz, new_xyz, gidx[, mom]): a feature-less SA level whose first conv is NOT materialised - its
+    BatchNorm statistics come in closed form (ops.sa_xyz_stats) and the second layer recomputes its rows in the operand
+    transform (ops.sa_xyz_linear); forward only (no tape).
     """
     prec = _PRECISIONS[precision or _default_precision]
     M = X.shape[0] if X is not None else None
@@ -154,7 +169,24 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
         _lib.set_tag(f"{tag}.{i}")
         fused_first = i == 0 and first_layer is not None
         Ymax = Ymin = None
-        if fused_first:
+        if xyz_first is not None and i == 0:
+            g = xyz_first
+            M = g["gidx"].numel()
+            if use_batch_stats and g.get("mom") is None:
+                g["mom"] = ops.group_moments(g["xyz"], g["new_xyz"], g["gidx"])
+            Y = None        # its statistics: derived from the moments inside the next layer's prologue
+        elif xyz_first is not None and i == 1:
+            g = xyz_first
+            res = ops.sa_xyz_linear(g["xyz"], g["new_xyz"], g["gidx"], convs[0].weight, convs[0].bias, conv.weight,
+                                    conv.bias, scale0=aff.scale, shift0=aff.shift, bn0=aff.bn, stats=stats,
+                                    pool_group=pool, want_y=(pool == 0), moments=g.get("mom"))
+            if res is None:
+                raise _lib.P2CError("sa_xyz_linear: shape not taken by the tensor-core kernel")
+            if pool:
+                Y, Ymax, Ymin = res
+            else:
+                Y = res
+        elif fused_first:
             # the level's first conv comes fused with the grouping gather (p2c_sa_first_layer)
             Y = first_layer(stats)
             M = Y.shape[0]
@@ -196,11 +228,12 @@ def mlp_stack(X: Tensor, K: int, convs, bns, training: bool, pool_group: int = 0
 
 def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Tensor],
                     trace: Optional[dict] = None, precision: Optional[str] = None, tag: str = "sa",
-                    fused_first: bool = True, tape: Optional[dict] = None, geo=None):
+                    fused_first: bool = True, tape: Optional[dict] = None, geo=None, mom: Optional[Tensor] = None):
     """PointNetSetAbstraction in point-major form (models/pointnet_util.py:181-207).
     xyz (B,N,3), feats (B*N, D) rows or None -> (new_xyz (B,S,3), new_feats (B*S, C)).
     tape: dict filled with what the backward of this level needs.
-    geo: (fps_idx, new_xyz, group_idx) computed earlier by `geometry_forward` (they depend on xyz only)."""
+    geo: (fps_idx, new_xyz, group_idx) computed earlier by `geometry_forward` (they depend on xyz only);
+    mom: ops.group_moments of the same grouping, when the geometry stage already reduced them."""
     B, N, _ = xyz.shape
     D = 0 if feats is None else feats.shape[1]
     _lib.set_tag(tag)
@@ -237,6 +270,18 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
             def first_layer(stats):
                 return ops.sa_first_layer(xyz, new_xyz, gidx, Qf, W0, conv0.bias, stats)
 
+            rows = B * gidx.shape[1] * gidx.shape[2]
+            N1 = sa.mlp_convs[1].weight.shape[0]
+            pool1 = pool if len(sa.mlp_convs) == 2 else 0
+            if (xyz_first_enabled and feats is None and tape is None and prec == _lib.PREC_3XTF32 and
+                    rows % max(pool1, 1) == 0 and
+                    _lib.load().p2c_linear_path(ops.pad4(C0), rows, N1, C0, 0, pool1, prec, 0) == 1):
+                # no input features and no tape: the first conv's rows are never written - closed-form BatchNorm
+                # statistics + recomputation inside the second layer's operand transform (ops.sa_xyz_linear)
+                out = mlp_stack(None, 3, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
+                                tag=tag, xyz_first=dict(xyz=xyz, new_xyz=new_xyz, gidx=gidx, mom=mom))
+                return new_xyz, out
+
             if tape is not None:
                 tape.update(fused=True, new_xyz=new_xyz, gidx=gidx)
             out = mlp_stack(None, 3 + D, sa.mlp_convs, sa.mlp_bns, sa.training, pool_group=pool, precision=precision,
@@ -261,6 +306,33 @@ def feature_propagation(fp, xyz1: Tensor, xyz2: Tensor, feats1: Optional[Tensor]
     D1 = 0 if feats1 is None else feats1.shape[1]
     D2 = feats2.shape[1]
     _lib.set_tag(tag)
+    prec = _PRECISIONS[precision or _default_precision]
+    conv0 = fp.mlp_convs[0]
+    C0 = conv0.weight.shape[0]
+    if (S == 1 and feats1 is not None and tape is None and group_bias_enabled and prec == _lib.PREC_3XTF32 and
+            N % 32 == 0 and D2 <= 3072 and B <= 256 and feats1.stride(0) % 4 == 0 and
+            _lib.load().p2c_linear_path(feats1.stride(0), B * N, C0, D1, 0, 0, prec, 1) == 2):
+        # one source point per cloud (fp3): `points2.repeat(1, N, 1)` + concat + conv (:298-299, :312, :317) is, by
+        # linearity, feats1 W[:, :D1]^T + (feats2 W[:, D1:]^T + b)[cloud] - the broadcast rows and the (B*N, D1+D2)
+        # concat buffer never exist, and the layer's K drops from D1 + D2 to D1 (fp3.0: 1280 -> 256)
+        W0 = conv0.weight.reshape(C0, -1)
+
+        def first_layer(stats):
+            per_cloud = ops.linear_small(feats2, W0[:, D1:], conv0.bias)            # (B, C0), fp32
+            wsplit = _scratch.wsplit.get((id(conv0), D1)) if _scratch is not None else None
+            if wsplit is None:
+                wsplit = ops.split_tf32_multi([W0[:, :D1]])[0]
+                net_slices = getattr(fp, "_p2c_owner_slices", None)
+                if net_slices is not None:
+                    net_slices[id(conv0)] = D1      # later forwards split the slice with all the other weights
+            return ops.linear_group_bias(feats1, wsplit, per_cloud, N, C0, D1, stats=stats)
+
+        Y, aff = mlp_stack(None, D1 + D2, fp.mlp_convs, fp.mlp_bns, fp.training, precision=precision, tag=tag,
+                           first_layer=first_layer)
+        _lib.set_tag(tag)
+        if materialize:
+            return ops.bn_relu_apply(Y, aff.scale, aff.shift, bn=aff.bn)
+        return Y, aff
     buf = torch.empty(B * N, D1 + D2, dtype=torch.float32, device=xyz1.device)
     if feats1 is not None:
         buf[:, :D1].copy_(feats1)           # skip features first (:312)
@@ -306,6 +378,7 @@ class Geometry:
     nn1_w: Tensor
     nn2_idx: Tensor
     nn2_w: Tensor
+    mom1: Optional[Tensor] = None      # ops.group_moments of level 1 (closed-form BatchNorm statistics of sa1.0)
 
     @staticmethod
     def empty(net, B: int, N: int, device) -> "Geometry":
@@ -314,11 +387,12 @@ class Geometry:
         return Geometry(e((B, N, 3), torch.float32), e((B, S1), torch.long), e((B, S1, 3), torch.float32),
                         e((B, S1, ns1), torch.long), e((B, S2), torch.long), e((B, S2, 3), torch.float32),
                         e((B, S2, ns2), torch.long), e((B, N, 3), torch.long), e((B, N, 3), torch.float32),
-                        e((B, S1, 3), torch.long), e((B, S1, 3), torch.float32))
+                        e((B, S1, 3), torch.long), e((B, S1, 3), torch.float32),
+                        torch.zeros(int(_lib.load().p2c_group_moments_size()), dtype=torch.float64, device=device))
 
 
 def geometry_forward(net, xyz: Tensor, fps_start: Optional[Sequence[Tensor]] = None,
-                     out: Optional[Geometry] = None) -> Geometry:
+                     out: Optional[Geometry] = None, moments: bool = True) -> Geometry:
     """FPS -> ball query (both levels) and the 3-NN searches of fp1 / fp2 for coordinates xyz (B,N,3) contiguous:
     models/pointnet_util.py:63-107 and :301-305.  out: a Geometry whose buffers are overwritten (static across
     CUDA-graph replays)."""
@@ -330,6 +404,7 @@ def geometry_forward(net, xyz: Tensor, fps_start: Optional[Sequence[Tensor]] = N
     s1 = fps_start[0] if fps_start is not None else draw_fps_start(B, N, dev)
     fps1, l1_xyz = ops.fps(xyz, net.sa1.npoint, s1, out=None if g is None else (g.fps1, g.l1_xyz))
     gidx1 = ops.ball_query(net.sa1.radius, net.sa1.nsample, xyz, l1_xyz, out=None if g is None else g.gidx1)
+    mom1 = ops.group_moments(xyz, l1_xyz, gidx1, out=None if g is None else g.mom1) if moments else None
     _lib.set_tag("sa2")
     s2 = fps_start[1] if fps_start is not None else draw_fps_start(B, l1_xyz.shape[1], dev)
     fps2, l2_xyz = ops.fps(l1_xyz, net.sa2.npoint, s2, out=None if g is None else (g.fps2, g.l2_xyz))
@@ -342,7 +417,7 @@ def geometry_forward(net, xyz: Tensor, fps_start: Optional[Sequence[Tensor]] = N
         if g.xyz.data_ptr() != xyz.data_ptr():
             g.xyz.copy_(xyz)
         return g
-    return Geometry(xyz, fps1, l1_xyz, gidx1, fps2, l2_xyz, gidx2, nn1[0], nn1[1], nn2[0], nn2[1])
+    return Geometry(xyz, fps1, l1_xyz, gidx1, fps2, l2_xyz, gidx2, nn1[0], nn1[1], nn2[0], nn2[1], mom1)
 
 
 def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = None,
@@ -360,7 +435,7 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     rec = (lambda: {}) if tape is not None else (lambda: None)
     r_sa1, r_sa2, r_sa3, r_fp3, r_fp2, r_fp1 = rec(), rec(), rec(), rec(), rec(), rec()
     if geo is None:
-        geo = geometry_forward(net, xyz, fps_start)
+        geo = geometry_forward(net, xyz, fps_start, moments=tape is None and feats0 is None and xyz_first_enabled)
     global _scratch
     outer, _scratch = _scratch, _ForwardScratch(net, precision)
     try:
@@ -376,11 +451,14 @@ def _backbone_features(net, xyz, feats0, geo, trace, precision, tape, r_sa1, r_s
     """The feature stage of backbone_forward (everything that involves weights)."""
     t1 = {} if trace is not None else None
     l1_xyz, l1 = set_abstraction(net.sa1, xyz, feats0, None, t1, precision, tag="sa1", tape=r_sa1,
-                                 geo=(geo.fps1, geo.l1_xyz, geo.gidx1))
+                                 geo=(geo.fps1, geo.l1_xyz, geo.gidx1), mom=geo.mom1)
     t2 = {} if trace is not None else None
     l2_xyz, l2 = set_abstraction(net.sa2, l1_xyz, l1, None, t2, precision, tag="sa2", tape=r_sa2,
                                  geo=(geo.fps2, geo.l2_xyz, geo.gidx2))
     l3_xyz, l3 = set_abstraction(net.sa3, l2_xyz, l2, None, None, precision, tag="sa3", tape=r_sa3)
+    if not hasattr(net, "_p2c_split_slices"):
+        net._p2c_split_slices = {}
+    net.fp3._p2c_owner_slices = net._p2c_split_slices
     l4 = feature_propagation(net.fp3, l2_xyz, l3_xyz, l2, l3, precision=precision, tag="fp3", tape=r_fp3)
     l5 = feature_propagation(net.fp2, l1_xyz, l2_xyz, l1, l4, precision=precision, tag="fp2", tape=r_fp2,
                              nn=(geo.nn2_idx, geo.nn2_w))
@@ -402,7 +480,8 @@ def _backbone_features(net, xyz, feats0, geo, trace, precision, tape, r_sa1, r_s
     Wcat = torch.cat([fc.weight.reshape(fc.weight.shape[0], -1) for fc in net.fc2], dim=0)
     bcat = torch.cat([fc.bias for fc in net.fc2], dim=0)
     _lib.set_tag("fc2")
-    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N, seed=seed, bn=aff_h.bn)
+    out = ops.head_masked(h, aff_h.scale, aff_h.shift, mask_cf, Wcat, bcat, B, N, seed=seed, bn=aff_h.bn,
+                          precision=_PRECISIONS[precision or _default_precision])
     if trace is not None:
         trace.update(sa1=t1, sa2=t2, l1_xyz=l1_xyz, l1=l1, l2_xyz=l2_xyz, l2=l2, l3=l3, l4=l4, l5=l5,
                      y6=y6, aff6=aff6, h=h, aff_h=aff_h)

@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import p2c_oracle as orc
-from point2cyl_b200 import ops, pipeline, synthetic
+from point2cyl_b200 import _lib, ops, pipeline, synthetic
 from point2cyl_b200.dropin.models import pointnet_util as dpu
 from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
 
@@ -233,12 +233,24 @@ def test_philox_dropout_backward_regenerates_the_same_mask():
     sc, sh = (torch.rand(C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
     W = torch.randn(Nout, C, generator=g).to(DEV)
     bias = torch.randn(Nout, generator=g).to(DEV)
-    Y = ops.head_masked(H, sc, sh, None, W, bias, B, N, seed=seed)
     A_ref = torch.relu(H * sc + sh) * mask
-    assert rel_err(Y, A_ref.double() @ W.double().t() + bias.double()) <= 1e-5
-    # the same through an explicit (B, C, N) mask tensor: bit-identical
+    Y_ref = A_ref.double() @ W.double().t() + bias.double()
+    # default precision: the tcgen05 layer kernel draws the mask in its operand transform - the same bits
+    Y_tc = ops.head_masked(H, sc, sh, None, W, bias, B, N, seed=seed)
+    assert rel_err(Y_tc, Y_ref) <= 1e-5
+    Y = ops.head_masked(H, sc, sh, None, W, bias, B, N, seed=seed, precision=_lib.PREC_FP32)
+    assert rel_err(Y, Y_ref) <= 1e-5
+    # the same through an explicit (B, C, N) mask tensor: bit-identical on the SIMT kernel
     mask_cf = mask.reshape(B, N, C).permute(0, 2, 1).contiguous()
     assert torch.equal(Y, ops.head_masked(H, sc, sh, mask_cf, W, bias, B, N))
+    # a pending BatchNorm folded by the head itself, ragged row count, wider C
+    for (B2, N2, C2) in ((3, 777, 128), (1, 130, 64), (2, 512, 192)):
+        H2 = torch.randn(B2 * N2, C2, generator=g).to(DEV)
+        sc2, sh2 = (torch.rand(C2, generator=g) + 0.5).to(DEV), torch.randn(C2, generator=g).to(DEV)
+        W2 = torch.randn(Nout, C2, generator=g).to(DEV)
+        a = ops.head_masked(H2, sc2, sh2, None, W2, bias, B2, N2, seed=seed)
+        b = ops.head_masked(H2, sc2, sh2, None, W2, bias, B2, N2, seed=seed, precision=_lib.PREC_FP32)
+        assert rel_err(a, b.double()) <= 1e-5, (B2, N2, C2)
     dOut = torch.randn(B * N, Nout, generator=g).to(DEV)
     dA, A = ops.head_bwd(dOut, None, W, B, N, H, sc, sh, seed=seed)
     dA2, A2 = ops.head_bwd(dOut, mask_cf, W, B, N, H, sc, sh)

@@ -1,3 +1,4 @@
+# (build first with P2C_NVCC_FLAGS=-DP2C_SS_DEBUG python -m point2cyl_b200.build --force: the toggles are compiled out otherwise)
 # the implicit-network bench with parts of the layer kernel switched off (P2C_SS_DBG bits: 1 epilogue body, 2 correction
 # read, 4 correction MMAs, 8 softplus' stores, 16 activation math, 32 TMA store of H)
 for m in ${IGR_EXP_MODES:-0 1 8 16 32 24 56}; do
