@@ -328,44 +328,59 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
   if (save_invstd) save_invstd[c] = (float)invstd;
 }
 
-// the pending BatchNorm folded by every CTA into shared memory (CTA 0 publishes it)
-__device__ __forceinline__ void fold_to_smem(const BnFoldDev& bn, float* s_sc, float* s_sh, int C) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) p2c_bn_fold_channel(bn, c, blockIdx.x == 0, s_sc[c], s_sh[c]);
+// The pending BatchNorm folded by the consumer: a CTA owns a block of 32 CHANNELS (blockIdx.x) and a range of rows
+// (blockIdx.y), so it folds only its 32 channels - one float64 division and square root per lane of its first warp -
+// instead of all C (with 2368 CTAs folding up to 1024 channels each these two kernels took 12-15 us for a few MB).
+// Thread = (channel lane, row lane): a warp covers the 32 channels of one row, one 128-byte line.
+__device__ __forceinline__ void fold_block(const BnFoldDev& bn, int C, float& sc, float& sh) {
+  __shared__ float s_f[2][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (threadIdx.x < 32) {
+    float a = 0.f, b = 0.f;
+    if (c < C) p2c_bn_fold_channel(bn, c, blockIdx.y == 0, a, b);
+    s_f[0][threadIdx.x] = a;
+    s_f[1][threadIdx.x] = b;
+  }
   __syncthreads();
+  sc = s_f[0][threadIdx.x & 31];
+  sh = s_f[1][threadIdx.x & 31];
 }
 
 __global__ void __launch_bounds__(256)
 bn_relu_apply_fold_kernel(const float* __restrict__ Y, int64_t ldy, const BnFoldDev bn, float* __restrict__ out,
-                          int64_t ldo, int64_t M, int C) {
-  extern __shared__ float s_fold[];
-  float* s_sc = s_fold;
-  float* s_sh = s_fold + C;
-  fold_to_smem(bn, s_sc, s_sh, C);
-  const int64_t total = M * C;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = e / C;
-    const int c = (int)(e - m * C);
-    out[m * ldo + c] = fmaxf(fmaf(__ldg(Y + m * ldy + c), s_sc[c], s_sh[c]), 0.f);
-  }
+                          int64_t ldo, int64_t M, int C, int64_t rows_per_cta) {
+  float sc, sh;
+  fold_block(bn, C, sc, sh);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (c >= C) return;
+  const int64_t m1 = min(M, ((int64_t)blockIdx.y + 1) * rows_per_cta);
+  for (int64_t m = (int64_t)blockIdx.y * rows_per_cta + (threadIdx.x >> 5); m < m1; m += 8)
+    out[m * ldo + c] = fmaxf(fmaf(__ldg(Y + m * ldy + c), sc, sh), 0.f);
 }
 
 __global__ void __launch_bounds__(256)
 pool_bn_relu_fold_kernel(const float* __restrict__ Ymax, const float* __restrict__ Ymin, const BnFoldDev bn,
-                         float* __restrict__ out, int64_t ldo, int64_t G, int C) {
-  extern __shared__ float s_fold[];
-  float* s_sc = s_fold;
-  float* s_sh = s_fold + C;
-  fold_to_smem(bn, s_sc, s_sh, C);
-  const int64_t total = G * C;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t g = e / C;
-    const int c = (int)(e - g * C);
-    const float s = s_sc[c];
-    const float v = s >= 0.f ? __ldg(Ymax + e) : __ldg(Ymin + e);
-    out[g * ldo + c] = fmaxf(fmaf(v, s, s_sh[c]), 0.f);
-  }
+                         float* __restrict__ out, int64_t ldo, int64_t G, int C, int64_t rows_per_cta) {
+  float sc, sh;
+  fold_block(bn, C, sc, sh);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (c >= C) return;
+  const float* src = sc >= 0.f ? Ymax : Ymin;
+  const int64_t g1 = min(G, ((int64_t)blockIdx.y + 1) * rows_per_cta);
+  for (int64_t g = (int64_t)blockIdx.y * rows_per_cta + (threadIdx.x >> 5); g < g1; g += 8)
+    out[g * ldo + c] = fmaxf(fmaf(__ldg(src + g * C + c), sc, sh), 0.f);
+}
+
+// grid of the two kernels above: (channel blocks, row ranges), about four CTAs per SM in total
+static inline dim3 fold_grid(int64_t rows, int C, int64_t* rows_per_cta) {
+  const int cb = (C + 31) / 32;
+  int64_t ry = (592 + cb - 1) / cb;
+  if (ry > (rows + 7) / 8) ry = (rows + 7) / 8;
+  if (ry < 1) ry = 1;
+  int64_t rpc = (rows + ry - 1) / ry;
+  rpc = (rpc + 7) / 8 * 8;
+  *rows_per_cta = rpc;
+  return dim3((unsigned)cb, (unsigned)((rows + rpc - 1) / rpc));
 }
 
 __global__ void __launch_bounds__(256)
@@ -533,15 +548,12 @@ extern "C" int p2c_bn_relu_apply(const float* Y, int64_t ldy, const float* scale
   if (int e = p2c_bn_fold_check(bn, C)) return e;
   const int64_t total = M * C;
   const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
-  if (bn && C <= 4096) {
-    bn_relu_apply_fold_kernel<<<blocks, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(Y, ldy, p2c_bn_fold_dev(bn),
-                                                                                           out, ldo, M, C);
+  if (bn) {
+    int64_t rpc;
+    const dim3 grid = fold_grid(M, C, &rpc);
+    bn_relu_apply_fold_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldy, p2c_bn_fold_dev(bn), out, ldo, M, C, rpc);
     P2C_RETURN_IF_CUDA_ERROR();
     return 0;
-  }
-  if (bn) {
-    if (int e = resolve_bn_fold(bn, (cudaStream_t)stream)) return e;
-    scale = bn->scale_out; shift = bn->shift_out;
   }
   bn_relu_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y, ldy, scale, shift, out, ldo, M, C);
   P2C_RETURN_IF_CUDA_ERROR();
@@ -555,15 +567,12 @@ extern "C" int p2c_pool_bn_relu(const float* Ymax, const float* Ymin, const floa
   if (int e = p2c_bn_fold_check(bn, C)) return e;
   const int64_t total = G * C;
   const int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
-  if (bn && C <= 4096) {
-    pool_bn_relu_fold_kernel<<<blocks, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(Ymax, Ymin, p2c_bn_fold_dev(bn),
-                                                                                          out, ldo, G, C);
+  if (bn) {
+    int64_t rpc;
+    const dim3 grid = fold_grid(G, C, &rpc);
+    pool_bn_relu_fold_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Ymax, Ymin, p2c_bn_fold_dev(bn), out, ldo, G, C, rpc);
     P2C_RETURN_IF_CUDA_ERROR();
     return 0;
-  }
-  if (bn) {
-    if (int e = resolve_bn_fold(bn, (cudaStream_t)stream)) return e;
-    scale = bn->scale_out; shift = bn->shift_out;
   }
   pool_bn_relu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Ymax, Ymin, scale, shift, out, ldo, G, C);
   P2C_RETURN_IF_CUDA_ERROR();

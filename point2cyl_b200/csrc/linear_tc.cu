@@ -159,7 +159,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         __ldg(a.g.W0 + (size_t)k * a.g.ldw0 + 2), a.g.b0 ? __ldg(a.g.b0 + k) : 0.f);
         if (a.in_scale != nullptr || a.bn.active) w = make_float4(sc * w.x, sc * w.y, sc * w.z, fmaf(sc, w.w, sh));
       }
-      s_w0[k] = w;
+      // stored as the packed operands of the transform: per four channels 16 floats
+      // [Ax0 Ax1 Ay0 Ay1 | Az0 Az1 c0 c1 | Ax2 Ax3 Ay2 Ay3 | Az2 Az3 c2 c3] - each LDS.128 yields two aligned pairs
+      float* q = reinterpret_cast<float*>(s_w0) + (k >> 2) * 16 + ((k >> 1) & 1) * 8 + (k & 1);
+      q[0] = w.x; q[2] = w.y; q[4] = w.z; q[6] = w.w;
     }
   }
   tc_fence_before();
@@ -342,22 +345,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float4* dbuf = s_d + (t & 1) * TC_BM;
         dbuf[tt] = make_float4(cur.px - cur.cx, cur.py - cur.cy, cur.pz - cur.cz, 0.f);
         asm volatile("bar.sync 2, 128;" ::: "memory");
+        float4 d[8];                                   // the centred coordinates of this thread's eight rows: once per tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = dbuf[row0 + 8 * i];
         for (int kb = 0; kb < KB; ++kb) {
           // channel pairs as packed operands: (A_x, A_y, A_z, c) of channels 4 cj + {0,1} and + {2,3}
-          const float4 w0 = s_w0[kb * TC_BK + cj * 4], w1 = s_w0[kb * TC_BK + cj * 4 + 1],
-                       w2 = s_w0[kb * TC_BK + cj * 4 + 2], w3 = s_w0[kb * TC_BK + cj * 4 + 3];
-          const float2 ax01 = make_float2(w0.x, w1.x), ay01 = make_float2(w0.y, w1.y), az01 = make_float2(w0.z, w1.z),
-                       c01 = make_float2(w0.w, w1.w);
-          const float2 ax23 = make_float2(w2.x, w3.x), ay23 = make_float2(w2.y, w3.y), az23 = make_float2(w2.z, w3.z),
-                       c23 = make_float2(w2.w, w3.w);
+          const float4* wq = s_w0 + (kb * (TC_BK / 4) + cj) * 4;
+          const float4 p0 = wq[0], p1 = wq[1], p2 = wq[2], p3 = wq[3];
+          const float2 ax01 = make_float2(p0.x, p0.y), ay01 = make_float2(p0.z, p0.w), az01 = make_float2(p1.x, p1.y),
+                       c01 = make_float2(p1.z, p1.w);
+          const float2 ax23 = make_float2(p2.x, p2.y), ay23 = make_float2(p2.z, p2.w), az23 = make_float2(p3.x, p3.y),
+                       c23 = make_float2(p3.z, p3.w);
           mbar_wait(&xt_empty[xs], xph ^ 1);
           uint8_t* hip = xt_sm + (size_t)xs * 2 * RAW_BYTES + toff;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 d = dbuf[row0 + 8 * i];
             float4 x;
-            if (dbg_mode & 1) { x = d; } else {
-              const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+            if (dbg_mode & 1) { x = d[i]; } else {
+              const float2 dx = make_float2(d[i].x, d[i].x), dy = make_float2(d[i].y, d[i].y), dz = make_float2(d[i].z, d[i].z);
               const float2 y01 = __ffma2_rn(az01, dz, __ffma2_rn(ay01, dy, __ffma2_rn(ax01, dx, c01)));
               const float2 y23 = __ffma2_rn(az23, dz, __ffma2_rn(ay23, dy, __ffma2_rn(ax23, dx, c23)));
               x = has_affine ? make_float4(fmaxf(y01.x, 0.f), fmaxf(y01.y, 0.f), fmaxf(y23.x, 0.f), fmaxf(y23.y, 0.f))
@@ -451,7 +456,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float NEG_INF = -__int_as_float(0x7f800000), POS_INF = __int_as_float(0x7f800000);
     const int G = a.pool_group;
     const int gshift = G ? 31 - __clz(G) : 0;
-    double s1 = 0.0, s2 = 0.0;
     float gmx = NEG_INF, gmn = POS_INF;                // running pool over the current group
     int dbg_n = 0;
     int ybuf = 0;
@@ -459,8 +463,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // a [32 x 32] box sticking out over channel N is stored by the warp itself (TMA stores clip at 16-byte granularity)
     const bool y_tma = a.Y != nullptr && a.y_tma && (n0 + cq * 32 + 32 <= a.N);
     const bool warp_live = n0 + cq * 32 < a.N;         // warp-uniform
-    float f1 = 0.f, f2 = 0.f;                          // fp32 partial sums, flushed to fp64 every few tiles
-    int since_flush = 0;
+    // BatchNorm sums across tiles as float-float pairs (Knuth two-sum: the rounding error of every addition is
+    // carried in the low word), converted to float64 once at the end - the fp64 pipe is slow here: two DADDs every
+    // four tiles showed up as 5 % of the kernel's stall samples (math-pipe throttle)
+    float h1 = 0.f, l1 = 0.f, h2 = 0.f, l2 = 0.f;
+    auto two_sum = [](float& hi, float& lo, float t) {
+      const float s_ = __fadd_rn(hi, t);
+      const float bb = __fadd_rn(s_, -hi);
+      lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(hi, -__fadd_rn(s_, -bb)), __fadd_rn(t, -bb)));
+      hi = s_;
+    };
     for (int t = (ACC == 2 ? grp : 0); t < ((ACC == 2 || grp == 0) ? my_tiles : 0); t += (ACC == 2 ? 2 : 1)) {
       const int ab = ACC == 2 ? (t & 1) : 0;
       const uint32_t accph = (ACC == 2 ? (uint32_t)(t >> 1) : (uint32_t)t) & 1u;
@@ -534,15 +546,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (ch == 0 && grp == 0) dbg_mark(dbgp, 2, dbg_n, t * 100 + c);
       }
-      f1 += t1;
-      f2 += t2;
-      if (++since_flush == 4) {                        // fp64 adds are slow here: one pair per four tiles (512 rows)
-        s1 += (double)f1; s2 += (double)f2;
-        f1 = f2 = 0.f; since_flush = 0;
-      }
+      two_sum(h1, l1, t1);
+      two_sum(h2, l2, t2);
     }
-    s1 += (double)f1;
-    s2 += (double)f2;
+    const double s1 = (double)h1 + (double)l1, s2 = (double)h2 + (double)l2;
     __syncwarp();
     if (y_tma && elect_one_sync()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (a.stats && n_ok) {
