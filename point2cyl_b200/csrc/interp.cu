@@ -127,51 +127,6 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
   }
 }
 
-// Gather-only interpolation with the source rows in SHARED memory: a CTA owns 32 channels of one cloud, loads that
-// column slab of all S source rows once (S x 128 B, coalesced) and walks the cloud's N queries - warp = 32 queries at a
-// time (lane l fetches query l's neighbours / weights, broadcast by shuffles), lane = channel.  The per-query kernel
-// above reads three 4 D-byte rows per query from L2 (12 N D bytes per cloud: 403 MB at B = 32 x N = 8192, D = 128 - it
-// ran at the L2 bandwidth, 55 us); here a source row crosses L2 once per cloud and the gathers hit shared memory.
-// Same rounding as above: (u w0 + v w1) + w w2, every operation rounded.
-__global__ void __launch_bounds__(512)
-three_nn_gather_slab_kernel(const float* __restrict__ feats2, int64_t ldf, const int64_t* __restrict__ idx,
-                            const float* __restrict__ w, int N, int S, float* __restrict__ out, int64_t ldo) {
-  extern __shared__ float slab[];                    // [S][32]
-  const int b = blockIdx.y, c0 = blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* f2 = feats2 + (size_t)b * S * ldf + c0 + lane;
-  for (int r0 = warp; r0 < S; r0 += 16 * 8) {          // eight rows in flight per warp
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = (r0 + 16 * u < S) ? __ldg(f2 + (size_t)(r0 + 16 * u) * ldf) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (r0 + 16 * u < S) slab[(r0 + 16 * u) * 32 + lane] = v[u];
-  }
-  __syncthreads();
-  float* o = out + (size_t)b * N * ldo + c0 + lane;
-  for (int q0 = warp * 32; q0 < N; q0 += 16 * 32) {
-    const int q = q0 + lane;
-    int packed = 0;
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-    if (q < N) {
-      const size_t e = ((size_t)b * N + q) * 3;
-      packed = (int)__ldg(idx + e) | ((int)__ldg(idx + e + 1) << 10) | ((int)__ldg(idx + e + 2) << 20);
-      w0 = __ldg(w + e); w1 = __ldg(w + e + 1); w2 = __ldg(w + e + 2);
-    }
-    const int nq = min(32, N - q0);
-#pragma unroll 4
-    for (int j = 0; j < nq; ++j) {
-      const int pk = __shfl_sync(P2C_FULL_MASK, packed, j);
-      const float a0 = __shfl_sync(P2C_FULL_MASK, w0, j), a1 = __shfl_sync(P2C_FULL_MASK, w1, j),
-                  a2 = __shfl_sync(P2C_FULL_MASK, w2, j);
-      const float u = slab[(pk & 1023) * 32 + lane], v = slab[((pk >> 10) & 1023) * 32 + lane],
-                  x = slab[((pk >> 20) & 1023) * 32 + lane];
-      o[(size_t)(q0 + j) * ldo] = __fadd_rn(__fadd_rn(__fmul_rn(u, a0), __fmul_rn(v, a1)), __fmul_rn(x, a2));
-    }
-  }
-}
-
 // S == 1: every point receives the single source row (models/pointnet_util.py:298-299).
 __global__ void __launch_bounds__(256)
 broadcast_rows_kernel(const float* __restrict__ feats2, int64_t ldf, int N, int D,
@@ -230,20 +185,6 @@ extern "C" int p2c_three_nn_search(const float* xyz1, const float* xyz2, int B, 
 extern "C" int p2c_three_nn_gather(const float* feats2, int64_t ldf, const int64_t* idx, const float* w, int B, int N,
                                    int S, int D, float* out, int64_t ldo, void* stream) {
   if (!feats2 || !idx || !w || !out || B <= 0 || N <= 0 || S <= 0 || D <= 0 || ldf < D || ldo < D) return P2C_EINVAL;
-  if (D % 32 == 0 && S <= 1024 && S > 1 && N >= 64) {
-    // source rows staged in shared memory per (cloud, 32-channel block)
-    const size_t smem = (size_t)S * 32 * sizeof(float);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static bool attr_set[64] = {false};            // per-device one-time setup (idempotent)
-    if (dev >= 64 || !attr_set[dev]) {
-      P2C_CUDA_TRY(cudaFuncSetAttribute(three_nn_gather_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-      if (dev < 64) attr_set[dev] = true;
-    }
-    three_nn_gather_slab_kernel<<<dim3(D / 32, B), 512, smem, (cudaStream_t)stream>>>(feats2, ldf, idx, w, N, S, out, ldo);
-    P2C_RETURN_IF_CUDA_ERROR();
-    return 0;
-  }
   dim3 grid(p2c_ceil_div(N, QPB), B);
   three_nn_interp_kernel<<<grid, QPB, 0, (cudaStream_t)stream>>>(nullptr, nullptr, feats2, ldf, N, S, D, out, ldo, nullptr,
                                                                  nullptr, idx, w);
