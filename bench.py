@@ -280,6 +280,8 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
     graphed = not getattr(train_step_numbers, "no_graph", False)
     tr = GraphedTrainer(net, batch, lr=1e-3) if graphed else Trainer(net, lr=1e-3)
 
+    loss_host = None
+
     def step_resident():
         return tr.step(None if graphed else batch)      # the graph's static inputs already hold `batch`
 
@@ -288,7 +290,11 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
             out = tr.step(host)                           # H2D of the six batch tensors into the static inputs, replay
         else:
             out = tr.step({k: host[k].to(dev, non_blocking=True) for k in point2cyl_b200.BATCH_KEYS})
-        out["loss_host"] = out["losses"].cpu()
+        nonlocal loss_host
+        if loss_host is None:
+            loss_host = torch.empty(out["losses"].shape, dtype=out["losses"].dtype).pin_memory()
+        loss_host.copy_(out["losses"], non_blocking=True)     # D2H of the loss scalars, stream-ordered, inside the event pair
+        out["loss_host"] = loss_host
         return out
 
     for _ in range(warmup):
@@ -538,17 +544,19 @@ def main():
     barrier = pd.barrier
 
     def timed(fn, steps):
-        """per-step CUDA-event time on the current stream, L2 flushed (untimed) between steps"""
-        ms = []
+        """per-step CUDA-event time on the current stream, L2 flushed (untimed, in stream order) between steps.  The host
+        does not wait between steps - it synchronises once after the last one - so a step's events bracket device work
+        only, never the host's launch latency of the next step (the caller's barrier + synchronize bracket the K steps)."""
+        evs = []
         for _ in range(steps):
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             fn()
             e.record()
-            e.synchronize()
-            ms.append(s.elapsed_time(e))
-        return ms
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in evs]
 
     graphed = pipe = None
     if not args.no_graph:
@@ -574,15 +582,21 @@ def main():
             return out
         return step_sequential()
 
+    losses_host = torch.empty(6, dtype=torch.float32).pin_memory()
+
     def step_e2e():
+        # the six loss scalars of the step go device -> pinned host inside the step's event pair (stream-ordered copy;
+        # the host reads them after the synchronize that ends the timed region)
         if pipe is not None:
             out = pipe.step(host)                 # H2D of the NEXT batch's six tensors + its coordinate stage, beside
-            out["losses_host"] = out["losses"].cpu()   # the layers + loss of the current one; D2H of its loss scalars
+            losses_host.copy_(out["losses"], non_blocking=True)   # the layers + loss of the current one; D2H of its losses
+            out["losses_host"] = losses_host
             pipe.join()
             return out
         if graphed is not None:
             out = graphed(host)                   # H2D of the six batch tensors, replay
-            out["losses_host"] = out["losses"].cpu()   # D2H of the loss scalars (synchronises)
+            losses_host.copy_(out["losses"], non_blocking=True)
+            out["losses_host"] = losses_host
             return out
         with torch.no_grad():
             return point2cyl_b200.forward_loss_host(net, host, device=dev)
