@@ -133,13 +133,9 @@ fps_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ start, int
 // thread-block cluster share one cloud, each owns a contiguous slice of ceil(N/CS) points (coordinates and running
 // distances in registers, the slice also in shared memory as SoA).  Per round every CTA reduces its slice to one
 // candidate (distance bits, global index, x, y, z), thread 0 stores it into slot [round & 1][rank] of EVERY CTA of
-// the cluster through distributed shared memory and then ARRIVES on that CTA's mbarrier of the round (remote
-// mbarrier.arrive.release.cluster: the stores of the arriving thread are visible to whoever acquires the barrier);
-// every thread waits on its own CTA's barrier for the CS arrivals and all CTAs pick the same winner (max distance,
-// lowest index) - whose coordinates travel with the candidate, so no CTA ever needs a point outside its slice.
-// (Round 1 published the candidates with a full barrier.cluster per round - every thread of every CTA through the
-// hardware cluster barrier, 1.2 us per round; here eight lanes arrive and the rest spin on a local mbarrier.)
-// Same arithmetic and tie-break as the single-CTA kernel: bit-exact.
+// the cluster through distributed shared memory, one cluster barrier publishes the CS candidates, and all CTAs pick
+// the same winner (max distance, lowest index) - whose coordinates travel with the candidate, so no CTA ever needs
+// a point outside its slice.  Same arithmetic and tie-break as the single-CTA kernel: bit-exact.
 constexpr int FPS_MAX_CS = 8;
 
 template <int PPT, int MAXT>
@@ -150,14 +146,8 @@ fps_cluster_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ st
   __shared__ unsigned s_val[2][32];
   __shared__ unsigned s_idx[2][32];
   __shared__ unsigned s_cand[2][FPS_MAX_CS][5];
-  __shared__ __align__(8) uint64_t s_bar[2];          // round & 1: CS arrivals (one per CTA of the cluster) complete a phase
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[i])), "r"(CS));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   const int T = blockDim.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -236,27 +226,9 @@ fps_cluster_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ st
         dst[2] = has ? __float_as_uint(xs[gidx]) : 0u;
         dst[3] = has ? __float_as_uint(ys[gidx]) : 0u;
         dst[4] = has ? __float_as_uint(zs[gidx]) : 0u;
-        // release-arrive on CTA `lane`'s barrier of this round: orders the five stores above before the arrival
-        uint32_t rbar;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                     : "=r"(rbar) : "r"((uint32_t)__cvta_generic_to_shared(&s_bar[buf])), "r"(lane));
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
       }
     }
-    {
-      // wait (acquire at cluster scope) until all CS candidates of this round have landed in this CTA
-      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[buf]);
-      const uint32_t parity = (uint32_t)(it >> 1) & 1u;
-      asm volatile(
-          "{\n\t"
-          ".reg .pred P1;\n\t"
-          "FPS_WAIT:\n\t"
-          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
-          "@P1 bra FPS_DONE;\n\t"
-          "bra FPS_WAIT;\n\t"
-          "FPS_DONE:\n\t"
-          "}" ::"r"(bar), "r"(parity) : "memory");
-    }
+    cluster.sync();
     unsigned bv = 0u, bi = 0xffffffffu;
     int br = 0;
     for (int r = 0; r < CS; ++r) {

@@ -68,14 +68,20 @@ with torch.no_grad():
                                 torch.ones(2, 2, dtype=torch.bool, device="cuda"))
 torch.cuda.synchronize()
 print("igr ok", float(out["im_loss"]))
-# the two-stage pipeline (second stream, SM budget, CUDA graphs)
-from point2cyl_b200.graph import PipelinedForwardLoss
-net.train()
-pipe = PipelinedForwardLoss(net, batch)
-pipe.prime(None)
-for _ in range(2):
-    o = pipe.step(None)
-pipe.join()
-torch.cuda.synchronize()
-print("pipelined ok", float(o["losses"][0]))
+# the two-stage pipeline (second stream, SM budget, CUDA graphs).  Under memcheck the script runs with
+# PYTORCH_NO_CUDA_MEMORY_CACHING=1 (every tensor its own cudaMalloc), and a cudaMalloc inside a stream capture is an error
+# by itself: the graph section is then skipped - its kernels are the ones exercised above.
+import os
+if os.environ.get("PYTORCH_NO_CUDA_MEMORY_CACHING") == "1":
+    print("pipelined skipped (allocator caching off: no stream capture)")
+else:
+    from point2cyl_b200.graph import PipelinedForwardLoss
+    net.train()
+    pipe = PipelinedForwardLoss(net, batch)
+    pipe.prime(None)
+    for _ in range(2):
+        o = pipe.step(None)
+    pipe.join()
+    torch.cuda.synchronize()
+    print("pipelined ok", float(o["losses"][0]))
 print("DONE")
