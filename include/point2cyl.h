@@ -180,6 +180,19 @@ int p2c_linear_act(const float* X, int64_t ldx, const float* w_split, int64_t ld
                    int K, int op, float beta, float oscale, float* Y, int64_t ldy, float* S, int64_t lds,
                    const float* Mul, int64_t ldmul, void* stream);
 
+/* One layer-GEMM of the implicit network's SECOND-ORDER backward (training through gradient(..., create_graph=True),
+ * IGR/network.py:8-17 + train_Point2Cyl.py:608-672, restated without autograd in oracle/igr_oracle.py
+ * implicit_backward_closed_form).  Same tensor-core kernel as p2c_linear_act, no bias, two more element-wise epilogues:
+ *   op 3 (adjoint of the reverse sweep, going up):  acc = X W^T with X = r_bar_i, W = W_i;  Y = acc * Mul * oscale is the
+ *         next layer's r_bar (Mul = softplus'(z_i));  Z = beta * acc * V * (1 - Mul) with V = a_i is the extra
+ *         pre-activation gradient a_bar_i * q_{i+1} * softplus''(z_i)  (softplus'' = beta s (1 - s), a_i = s_i q_{i+1});
+ *   op 4 (backward of the forward sweep, going down):  Y = acc * Mul * oscale + V with X = delta_i, W = W_i^T,
+ *         Mul = softplus'(z_{i-1}), V = that extra term of layer i-1 (Y may alias V).
+ * Mul / V / Y / Z are (M, N) row matrices; Z is written for op 3 only. */
+int p2c_linear_act_bwd(const float* X, int64_t ldx, const float* w_split, int64_t ldws, int M, int N, int K, int op,
+                       float beta, float oscale, float* Y, int64_t ldy, const float* Mul, int64_t ldmul, const float* V,
+                       int64_t ldv, float* Z, int64_t ldz, void* stream);
+
 /* bf16 copy of a weight matrix for P2C_PREC_BF16: out (N, ldw) bf16 (round-to-nearest), rows zero padded to ldw
  * (multiple of 8) elements.  Pass it as w_split (ldws = ldw) to p2c_linear with precision P2C_PREC_BF16: the layer then
  * runs ONE tcgen05 kind::f16 pass on bf16 operands with fp32 accumulation (not fp32-faithful; BASELINE.json's bf16
@@ -478,6 +491,26 @@ int p2c_igr_rowdots(const float* A, int64_t lda, int64_t M, int C, const float* 
  * train_Point2Cyl.py:627-647. */
 int p2c_igr_loss_terms(const float* f_on, const float* g_on, const float* normals, const float* g_off, int instances,
                        int S, int S_off, float* out /* (instances, 3) */, void* stream);
+/* ---- its backward (oracle/igr_oracle.py implicit_backward_closed_form; the layer GEMMs are p2c_linear_act_bwd and
+ * p2c_wgrad) ----
+ * out[j, c] += scale * sum_m G[m, j] * A[m, c], NV in {1, 2} rows of out; G NULL (NV = 1) = plain column sums: the
+ * 512 -> 1 output layer's weight gradient from both sweeps. */
+int p2c_igr_colsums(const float* A, int64_t lda, int64_t M, int C, const float* G, int64_t ldg, int NV, float scale,
+                    float* out, int64_t ldo, void* stream);
+/* out[m, c] = ZE[m, c] + S[m, c] * f_bar[m] * w[c]: pre-activation gradient of the last hidden layer (the output
+ * layer's data gradient is an outer product).  ZE NULL = no input-gradient loss, f_bar NULL = no value loss. */
+int p2c_igr_seed_delta(const float* ZE, int64_t ldz, const float* S, int64_t lds, const float* f_bar, const float* w,
+                       int64_t M, int C, float* out, int64_t ldo, void* stream);
+/* Backward of add_latent over one block of instances x S rows: dlatent[i, :E] += scale * sum_p DX[i*S+p, :E];
+ * dpts[r, 0..1] (+)= scale * DX[r, E..E+1] when dpts != NULL. */
+int p2c_igr_latent_grad(const float* DX, int64_t lddx, int instances, int S, int E, float scale, float* dlatent,
+                        float* dpts, int accumulate_pts, void* stream);
+/* Backward of p2c_igr_loss_terms: dterms (instances, 3) -> f_bar (instances*S), g_bar_on (instances*S, 2),
+ * g_bar_off (instances*S_off, 2), with torch's sub-gradient conventions (sign(0) = 0, d||v||/dv = 0 at v = 0, torch.min
+ * routes a tie to its first argument |g - n|). */
+int p2c_igr_loss_terms_bwd(const float* f_on, const float* g_on, const float* normals, const float* g_off, int instances,
+                           int S, int S_off, const float* dterms, float* f_bar, float* g_bar_on, float* g_bar_off,
+                           void* stream);
 
 #ifdef __cplusplus
 }

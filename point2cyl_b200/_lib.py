@@ -56,6 +56,8 @@ SIGNATURES = {
     "p2c_split_tf32_multi": [vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "p2c_linear_act": [c_f32p, i64, c_f32p, i64, c_f32p, i32, i32, i32, i32, f32, f32, c_f32p, i64, c_f32p, i64, c_f32p,
                        i64, vp],
+    "p2c_linear_act_bwd": [c_f32p, i64, c_f32p, i64, i32, i32, i32, i32, f32, f32, c_f32p, i64, c_f32p, i64, c_f32p, i64,
+                           c_f32p, i64, vp],
     "p2c_cast_bf16": [c_f32p, i32, i32, vp, i64, vp],
     "p2c_linear_path": [i64, i32, i32, i32, i32, i32, i32, i32],
     "p2c_debug_set_timeline": [vp],
@@ -112,6 +114,10 @@ SIGNATURES = {
     "p2c_igr_scale_cols": [c_f32p, i64, c_f32p, i64, i32, c_f32p, i64, vp],
     "p2c_igr_rowdots": [c_f32p, i64, i64, i32, c_f32p, i64, i64, i32, c_f32p, f32, c_f32p, i64, i32, vp],
     "p2c_igr_loss_terms": [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, c_f32p, vp],
+    "p2c_igr_colsums": [c_f32p, i64, i64, i32, c_f32p, i64, i32, f32, c_f32p, i64, vp],
+    "p2c_igr_seed_delta": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, i64, i32, c_f32p, i64, vp],
+    "p2c_igr_latent_grad": [c_f32p, i64, i32, i32, i32, f32, c_f32p, c_f32p, i32, vp],
+    "p2c_igr_loss_terms_bwd": [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, c_f32p, c_f32p, c_f32p, c_f32p, vp],
     "p2c_adam_step": [c_f32p, c_f32p, c_f32p, c_f32p, i64, f32, f32, f32, f32, f32, i32, f32, vp],
 }
 

@@ -36,6 +36,11 @@ struct SsArgs {
   int s_tma;                     // the second output S leaves through TMA stores too
   const float* mul; int64_t ldmul;
   float* S; int64_t lds;
+  // second-order backward of the implicit network (p2c_linear_act_bwd), no bias:
+  //   EPI 3: Y = acc * Mul * oscale, S = beta * acc * mul2 * (1 - Mul)   (adjoint of the reverse sweep: Mul = softplus',
+  //          mul2 = a_i, so S is the extra pre-activation gradient a_bar * q * softplus'')
+  //   EPI 4: Y = acc * Mul * oscale + mul2                              (data gradient with that extra term injected)
+  const float* mul2; int64_t ldmul2;
   int raw_hi;                    // RAW tile = hi operand, XT ring holds lo only (no operand transform needed)
   const float* bias_rows; int bias_group;   // EPI 0: bias[(row / bias_group), n] (N floats per group of rows) in place of bias[n]
   int dbg_mode;                  // tools only (env P2C_SS_DBG): 1 skip the epilogue body, 2 skip the correction read,
@@ -356,7 +361,7 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int m0 = tile_mt(t) * TC_BM, n0 = tile_nt(t) * TC_BN;
       const int n = n0 + ch;
       const bool n_ok = n < a.N;
-      if (EPI == 2 && n_ok) {
+      if (EPI >= 2 && n_ok) {
         // the multiplier rows this warp will read in its two chunks: pull them into L2 while the MMAs of the tile run
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -416,8 +421,16 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               }
               a.Y[row * a.ldy + n] = h * a.oscale;
               if (a.s_tma) a.S[row * a.lds + n] = sg;
-            } else {
+            } else if (EPI == 2) {
               a.Y[row * a.ldy + n] = z * __ldg(a.mul + row * a.ldmul + n) * a.oscale;
+            } else {
+              const float m = __ldg(a.mul + row * a.ldmul + n), v = __ldg(a.mul2 + row * a.ldmul2 + n);
+              if (EPI == 3) {
+                a.Y[row * a.ldy + n] = z * m * a.oscale;
+                a.S[row * a.lds + n] = a.beta * z * v * (1.f - m);
+              } else {
+                a.Y[row * a.ldy + n] = fmaf(z * m, a.oscale, v);
+              }
             }
           }
           continue;
@@ -454,10 +467,24 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
           } else {
             const float* mp = a.mul + (size_t)mrow * a.ldmul + n;
+            const float* vp = EPI >= 3 ? a.mul2 + (size_t)mrow * a.ldmul2 + n : nullptr;
+            float* zp = EPI == 3 ? a.S + (size_t)mrow * a.lds + n : nullptr;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float m = (n_ok && j < jmax) ? __ldg(mp + (size_t)j * a.ldmul) : 0.f;   // warp = 128 B of row mrow+j
-              st[j * 32 + lane] = (__uint_as_float(raw[j]) + bias) * m * a.oscale;
+              const bool ok = n_ok && j < jmax;
+              const float m = ok ? __ldg(mp + (size_t)j * a.ldmul) : 0.f;   // warp = 128 B of row mrow+j
+              const float z = __uint_as_float(raw[j]) + bias;
+              if (EPI == 2) {
+                st[j * 32 + lane] = z * m * a.oscale;
+              } else {
+                const float v = ok ? __ldg(vp + (size_t)j * a.ldmul2) : 0.f;
+                if (EPI == 3) {
+                  st[j * 32 + lane] = z * m * a.oscale;
+                  if (ok) zp[(size_t)j * a.lds] = a.beta * z * v * (1.f - m);
+                } else {
+                  st[j * 32 + lane] = fmaf(z * m, a.oscale, v);
+                }
+              }
             }
             fence_proxy_async();
             __syncwarp();
@@ -630,7 +657,8 @@ int p2c_linear_tc_ss_plan(int64_t ldx, int x_aligned16, int K, int has_mask, int
 }
 
 struct SsEpiHost { int op; float beta, oscale; float* S; int64_t lds; const float* mul; int64_t ldmul;
-                   const float* bias_rows = nullptr; int bias_group = 0; };
+                   const float* bias_rows = nullptr; int bias_group = 0;
+                   const float* mul2 = nullptr; int64_t ldmul2 = 0; };
 
 static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split, int64_t ldws, const float* bias,
                                const float* in_scale, const float* in_shift, float* Y, int64_t ldy, int M, int N, int K,
@@ -685,7 +713,7 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   if (s_tma && (rc = make_map_2d(&tmS, epi.S, N, M, epi.lds, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   SsArgs a{bias, in_scale, in_shift, Y, ldy, M, N, K, KB, stats, pool_group, Ymax, Ymin, raw, xt,
            (M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN, y_tma, p2c_bn_fold_dev(in_bn),
-           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds, raw_hi, epi.bias_rows, epi.bias_group,
+           epi.beta, epi.oscale, s_tma, epi.mul, epi.ldmul, epi.S, epi.lds, epi.mul2, epi.ldmul2, raw_hi, epi.bias_rows, epi.bias_group,
            getenv("P2C_SS_DBG") ? atoi(getenv("P2C_SS_DBG")) : 0};
   const SsSmem L = ss_smem_layout(KB, raw, xt, y_tma, raw_hi);
   int dev = 0;
@@ -696,6 +724,8 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
     P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(linear_tc_ss_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
@@ -709,6 +739,10 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
     linear_tc_ss_kernel<false, 1><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
   else if (epi.op == 2)
     linear_tc_ss_kernel<false, 2><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
+  else if (epi.op == 3)
+    linear_tc_ss_kernel<false, 3><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
+  else if (epi.op == 4)
+    linear_tc_ss_kernel<false, 4><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
   else
     linear_tc_ss_kernel<false, 0><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
   P2C_RETURN_IF_CUDA_ERROR();
@@ -746,5 +780,20 @@ extern "C" int p2c_linear_act(const float* X, int64_t ldx, const float* w_split,
     if (oscale != 1.f) return P2C_EUNSUPPORTED;
   }
   return linear_tc_ss_launch(X, ldx, w_split, ldws, bias, nullptr, nullptr, Y, ldy, M, N, K, nullptr, 0, nullptr, nullptr,
+                             0, nullptr, epi, (cudaStream_t)stream);
+}
+
+// One layer of the implicit network's second-order backward on the tensor cores (3xTF32): see include/point2cyl.h
+extern "C" int p2c_linear_act_bwd(const float* X, int64_t ldx, const float* w_split, int64_t ldws, int M, int N, int K,
+                                  int op, float beta, float oscale, float* Y, int64_t ldy, const float* Mul,
+                                  int64_t ldmul, const float* V, int64_t ldv, float* Z, int64_t ldz, void* stream) {
+  if (!X || !w_split || !Y || !Mul || !V || M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || ldws < K) return P2C_EINVAL;
+  if ((op != 3 && op != 4) || ldmul < N || ldv < N || (op == 3 && (!Z || ldz < N))) return P2C_EINVAL;
+  if (!p2c_linear_tc_ss_plan(ldx, (reinterpret_cast<uintptr_t>(X) & 15) == 0, K, 0, 0, P2C_PREC_3XTF32))
+    return P2C_EUNSUPPORTED;
+  SsEpiHost epi{op, beta, oscale, op == 3 ? Z : nullptr, ldz, Mul, ldmul};
+  epi.mul2 = V;
+  epi.ldmul2 = ldv;
+  return linear_tc_ss_launch(X, ldx, w_split, ldws, nullptr, nullptr, nullptr, Y, ldy, M, N, K, nullptr, 0, nullptr, nullptr,
                              0, nullptr, epi, (cudaStream_t)stream);
 }

@@ -6,7 +6,9 @@ constructor signatures and state_dict keys; forward passes run on the libp2c.so 
     sk_pred = implicit_net(sk_pnts)               # forward sweep; keeps softplus'(z) because the input asks for a gradient
     mnfld_grad = gradient(sk_pnts, sk_pred)       # closed-form reverse sweep, last two columns (reference :8-17)
 
-Values only: the outputs carry no autograd graph (the second-order backward is not built yet).
+With grad mode on, `sk_pred`, `mnfld_grad` and the latent codes are autograd nodes whose backward runs the closed-form
+sweeps of point2cyl_b200.igr (implicit_backward, the encoder's layer backward): `im_loss.backward()` of the unmodified
+training loop fills the gradients of ImplicitNet and PointNetEncoder (train_Point2Cyl.py:608-672, :686-690).
 """
 import numpy as np
 import torch
@@ -42,10 +44,7 @@ class ImplicitNet(nn.Module):
         self.activation = nn.Softplus(beta=beta) if beta > 0 else nn.ReLU()
 
     def forward(self, input):
-        f, ctx = igr.implicit_forward(self, x=input, want_grad=bool(input.requires_grad))
-        if ctx is not None:
-            f._p2c_igr = ctx
-        return f
+        return igr.implicit_net_forward(self, input)
 
 
 class PointNetEncoder(nn.Module):

@@ -338,6 +338,21 @@ def linear_act(X: Tensor, w_split: Tensor, bias: Optional[Tensor], N: int, K: in
     return out
 
 
+def linear_act_bwd(X: Tensor, w_split: Tensor, N: int, K: int, op: int, mul: Tensor, v: Tensor, out: Tensor,
+                   beta: float = 100.0, oscale: float = 1.0, Z: Optional[Tensor] = None) -> Tensor:
+    """One layer-GEMM of the implicit network's second-order backward (p2c_linear_act_bwd): op 3 writes
+    out = acc * mul * oscale and Z = beta * acc * v * (1 - mul); op 4 writes out = acc * mul * oscale + v."""
+    need_cuda(X, w_split, mul, v, out)
+    X = _rows(X)
+    for t in (mul, v, out) + ((Z,) if Z is not None else ()):
+        _rows(t)
+    M = X.shape[0]
+    call("p2c_linear_act_bwd", ptr(X), X.stride(0), ptr(w_split), w_split.shape[-1], M, N, K, op, float(beta),
+         float(oscale), ptr(out), out.stride(0), ptr(mul), mul.stride(0), ptr(v), v.stride(0), ptr(Z),
+         0 if Z is None else Z.stride(0), stream_ptr())
+    return out
+
+
 def cast_bf16(W: Tensor) -> Tensor:
     """(N, pad8(K)) bf16 copy of a weight matrix for the bf16 tensor-core path (P2C_PREC_BF16)."""
     W2 = W.reshape(W.shape[0], -1)

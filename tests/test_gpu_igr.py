@@ -158,3 +158,135 @@ def test_implicit_network_larger_batch_vs_oracle():
     x = torch.cat([orc.add_latent(on, latent), orc.add_latent(off, latent)])
     f_ref, g_ref = orc.implicit_forward_with_input_grad(sd, x)
     assert rel_err(f, f_ref) <= TOL and rel_err(gx, g_ref) <= TOL
+
+
+# ---- second-order backward: training through the input gradient (train_Point2Cyl.py:608-672 + backward()) ----------
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).detach().cpu().double().reshape(-1)
+    b = torch.as_tensor(b).detach().cpu().double().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_linear_act_bwd_epilogues_against_fp64():
+    """p2c_linear_act_bwd on its own: op 3 (two outputs) and op 4 (addend, in place), ragged N / K (254)."""
+    g = torch.Generator().manual_seed(1)
+    for M, N, K in [(1000, 512, 512), (300, 254, 512), (513, 512, 254), (2048, 512, 258)]:
+        X = torch.zeros(M, ops.pad4(K))
+        X[:, :K] = torch.randn(M, K, generator=g) * 0.05
+        W = torch.randn(N, K, generator=g) / K ** 0.5
+        mul, v = torch.rand(M, N, generator=g), torch.randn(M, N, generator=g)
+        pad = lambda t: torch.nn.functional.pad(t, (0, ops.pad4(N) - N)).to(DEV)
+        ws = ops.split_tf32_multi([W.to(DEV)])[0]
+        acc = X[:, :K].double() @ W.double().t()
+        Y = torch.full((M, ops.pad4(N)), 7.0, device=DEV)
+        Z = torch.full((M, ops.pad4(N)), 7.0, device=DEV)
+        ops.linear_act_bwd(X.to(DEV)[:, :K], ws, N, K, 3, pad(mul)[:, :N], pad(v)[:, :N], Y[:, :N], beta=100.0,
+                           oscale=2.0 ** -0.5, Z=Z[:, :N])
+        assert rel_err(Y[:, :N], acc * mul.double() * 2.0 ** -0.5) <= 1e-5
+        assert rel_err(Z[:, :N], 100.0 * acc * v.double() * (1.0 - mul.double())) <= 1e-5
+        assert bool((Y[:, N:] == 7.0).all()) and bool((Z[:, N:] == 7.0).all())
+        buf = pad(v).clone()
+        ops.linear_act_bwd(X.to(DEV)[:, :K], ws, N, K, 4, pad(mul)[:, :N], buf[:, :N], buf[:, :N], oscale=0.5)
+        assert rel_err(buf[:, :N], acc * mul.double() * 0.5 + v.double()) <= 1e-5
+
+
+@pytest.mark.parametrize("which", ["both", "f_only", "g_only"])
+def test_implicit_backward_vs_closed_form_oracle(which):
+    """implicit_backward (kernels) against oracle.implicit_backward_closed_form evaluated in float64 on the same
+    inputs and upstream gradients: every weight / bias gradient and d L / d x.  The oracle's closed form is itself
+    checked against torch's double backward in tests/test_oracle_igr.py."""
+    net, _, _ = nets(7)
+    g = torch.Generator().manual_seed(8)
+    I, S = 8, 128
+    latent = torch.nn.functional.normalize(torch.randn(I, 256, generator=g), dim=1)
+    on = torch.rand(I, S, 2, generator=g) * 2 - 1
+    off = torch.rand(I, S + S // 8, 2, generator=g) * 3.6 - 1.8
+    f, ctx = igr.implicit_forward(net, latent=latent.to(DEV), pts=[on.to(DEV), off.to(DEV)])
+    igr.implicit_input_gradient(ctx)
+    R = ctx.R
+    f_bar = torch.randn(R, 1, generator=g) / R if which != "g_only" else None
+    g_bar = torch.randn(R, 2, generator=g) / R if which != "f_only" else None
+    grads, dx = igr.implicit_backward(ctx, None if f_bar is None else f_bar.to(DEV), None if g_bar is None else g_bar.to(DEV))
+    sd = {k: v.double() for k, v in orc.implicit_init(seed=7).items()}
+    x = torch.cat([orc.add_latent(on, latent), orc.add_latent(off, latent)]).double()
+    ref_g, ref_dx = orc.implicit_backward_closed_form(
+        sd, x, torch.zeros(R, 1).double() if f_bar is None else f_bar.double(),
+        torch.zeros(R, 2).double() if g_bar is None else g_bar.double())
+    named = dict(net.named_parameters())
+    for k, ref in ref_g.items():
+        assert rel_l2(grads[named[k]], ref) <= TOL, (k, rel_l2(grads[named[k]], ref))
+    assert rel_l2(dx, ref_dx) <= TOL
+    dlat = igr.latent_grad(ctx, dx)
+    ref_dlat = ref_dx[:I * S, :256].reshape(I, S, 256).sum(1) + ref_dx[I * S:, :256].reshape(I, S + S // 8, 256).sum(1)
+    assert rel_l2(dlat, ref_dlat) <= TOL
+
+
+def _golden_grad_check(prefix, module, g, tol):
+    """Sampled entries (first 2048) and L2 norm of every parameter gradient against the reference's.  A conv bias in
+    front of a train-mode BatchNorm has an exactly zero gradient (the batch mean removes it): the reference's value is
+    float32 rounding noise there, so such entries are compared on the scale of the module's largest gradient."""
+    names = [n for n, _ in module.named_parameters()]
+    top = max(float(g[f"gradnorm_{prefix}.{n}"]) for n in names)
+    for pname, p in module.named_parameters():
+        want, nrm = g[f"grad_{prefix}.{pname}"], float(g[f"gradnorm_{prefix}.{pname}"])
+        assert p.grad is not None, (prefix, pname)
+        got = p.grad.detach().reshape(-1)
+        if nrm <= 1e-5 * top:
+            assert float(got.double().norm()) <= 1e-4 * top, (prefix, pname, float(got.double().norm()), top)
+            continue
+        e_n = abs(float(got.double().norm()) - nrm) / nrm
+        e_s = rel_l2(got[:want.size], want) if float(np.linalg.norm(want)) > 1e-3 * nrm else 0.0
+        assert e_n <= tol and e_s <= tol, (prefix, pname, e_n, e_s)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("literal", [False, True])
+def test_sketch_training_step_golden(golden_dir, name, literal):
+    """im_loss.backward() on the drop-in modules against the gradients the REFERENCE produced for the same step
+    (tests/golden/igr_*.npz: every parameter of ImplicitNet, of the trained encoder and of the gt encoder, plus
+    d im_loss / d latent codes).  literal: the reference's own loss lines (train_Point2Cyl.py:608-672, read from the staged
+    baseline/_ref file) exec'd on the drop-ins - value node + gradient() node; otherwise igr.sketch_loss_block (one
+    fused node)."""
+    g = np.load(os.path.join(golden_dir, name))
+    B, K, S, seed, is_l2 = (int(v) for v in g["meta"])
+    net, enc, enc_gt = nets(seed)
+    sk = torch.from_numpy(g["gt_sketches"]).reshape(B * K, S, 4).to(DEV)
+    mask_gt = torch.from_numpy(g["mask_gt"]).to(DEV)
+    latent_codes = enc(torch.from_numpy(g["global_pc"]).to(DEV))
+    latent_codes.retain_grad()
+    sk_pnts, sk_normals = sk[:, :, :2].contiguous(), sk[:, :, 2:].contiguous()
+    latent_codes_gt = enc_gt(torch.cat((sk_pnts, sk_normals), dim=-1))
+    off = torch.from_numpy(g["nonmnfld_pnts"]).reshape(B * K, S + S // 8, 2).to(DEV)
+    if literal:
+        from baseline import ref_arm
+        root = ref_arm.reference_root()
+        if root is None or not os.path.exists(os.path.join(root, "train_Point2Cyl.py")):
+            pytest.skip("baseline/_ref not staged")
+        import textwrap
+        lines = open(os.path.join(root, "train_Point2Cyl.py")).readlines()[607:672]
+        src = textwrap.dedent("".join(l.replace("\t", "    ") for l in lines))
+        assert src.startswith("if WITH_IM_LOSS:") and src.rstrip().endswith("im_loss += latent_loss")
+        from point2cyl_b200.dropin.losses import reduce_mean_masked_instance
+
+        class FixedSampler:                      # the golden's off-surface sample (the reference drew it on the CPU)
+            def get_points(self, pc):
+                return off
+
+        ns = dict(torch=torch, sampler=FixedSampler(), add_latent=dnet.add_latent, gradient=dnet.gradient,
+                  implicit_net=net, reduce_mean_masked_instance=reduce_mean_masked_instance, mask_gt=mask_gt,
+                  sk_pnts=sk_pnts, sk_normals=sk_normals, latent_codes=latent_codes, latent_codes_gt=latent_codes_gt,
+                  batch_size=B, K=K, WITH_IM_LOSS=True, IS_L2=bool(is_l2), pcs=sk)
+        exec(src, ns)
+        im_loss = ns["im_loss"]
+    else:
+        im_loss = igr.sketch_loss_block(net, latent_codes, latent_codes_gt, sk_pnts, sk_normals, off, mask_gt,
+                                        bool(is_l2))["im_loss"]
+    assert rel_err(im_loss, g["im_loss"]) <= TOL
+    im_loss.backward()
+    assert rel_l2(latent_codes.grad, g["d_latent"]) <= TOL
+    _golden_grad_check("net", net, g, TOL)
+    # the encoders' gradients pass through train-mode BatchNorm over B*K*S = 384 / 1024 rows (tests/adjudication.py)
+    _golden_grad_check("enc", enc, g, 5e-4)
+    _golden_grad_check("encgt", enc_gt, g, 5e-4)
