@@ -453,12 +453,42 @@ def run_igr(args, rank, world, dev, pd):
         _lib_mod.profile_start()
         step()
         prof = _lib_mod.profile_stop()
+    # the training step of the same block: im_loss.backward() through the closed-form second-order sweeps
+    # (igr.implicit_backward) and the encoders' layer backward, torch.optim.Adam as in the script (train_Point2Cyl.py:686-690)
+    params = [p for m in (net, enc, enc_gt) for p in m.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-4)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        o = step()
+        o["im_loss"].backward()
+        opt.step()
+        return o
+
+    tms = []
+    for it in range(2 + max(3, args.steps // 2)):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        train_step()
+        e.record()
+        e.synchronize()
+        if it >= 2:
+            tms.append(s.elapsed_time(e))
+    _lib_mod.profile_start()
+    train_step()
+    tprof = _lib_mod.profile_stop()
     pd.barrier()
     clk = clocks.stop()
     tot = pd.reduce_max(sum(ms), dev)
+    ttot = pd.reduce_max(sum(tms), dev)
     if rank == 0:
         pk = peaks()
         R = I * (S + S + S // 8)
+        bwd_ms = {}
+        for n, tag, t in tprof:
+            if "bwd" in tag:
+                bwd_ms[n] = round(bwd_ms.get(n, 0.0) + t, 3)
         fwd = 2.0 * (258 * 512 + 2 * 512 * 512 + 512 * 254 + 4 * 512 * 512 + 512)
         rev = 2.0 * (5 * 512 * 512 + 2 * 512 * 254)
         flops = R * (fwd + rev)
@@ -486,6 +516,10 @@ def run_igr(args, rank, world, dev, pd):
                                  "lo*hi + hi*lo) / summed CUDA-event time of the 15 layer launches; algorithmic work per row "
                                  f"{fwd + rev:.0f} FLOP (forward {fwd:.0f}, input-gradient sweep {rev:.0f})"},
             "losses": {k: float(out[k]) for k in ("im_loss", "mnfld_loss", "grad_loss", "normals_loss", "latent_loss")},
+            "train_step": {"metric": "sketch instances/sec, the same block + im_loss.backward() + Adam",
+                           "value": I * world * len(tms) / (ttot / 1e3), "unit": "instances/s",
+                           "ms_per_step": ttot / len(tms), "steps": len(tms), "gpu_launches": len(tprof),
+                           "backward_ms_by_entry_point": bwd_ms},
             "gpu_launches": len(prof), "stages": stages, "clocks": clk}), flush=True)
     if world > 1:
         dist.destroy_process_group()

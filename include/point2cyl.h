@@ -156,6 +156,20 @@ int p2c_sa_xyz_linear(const float* xyz, const float* new_xyz, const int64_t* idx
                       const float* b1, int N1, float* Y,
                       int64_t ldy, double* stats, int pool_group, float* Ymax, float* Ymin, void* stream);
 
+/* A WHOLE feature-less set-abstraction level as ONE kernel (csrc/sa_stack_tc.cu; models/pointnet_util.py:130-139,
+ * 181-207 for sa1: gather, Conv2d 3 -> C0 + BN + ReLU, C0 -> C1 + BN + ReLU, C1 -> C2 + BN + ReLU, max over nsample),
+ * for BatchNorm layers whose statistics are known before the launch: eval mode (running statistics, bn->stats NULL;
+ * eval.py) or caller-supplied sums.  Reads only xyz / new_xyz / idx and the weights, writes only the pooled
+ * post-BN/ReLU rows out (B*S, C2): no activation of the level crosses HBM.  The two 64-wide contractions run on tcgen05
+ * (3xTF32: fp32-faithful), chained through shared memory (rows-as-lanes for C0 -> C1 with both operands in shared
+ * memory, channels-as-lanes with the weights in tensor memory for C1 -> C2, whose epilogue pools in registers).
+ * bn0 / bn1 / bn2: the three BatchNorm descriptors (scale_out / shift_out are written as by every folding consumer).
+ * C0 = C1 = 64, C2 <= 128, nsample in {32, 64, 128}; P2C_EUNSUPPORTED otherwise (the caller runs the per-layer path). */
+int p2c_sa_stack_fused(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S, int nsample,
+                       const float* W0, int64_t ldw0, const float* b0, const p2c_bn_fold* bn0, const float* W1,
+                       const float* b1, const p2c_bn_fold* bn1, const float* W2, const float* b2,
+                       const p2c_bn_fold* bn2, int C0, int C1, int C2, float* out, int64_t ldo, void* stream);
+
 
 /* hi/lo tf32 split of a weight matrix for the large-K tensor-core kernel: out[0][n][k] = w with the low 13
  * mantissa bits cleared, out[1][n][k] = w - hi; rows padded with zeros to ldw (multiple of 4) floats.

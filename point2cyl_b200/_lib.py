@@ -50,6 +50,8 @@ SIGNATURES = {
     "p2c_sa_xyz_stats": [c_f64p, i64, c_f32p, i64, c_f32p, i32, c_f64p, vp],
     "p2c_sa_xyz_linear": [c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, c_f32p, i64, c_f32p, i32, c_f32p, c_f32p, bnp,
                           c_f64p, c_f32p, c_f32p, i32, c_f32p, i64, c_f64p, i32, c_f32p, c_f32p, vp],
+    "p2c_sa_stack_fused": [c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, c_f32p, i64, c_f32p, bnp, c_f32p, c_f32p, bnp,
+                           c_f32p, c_f32p, bnp, i32, i32, i32, c_f32p, i64, vp],
     "p2c_linear": [c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, c_f32p, i64, i32, i32, i32,
                    c_f64p, i32, c_f32p, c_f32p, i32, c_f32p, i64, bnp, vp],
     "p2c_split_tf32": [c_f32p, i32, i32, c_f32p, i64, vp],

@@ -366,8 +366,10 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int row = m0 + c_lo * 32 + j * 32 + lane;
-          if (row < a.M)
+          if (row < a.M) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mul + (size_t)row * a.ldmul + n0 + q * 32));
+            if (EPI >= 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mul2 + (size_t)row * a.ldmul2 + n0 + q * 32));
+          }
         }
       }
       // A [32 x 32] box that sticks out over channel N is NOT left to the TMA unit (measured: its stores clip at

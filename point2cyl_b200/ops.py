@@ -214,6 +214,30 @@ def sa_xyz_linear(xyz: Tensor, new_xyz: Tensor, idx: Tensor, W0: Tensor, b0: Opt
     return Y
 
 
+def sa_stack_fused(xyz: Tensor, new_xyz: Tensor, idx: Tensor, convs, bns: "list[PendingBN]",
+                   out: Optional[Tensor] = None) -> Optional[Tensor]:
+    """A whole feature-less SA level in ONE kernel (p2c_sa_stack_fused): gather + three conv/BN/ReLU layers + max over
+    the neighbours, for BatchNorms whose statistics are known up front (eval mode).  convs: the level's three 1x1
+    convs, bns: their PendingBN descriptors.  -> pooled post-BN/ReLU rows (B*S, C2), or None when the kernel does not
+    take the shape (the caller then runs the per-layer path)."""
+    need_cuda(xyz, new_xyz, idx)
+    xyz, new_xyz = _cloud(xyz), _cloud(new_xyz)
+    B, N, _ = xyz.shape
+    S, ns = idx.shape[1], idx.shape[2]
+    W = [c.weight.reshape(c.weight.shape[0], -1) for c in convs]
+    C0, C1, C2 = (w.shape[0] for w in W)
+    if (len(convs) != 3 or W[0].shape[1] != 3 or C0 != 64 or C1 != 64 or C2 > 128 or ns not in (32, 64, 128) or
+            B * S * ns >= 2 ** 31):
+        return None
+    if out is None:
+        out = torch.empty(B * S, C2, dtype=torch.float32, device=xyz.device)
+    W = [w if w.is_contiguous() else w.contiguous() for w in W]
+    call("p2c_sa_stack_fused", ptr(xyz.contiguous()), ptr(new_xyz.contiguous()), ptr(idx.contiguous()), B, N, S, ns,
+         ptr(W[0]), W[0].stride(0), ptr(convs[0].bias), bns[0].fold(), ptr(W[1]), ptr(convs[1].bias), bns[1].fold(),
+         ptr(W[2]), ptr(convs[2].bias), bns[2].fold(), C0, C1, C2, ptr(out), out.stride(0), stream_ptr())
+    return out
+
+
 def linear(X: Tensor, W: Tensor, bias: Optional[Tensor], K: Optional[int] = None,
            in_scale: Optional[Tensor] = None, in_shift: Optional[Tensor] = None,
            in_mask: Optional[Tensor] = None, stats: Optional[Tensor] = None, pool_group: int = 0,

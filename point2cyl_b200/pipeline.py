@@ -49,6 +49,10 @@ group_bias_enabled = True
 # sa1 without its first layer's activations (set_abstraction -> ops.sa_xyz_linear); False = always materialise them
 xyz_first_enabled = True
 
+# eval-mode BatchNorm: a feature-less SA level (sa1) as ONE kernel - gather, three conv/BN/ReLU layers, max-pool
+# (set_abstraction -> ops.sa_stack_fused); False = the per-layer kernels
+stack_fused_enabled = True
+
 
 def torch_dropout_mask(ones: Tensor, p: float = 0.5) -> Tensor:
     return F.dropout(ones, p=p)
@@ -273,6 +277,19 @@ def set_abstraction(sa, xyz: Tensor, feats: Optional[Tensor], start: Optional[Te
             rows = B * gidx.shape[1] * gidx.shape[2]
             N1 = sa.mlp_convs[1].weight.shape[0]
             pool1 = pool if len(sa.mlp_convs) == 2 else 0
+            if (stack_fused_enabled and feats is None and tape is None and prec == _lib.PREC_3XTF32 and
+                    not sa.training and len(sa.mlp_convs) == 3 and
+                    all(bn.running_mean is not None for bn in sa.mlp_bns)):
+                # running statistics: every BatchNorm of the level is known before the launch, so the whole level is one
+                # kernel and none of its activations reaches HBM (csrc/sa_stack_tc.cu)
+                pend = [ops.PendingBN(None, rows, bn.weight, bn.bias, bn.eps, _bn_momentum(bn), False, bn.running_mean,
+                                      bn.running_var,
+                                      out=None if _scratch is None else _scratch.take_floats(4 * bn.weight.shape[0]))
+                        for bn in sa.mlp_bns]
+                _lib.set_tag(tag + ".fused")
+                out = ops.sa_stack_fused(xyz, new_xyz, gidx, list(sa.mlp_convs), pend)
+                if out is not None:
+                    return new_xyz, out
             if (xyz_first_enabled and feats is None and tape is None and prec == _lib.PREC_3XTF32 and
                     rows % max(pool1, 1) == 0 and
                     _lib.load().p2c_linear_path(ops.pad4(C0), rows, N1, C0, 0, pool1, prec, 0) == 1):
@@ -435,7 +452,8 @@ def backbone_forward(net, x: Tensor, fps_start: Optional[Sequence[Tensor]] = Non
     rec = (lambda: {}) if tape is not None else (lambda: None)
     r_sa1, r_sa2, r_sa3, r_fp3, r_fp2, r_fp1 = rec(), rec(), rec(), rec(), rec(), rec()
     if geo is None:
-        geo = geometry_forward(net, xyz, fps_start, moments=tape is None and feats0 is None and xyz_first_enabled)
+        geo = geometry_forward(net, xyz, fps_start,
+                               moments=tape is None and feats0 is None and xyz_first_enabled and net.training)
     global _scratch
     outer, _scratch = _scratch, _ForwardScratch(net, precision)
     try:

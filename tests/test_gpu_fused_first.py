@@ -195,3 +195,81 @@ def test_backbone_with_and_without_fp3_concat(train):
             assert torch.equal(outs[2][0]["X_raw"], b["X_raw"])
     finally:
         pipeline.dropout_mask_fn, pipeline.group_bias_enabled = real_mask, real_flag
+
+
+# ---- a whole feature-less SA level as ONE kernel in eval mode (p2c_sa_stack_fused, csrc/sa_stack_tc.cu) -------------
+
+
+def _sa_module(C2, ns, S, radius, seed):
+    from point2cyl_b200.dropin.models.pointnet_util import PointNetSetAbstraction
+    torch.manual_seed(seed)
+    sa = PointNetSetAbstraction(npoint=S, radius=radius, nsample=ns, in_channel=3, mlp=[64, 64, C2], group_all=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    for bn in sa.mlp_bns:                       # non-trivial running statistics, some NEGATIVE scales (the min branch)
+        C_ = bn.weight.shape[0]
+        bn.weight.data = (torch.rand(C_, generator=g) + 0.5) * torch.where(torch.rand(C_, generator=g) < 0.25, -1.0, 1.0)
+        bn.bias.data = torch.randn(C_, generator=g) * 0.3
+        bn.running_mean.data = torch.randn(C_, generator=g) * 0.2
+        bn.running_var.data = torch.rand(C_, generator=g) + 0.3
+    return sa.to(DEV).eval()
+
+
+@pytest.mark.parametrize("B,N,S,ns,C2", [(2, 2048, 128, 64, 128), (3, 1000, 50, 32, 128), (1, 4096, 512, 64, 128),
+                                         (2, 700, 27, 64, 96), (2, 900, 9, 128, 128), (1, 300, 1, 32, 64)])
+def test_sa_stack_fused_equals_per_layer_path_and_fp64(B, N, S, ns, C2):
+    """The one-kernel level against (a) the per-layer kernels (p2c_sa_xyz_linear + p2c_linear + p2c_pool_bn_relu) and
+    (b) a float64 restatement of models/pointnet_util.py:130-139, 200-205 in eval mode, partial last tile and partial
+    channel count included."""
+    sa = _sa_module(C2, ns, S, 0.25, seed=N + S)
+    xyz, new_xyz, gidx, g = _grouping(B, N, S, ns, 0.25, N + S)
+    with torch.no_grad():
+        assert pipeline.stack_fused_enabled
+        _, fused = pipeline.set_abstraction(sa, xyz, None, None, geo=(None, new_xyz, gidx))
+        pipeline.stack_fused_enabled = False
+        try:
+            _, layered = pipeline.set_abstraction(sa, xyz, None, None, geo=(None, new_xyz, gidx))
+        finally:
+            pipeline.stack_fused_enabled = True
+    assert fused.shape == (B * S, C2) and layered.shape == fused.shape
+    # float64 restatement
+    idx = gidx.cpu()
+    x = xyz.cpu().double()
+    grouped = torch.stack([x[b][idx[b]] for b in range(B)]) - new_xyz.cpu().double()[:, :, None, :]   # (B,S,ns,3)
+    h = grouped.reshape(B * S * ns, 3)
+    for conv, bn in zip(sa.mlp_convs, sa.mlp_bns):
+        W = conv.weight.detach().cpu().double().reshape(conv.weight.shape[0], -1)
+        h = h @ W.t() + conv.bias.detach().cpu().double()
+        h = (h - bn.running_mean.cpu().double()) / torch.sqrt(bn.running_var.cpu().double() + bn.eps) \
+            * bn.weight.detach().cpu().double() + bn.bias.detach().cpu().double()
+        h = torch.relu(h)
+    exact = h.reshape(B * S, ns, C2).max(dim=1)[0]
+    assert rel_err(fused, exact) <= 1e-5
+    assert rel_err(layered, exact) <= 1e-5
+    assert rel_err(fused, layered) <= 1e-5
+
+
+def test_eval_backbone_uses_the_fused_level_and_matches_per_layer():
+    """Whole backbone in eval mode at a config-2-like shape: with and without the fused sa1 kernel."""
+    B, N, K = 2, 8192, 8
+    data = synthetic.s_cyl(B, N, K, seed=11)
+    torch.manual_seed(3)
+    net = backbone(output_sizes=[3, 2 * K]).to(DEV).eval()
+    pcs = data["pcs"].to(DEV)
+    start = [torch.randint(0, N, (B,)).to(DEV), torch.randint(0, 512, (B,)).to(DEV)]
+    mask = ((torch.rand(B, 128, N) > 0.5).float() * 2.0).to(DEV)      # the head's dropout is always on (:60): fix it
+    real = pipeline.dropout_mask_fn
+    pipeline.dropout_mask_fn = lambda ones, p=0.5: mask
+    try:
+        _lib.profile_start()
+        with torch.no_grad():
+            a = pipeline.backbone_forward(net, pcs, start)
+        names = [n for n, _, _ in _lib.profile_stop()]
+        assert "p2c_sa_stack_fused" in names and "p2c_sa_xyz_linear" not in names
+        pipeline.stack_fused_enabled = False
+        with torch.no_grad():
+            b = pipeline.backbone_forward(net, pcs, start)
+    finally:
+        pipeline.stack_fused_enabled = True
+        pipeline.dropout_mask_fn = real
+    for u, v in zip(a, b):
+        assert rel_err(u, v) <= 1e-5
