@@ -442,6 +442,19 @@ int p2c_pool_bwd_apply(const float* dOut, int64_t ldd, const float* Ymax, const 
                        int64_t ldy, const float* scale, const float* shift, const float* coef, int64_t G, int group,
                        int C, float* dY, int64_t lddy, void* stream);
 
+/* p2c_bn_bwd_coef folded into the kernel that applies it (one launch per layer instead of two; same float64
+ * coefficient arithmetic, evaluated per thread for its own channels): dgamma / dbeta are accumulated by exactly one
+ * thread per channel.  p2c_bn_bwd_apply_fused needs C / 4 to divide 256 or be a multiple of it (P2C_EUNSUPPORTED
+ * otherwise: run the two-kernel form). */
+int p2c_bn_bwd_apply_fused(const float* dA, int64_t ldda, const float* Y, int64_t ldy, const float* scale,
+                           const float* shift, const double* sums, int64_t count, const float* gamma,
+                           const float* mean, const float* invstd, int training, float* dgamma, float* dbeta,
+                           int64_t M, int C, float* dY, int64_t lddy, void* stream);
+int p2c_pool_bwd_apply_fused(const float* dOut, int64_t ldd, const float* Ymax, const float* Ymin, const float* Y,
+                             int64_t ldy, const float* scale, const float* shift, const double* sums, int64_t count,
+                             const float* gamma, const float* mean, const float* invstd, int training, float* dgamma,
+                             float* dbeta, int64_t G, int group, int C, float* dY, int64_t lddy, void* stream);
+
 /* Weight / bias gradient of a 1x1 conv — autograd of Conv2d/Conv1d at models/pointnet_util.py:201, :317,
  * pointnet_extrusion.py:58-65:  dW[n,k] += sum_m dY[m,n] * A[m,k], db[n] += sum_m dY[m,n], with the layer input
  * A recomputed from the raw previous activation exactly as p2c_linear's operand load does

@@ -104,6 +104,10 @@ SIGNATURES = {
     "p2c_bn_bwd_apply": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i32, c_f32p, i64, vp],
     "p2c_pool_bwd_apply": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, i32, i32, c_f32p,
                            i64, vp],
+    "p2c_bn_bwd_apply_fused": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_f64p, i64, c_f32p, c_f32p, c_f32p, i32,
+                               c_f32p, c_f32p, i64, i32, c_f32p, i64, vp],
+    "p2c_pool_bwd_apply_fused": [c_f32p, i64, c_f32p, c_f32p, c_f32p, i64, c_f32p, c_f32p, c_f64p, i64, c_f32p, c_f32p,
+                                 c_f32p, i32, c_f32p, c_f32p, i64, i32, i32, c_f32p, i64, vp],
     "p2c_wgrad": [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, c_f32p, i32, i64, i32, i32, c_f32p, i64, c_f32p, i32, vp],
     "p2c_wgrad_path": [i64, i64, i64, i32, i32, i32],
     "p2c_sa_first_bwd": [c_f32p, i64, c_f32p, c_f32p, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, c_f32p, i64,

@@ -43,16 +43,30 @@ def _layer_backward(rec: dict, dA: Tensor, grad_of: GradOf, precision: int, need
     a max-pooled layer.  Returns (dY raw-output gradient, dA_prev or None)."""
     bn, conv = rec["bn"], rec["conv"]
     scale, shift = rec["scale"], rec["shift"]
+    C_ = rec["Y"].shape[1]
+    fused = ops.bn_bwd_fusable(C_)       # the per-channel coefficients are evaluated inside the applying kernel
     if rec["pool"]:
         sums = ops.pool_bwd_reduce(dA, rec["Ymax"], rec["Ymin"], scale, shift)
     else:
         sums = ops.bn_bwd_reduce(dA, rec["Y"], scale, shift)
-    coef = ops.bn_bwd_coef(sums, rec["M"], bn.weight, rec["mean"], rec["invstd"], rec["batch_stats"],
-                           grad_of(bn.weight), grad_of(bn.bias))
+    coef = None
+    if not fused:
+        coef = ops.bn_bwd_coef(sums, rec["M"], bn.weight, rec["mean"], rec["invstd"], rec["batch_stats"],
+                               grad_of(bn.weight), grad_of(bn.bias))
     if rec["pool"]:
-        dY = ops.pool_bwd_apply(dA, rec["Ymax"], rec["Ymin"], rec["Y"], scale, shift, coef, rec["pool"])
+        if fused:
+            dY = ops.pool_bwd_apply_fused(dA, rec["Ymax"], rec["Ymin"], rec["Y"], scale, shift, sums, rec["M"],
+                                          bn.weight, rec["mean"], rec["invstd"], rec["batch_stats"],
+                                          grad_of(bn.weight), grad_of(bn.bias), rec["pool"])
+        else:
+            dY = ops.pool_bwd_apply(dA, rec["Ymax"], rec["Ymin"], rec["Y"], scale, shift, coef, rec["pool"])
     else:
-        dY = ops.bn_bwd_apply(dA, rec["Y"], scale, shift, coef, out=dA if dA.is_contiguous() else None)
+        out = dA if dA.is_contiguous() else None
+        if fused:
+            dY = ops.bn_bwd_apply_fused(dA, rec["Y"], scale, shift, sums, rec["M"], bn.weight, rec["mean"],
+                                        rec["invstd"], rec["batch_stats"], grad_of(bn.weight), grad_of(bn.bias), out=out)
+        else:
+            dY = ops.bn_bwd_apply(dA, rec["Y"], scale, shift, coef, out=out)
     if rec["fused_first"]:
         return dY, None
     aff = rec["in_aff"]

@@ -97,6 +97,32 @@ pool_bwd_reduce_kernel(const float* __restrict__ dOut, int64_t ldd, const float*
   atomicAdd(sums + C + c, (double)s2);
 }
 
+// The per-channel part of BatchNorm's backward, evaluated by the kernel that APPLIES it (p2c_bn_bwd_apply_fused /
+// p2c_pool_bwd_apply_fused) instead of by a micro-launch per layer: same float64 arithmetic as bn_bwd_coef_kernel.
+struct BnBwdCoefIn {
+  const double* sums; double count;
+  const float* gamma; const float* mean; const float* invstd;
+  int training;
+  float* dgamma; float* dbeta;
+};
+__device__ __forceinline__ void bn_bwd_coef_channel(const BnBwdCoefIn& ci, int c, int C, bool writer, float& a_out,
+                                                    float& b_out, float& c_out) {
+  const double s1 = ci.sums[c], s2 = ci.sums[C + c];
+  const double mu = ci.mean[c], is = ci.invstd[c], g = ci.gamma ? (double)ci.gamma[c] : 1.0;
+  const double dg = is * (s2 - mu * s1);
+  const double a = g * is;
+  double b = 0.0, cc = 0.0;
+  if (ci.training) {
+    b = -a * is * dg / ci.count;
+    cc = -a * s1 / ci.count - b * mu;
+  }
+  a_out = (float)a; b_out = (float)b; c_out = (float)cc;
+  if (writer) {
+    if (ci.dgamma) ci.dgamma[c] += (float)dg;
+    if (ci.dbeta) ci.dbeta[c] += (float)s1;
+  }
+}
+
 __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ mean, const float* __restrict__ invstd, int training,
                                    float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -148,19 +174,59 @@ bn_bwd_apply_kernel(const float* __restrict__ dA, int64_t ldda, const float* __r
   }
 }
 
+// p2c_bn_bwd_apply with the coefficients computed in the kernel: every CTA evaluates the C channels once (float64,
+// shared memory); the launch geometry keeps a thread on ONE group of four channels (gridDim.x * 256 is a multiple of
+// C / 4), so a, b, c are twelve registers read once per thread
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fused_kernel(const float* __restrict__ dA, int64_t ldda, const float* __restrict__ Y, int64_t ldy,
+                          const float* __restrict__ scale, const float* __restrict__ shift, const BnBwdCoefIn ci,
+                          int64_t M, int C, float* __restrict__ dY, int64_t lddy) {
+  extern __shared__ __align__(16) float s_coef[];      // [3][C]: a | b | c, one float64 evaluation per channel and CTA
+  const int C4 = C >> 2;
+  const int64_t total = M * C4;
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(e0 % C4) * 4;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x)
+    bn_bwd_coef_channel(ci, ch, C, blockIdx.x == 0, s_coef[ch], s_coef[C + ch], s_coef[2 * C + ch]);
+  __syncthreads();
+  float a[4], b[4], k[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a[i] = s_coef[c + i]; b[i] = s_coef[C + c + i]; k[i] = s_coef[2 * C + c + i]; }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+  for (int64_t e = e0; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / C4;
+    const float4 y = __ldg(reinterpret_cast<const float4*>(Y + m * ldy + c));
+    float4 g = __ldg(reinterpret_cast<const float4*>(dA + m * ldda + c));
+    if (!(fmaf(y.x, sc.x, sh.x) > 0.f)) g.x = 0.f;
+    if (!(fmaf(y.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
+    if (!(fmaf(y.z, sc.z, sh.z) > 0.f)) g.z = 0.f;
+    if (!(fmaf(y.w, sc.w, sh.w) > 0.f)) g.w = 0.f;
+    float4 o;
+    o.x = fmaf(a[0], g.x, fmaf(b[0], y.x, k[0]));
+    o.y = fmaf(a[1], g.y, fmaf(b[1], y.y, k[1]));
+    o.z = fmaf(a[2], g.z, fmaf(b[2], y.z, k[2]));
+    o.w = fmaf(a[3], g.w, fmaf(b[3], y.w, k[3]));
+    *reinterpret_cast<float4*>(dY + m * lddy + c) = o;
+  }
+}
+
 // one thread per (group, channel): walk the group's rows, route dOut to the first row that attains the pooled value
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
 pool_bwd_apply_kernel(const float* __restrict__ dOut, int64_t ldd, const float* __restrict__ Ymax,
                       const float* __restrict__ Ymin, const float* __restrict__ Y, int64_t ldy,
                       const float* __restrict__ scale, const float* __restrict__ shift,
-                      const float* __restrict__ coef, int64_t G, int group, int C, float* __restrict__ dY,
-                      int64_t lddy) {
+                      const float* __restrict__ coef, const BnBwdCoefIn ci, int64_t G, int group, int C,
+                      float* __restrict__ dY, int64_t lddy) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= G * C) return;
   const int64_t g = e / C;
   const int c = (int)(e - g * C);
   const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-  const float a = __ldg(coef + c), b = __ldg(coef + C + c), k = __ldg(coef + 2 * C + c);
+  float a, b, k;
+  if (FUSED) bn_bwd_coef_channel(ci, c, C, g == 0, a, b, k);
+  else { a = __ldg(coef + c); b = __ldg(coef + C + c); k = __ldg(coef + 2 * C + c); }
   const float ysel = sc >= 0.f ? __ldg(Ymax + g * C + c) : __ldg(Ymin + g * C + c);
   float d = __ldg(dOut + g * ldd + c);
   if (!(fmaf(ysel, sc, sh) > 0.f)) d = 0.f;
@@ -538,8 +604,48 @@ extern "C" int p2c_pool_bwd_apply(const float* dOut, int64_t ldd, const float* Y
                                   int group, int C, float* dY, int64_t lddy, void* stream) {
   if (!dOut || !Ymax || !Ymin || !Y || !scale || !shift || !coef || !dY || G <= 0 || group <= 0 || C <= 0)
     return P2C_EINVAL;
-  pool_bwd_apply_kernel<<<p2c_ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(dOut, ldd, Ymax, Ymin, Y, ldy, scale,
-                                                                                    shift, coef, G, group, C, dY, lddy);
+  pool_bwd_apply_kernel<false><<<p2c_ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      dOut, ldd, Ymax, Ymin, Y, ldy, scale, shift, coef, BnBwdCoefIn{}, G, group, C, dY, lddy);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+// p2c_bn_bwd_coef + p2c_bn_bwd_apply in one launch (see include/point2cyl.h)
+extern "C" int p2c_bn_bwd_apply_fused(const float* dA, int64_t ldda, const float* Y, int64_t ldy, const float* scale,
+                                      const float* shift, const double* sums, int64_t count, const float* gamma,
+                                      const float* mean, const float* invstd, int training, float* dgamma,
+                                      float* dbeta, int64_t M, int C, float* dY, int64_t lddy, void* stream) {
+  if (!dA || !Y || !scale || !shift || !sums || !mean || !invstd || !dY || M <= 0 || C <= 0 || count <= 0)
+    return P2C_EINVAL;
+  if (C % 4 || ldda % 4 || ldy % 4 || lddy % 4 ||
+      ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY) |
+        reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15))
+    return P2C_EALIGN;
+  const int C4 = C / 4;
+  if (256 % C4 != 0 && C4 % 256 != 0) return P2C_EUNSUPPORTED;     // a thread must stay on one channel group
+  const int64_t total = M * C4;
+  int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
+  const int per = C4 > 256 ? C4 / 256 : 1;                          // blocks per full set of channel groups
+  blocks = (blocks + per - 1) / per * per;
+  const BnBwdCoefIn ci{sums, (double)count, gamma, mean, invstd, training, dgamma, dbeta};
+  if (C > 4096) return P2C_EUNSUPPORTED;
+  bn_bwd_apply_fused_kernel<<<blocks, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(dA, ldda, Y, ldy, scale, shift, ci, M, C,
+                                                                                          dY, lddy);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
+extern "C" int p2c_pool_bwd_apply_fused(const float* dOut, int64_t ldd, const float* Ymax, const float* Ymin,
+                                        const float* Y, int64_t ldy, const float* scale, const float* shift,
+                                        const double* sums, int64_t count, const float* gamma, const float* mean,
+                                        const float* invstd, int training, float* dgamma, float* dbeta, int64_t G,
+                                        int group, int C, float* dY, int64_t lddy, void* stream) {
+  if (!dOut || !Ymax || !Ymin || !Y || !scale || !shift || !sums || !mean || !invstd || !dY || G <= 0 || group <= 0 ||
+      C <= 0 || count <= 0)
+    return P2C_EINVAL;
+  const BnBwdCoefIn ci{sums, (double)count, gamma, mean, invstd, training, dgamma, dbeta};
+  pool_bwd_apply_kernel<true><<<p2c_ceil_div(G * C, 256), 256, 0, (cudaStream_t)stream>>>(
+      dOut, ldd, Ymax, Ymin, Y, ldy, scale, shift, nullptr, ci, G, group, C, dY, lddy);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

@@ -903,6 +903,37 @@ def pool_bwd_apply(dOut: Tensor, Ymax: Tensor, Ymin: Tensor, Y: Tensor, scale: T
     return dY
 
 
+def bn_bwd_fusable(C_: int) -> bool:
+    """p2c_bn_bwd_apply_fused keeps a thread on one group of four channels: C / 4 divides 256 (or is a multiple)."""
+    return C_ % 4 == 0 and (256 % (C_ // 4) == 0 or (C_ // 4) % 256 == 0)
+
+
+def bn_bwd_apply_fused(dA: Tensor, Y: Tensor, scale: Tensor, shift: Tensor, sums: Tensor, count: int, gamma: Tensor,
+                       mean: Tensor, invstd: Tensor, training: bool, dgamma: Optional[Tensor],
+                       dbeta: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
+    """bn_bwd_coef + bn_bwd_apply in one launch (the coefficients are evaluated by the applying kernel)."""
+    dA, Y = _rows(dA), _rows(Y)
+    M, C_ = Y.shape
+    if out is None:
+        out = torch.empty(M, C_, dtype=torch.float32, device=Y.device)
+    call("p2c_bn_bwd_apply_fused", ptr(dA), dA.stride(0), ptr(Y), Y.stride(0), ptr(scale), ptr(shift), ptr(sums), count,
+         ptr(gamma), ptr(mean), ptr(invstd), 1 if training else 0, ptr(dgamma), ptr(dbeta), M, C_, ptr(out),
+         out.stride(0), stream_ptr())
+    return out
+
+
+def pool_bwd_apply_fused(dOut: Tensor, Ymax: Tensor, Ymin: Tensor, Y: Tensor, scale: Tensor, shift: Tensor,
+                         sums: Tensor, count: int, gamma: Tensor, mean: Tensor, invstd: Tensor, training: bool,
+                         dgamma: Optional[Tensor], dbeta: Optional[Tensor], group: int) -> Tensor:
+    dOut, Y = _rows(dOut), _rows(Y)
+    G, C_ = Ymax.shape
+    dY = torch.empty(G * group, C_, dtype=torch.float32, device=Y.device)
+    call("p2c_pool_bwd_apply_fused", ptr(dOut), dOut.stride(0), ptr(Ymax), ptr(Ymin), ptr(Y), Y.stride(0), ptr(scale),
+         ptr(shift), ptr(sums), count, ptr(gamma), ptr(mean), ptr(invstd), 1 if training else 0, ptr(dgamma), ptr(dbeta),
+         G, group, C_, ptr(dY), dY.stride(0), stream_ptr())
+    return dY
+
+
 def wgrad(dY: Tensor, X: Tensor, K: int, dW: Tensor, db: Optional[Tensor], in_scale: Optional[Tensor] = None,
           in_shift: Optional[Tensor] = None, mask_cf: Optional[Tensor] = None,
           precision: int = _lib.PREC_3XTF32) -> None:
