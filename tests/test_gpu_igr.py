@@ -286,7 +286,7 @@ def test_sketch_training_step_golden(golden_dir, name, literal):
     assert rel_err(im_loss, g["im_loss"]) <= TOL
     im_loss.backward()
     assert rel_l2(latent_codes.grad, g["d_latent"]) <= TOL
+    # measured (tests/tools/igr_grad_err.py): net <= 3.0e-5, encoders <= 2.3e-5, d latent <= 1.1e-5
     _golden_grad_check("net", net, g, TOL)
-    # the encoders' gradients pass through train-mode BatchNorm over B*K*S = 384 / 1024 rows (tests/adjudication.py)
-    _golden_grad_check("enc", enc, g, 5e-4)
-    _golden_grad_check("encgt", enc_gt, g, 5e-4)
+    _golden_grad_check("enc", enc, g, TOL)
+    _golden_grad_check("encgt", enc_gt, g, TOL)

@@ -68,6 +68,22 @@ with torch.no_grad():
                                 torch.ones(2, 2, dtype=torch.bool, device="cuda"))
 torch.cuda.synchronize()
 print("igr ok", float(out["im_loss"]))
+# its training step: the second-order backward (p2c_linear_act_bwd op 3 / op 4, tensor-core wgrad on 1088 rows, colsums,
+# seed delta, latent gradient, loss-term backward) and the encoder's layer backward
+lat = ienc(torch.rand(4, 128, 4, device="cuda"))
+sk2 = torch.rand(4, 128, 4, device="cuda")
+out = igr.sketch_loss_block(inet, lat, lat.detach(), sk2[:, :, :2], sk2[:, :, 2:], torch.rand(4, 144, 2, device="cuda"),
+                            torch.ones(2, 2, dtype=torch.bool, device="cuda"))
+out["im_loss"].backward()
+torch.cuda.synchronize()
+print("igr backward ok", float(inet.lin0.weight.grad.abs().max()), float(ienc.fc.weight.grad.abs().max()))
+# eval-mode sa1 as one kernel (p2c_sa_stack_fused: chained tcgen05 layers through shared / tensor memory)
+from point2cyl_b200 import pipeline
+net.eval()
+with torch.no_grad():
+    ev = pipeline.backbone_forward(net, batch["pcs"], None)
+torch.cuda.synchronize()
+print("eval fused sa1 ok", float(ev[0].abs().mean()))
 # the two-stage pipeline (second stream, SM budget, CUDA graphs).  Under memcheck the script runs with
 # PYTORCH_NO_CUDA_MEMORY_CACHING=1 (every tensor its own cudaMalloc), and a cudaMalloc inside a stream capture is an error
 # by itself: the graph section is then skipped - its kernels are the ones exercised above.
