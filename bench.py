@@ -752,6 +752,30 @@ def main():
             roof["tf32_mma_frac_of_tf32_peak"] = 3.0 * tf / pk["tf32"]
             roof["tf32_peak"] = {"tflops": pk["tf32"], "source": pk["tf32_src"]}
             roof["frac_of_per_layer_floor"] = floor_us / meas_us if meas_us else None
+    # ---- inference mode (eval.py: BatchNorm on running statistics): sa1 then runs as ONE kernel (p2c_sa_stack_fused) ----
+    eval_leg = None
+    if rank == 0 and graphed is not None:
+        net.eval()
+        try:
+            ge = GraphedForwardLoss(net, batch, precision=args.precision)
+            for _ in range(3):
+                ge()
+            ems = timed(ge, 10)
+            _lib.profile_start()
+            with torch.no_grad():
+                pipeline.forward_loss(net, batch)
+            names = {}
+            for n_, tg, t in _lib.profile_stop():
+                names[n_] = round(names.get(n_, 0.0) + t * 1e3, 1)
+            eval_leg = {"metric": "point-clouds/sec forward+loss, eval-mode BatchNorm (one batch at a time, CUDA graph)",
+                        "value": B_PER_GPU * 10 / (sum(ems) / 1e3), "unit": UNIT, "ms_per_step": sum(ems) / 10,
+                        "train_mode_same_launch_mode_ms": total_ms_seq / args.steps,
+                        "sa1_one_kernel_us": names.get("p2c_sa_stack_fused"),
+                        "what": "sa1 (gather, 3->64->64->128 conv/BN/ReLU, max-pool) is ONE tcgen05 kernel here "
+                                "(csrc/sa_stack_tc.cu): no activation of the level crosses HBM"}
+            del ge
+        finally:
+            net.train()
     # ---- the training step of configs[3] on the same batch (all ranks: it contains the gradient all-reduce) ----
     train = train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps=10, warmup=3)
     cpu = eager = None
@@ -776,7 +800,7 @@ def main():
                                                      "unit": UNIT, "ms_per_step": total_ms_seq / args.steps,
                                                      "what": "one batch at a time (graph.GraphedForwardLoss): per-batch latency"},
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "gpu_eager_reference": eager, "stages": stages, "train_step": train}), flush=True)
+            "gpu_eager_reference": eager, "stages": stages, "eval_forward": eval_leg, "train_step": train}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -17,6 +17,8 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_re
 timeout 300 python bench.py --workload train --steps 20 --warmup 5 > $o/${tag}_train.json 2>> $o/${tag}_bench.err
 timeout 300 python bench.py --workload igr --steps 5 --warmup 3 > $o/${tag}_igr.json 2>> $o/${tag}_bench.err
 timeout 300 python bench.py --workload stress --steps 10 --warmup 3 > $o/${tag}_stress.json 2>> $o/${tag}_bench.err
+# eval-mode sa1: the one-kernel level against the per-layer kernels
+timeout 300 python tools/bench_sa_stack.py 2>> $o/${tag}_bench.err | tail -1 > $o/${tag}_sa_stack.json
 python - <<P
 import json
 for n in ("bench", "reference", "train", "igr", "stress"):
