@@ -38,6 +38,10 @@ const char* p2c_arch(void);      /* "sm_100a" */
  * sets it so that the coordinate-only stage of the next batch (FPS, ball query, 3-NN search: small grids) runs on a
  * second stream beside the per-point MLP layers of the current batch. */
 int p2c_set_sm_budget(int sms);
+/* Programmatic dependent launch (griddepcontrol) for the kernels that support it: their CTAs may be scheduled while the
+ * predecessor in the stream drains and wait for its completion after their local prologue.  Default on; returns the
+ * previous setting. */
+int p2c_set_pdl(int on);
 
 /* Farthest point sampling — replaces farthest_point_sample, models/pointnet_util.py:63-84, fused
  * with the gather of the sampled centres (index_points, :43-60, as used at :124).

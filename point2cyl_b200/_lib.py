@@ -37,6 +37,7 @@ SIGNATURES = {
     "p2c_version": [],
     "p2c_arch": [],
     "p2c_set_sm_budget": [i32],
+    "p2c_set_pdl": [i32],
     "p2c_fps": [c_f32p, c_i64p, i32, i32, i32, c_i64p, c_f32p, vp],
     "p2c_ball_query": [c_f32p, c_f32p, i32, i32, i32, f32, i32, c_i64p, vp],
     "p2c_group": [c_f32p, c_f32p, i64, c_f32p, c_i64p, i32, i32, i32, i32, i32, c_f32p, i64, vp],
@@ -153,6 +154,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.argtypes = argtypes
         fn.restype = C.c_char_p if name == "p2c_arch" else C.c_int
+    if os.environ.get("P2C_PDL") is not None:          # A/B switch for measurements (default: on)
+        lib.p2c_set_pdl(int(os.environ["P2C_PDL"] != "0"))
     _lib = lib
     return lib
 

@@ -28,6 +28,28 @@ static inline int p2c_sm_budget(int device_sms) {
   return (g_p2c_sm_budget > 0 && g_p2c_sm_budget < device_sms) ? g_p2c_sm_budget : device_sms;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched through p2c_launch with g_p2c_pdl set may be scheduled while
+// its predecessor in the stream is still draining - its CTAs take SMs as they free up, run their local prologue
+// (barrier init, tensor-memory allocation, descriptor prefetch) and block in p2c_grid_dep_wait() until the predecessor
+// has COMPLETED and its writes are visible; nothing produced or consumed by a predecessor may be touched before that call.
+// p2c_grid_dep_launch() (issued after the wait, so that "the dependent runs" implies "my own predecessor is complete")
+// lets the next kernel in the stream start the same way.  Both are no-ops for a kernel launched without the attribute.
+extern int g_p2c_pdl;
+__device__ __forceinline__ void p2c_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void p2c_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t p2c_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_p2c_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // "xyz-first" operand of the tcgen05 layer kernel (linear_tc.cu, p2c_sa_xyz_linear): the layer's input rows are not
 // read from memory - row r = (b, s, j) is relu(bn0(W0 (xyz[b, idx[r]] - new_xyz[b, s]) + b0)), the first (xyz-only)
 // conv of a set-abstraction level recomputed in the operand transform (three FMAs per element) instead of written by

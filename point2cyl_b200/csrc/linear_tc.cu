@@ -131,6 +131,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  p2c_grid_dep_wait();          // everything above is local to the CTA; below: statistics / activations of predecessors
+  p2c_grid_dep_launch();
   for (int k = tid; k < KPAD; k += LTC_THREADS) {
     float sc = 0.f, sh = 0.f;
     if (k < a.K) {
@@ -677,8 +679,8 @@ int p2c_linear_tc(const float* X, int64_t ldx, const float* W, const float* bias
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
   dim3 grid(gx, n_tiles);
-  if (a.dbg || a.dbg_mode) linear_tc_kernel<true><<<grid, LTC_THREADS, L.total + 1024, st>>>(tm, tmY, a);
-  else linear_tc_kernel<false><<<grid, LTC_THREADS, L.total + 1024, st>>>(tm, tmY, a);
+  if (a.dbg || a.dbg_mode) P2C_CUDA_TRY(p2c_launch(linear_tc_kernel<true>, grid, dim3(LTC_THREADS), L.total + 1024, st, tm, tmY, a));
+  else P2C_CUDA_TRY(p2c_launch(linear_tc_kernel<false>, grid, dim3(LTC_THREADS), L.total + 1024, st, tm, tmY, a));
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

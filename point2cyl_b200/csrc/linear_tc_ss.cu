@@ -165,6 +165,8 @@ linear_tc_ss_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);      // 2 x (main accumulator | correction accumulator), 128 columns each
+  p2c_grid_dep_wait();          // (common.cuh) above: CTA-local setup; below: data of predecessor kernels
+  p2c_grid_dep_launch();
   for (int k = tid; !raw_hi && k < KPAD; k += SS_THREADS) {
     float sc = 0.f, sh = 0.f;
     if (k < a.K) {
@@ -735,18 +737,14 @@ static int linear_tc_ss_launch(const float* X, int64_t ldx, const float* w_split
   const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  if (bf16)
-    linear_tc_ss_kernel<true, 0><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
-  else if (epi.op == 1)
-    linear_tc_ss_kernel<false, 1><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
-  else if (epi.op == 2)
-    linear_tc_ss_kernel<false, 2><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
-  else if (epi.op == 3)
-    linear_tc_ss_kernel<false, 3><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
-  else if (epi.op == 4)
-    linear_tc_ss_kernel<false, 4><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
-  else
-    linear_tc_ss_kernel<false, 0><<<grid, SS_THREADS, L.total + 1024, st>>>(tmX, tmWhi, tmWlo, tmY, tmS, a);
+  const dim3 g3(grid), b3(SS_THREADS);
+  const size_t sm = L.total + 1024;
+  if (bf16) P2C_CUDA_TRY(p2c_launch(linear_tc_ss_kernel<true, 0>, g3, b3, sm, st, tmX, tmWhi, tmWlo, tmY, tmS, a));
+  else if (epi.op == 1) P2C_CUDA_TRY(p2c_launch(linear_tc_ss_kernel<false, 1>, g3, b3, sm, st, tmX, tmWhi, tmWlo, tmY, tmS, a));
+  else if (epi.op == 2) P2C_CUDA_TRY(p2c_launch(linear_tc_ss_kernel<false, 2>, g3, b3, sm, st, tmX, tmWhi, tmWlo, tmY, tmS, a));
+  else if (epi.op == 3) P2C_CUDA_TRY(p2c_launch(linear_tc_ss_kernel<false, 3>, g3, b3, sm, st, tmX, tmWhi, tmWlo, tmY, tmS, a));
+  else if (epi.op == 4) P2C_CUDA_TRY(p2c_launch(linear_tc_ss_kernel<false, 4>, g3, b3, sm, st, tmX, tmWhi, tmWlo, tmY, tmS, a));
+  else P2C_CUDA_TRY(p2c_launch(linear_tc_ss_kernel<false, 0>, g3, b3, sm, st, tmX, tmWhi, tmWlo, tmY, tmS, a));
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

@@ -11,6 +11,7 @@
 // coordinates.  The kernel is HBM bound on its only large stream, the raw output Y (4*C bytes per row);
 // Qf rows come from L2.  BatchNorm sum / sum-of-squares are accumulated per lane and folded once per CTA.
 // One warp per row, lane = C/32 consecutive channels.
+#include <cstdlib>
 #include "bn_fold.cuh"
 
 namespace {
@@ -229,6 +230,15 @@ extern "C" int p2c_sa_xyz_stats(const double* partials, int64_t rows, const floa
   return 0;
 }
 
+int p2c_sa_pair_tc(const P2cXyzFirst& g, int B, const float* scale0, const float* shift0, const p2c_bn_fold* bn0,
+                   const float* W1, const float* b1, int C0, int N1, float* Y, int64_t ldy, double* stats,
+                   cudaStream_t st);
+static bool getenv_pair_enabled() {            // P2C_SA_PAIR=0: A/B switch back to the channels-as-lanes kernel
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("P2C_SA_PAIR"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 extern "C" int p2c_sa_xyz_linear(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                                  int nsample, const float* W0, int64_t ldw0, const float* b0, int C0,
                                  const float* scale0, const float* shift0, const p2c_bn_fold* bn0,
@@ -247,6 +257,11 @@ extern "C" int p2c_sa_xyz_linear(const float* xyz, const float* new_xyz, const i
   if (pool_group && (!Ymax || !Ymin || rows % pool_group != 0)) return P2C_EINVAL;
   if (moments && bn0 && bn0->stats && bn0->count != rows) return P2C_EINVAL;
   const P2cXyzFirst g{xyz, new_xyz, idx, W0, ldw0, b0, N, S, nsample, moments ? moments + MOM_CTAS * 9 : nullptr};
+  if (!pool_group && Y && getenv_pair_enabled()) {
+    // a 64 -> 64 second layer whose rows are kept: rows-as-lanes form (half the tensor time), sa_stack_tc.cu MODE 1
+    const int rc = p2c_sa_pair_tc(g, B, scale0, shift0, bn0, W1, b1, C0, N1, Y, ldy, stats, (cudaStream_t)stream);
+    if (rc != P2C_EUNSUPPORTED) return rc;
+  }
   return p2c_linear_tc(nullptr, 0, W1, b1, scale0, shift0, nullptr, 0, Y, ldy, (int)rows, N1, C0, stats, pool_group,
                        Ymax, Ymin, P2C_PREC_3XTF32, bn0, (cudaStream_t)stream, nullptr, &g);
 }

@@ -27,6 +27,25 @@
 //   warps 12-15  final epilogue, thread = channel: max / min over the tile's rows per pool group, then
 //                relu(scale * ((scale >= 0 ? max : min) + bias) + shift) -> out
 //   warp 2       TMEM allocator (512 columns: 2 x 64 acc2 | 2 x 128 acc3 | W2 hi 64 | W2 lo 64)
+//
+// MODE 1 (train mode: p2c_sa_xyz_linear for a 64 -> 64 second layer whose rows are kept, sa1.1 of the backbone).  The batch
+// statistics of conv1's output are what the NEXT kernel needs, so the stack stops after conv1 - and everything per row
+// happens in TENSOR MEMORY (640 threads, two transform groups):
+//   transform   thread = row: [dx dy dz 1] as tf32 hi | lo -> tcgen05.st (A operand of conv0); later conv0's accumulator
+//   (2 x 4 w.)  row comes back (tcgen05.ld), ReLU, hi | lo, tcgen05.st again (A operand of conv1).  No shared memory.
+//   MMA warp    MMA1(t): D1 = [d | 1] [A | c]^T (conv0 with its BatchNorm folded into the coefficient tile, K = 8);
+//               L2(t-1): acc2 = X1 W1^T + 1 b1^T (K = 64 + one k-step of a column of ones against the bias tile); both TS
+//               form with ROWS as the UMMA M and the 64 channels as N: half the tensor time of the channels-as-lanes kernel
+//               (linear_tc.cu pads 64 channels to 128 lanes), B operands (8 KB tiles) resident in shared memory
+//   epilogue 1  thread = row: accumulator row -> [128 rows x 64 channels] staging tile in the SWIZZLE_128B layout
+//   epilogue 2  one lane issues two TMA stores (the tensor map un-swizzles); 128 threads read the tile COLUMN-wise
+//               (thread = channel x row half, conflict-free) for the BatchNorm sum / sum of squares - the cross-row
+//               reduction that the channels-as-lanes form gets for free
+// How it got here (config 2, 1,048,576 rows; channels-as-lanes kernel: 101 us): rows-as-lanes with both operands from shared
+// memory 115-135 us; A operand in tensor memory but conv0 evaluated by the transform threads from coefficients in shared
+// memory 92 us (ncu: the transform warps wait for their buffer, the epilogue's bias LDS stalls - 64 broadcast LDS.128 per
+// row and tile saturate the shared-memory data path, 4 cycles each); conv0 and the bias moved onto the tensor core: 69 us
+// (60 us without the store and the statistics; HBM floor 42 us).
 #include <cstdlib>
 
 #include "bn_fold.cuh"
@@ -45,6 +64,12 @@ constexpr uint32_t ST_W1_TILE = ST_C1 * TC_BK * 4;  // 8 KB: [64 channels][32 fl
 // kind::tf32, fp32 accumulate, K-major A and B, M = 128 rows, N = 64 channels
 constexpr uint32_t ST_IDESC_L2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ST_C1 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
+constexpr uint32_t ST_W0T_OFF = 0;                  // MODE 1, inside the XT1 region: conv0 coefficient tile (hi | lo)
+constexpr uint32_t ST_B1T_OFF = 2 * ST_W1_TILE;     // MODE 1: conv1 bias tile (hi | lo)
+// MODE 1 tensor-memory columns: acc2 2 x 64 | XA 2 x 144 (hi 64 | ones 8 | lo 64 | pad 8) | DV 2 x 16 (hi 8 | lo 8) | D1 64
+constexpr uint32_t ST_XA_COLS = 144, ST_XA_ONE = 64, ST_XA_LO = 72;
+constexpr uint32_t ST_TM_XA = 128, ST_TM_DV = ST_TM_XA + 2 * ST_XA_COLS, ST_TM_D1 = ST_TM_DV + 32;
+static_assert(ST_TM_D1 + 64 == 512, "MODE 1 tensor-memory budget");
 constexpr uint32_t ST_XT1_OFF = 0;
 constexpr uint32_t ST_XT2_OFF = ST_XT1_OFF + ST_XT1 * ST_STAGE;
 constexpr uint32_t ST_W1_OFF = ST_XT2_OFF + ST_XT2 * ST_STAGE;        // [kb][hi | lo]
@@ -64,6 +89,9 @@ struct StArgs {
   BnFoldDev bn0, bn1, bn2;
   float* out; int64_t ldo;
   int M, C2, pool, m_tiles;
+  // MODE 1
+  const float* scale0; const float* shift0;   // conv0's folded BatchNorm as arrays (instead of bn0)
+  double* stats;                                // 2 x 64 float64 sums of conv1's raw output, accumulated
 };
 
 __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -77,8 +105,11 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       : "memory");
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 1)
-sa_stack_kernel(const StArgs a) {
+// MODE 1 runs a second group of four transform warps (warps 16-19: 640 threads, 94 registers): group g owns the tiles
+// t = g (mod 2) and the A-operand buffer g in tensor memory
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 1 ? ST_THREADS + 128 : ST_THREADS, 1)
+sa_stack_kernel(const __grid_constant__ CUtensorMap tmY, const StArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* xt1_sm = smem + ST_XT1_OFF;
@@ -100,6 +131,8 @@ sa_stack_kernel(const StArgs a) {
   uint64_t* acc3_full = acc2_empty + 2;
   uint64_t* acc3_empty = acc3_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc3_empty + 2);
+  uint64_t* d1_full = bars + 24;                // [2] MODE 1: conv0's accumulator holds a tile of transform group g (a group sees
+                                                // only every other tile, so each group needs its OWN phase sequence)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -108,11 +141,12 @@ sa_stack_kernel(const StArgs a) {
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ST_XT1; ++s) { mbar_init(&xt1_full[s], 4); mbar_init(&xt1_empty[s], 1); }
-    for (int s = 0; s < ST_XT2; ++s) { mbar_init(&xt2_full[s], 4); mbar_init(&xt2_empty[s], 1); }
+    for (int s = 0; s < ST_XT2; ++s) { mbar_init(&xt2_full[s], 4); mbar_init(&xt2_empty[s], MODE == 1 ? 4 : 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc2_full[s], 1); mbar_init(&acc2_empty[s], 4);
       mbar_init(&acc3_full[s], 1); mbar_init(&acc3_empty[s], 4);
     }
+    mbar_init(&d1_full[0], 1); mbar_init(&d1_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -121,18 +155,58 @@ sa_stack_kernel(const StArgs a) {
     // operands of the transform (see linear_tc.cu): per four channels [Ax0 Ax1 Ay0 Ay1 | Az0 Az1 c0 c1 | Ax2 ... ]
     const int k = tid;
     float sc, sh;
+    if (MODE == 1 && a.bn0.active && a.g.moments && a.bn0.stats) {
+      // train mode: the first conv's batch statistics in closed form from the nine coordinate moments (bn_fold.cuh)
+      double sum, sumsq;
+      p2c_xyz_first_sums(a.g.moments, a.bn0.count, (double)__ldg(a.g.W0 + (size_t)k * a.g.ldw0),
+                         (double)__ldg(a.g.W0 + (size_t)k * a.g.ldw0 + 1), (double)__ldg(a.g.W0 + (size_t)k * a.g.ldw0 + 2),
+                         a.g.b0 ? (double)__ldg(a.g.b0 + k) : 0.0, sum, sumsq);
+      if (writer) {
+        const_cast<double*>(a.bn0.stats)[k] = sum;
+        const_cast<double*>(a.bn0.stats)[a.bn0.C + k] = sumsq;
+      }
+      p2c_bn_fold_sums(a.bn0, k, writer, sum, sumsq, sc, sh);
+    } else if (MODE == 1 && !a.bn0.active) {
+      sc = __ldg(a.scale0 + k); sh = __ldg(a.shift0 + k);
+    } else
     p2c_bn_fold_channel(a.bn0, k, writer, sc, sh);
     const float* w = a.g.W0 + (size_t)k * a.g.ldw0;
     const float b = a.g.b0 ? __ldg(a.g.b0 + k) : 0.f;
+    if (MODE == 1) {
+      // conv0 runs on the tensor core too (below): its coefficients [Ax Ay Az c 0 0 0 0] are row k of a K-major
+      // SWIZZLE_128B B-operand tile (hi | lo) in the otherwise unused XT1 region; the tile behind it holds conv1's bias as
+      // the B operand of one more k-step against a column of ones
+      const float v[4] = {sc * __ldg(w), sc * __ldg(w + 1), sc * __ldg(w + 2), fmaf(sc, b, sh)};
+      float4 h4, l4;
+      float* hp = &h4.x; float* lp = &l4.x;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { hp[i] = __uint_as_float(__float_as_uint(v[i]) & 0xffffe000u); lp[i] = v[i] - hp[i]; }
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint8_t* t0 = xt1_sm + ST_W0T_OFF + k * 128;
+      const uint32_t c0 = ((0u ^ (uint32_t)(k & 7)) << 4), c1 = ((1u ^ (uint32_t)(k & 7)) << 4);
+      *reinterpret_cast<float4*>(t0 + c0) = h4;                  *reinterpret_cast<float4*>(t0 + c1) = z4;
+      *reinterpret_cast<float4*>(t0 + ST_W1_TILE + c0) = l4;     *reinterpret_cast<float4*>(t0 + ST_W1_TILE + c1) = z4;
+      const float b1v = a.b1 ? __ldg(a.b1 + k) : 0.f;
+      const float b1h = __uint_as_float(__float_as_uint(b1v) & 0xffffe000u);
+      uint8_t* tb = xt1_sm + ST_B1T_OFF + k * 128;
+      *reinterpret_cast<float4*>(tb + c0) = make_float4(b1h, 0.f, 0.f, 0.f);                *reinterpret_cast<float4*>(tb + c1) = z4;
+      *reinterpret_cast<float4*>(tb + ST_W1_TILE + c0) = make_float4(b1v - b1h, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(tb + ST_W1_TILE + c1) = z4;
+    } else {
     float* q = reinterpret_cast<float*>(s_w0) + (k >> 2) * 16 + ((k >> 1) & 1) * 8 + (k & 1);
     q[0] = sc * __ldg(w); q[2] = sc * __ldg(w + 1); q[4] = sc * __ldg(w + 2); q[6] = fmaf(sc, b, sh);
+    }
   } else if (tid < ST_C0 + ST_C1) {
     const int k = tid - ST_C0;
-    float sc, sh;
-    p2c_bn_fold_channel(a.bn1, k, writer, sc, sh);
-    s_sc2[k] = sc;
-    s_sh2[k] = fmaf(sc, a.b1 ? __ldg(a.b1 + k) : 0.f, sh);
-  } else if (tid < ST_C0 + ST_C1 + 128) {
+    if (MODE == 1) {
+      s_sh2[k] = a.b1 ? __ldg(a.b1 + k) : 0.f;       // the raw output keeps its bias; BatchNorm comes in the consumer
+    } else {
+      float sc, sh;
+      p2c_bn_fold_channel(a.bn1, k, writer, sc, sh);
+      s_sc2[k] = sc;
+      s_sh2[k] = fmaf(sc, a.b1 ? __ldg(a.b1 + k) : 0.f, sh);
+    }
+  } else if (MODE == 0 && tid < ST_C0 + ST_C1 + 128) {
     const int n = tid - ST_C0 - ST_C1;
     float sc = 0.f, sh = 0.f;
     if (n < a.C2) p2c_bn_fold_channel(a.bn2, n, writer, sc, sh);
@@ -157,9 +231,20 @@ sa_stack_kernel(const StArgs a) {
   const uint32_t tm_acc2 = tmem_base;                 // + ab * 64
   const uint32_t tm_acc3 = tmem_base + 128;           // + ab * 128
   const uint32_t tm_w2 = tmem_base + 384;             // hi [0, 64) | lo [64, 128)
+  const uint32_t tm_xa = tmem_base + ST_TM_XA;        // MODE 1: conv0's output as the A operand of L2, [buf] x ST_XA_COLS
+  const uint32_t tm_dv = tmem_base + ST_TM_DV;        // MODE 1: [d | 1] as the A operand of conv0, [buf] x (hi 8 | lo 8)
+  const uint32_t tm_d1 = tmem_base + ST_TM_D1;        // MODE 1: conv0's accumulator (single)
+  if (MODE == 1 && ((warp >= 8 && warp < 12))) {
+    // the constant column of ones (and its seven zero neighbours) of both XA buffers: A operand of the bias k-step
+    const uint32_t one[8] = {__float_as_uint(1.0f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    const uint32_t la = (uint32_t)((warp & 3) * 32) << 16;
+    tmem_st8(tm_xa + la + ST_XA_ONE, one);
+    tmem_st8(tm_xa + ST_XA_COLS + la + ST_XA_ONE, one);
+    tmem_wait_st();
+  }
 
   // W2 (C2, C1) -> tensor memory (thread = output channel; hi | lo), zero padded beyond C2
-  if (warp >= 8 && warp < 12) {
+  if (MODE == 0 && warp >= 8 && warp < 12) {
     const int q = warp & 3;
     const int n = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -236,14 +321,70 @@ sa_stack_kernel(const StArgs a) {
         __syncwarp();
       }
     };
-    if (my_tiles > 0) issue_l2(0);
-    for (int t = 0; t < my_tiles; ++t) {
-      if (t + 1 < my_tiles) issue_l2(t + 1);
-      issue_l3(t);
+    if (MODE == 1) {
+      // conv0 AND conv1 on the tensor core, A operands in TENSOR MEMORY (lane = row, written by the transform warps with
+      // tcgen05.st), B operands (coefficients, W1, bias) resident in shared memory:
+      //   MMA1(t):   D1 = [d | 1] [A | c]^T            K = 8, three tf32 passes
+      //   L2(t-1):   acc2 = X1 W1^T + 1 b1^T           K = 64 + the bias k-step against the column of ones
+      // Measured on the way here: the SS form of L2 and a transform that read its coefficients from shared memory were both
+      // bound by the shared-memory data path (operand reads + 64 broadcast LDS.128 per row), not by the tensor pipe.
+      const uint32_t w0t = smem_u32(xt1_sm + ST_W0T_OFF), b1t = smem_u32(xt1_sm + ST_B1T_OFF);
+      const uint64_t w0hi = make_kmajor_sw128_desc(w0t), w0lo = make_kmajor_sw128_desc(w0t + ST_W1_TILE);
+      const uint64_t b1hi = make_kmajor_sw128_desc(b1t), b1lo = make_kmajor_sw128_desc(b1t + ST_W1_TILE);
+      for (int t = 0; t <= my_tiles; ++t) {
+        if (t < my_tiles) {
+          const int db = t & 1;
+          mbar_wait(&acc3_empty[db], ((uint32_t)(t >> 1)) & 1u);            // dv_full[db]
+          mbar_wait(&xt1_full[2], ((uint32_t)t & 1u) ^ 1u);                 // d1_empty
+          tc_fence_after();
+          const uint32_t dv = tm_dv + (uint32_t)db * 16u;
+          if (elect_one_sync()) {
+            umma_tf32_ts(tm_d1, dv, w0hi, ST_IDESC_L2, 0u);
+            umma_tf32_ts(tm_d1, dv + 8u, w0hi, ST_IDESC_L2, 1u);
+            umma_tf32_ts(tm_d1, dv, w0lo, ST_IDESC_L2, 1u);
+            umma_commit(&acc3_full[db]);                                    // dv_empty[db]
+            umma_commit(&d1_full[db]);
+          }
+          __syncwarp();
+        }
+        if (t >= 1) {
+          const int u = t - 1, ab = u & 1;
+          mbar_wait(&acc2_empty[ab], (((uint32_t)(u >> 1)) & 1u) ^ 1u);
+          mbar_wait(&xt1_full[ab], ((uint32_t)(u >> 1)) & 1u);              // xa_full[ab]
+          tc_fence_after();
+          const uint32_t d = tm_acc2 + (uint32_t)ab * ST_C1;
+          const uint32_t xa = tm_xa + (uint32_t)ab * ST_XA_COLS;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kb = 0; kb < ST_KB; ++kb) {
+              const uint32_t w_hi = smem_u32(w1_sm + (size_t)(kb * 2) * ST_W1_TILE);
+              const uint64_t bhi = make_kmajor_sw128_desc(w_hi), blo = make_kmajor_sw128_desc(w_hi + ST_W1_TILE);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t x_hi = xa + (uint32_t)(kb * TC_BK + ks * 8), x_lo = x_hi + ST_XA_LO;
+                umma_tf32_ts(d, x_hi, bhi + (uint64_t)(ks * 2), ST_IDESC_L2, (kb | ks) != 0);
+                umma_tf32_ts(d, x_lo, bhi + (uint64_t)(ks * 2), ST_IDESC_L2, 1u);
+                umma_tf32_ts(d, x_hi, blo + (uint64_t)(ks * 2), ST_IDESC_L2, 1u);
+              }
+            }
+            umma_tf32_ts(d, xa + ST_XA_ONE, b1hi, ST_IDESC_L2, 1u);         // + bias: 1 * b_hi + 1 * b_lo (exact operands)
+            umma_tf32_ts(d, xa + ST_XA_ONE, b1lo, ST_IDESC_L2, 1u);
+            umma_commit(&xt1_empty[ab]);                                    // xa_empty[ab]
+            umma_commit(&acc2_full[ab]);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      if (my_tiles > 0) issue_l2(0);
+      for (int t = 0; t < my_tiles; ++t) {
+        if (t + 1 < my_tiles) issue_l2(t + 1);
+        issue_l3(t);
+      }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if ((warp >= 8 && warp < 12) || warp >= 16) {
     // ===== L1: gather + conv0 + BN + ReLU -> XT1 ring (the xyz-first operand transform of linear_tc.cu) =====
-    const int tt = tid - 256;
+    const int tt = (warp & 3) * 32 + lane;          // row of the tile (MODE 0: tid - 256)
     const int cj = tt & 7, r7 = (tt >> 3) & 7, hf = tt >> 6;
     const uint32_t toff = (uint32_t)(hf * 8192 + r7 * 128 + ((cj ^ r7) << 4));
     const int row0 = hf * 64 + r7;
@@ -267,8 +408,70 @@ sa_stack_kernel(const StArgs a) {
       return Raw6{ldg_f(pp), ldg_f(pp + 1), ldg_f(pp + 2), ldg_f(cc), ldg_f(cc + 1), ldg_f(cc + 2)};
     };
     int xs = 0; uint32_t xph = 0;
-    int64_t i1 = load_idx(1);
-    Raw6 cur = load_pc(0, load_idx(0));
+    const int tg = (MODE == 1 && warp >= 16) ? 1 : 0;      // transform group (MODE 1): tiles tg, tg + 2, ...
+    const int tstep = MODE == 1 ? 2 : 1;
+    int64_t i1 = load_idx(tg + tstep);
+    Raw6 cur = load_pc(tg, load_idx(tg));
+    if (MODE == 1) {
+      // thread = row.  [A] its centred coordinates, split into tf32 hi | lo with the constant 1 of the bias column, go into
+      // tensor memory as the A operand of conv0; [B] conv0's accumulator row comes back, ReLU, hi | lo split, and goes into
+      // tensor memory again as the A operand of conv1.  No shared-memory traffic at all in this role.
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      for (int t = tg; t < my_tiles; t += 2) {
+        const int64_t i2 = load_idx(t + 4);
+        const Raw6 nxt = load_pc(t + 2, i1);
+        const int ab = t & 1;                         // = tg: this group's DV / XA buffers
+        const uint32_t ph = ((uint32_t)(t >> 1)) & 1u;
+        {
+          const float d3[3] = {cur.px - cur.cx, cur.py - cur.cy, cur.pz - cur.cz};
+          uint32_t hi[8] = {0u, 0u, 0u, __float_as_uint(1.0f), 0u, 0u, 0u, 0u}, lo[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            hi[i] = __float_as_uint(d3[i]) & 0xffffe000u;
+            lo[i] = __float_as_uint(d3[i] - __uint_as_float(hi[i]));
+          }
+          mbar_wait(&acc3_full[ab], ph ^ 1u);                                // dv_empty[ab]
+          tc_fence_after();
+          tmem_st8(tm_dv + (uint32_t)ab * 16u + lane_addr, hi);
+          tmem_st8(tm_dv + (uint32_t)ab * 16u + 8u + lane_addr, lo);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc3_empty[ab]);                       // dv_full[ab]
+        }
+        mbar_wait(&d1_full[ab], ph);
+        mbar_wait(&xt1_empty[ab], ph ^ 1u);                                  // xa_empty[ab]
+        tc_fence_after();
+        const uint32_t xa = tm_xa + (uint32_t)ab * ST_XA_COLS + lane_addr;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[16], hi[16], lo[16];
+          tmem_ld16(tm_d1 + lane_addr + (uint32_t)(c * 16), raw);
+          tmem_wait_ld();
+          if (c == 3) {                                                      // D1 is read: conv0 of the next tile may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xt1_full[2]);                        // d1_empty
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float x0 = fmaxf(__uint_as_float(raw[j]), 0.f), x1 = fmaxf(__uint_as_float(raw[j + 1]), 0.f);
+            const uint32_t h0 = __float_as_uint(x0) & 0xffffe000u, h1 = __float_as_uint(x1) & 0xffffe000u;
+            const float2 l = __fadd2_rn(make_float2(x0, x1), make_float2(-__uint_as_float(h0), -__uint_as_float(h1)));
+            hi[j] = h0; hi[j + 1] = h1;
+            lo[j] = __float_as_uint(l.x); lo[j + 1] = __float_as_uint(l.y);
+          }
+          tmem_st16(xa + (uint32_t)(c * 16), hi);
+          tmem_st16(xa + ST_XA_LO + (uint32_t)(c * 16), lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xt1_full[ab]);                           // xa_full[ab]
+        cur = nxt;
+        i1 = i2;
+      }
+    } else
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t i2 = load_idx(t + 2);
       const Raw6 nxt = load_pc(t + 1, i1);
@@ -311,7 +514,104 @@ sa_stack_kernel(const StArgs a) {
       cur = nxt;
       i1 = i2;
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (MODE == 1 && warp >= 4 && warp < 8) {
+    // ===== MODE 1 epilogue, part 1 (thread = row): raw output row + bias -> swizzled staging tile =====
+    const int q = warp & 3;
+    const int tt = tid - 128;                          // 0..127 = row of the tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t roff = (uint32_t)tt * 128u;
+    const uint32_t rx = (uint32_t)(tt & 7);
+    for (int t = 0; t < my_tiles; ++t) {
+      const int ab = t & 1;
+      uint8_t* sbuf = xt2_sm + (size_t)(t & 1) * ST_STAGE;       // [kb][128 rows][128 B], SWIZZLE_128B
+      // xt2_empty[b] = "staging buffer b is free": the statistics warps have read it and its bulk store has drained it
+      mbar_wait(&xt2_empty[t & 1], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+      mbar_wait(&acc2_full[ab], ((uint32_t)(t >> 1)) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < ST_KB; ++kb) {
+        uint32_t raw[32];
+        tmem_ld32(tm_acc2 + (uint32_t)ab * ST_C1 + (uint32_t)(kb * TC_BK) + lane_addr, raw);
+        tmem_wait_ld();
+        if (kb == ST_KB - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_empty[ab]);
+        }
+        uint8_t* dst = sbuf + (size_t)kb * RAW_BYTES + roff;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)                  // (the bias is already in the accumulator: the MMA's last k-step)
+          *reinterpret_cast<float4*>(dst + (((uint32_t)c ^ rx) << 4)) =
+              make_float4(__uint_as_float(raw[4 * c]), __uint_as_float(raw[4 * c + 1]), __uint_as_float(raw[4 * c + 2]),
+                          __uint_as_float(raw[4 * c + 3]));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xt2_full[t & 1]);    // "staging buffer b holds tile t" (4 arrivals)
+    }
+  } else if (MODE == 1 && warp >= 12) {
+    // ===== MODE 1 epilogue, part 2: TMA store of the staged tile; BatchNorm sums column-wise (thread = channel x half) =====
+    const int tt = tid - 384;                          // 0..127
+    const int sc_c = tt & 63, sh_h = tt >> 6;          // channel, row half
+    const uint32_t soff = (uint32_t)((sc_c >> 5) * RAW_BYTES + (sc_c & 3) * 4);
+    const uint32_t scq = (uint32_t)((sc_c & 31) >> 2);
+    float h1 = 0.f, l1 = 0.f, h2 = 0.f, l2 = 0.f;      // float-float running sums (see linear_tc.cu)
+    auto two_sum = [](float& hi, float& lo, float t) {
+      const float s_ = __fadd_rn(hi, t);
+      const float bb = __fadd_rn(s_, -hi);
+      lo = __fadd_rn(lo, __fadd_rn(__fadd_rn(hi, -__fadd_rn(s_, -bb)), __fadd_rn(t, -bb)));
+      hi = s_;
+    };
+    for (int t = 0; t < my_tiles; ++t) {
+      const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BM;
+      uint8_t* sbuf = xt2_sm + (size_t)(t & 1) * ST_STAGE;
+      mbar_wait(&xt2_full[t & 1], ((uint32_t)(t >> 1)) & 1u);
+      if (tt == 0) {
+#pragma unroll
+        for (int kb = 0; kb < ST_KB; ++kb)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(sbuf + (size_t)kb * RAW_BYTES)), "r"(kb * TC_BK), "r"(m0)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (a.stats) {
+        const int r_lo = sh_h * 64;
+        const int valid = min(64, a.M - m0 - r_lo);    // rows past M hold relu(c) of a zero offset: not statistics
+        float t1 = 0.f, t2 = 0.f;
+        const uint8_t* src = sbuf + soff + (size_t)r_lo * 128;
+        if (valid == 64) {
+          float2 p1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, p2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float v0 = *reinterpret_cast<const float*>(src + i * 128 + ((scq ^ (uint32_t)(i & 7)) << 4));
+            const float v1 = *reinterpret_cast<const float*>(src + (i + 1) * 128 + ((scq ^ (uint32_t)((i + 1) & 7)) << 4));
+            const float2 y = make_float2(v0, v1);
+            p1[(i >> 1) & 1] = __fadd2_rn(p1[(i >> 1) & 1], y);
+            p2[(i >> 1) & 1] = __ffma2_rn(y, y, p2[(i >> 1) & 1]);
+          }
+          t1 = (p1[0].x + p1[0].y) + (p1[1].x + p1[1].y);
+          t2 = (p2[0].x + p2[0].y) + (p2[1].x + p2[1].y);
+        } else {
+          for (int i = 0; i < valid; ++i) {
+            const float v = *reinterpret_cast<const float*>(src + i * 128 + ((scq ^ (uint32_t)(i & 7)) << 4));
+            t1 += v;
+            t2 = fmaf(v, v, t2);
+          }
+        }
+        two_sum(h1, l1, t1);
+        two_sum(h2, l2, t2);
+      }
+      // the buffer is free once the bulk store has read it (issued by thread 0 of this role) and every warp here is done
+      if (tt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xt2_empty[t & 1]);
+    }
+    if (tt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (a.stats) {
+      atomicAdd(a.stats + sc_c, (double)h1 + (double)l1);
+      atomicAdd(a.stats + ST_C1 + sc_c, (double)h2 + (double)l2);
+    }
+  } else if (MODE == 0 && warp >= 4 && warp < 8) {
     // ===== mid epilogue: thread = row of the tile; acc2 -> BN + ReLU -> hi | lo -> XT2 (operand of L3) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -359,7 +659,7 @@ sa_stack_kernel(const StArgs a) {
         if (lane == 0) mbar_arrive(&xt2_full[kb]);
       }
     }
-  } else if (warp >= 12) {
+  } else if (MODE == 0 && warp >= 12) {
     // ===== final epilogue: thread = output channel; pool over the rows of each group, then BN + ReLU =====
     const int q = warp & 3;
     const int n = q * 32 + lane;
@@ -419,6 +719,43 @@ sa_stack_kernel(const StArgs a) {
 
 }  // namespace
 
+// p2c_sa_xyz_linear for a 64 -> 64 second layer with its raw output kept (sa1.1 in train mode): MODE 1 of the kernel
+// above.  P2C_EUNSUPPORTED = shape not taken (the caller runs the channels-as-lanes kernel of linear_tc.cu).
+int p2c_sa_pair_tc(const P2cXyzFirst& g, int B, const float* scale0, const float* shift0, const p2c_bn_fold* bn0,
+                   const float* W1, const float* b1, int C0, int N1, float* Y, int64_t ldy, double* stats,
+                   cudaStream_t st) {
+  if (C0 != ST_C0 || N1 != ST_C1 || !Y) return P2C_EUNSUPPORTED;
+  if (!bn0 && !scale0) return P2C_EUNSUPPORTED;                    // a first conv without BatchNorm + ReLU: other kernel
+  if ((ldy % 4) != 0 || (reinterpret_cast<uintptr_t>(Y) & 15) != 0) return P2C_EUNSUPPORTED;
+  const int64_t rows = (int64_t)B * g.S * g.ns;
+  if (rows > 0x7fffffff) return P2C_EUNSUPPORTED;
+  CUtensorMap tmY;
+  if (int rc = make_map_2d(&tmY, Y, (uint64_t)N1, (uint64_t)rows, (uint64_t)ldy, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
+  StArgs a{};
+  a.g = g;
+  a.W1 = W1; a.b1 = b1;
+  a.bn0 = p2c_bn_fold_dev(bn0);
+  a.scale0 = scale0; a.shift0 = shift0;
+  a.M = (int)rows; a.m_tiles = (int)((rows + TC_BM - 1) / TC_BM);
+  a.stats = stats;
+  a.pool = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int sms_of[64] = {0};
+  if (dev < 64 && sms_of[dev] == 0) {
+    P2C_CUDA_TRY(cudaFuncSetAttribute(sa_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms_of[dev] = n;
+  }
+  const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
+  const int grid = a.m_tiles < sms ? a.m_tiles : sms;
+  sa_stack_kernel<1><<<grid, ST_THREADS + 128, ST_SMEM, st>>>(tmY, a);
+  P2C_RETURN_IF_CUDA_ERROR();
+  return 0;
+}
+
 // See include/point2cyl.h
 extern "C" int p2c_sa_stack_fused(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S,
                                   int nsample, const float* W0, int64_t ldw0, const float* b0, const p2c_bn_fold* bn0,
@@ -443,14 +780,15 @@ extern "C" int p2c_sa_stack_fused(const float* xyz, const float* new_xyz, const 
   cudaGetDevice(&dev);
   static int sms_of[64] = {0};
   if (dev < 64 && sms_of[dev] == 0) {
-    P2C_CUDA_TRY(cudaFuncSetAttribute(sa_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    P2C_CUDA_TRY(cudaFuncSetAttribute(sa_stack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     sms_of[dev] = n;
   }
   const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int grid = a.m_tiles < sms ? a.m_tiles : sms;
-  sa_stack_kernel<<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(a);
+  CUtensorMap none{};                    // MODE 0 stores nothing through TMA
+  sa_stack_kernel<0><<<grid, ST_THREADS, ST_SMEM, (cudaStream_t)stream>>>(none, a);
   P2C_RETURN_IF_CUDA_ERROR();
   return 0;
 }

@@ -27,12 +27,19 @@ def timed(fn, reps=5):
     return min(ts[1:])
 
 
+if os.environ.get("PAIR_EXP"):
+    # sa1.1 alone: P2C_SA_PAIR=0 (channels-as-lanes kernel of linear_tc.cu) against =1 (rows-as-lanes, sa_stack_tc.cu MODE 1)
+    W1, b1 = (torch.randn(64, 64, generator=g) / 8).cuda(), torch.randn(64, generator=g).cuda()
+    st = torch.zeros(128, dtype=torch.float64, device="cuda")
+    t = timed(lambda: ops.sa_xyz_linear(xyz, cxyz, gidx, W0, b0, W1, b1, scale0=sc, shift0=sh, stats=st, pool_group=0, want_y=True), reps=8)
+    print(f"sa_xyz_linear 64 -> 64: {t:.1f} us  (P2C_SA_PAIR={os.environ.get('P2C_SA_PAIR')})")
+    sys.exit(0)
 for N1, pool in ((64, 0), (128, 64)):
     W1, b1 = (torch.randn(N1, 64, generator=g) / 8).cuda(), torch.randn(N1, generator=g).cuda()
     st = torch.zeros(2 * N1, dtype=torch.float64, device="cuda")
     Y0 = ops.sa_first_layer(xyz, cxyz, gidx, None, W0, b0, None)
     print(f"64 -> {N1} pool {pool}: sa_first_layer {timed(lambda: ops.sa_first_layer(xyz, cxyz, gidx, None, W0, b0, None)):.1f} us")
-    for mode in ("0", "1", "2", "16", "17", "19"):
+    for mode in os.environ.get("MODES", "0 1 2 16 17 19").split():
         os.environ["P2C_TC_DBG"] = mode
         t_lin = timed(lambda: ops.linear(Y0, W1, b1, in_scale=sc, in_shift=sh, stats=st, pool_group=pool, want_y=(pool == 0), precision=1))
         t_xyz = timed(lambda: ops.sa_xyz_linear(xyz, cxyz, gidx, W0, b0, W1, b1, scale0=sc, shift0=sh, stats=st, pool_group=pool, want_y=(pool == 0)))
