@@ -524,8 +524,10 @@ sa_stack_kernel(const __grid_constant__ CUtensorMap tmY, const StArgs a) {
     for (int t = 0; t < my_tiles; ++t) {
       const int ab = t & 1;
       uint8_t* sbuf = xt2_sm + (size_t)(t & 1) * ST_STAGE;       // [kb][128 rows][128 B], SWIZZLE_128B
-      // xt2_empty[b] = "staging buffer b is free": the statistics warps have read it and its bulk store has drained it
-      mbar_wait(&xt2_empty[t & 1], (((uint32_t)(t >> 1)) & 1u) ^ 1u);
+      // the staging buffers are handed over with NAMED barriers (producer: bar.arrive, consumer: bar.sync, 256 threads; ids
+      // 4 / 5 = "buffer b holds tile t", 6 / 7 = "buffer b is free: the statistics warps have read it and its bulk store has
+      // drained it") - both sides touch the tile with ordinary loads / stores, and named barriers are what racecheck follows
+      if (t >= 2) asm volatile("bar.sync %0, 256;" ::"r"(6 + (t & 1)) : "memory");
       mbar_wait(&acc2_full[ab], ((uint32_t)(t >> 1)) & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -546,8 +548,7 @@ sa_stack_kernel(const __grid_constant__ CUtensorMap tmY, const StArgs a) {
                           __uint_as_float(raw[4 * c + 3]));
       }
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xt2_full[t & 1]);    // "staging buffer b holds tile t" (4 arrivals)
+      asm volatile("bar.arrive %0, 256;" ::"r"(4 + (t & 1)) : "memory");
     }
   } else if (MODE == 1 && warp >= 12) {
     // ===== MODE 1 epilogue, part 2: TMA store of the staged tile; BatchNorm sums column-wise (thread = channel x half) =====
@@ -565,7 +566,7 @@ sa_stack_kernel(const __grid_constant__ CUtensorMap tmY, const StArgs a) {
     for (int t = 0; t < my_tiles; ++t) {
       const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BM;
       uint8_t* sbuf = xt2_sm + (size_t)(t & 1) * ST_STAGE;
-      mbar_wait(&xt2_full[t & 1], ((uint32_t)(t >> 1)) & 1u);
+      asm volatile("bar.sync %0, 256;" ::"r"(4 + (t & 1)) : "memory");
       if (tt == 0) {
 #pragma unroll
         for (int kb = 0; kb < ST_KB; ++kb)
@@ -603,8 +604,7 @@ sa_stack_kernel(const __grid_constant__ CUtensorMap tmY, const StArgs a) {
       }
       // the buffer is free once the bulk store has read it (issued by thread 0 of this role) and every warp here is done
       if (tt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xt2_empty[t & 1]);
+      if (t + 2 < my_tiles) asm volatile("bar.arrive %0, 256;" ::"r"(6 + (t & 1)) : "memory");   // (no arrival nobody waits for)
     }
     if (tt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (a.stats) {

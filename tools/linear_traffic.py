@@ -3,7 +3,7 @@ kernels of ONE forward+loss step) into profiles/linear_traffic.json, stamped wit
 measured on (bench.py reports `roofline.traffic` only when that sha matches the sources it runs).
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-        -k regex:linear_tc --csv --log-file gpurun_out/linear_dram.csv python tools/one_step.py
+        -k 'regex:linear_tc|sa_stack' --csv --log-file gpurun_out/linear_dram.csv python tools/one_step.py
     python tools/linear_traffic.py gpurun_out/linear_dram.csv [launches per step]
 """
 import csv, json, os, sys

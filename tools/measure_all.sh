@@ -7,7 +7,7 @@ mkdir -p $o
 timeout 600 python -m pytest tests -q -m gpu > $o/${tag}_tests.log 2>&1; tail -3 $o/${tag}_tests.log
 # DRAM traffic of the tensor-core layer launches of one step, stamped with the kernel-source sha (-> roofline.traffic)
 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k regex:linear_tc --csv --log-file $o/${tag}_linear_dram.csv python tools/one_step.py 1 > /dev/null 2>&1
+    -k 'regex:linear_tc|sa_stack' --csv --log-file $o/${tag}_linear_dram.csv python tools/one_step.py 1 > /dev/null 2>&1
 python tools/linear_traffic.py $o/${tag}_linear_dram.csv 17
 # launch list of two steps (per-launch durations, cold cache, serialised)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches.csv \
