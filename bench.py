@@ -597,7 +597,8 @@ def main():
         from point2cyl_b200.graph import GraphedForwardLoss, PipelinedForwardLoss
         graphed = GraphedForwardLoss(net, batch, precision=args.precision)
         if args.mode == "pipelined" and args.workload == "forward_loss":
-            pipe = PipelinedForwardLoss(net, batch, precision=args.precision)
+            gsm = os.environ.get("P2C_GEO_SMS")          # tools: sweep of the SMs left to the coordinate stage
+            pipe = PipelinedForwardLoss(net, batch, precision=args.precision, geometry_sms=int(gsm) if gsm else None)
             pipe.prime(None)
 
     def step_eager():
