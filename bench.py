@@ -534,10 +534,11 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("P2C_PRECISION", "3xtf32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sequential"],
-                    help="pipelined (default): graph.PipelinedForwardLoss - the coordinate-only stage of batch i+1 "
-                         "runs on a second stream under the layers of batch i; sequential: one batch at a time "
-                         "(graph.GraphedForwardLoss)")
+    ap.add_argument("--mode", default="deep", choices=["deep", "pipelined", "sequential"],
+                    help="deep (default): graph.DeepPipelinedForwardLoss - per step the coordinate-only stage of batch i+1 "
+                         "(second stream), the layers of batch i (main stream) and the loss block of batch i-1 (third "
+                         "stream); pipelined: graph.PipelinedForwardLoss - two stages, the loss behind the layers on the "
+                         "main stream; sequential: one batch at a time (graph.GraphedForwardLoss)")
     ap.add_argument("--workload", default="forward_loss", choices=["forward_loss", "train", "stress", "igr"],
                     help="forward_loss = BASELINE.json configs[1] (the headline metric, default); train = configs[3], "
                          "the data-parallel training step (32 clouds per GPU); stress = configs[4], FPS + ball query "
@@ -596,10 +597,16 @@ def main():
     if not args.no_graph:
         from point2cyl_b200.graph import GraphedForwardLoss, PipelinedForwardLoss
         graphed = GraphedForwardLoss(net, batch, precision=args.precision)
-        if args.mode == "pipelined" and args.workload == "forward_loss":
+        if args.mode in ("pipelined", "deep") and args.workload == "forward_loss":
             gsm = os.environ.get("P2C_GEO_SMS")          # tools: sweep of the SMs left to the coordinate stage
-            pipe = PipelinedForwardLoss(net, batch, precision=args.precision, geometry_sms=int(gsm) if gsm else None)
-            pipe.prime(None)
+            if args.mode == "deep":
+                from point2cyl_b200.graph import DeepPipelinedForwardLoss
+                pipe = DeepPipelinedForwardLoss(net, batch, precision=args.precision, geometry_sms=int(gsm) if gsm else None)
+                pipe.prime(None)
+                pipe.step(None)                          # fill the third stage: every later step returns a loss
+            else:
+                pipe = PipelinedForwardLoss(net, batch, precision=args.precision, geometry_sms=int(gsm) if gsm else None)
+                pipe.prime(None)
 
     def step_eager():
         with torch.no_grad():
@@ -794,9 +801,14 @@ def main():
                     "d2h_bytes_per_step": 24 + (0 if graphed is not None else B_PER_GPU * K_INST * K_INST * 4 + B_PER_GPU * 4), "ms_per_step": total_ms_e2e / args.steps},
             "gpu_launches": launches,
             "launch_mode": "eager" if graphed is None else ("cuda_graph" if pipe is None else
-                           f"cuda_graphs, two-stage pipeline over batches (coordinate stage of batch i+1 on a second stream, "
-                           f"{pipe.geometry_sms} SMs left to it, beside the layers + loss of batch i; one batch of every kind "
-                           "of work per step, side stream joined inside the timed region)"),
+                           (f"cuda_graphs, three-stage pipeline over batches: coordinate stage of batch i+1 (second stream, "
+                            f"{pipe.geometry_sms} SMs left to it) | layers of batch i (main stream) | loss block of batch i-1 "
+                            "(third stream); one batch of every kind of work per step, launched and completed inside the "
+                            "timed region (side streams joined); the step returns the loss of batch i-1"
+                            if args.mode == "deep" else
+                            f"cuda_graphs, two-stage pipeline over batches (coordinate stage of batch i+1 on a second stream, "
+                            f"{pipe.geometry_sms} SMs left to it, beside the layers + loss of batch i; one batch of every kind "
+                            "of work per step, side stream joined inside the timed region)")),
             "sequential": None if pipe is None else {"value": B_PER_GPU * world * args.steps / (total_ms_seq / 1e3),
                                                      "unit": UNIT, "ms_per_step": total_ms_seq / args.steps,
                                                      "what": "one batch at a time (graph.GraphedForwardLoss): per-batch latency"},

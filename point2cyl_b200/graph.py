@@ -317,3 +317,192 @@ class PipelinedForwardLoss:
         main = torch.cuda.current_stream(self.device)
         main.wait_event(self.geo_done[self.cur])
         main.wait_event(self.labels_done[self.cur])
+
+
+class DeepPipelinedForwardLoss:
+    """PipelinedForwardLoss with the LOSS BLOCK as a third stage: per step
+
+        geometry of batch i+1 (second stream)  |  backbone layers of batch i (main stream)  |  loss of batch i-1 (third stream)
+
+    over three buffer slots.  The loss block is ~0.14 ms of short, dependent kernels on a handful of SMs (statistics pass,
+    cost, on-device assignment, base/barrel pass, 3x3 eigen-solves); at the end of the main stream it keeps the feature
+    stage's SMs idle - beside the next batch's layers it is free.  Every step() still does one batch's worth of every
+    kind of work, launched and (after join()) completed inside the step; what it returns is the loss of the batch
+    staged TWO calls earlier (None while the pipeline fills; `flush()` drains the last one).  Same results as
+    pipeline.forward_loss on the same batches in the same order."""
+
+    SLOTS = 3
+
+    def __init__(self, net, example: Dict[str, torch.Tensor], weights=(1.0,) * 5, norm_eig: bool = False,
+                 precision: Optional[str] = None, geometry_sms: Optional[int] = None, auto_rebuild: bool = True):
+        self.net = net
+        dev = next(net.parameters()).device
+        self.device = dev
+        self.weights, self.norm_eig, self.precision, self.auto_rebuild = weights, norm_eig, precision, auto_rebuild
+        B, N, _ = example["pcs"].shape
+        self.B, self.N = B, N
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.geometry_sms = min(B, sms // 4) if geometry_sms is None else int(geometry_sms)
+        self.feature_sms = sms - self.geometry_sms
+        S = self.SLOTS
+        self.static = [{k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS} for _ in range(S)]
+        self.geo = [pipeline.Geometry.empty(net, B, N, dev) for _ in range(S)]
+        self.geo_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.loss_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self.geo_stream):
+            self.starts = [StartRing(B, (N, net.sa1.npoint), dev) for _ in range(S)]
+        ev = lambda: [torch.cuda.Event() for _ in range(S)]
+        self.geo_done, self.labels_done, self.back_done, self.loss_done = ev(), ev(), ev(), ev()
+        self.i = 0                    # batch index of the CURRENT batch (slot i % 3)
+        self.staged = -1              # highest batch index staged
+        self.backboned = -1           # highest batch index whose backbone has been launched
+        self.lossed = -1
+        self.captures = 0
+        self._capture()
+
+    def _geometry(self, s: int):
+        return pipeline.geometry_forward(self.net, self.static[s]["pcs"], self.starts[s].dev, out=self.geo[s])
+
+    def _capture(self):
+        from . import ops
+        dev = self.device
+        self._key = bn_state_key(self.net)
+        buffers = {k: v.clone() for k, v in self.net.named_buffers()}
+        torch.cuda.synchronize(dev)
+        prev = ops.set_sm_budget(self.feature_sms)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():       # eager warm-up outside the capture
+                for s in range(self.SLOTS):
+                    self.starts[s].draw()
+                    self._geometry(s)
+                    pipeline.forward_loss(self.net, self.static[s], weights=self.weights, norm_eig=self.norm_eig,
+                                          precision=self.precision, geo=self.geo[s])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.g_geo, self.g_back, self.g_loss, self.out = [], [], [], []
+            for s in range(self.SLOTS):
+                b = self.static[s]
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g):
+                    self._geometry(s)
+                self.g_geo.append(g)
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g):
+                    X_raw, W_raw = pipeline.backbone_forward(self.net, b["pcs"], None, precision=self.precision,
+                                                             geo=self.geo[s])
+                self.g_back.append(g)
+                gl = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(gl, pool=g.pool()):
+                    out = pipeline.loss_forward(b["pcs"], X_raw, W_raw, b["normals"], b["inst"], b["bb"], b["axes"],
+                                                b["centers"], self.weights, self.norm_eig)
+                    out.update(X_raw=X_raw, W_raw=W_raw)
+                self.g_loss.append(gl)
+                self.out.append(out)
+        finally:
+            ops.set_sm_budget(prev)
+        with torch.no_grad():
+            for k, v in self.net.named_buffers():
+                v.copy_(buffers[k])
+        torch.cuda.synchronize(dev)
+        self.captures += 1
+
+    def stale(self) -> bool:
+        return self._key != bn_state_key(self.net)
+
+    def rebuild_if_stale(self) -> bool:
+        if not self.stale():
+            return False
+        torch.cuda.synchronize(self.device)
+        self._capture()
+        return True
+
+    def _stage(self, j: int, batch: Optional[Dict[str, torch.Tensor]]):
+        """Batch j -> slot j % 3 (H2D when it lives in host memory), then its geometry stage, all off the main stream."""
+        s = j % self.SLOTS
+        cur = torch.cuda.current_stream(self.device)
+        if batch is not None:
+            for k in BATCH_KEYS:
+                if tuple(batch[k].shape) != tuple(self.static[0][k].shape):
+                    raise _lib.P2CError(f"DeepPipelinedForwardLoss was captured for {k} of shape "
+                                        f"{tuple(self.static[0][k].shape)}, got {tuple(batch[k].shape)}: build a new one")
+        for st in (self.geo_stream, self.copy_stream):
+            st.wait_event(self.back_done[s])                       # the slot's previous batch (j - 3) has been consumed:
+            st.wait_event(self.loss_done[s])                       # its backbone read the geometry, its loss the labels / pcs
+            st.wait_stream(cur)
+        with torch.cuda.stream(self.geo_stream):
+            if batch is not None:
+                self.static[s]["pcs"].copy_(batch["pcs"], non_blocking=True)
+            self.starts[s].draw()
+            self.g_geo[s].replay()
+            self.geo_done[s].record(self.geo_stream)
+        with torch.cuda.stream(self.copy_stream):
+            if batch is not None:
+                for k in BATCH_KEYS:
+                    if k != "pcs":
+                        self.static[s][k].copy_(batch[k], non_blocking=True)
+            self.labels_done[s].record(self.copy_stream)
+        self.staged = j
+
+    def prime(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        if self.stale() and self.auto_rebuild:
+            self.rebuild_if_stale()
+        self._stage(self.i, batch)
+
+    def _launch_loss(self, j: int):
+        s = j % self.SLOTS
+        self.loss_stream.wait_event(self.back_done[s])
+        self.loss_stream.wait_event(self.labels_done[s])
+        with torch.cuda.stream(self.loss_stream):
+            self.g_loss[s].replay()
+            self.loss_done[s].record(self.loss_stream)
+        self.lossed = j
+
+    def step(self, next_batch: Optional[Dict[str, torch.Tensor]] = None) -> Optional[Dict[str, torch.Tensor]]:
+        """Backbone of the current batch i, loss of batch i-1 beside it, `next_batch` staged as batch i+1.  Returns the
+        outputs of batch i-1 (None on the first call after prime())."""
+        if self.stale():
+            if not self.auto_rebuild:
+                raise RuntimeError("DeepPipelinedForwardLoss: mode or BatchNorm momentum changed; call rebuild_if_stale()")
+            self.rebuild_if_stale()
+        if self.staged < self.i:
+            self.prime(None)
+        i = self.i
+        c = i % self.SLOTS
+        main = torch.cuda.current_stream(self.device)
+        self._stage(i + 1, next_batch)
+        prev = None
+        if self.backboned == i - 1 and i - 1 >= 0 and self.lossed < i - 1:
+            self._launch_loss(i - 1)                     # beside the layers of batch i
+            prev = (i - 1) % self.SLOTS
+        main.wait_event(self.geo_done[c])
+        main.wait_event(self.loss_done[c])               # the loss of batch i - 3 has read this slot's network outputs
+        self.g_back[c].replay()
+        self.back_done[c].record(main)
+        self.backboned = i
+        self.i = i + 1
+        if prev is None:
+            return None
+        main.wait_event(self.loss_done[prev])            # the caller's stream may read the returned tensors
+        return self.out[prev]
+
+    def flush(self) -> Optional[Dict[str, torch.Tensor]]:
+        """Loss of the last batch whose backbone has run (drains the pipeline's third stage)."""
+        j = self.backboned
+        if j < 0:
+            return None
+        if self.lossed < j:
+            self._launch_loss(j)
+        torch.cuda.current_stream(self.device).wait_event(self.loss_done[j % self.SLOTS])
+        return self.out[j % self.SLOTS]
+
+    def join(self) -> None:
+        """Make the caller's stream wait for everything launched by the last step() on the side streams."""
+        main = torch.cuda.current_stream(self.device)
+        s = self.i % self.SLOTS
+        main.wait_event(self.geo_done[s])
+        main.wait_event(self.labels_done[s])
+        if self.lossed >= 0:
+            main.wait_event(self.loss_done[self.lossed % self.SLOTS])

@@ -389,3 +389,58 @@ def test_pipelined_forward_loss_equals_sequential():
         assert ops.set_sm_budget(0) == 0                            # the budget is only set while capturing
     finally:
         pipeline.dropout_mask_fn = real
+
+
+def test_deep_pipelined_forward_loss_equals_sequential():
+    """graph.DeepPipelinedForwardLoss (three stages over three slots: geometry of batch i+1 | layers of batch i | loss of
+    batch i-1 on a third stream) returns, one call later, what pipeline.forward_loss returns for the same batches in
+    the same order - including a run longer than the slot count (slot reuse) and the drained last batch."""
+    from point2cyl_b200 import pin_batch
+    from point2cyl_b200.graph import DeepPipelinedForwardLoss
+    B, N, K = 4, 2048, 4
+    nb = 7
+    batches = [synthetic.s_cyl(B, N, K, 200 + i) for i in range(nb)]
+    real = pipeline.dropout_mask_fn
+    pipeline.dropout_mask_fn = lambda ones, p=0.5: ones
+    try:
+        net = _small_net(K).train()
+        state = {k: v.clone() for k, v in net.state_dict().items()}
+        torch.manual_seed(78)
+        ref = []
+        for b in batches:
+            with torch.no_grad():
+                o = pipeline.forward_loss(net, {k: v.to(DEV) for k, v in b.items()})
+            ref.append({k: o[k].clone() for k in ("losses", "X_raw", "W_raw", "matching_indices")})
+        ref_state = {k: v.clone() for k, v in net.state_dict().items()}
+        net.load_state_dict(state)
+        pipe = DeepPipelinedForwardLoss(net, {k: v.to(DEV) for k, v in batches[0].items()})
+        for k, v in net.state_dict().items():                       # capture is not a training step
+            assert torch.equal(v, state[k]), k
+        torch.manual_seed(78)
+        host = [pin_batch(b) for b in batches]
+        pipe.prime(host[0])
+        outs = []
+        for i in range(nb):
+            out = pipe.step(host[i + 1] if i + 1 < nb else None)
+            if i == 0:
+                assert out is None                                   # the third stage is still empty
+            else:
+                torch.cuda.synchronize()
+                outs.append({k: out[k].clone() for k in ref[0]})
+        last = pipe.flush()
+        torch.cuda.synchronize()
+        outs.append({k: last[k].clone() for k in ref[0]})
+        assert len(outs) == nb
+        for i, (o, r) in enumerate(zip(outs, ref)):
+            assert torch.equal(o["matching_indices"], r["matching_indices"]), i
+            assert rel_err(o["losses"], r["losses"]) <= TOL, i
+            assert rel_err(o["X_raw"], r["X_raw"]) <= TOL and rel_err(o["W_raw"], r["W_raw"]) <= TOL, i
+        pipe.join()
+        torch.cuda.synchronize()
+        for k, v in net.state_dict().items():
+            if v.is_floating_point():
+                assert rel_err(v, ref_state[k]) <= TOL, k
+            else:
+                assert torch.equal(v, ref_state[k]), k
+    finally:
+        pipeline.dropout_mask_fn = real
