@@ -601,7 +601,8 @@ def main():
             gsm = os.environ.get("P2C_GEO_SMS")          # tools: sweep of the SMs left to the coordinate stage
             if args.mode == "deep":
                 from point2cyl_b200.graph import DeepPipelinedForwardLoss
-                pipe = DeepPipelinedForwardLoss(net, batch, precision=args.precision, geometry_sms=int(gsm) if gsm else None)
+                pipe = DeepPipelinedForwardLoss(net, batch, precision=args.precision, geometry_sms=int(gsm) if gsm else None,
+                                                partition=os.environ.get("P2C_PARTITION", "soft"))
                 pipe.prime(None)
                 pipe.step(None)                          # fill the third stage: every later step returns a loss
             else:

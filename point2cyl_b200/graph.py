@@ -329,12 +329,21 @@ class DeepPipelinedForwardLoss:
     stage's SMs idle - beside the next batch's layers it is free.  Every step() still does one batch's worth of every
     kind of work, launched and (after join()) completed inside the step; what it returns is the loss of the batch
     staged TWO calls earlier (None while the pipeline fills; `flush()` drains the last one).  Same results as
-    pipeline.forward_loss on the same batches in the same order."""
+    pipeline.forward_loss on the same batches in the same order.
+
+    partition="soft" (default): plain streams and a capped grid for the persistent layer kernels.  partition="green": the
+    SMs are split HARD with CUDA green contexts (point2cyl_b200.partition; needs the cuda-python driver bindings, falls back
+    to "soft" without them) - the layers' graph is captured on a stream that owns all but `geometry_sms` SMs (a multiple of
+    8, default 48), the coordinate and loss graphs on streams that own the rest: neither side's CTAs can land on the other's
+    SMs.  Measured at config 2: device-resident step 1.132 -> 1.096 ms at 48 SMs (32: 1.39, 40: 1.20, 56: 1.17), but the
+    end-to-end step (host copies in front of the coordinate stage, which can no longer borrow SMs) 1.135 -> 1.176 ms - hence
+    not the default."""
 
     SLOTS = 3
 
     def __init__(self, net, example: Dict[str, torch.Tensor], weights=(1.0,) * 5, norm_eig: bool = False,
-                 precision: Optional[str] = None, geometry_sms: Optional[int] = None, auto_rebuild: bool = True):
+                 precision: Optional[str] = None, geometry_sms: Optional[int] = None, auto_rebuild: bool = True,
+                 partition: str = "soft"):
         self.net = net
         dev = next(net.parameters()).device
         self.device = dev
@@ -342,14 +351,24 @@ class DeepPipelinedForwardLoss:
         B, N, _ = example["pcs"].shape
         self.B, self.N = B, N
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self.geometry_sms = min(B, sms // 4) if geometry_sms is None else int(geometry_sms)
-        self.feature_sms = sms - self.geometry_sms
+        self.part = None
+        if partition == "green":
+            from .partition import SmPartition
+            want = 48 if geometry_sms is None else int(geometry_sms)
+            self.part = SmPartition.create(dev, (want + 7) // 8 * 8)
+        if self.part is not None:
+            self.geometry_sms, self.feature_sms = self.part.small_sms, self.part.big_sms
+        else:
+            self.geometry_sms = min(B, sms // 4) if geometry_sms is None else int(geometry_sms)
+            self.feature_sms = sms - self.geometry_sms
+        self.partition = "green" if self.part is not None else "soft"
         S = self.SLOTS
         self.static = [{k: torch.empty_like(example[k], device=dev).copy_(example[k]) for k in BATCH_KEYS} for _ in range(S)]
         self.geo = [pipeline.Geometry.empty(net, B, N, dev) for _ in range(S)]
-        self.geo_stream = torch.cuda.Stream(device=dev)
+        self.geo_stream = self.part.small_stream() if self.part is not None else torch.cuda.Stream(device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self.loss_stream = torch.cuda.Stream(device=dev)
+        self.loss_stream = self.part.small_stream() if self.part is not None else torch.cuda.Stream(device=dev)
+        self.feat_stream = self.part.big_stream() if self.part is not None else None
         with torch.cuda.stream(self.geo_stream):
             self.starts = [StartRing(B, (N, net.sa1.npoint), dev) for _ in range(S)]
         ev = lambda: [torch.cuda.Event() for _ in range(S)]
@@ -385,17 +404,19 @@ class DeepPipelinedForwardLoss:
             self.g_geo, self.g_back, self.g_loss, self.out = [], [], [], []
             for s in range(self.SLOTS):
                 b = self.static[s]
+                # a kernel node keeps the green context of the stream it was captured on: the capture streams ARE the partition
+                cap_small = self.geo_stream if self.part is not None else None
                 g = torch.cuda.CUDAGraph()
-                with torch.no_grad(), torch.cuda.graph(g):
+                with torch.no_grad(), torch.cuda.graph(g, stream=cap_small):
                     self._geometry(s)
                 self.g_geo.append(g)
                 g = torch.cuda.CUDAGraph()
-                with torch.no_grad(), torch.cuda.graph(g):
+                with torch.no_grad(), torch.cuda.graph(g, stream=self.feat_stream):
                     X_raw, W_raw = pipeline.backbone_forward(self.net, b["pcs"], None, precision=self.precision,
                                                              geo=self.geo[s])
                 self.g_back.append(g)
                 gl = torch.cuda.CUDAGraph()
-                with torch.no_grad(), torch.cuda.graph(gl, pool=g.pool()):
+                with torch.no_grad(), torch.cuda.graph(gl, pool=g.pool(), stream=self.loss_stream if self.part is not None else None):
                     out = pipeline.loss_forward(b["pcs"], X_raw, W_raw, b["normals"], b["inst"], b["bb"], b["axes"],
                                                 b["centers"], self.weights, self.norm_eig)
                     out.update(X_raw=X_raw, W_raw=W_raw)
@@ -477,10 +498,16 @@ class DeepPipelinedForwardLoss:
         if self.backboned == i - 1 and i - 1 >= 0 and self.lossed < i - 1:
             self._launch_loss(i - 1)                     # beside the layers of batch i
             prev = (i - 1) % self.SLOTS
-        main.wait_event(self.geo_done[c])
-        main.wait_event(self.loss_done[c])               # the loss of batch i - 3 has read this slot's network outputs
-        self.g_back[c].replay()
-        self.back_done[c].record(main)
+        fs = self.feat_stream if self.feat_stream is not None else main
+        if fs is not main:
+            fs.wait_stream(main)                         # (whatever the caller enqueued before this step)
+        fs.wait_event(self.geo_done[c])
+        fs.wait_event(self.loss_done[c])                 # the loss of batch i - 3 has read this slot's network outputs
+        with torch.cuda.stream(fs):
+            self.g_back[c].replay()
+            self.back_done[c].record(fs)
+        if fs is not main:
+            main.wait_event(self.back_done[c])           # the caller's stream stays ordered behind the layers
         self.backboned = i
         self.i = i + 1
         if prev is None:
