@@ -391,8 +391,10 @@ def test_pipelined_forward_loss_equals_sequential():
         pipeline.dropout_mask_fn = real
 
 
-def test_deep_pipelined_forward_loss_equals_sequential():
-    """graph.DeepPipelinedForwardLoss (three stages over three slots: geometry of batch i+1 | layers of batch i | loss of
+@pytest.mark.parametrize("partition", ["soft", "green"])
+def test_deep_pipelined_forward_loss_equals_sequential(partition):
+    """(green: the SMs split hard between the layers and the other two stages with CUDA green contexts.)
+    graph.DeepPipelinedForwardLoss (three stages over three slots: geometry of batch i+1 | layers of batch i | loss of
     batch i-1 on a third stream) returns, one call later, what pipeline.forward_loss returns for the same batches in
     the same order - including a run longer than the slot count (slot reuse) and the drained last batch."""
     from point2cyl_b200 import pin_batch
@@ -413,7 +415,12 @@ def test_deep_pipelined_forward_loss_equals_sequential():
             ref.append({k: o[k].clone() for k in ("losses", "X_raw", "W_raw", "matching_indices")})
         ref_state = {k: v.clone() for k, v in net.state_dict().items()}
         net.load_state_dict(state)
-        pipe = DeepPipelinedForwardLoss(net, {k: v.to(DEV) for k, v in batches[0].items()})
+        pipe = DeepPipelinedForwardLoss(net, {k: v.to(DEV) for k, v in batches[0].items()}, partition=partition)
+        if partition == "green" and pipe.partition != "green":
+            pytest.skip("green contexts unavailable (cuda-python driver bindings / driver support)")
+        if partition == "green":
+            assert pipe.geometry_sms % 8 == 0 and pipe.geometry_sms + pipe.feature_sms == \
+                torch.cuda.get_device_properties(0).multi_processor_count
         for k, v in net.state_dict().items():                       # capture is not a training step
             assert torch.equal(v, state[k]), k
         torch.manual_seed(78)
