@@ -440,8 +440,9 @@ class DeepPipelinedForwardLoss:
         self._capture()
         return True
 
-    def _stage(self, j: int, batch: Optional[Dict[str, torch.Tensor]]):
-        """Batch j -> slot j % 3 (H2D when it lives in host memory), then its geometry stage, all off the main stream."""
+    def _stage(self, j: int, batch: Optional[Dict[str, torch.Tensor]], after: Optional[torch.cuda.Event] = None):
+        """Batch j -> slot j % 3 (H2D when it lives in host memory), then its geometry stage, all off the main stream.
+        after: the point of the caller's stream the staging is ordered behind (default: everything enqueued so far)."""
         s = j % self.SLOTS
         cur = torch.cuda.current_stream(self.device)
         if batch is not None:
@@ -452,7 +453,10 @@ class DeepPipelinedForwardLoss:
         for st in (self.geo_stream, self.copy_stream):
             st.wait_event(self.back_done[s])                       # the slot's previous batch (j - 3) has been consumed:
             st.wait_event(self.loss_done[s])                       # its backbone read the geometry, its loss the labels / pcs
-            st.wait_stream(cur)
+            if after is not None:
+                st.wait_event(after)
+            else:
+                st.wait_stream(cur)
         with torch.cuda.stream(self.geo_stream):
             if batch is not None:
                 self.static[s]["pcs"].copy_(batch["pcs"], non_blocking=True)
@@ -493,19 +497,23 @@ class DeepPipelinedForwardLoss:
         i = self.i
         c = i % self.SLOTS
         main = torch.cuda.current_stream(self.device)
-        self._stage(i + 1, next_batch)
-        prev = None
-        if self.backboned == i - 1 and i - 1 >= 0 and self.lossed < i - 1:
-            self._launch_loss(i - 1)                     # beside the layers of batch i
-            prev = (i - 1) % self.SLOTS
+        # enqueue order = placement order on an idle GPU: the layers first (their persistent CTAs take their SMs before the
+        # small CTAs of the other two stages can), then the loss block, then the staging + coordinate stage of the next batch
+        entry = torch.cuda.Event()
+        entry.record(main)                               # whatever the caller enqueued before this step
         fs = self.feat_stream if self.feat_stream is not None else main
         if fs is not main:
-            fs.wait_stream(main)                         # (whatever the caller enqueued before this step)
+            fs.wait_event(entry)
         fs.wait_event(self.geo_done[c])
         fs.wait_event(self.loss_done[c])                 # the loss of batch i - 3 has read this slot's network outputs
         with torch.cuda.stream(fs):
             self.g_back[c].replay()
             self.back_done[c].record(fs)
+        prev = None
+        if self.backboned == i - 1 and i - 1 >= 0 and self.lossed < i - 1:
+            self._launch_loss(i - 1)                     # beside the layers of batch i
+            prev = (i - 1) % self.SLOTS
+        self._stage(i + 1, next_batch, after=entry)      # (ordered behind the step's entry, not behind its layers)
         if fs is not main:
             main.wait_event(self.back_done[c])           # the caller's stream stays ordered behind the layers
         self.backboned = i
