@@ -148,7 +148,10 @@ int p2c_linear_group_bias(const float* X, int64_t ldx, const float* w_split, int
  * p2c_sa_xyz_linear derives the first layer's sum / sum-of-squares itself (and stores them into bn0->stats);
  * p2c_sa_xyz_stats is the same closed form as a stand-alone kernel (writes the 2C sums where p2c_sa_first_layer
  * would have accumulated them).  scale0 / shift0 or bn0 as in p2c_linear.
- * Returns P2C_EUNSUPPORTED for shapes the tcgen05 kernel does not take (the caller then runs p2c_sa_first_layer). */
+ * Returns P2C_EUNSUPPORTED for shapes the tcgen05 kernel does not take (the caller then runs p2c_sa_first_layer).
+ * A 64 -> 64 second layer whose rows are kept (C0 = N1 = 64, pool_group = 0, Y != NULL: sa1.1 of the backbone) runs on the
+ * rows-as-lanes kernel of csrc/sa_stack_tc.cu - conv0, conv1 and its bias on the tensor core, every A operand in tensor
+ * memory - same semantics, results within fp32 rounding of the other kernel (env P2C_SA_PAIR=0 selects that one). */
 int p2c_group_moments_size(void);
 int p2c_group_moments(const float* xyz, const float* new_xyz, const int64_t* idx, int B, int N, int S, int nsample,
                       double* moments, void* stream);
