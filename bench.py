@@ -276,18 +276,34 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
     device-resident and end-to-end (pinned host batch -> H2D -> step -> loss scalar D2H) clouds/s over all ranks."""
     import point2cyl_b200
     from point2cyl_b200 import _lib
-    from point2cyl_b200.train import GraphedTrainer, Trainer
+    from point2cyl_b200.train import GraphedTrainer, PipelinedTrainer, Trainer
     graphed = not getattr(train_step_numbers, "no_graph", False)
-    tr = GraphedTrainer(net, batch, lr=1e-3) if graphed else Trainer(net, lr=1e-3)
+    ms_seq = None
+    if graphed:
+        # one batch at a time (one CUDA graph pair per step): the per-batch latency figure, reported beside the pipelined one
+        seq = GraphedTrainer(net, batch, lr=1e-3)
+        for _ in range(warmup):
+            seq.step(None)
+        pd.barrier()
+        ms_seq = timed(lambda: seq.step(None), steps)
+        del seq
+        tr = PipelinedTrainer(net, batch, lr=1e-3)       # re-flattens the parameters: `seq` must not be used after this
+        tr.prime(None)
+    else:
+        tr = Trainer(net, lr=1e-3)
 
     loss_host = None
 
     def step_resident():
-        return tr.step(None if graphed else batch)      # the graph's static inputs already hold `batch`
+        if graphed:
+            out = tr.step(None)                           # both slots already hold `batch`; coordinate stage of the next
+            tr.join()                                     # one runs beside this step and ends inside the timed region
+            return out
+        return tr.step(batch)
 
     def step_e2e():
         if graphed:
-            out = tr.step(host)                           # H2D of the six batch tensors into the static inputs, replay
+            out = tr.step(host)                           # H2D of the NEXT batch's six tensors beside this step, replay
         else:
             out = tr.step({k: host[k].to(dev, non_blocking=True) for k in point2cyl_b200.BATCH_KEYS})
         nonlocal loss_host
@@ -295,6 +311,8 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
             loss_host = torch.empty(out["losses"].shape, dtype=out["losses"].dtype).pin_memory()
         loss_host.copy_(out["losses"], non_blocking=True)     # D2H of the loss scalars, stream-ordered, inside the event pair
         out["loss_host"] = loss_host
+        if graphed:
+            tr.join()
         return out
 
     for _ in range(warmup):
@@ -309,6 +327,7 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
     ms_e2e = timed(step_e2e, steps)
     pd.barrier()
     tot, tot_e2e = pd.reduce_max(sum(ms), dev), pd.reduce_max(sum(ms_e2e), dev)
+    tot_seq = None if ms_seq is None else pd.reduce_max(sum(ms_seq), dev)
     clouds = B_PER_GPU * world * steps
     n_param = tr.flat_param.numel()
     return {"metric": "point-clouds/sec training step (forward+loss+backward+grad all-reduce+Adam), B=32/GPU N=8192 K=8",
@@ -316,7 +335,12 @@ def train_step_numbers(net, batch, host, flush, timed, pd, dev, world, steps, wa
             "e2e": {"value": clouds / (tot_e2e / 1e3), "unit": UNIT, "ms_per_step": tot_e2e / steps,
                     "h2d_bytes_per_step": point2cyl_b200.h2d_bytes(host), "d2h_bytes_per_step": 24},
             "gpu_launches": launches, "steps": steps, "warmup": warmup,
-            "launch_mode": "cuda_graph (forward+loss+backward) + all-reduce + Adam" if graphed else "eager",
+            "launch_mode": ("cuda_graphs, two-stage pipeline over batches: coordinate stage of batch i+1 (second stream) | "
+                            "layers + loss + backward of batch i, then all-reduce + Adam (main stream); one batch of every "
+                            "kind of work per step, side stream joined inside the timed region") if graphed else "eager",
+            "sequential": None if ms_seq is None else {
+                "value": clouds / (tot_seq / 1e3), "unit": UNIT, "ms_per_step": tot_seq / steps,
+                "what": "one batch at a time (train.GraphedTrainer): per-batch latency"},
             "collective": None if world == 1 else f"one NCCL sum all-reduce of the flat fp32 gradient ({n_param} floats)",
             "parameters": n_param, "global_batch": B_PER_GPU * world}
 
@@ -336,8 +360,8 @@ def run_train(args, rank, world, dev, pd, net, host, batch, flush, timed):
         print(json.dumps({"metric": t["metric"], "value": t["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": t["ms_per_step"], "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
-                          "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "launch_mode": t["launch_mode"], "clocks": clk,
-                          "collective": t["collective"]}), flush=True)
+                          "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "launch_mode": t["launch_mode"], "sequential": t.get("sequential"),
+                          "clocks": clk, "collective": t["collective"]}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -17,8 +17,9 @@
 // buffers.  3xTF32 like the forward: dYhi*Ahi + dYlo*Ahi + dYhi*Alo, fp32 accumulate (fp32-faithful).
 // kind::tf32 reads the upper 19 bits of an fp32 word and ignores the low 13 mantissa bits, so the RAW fp32 tile IS
 // the "hi" operand: only lo = x - trunc(x) is written by the transform (and Ahi when the operand load folds a
-// BatchNorm+ReLU).  That keeps three 32 KB TMA stages in flight per SM instead of two; a RAW stage is released by
-// the MMA's commit, not by the transform.
+// BatchNorm+ReLU - written IN PLACE over the RAW X boxes: every transform thread overwrites exactly the words it read,
+// so no second buffer is needed).  That keeps four 32 KB TMA stages in flight per SM and three transformed stages
+// ahead of the tensor core; a RAW stage is released by the MMA's commit, not by the transform.
 //
 // Warp roles (384 threads, 1 CTA/SM): warp 0 TMA producer (8 boxes = 32 KB per 32-row stage), warp 1 MMA issuer,
 // warp 2 TMEM allocator, warps 4-11 operand transform, warps 4-7 afterwards the epilogue (thread = dW row n).
@@ -33,8 +34,8 @@ constexpr int WG_ROWS = 32;                  // rows per stage = 4 UMMA k-steps 
 constexpr int WG_BOX = WG_ROWS * 128;        // bytes of one [32 rows x 32 channels] box
 constexpr int WG_OP = 4 * WG_BOX;            // one operand stage: 128 channels = 16 KB
 constexpr int WG_RAW_STAGE = 2 * WG_OP;      // dY | X      (TMA destination; also the tf32 "hi" operands, see below)
-constexpr int WG_XT_STAGE = 3 * WG_OP;       // dYlo | Alo | Ahi (Ahi only when a BatchNorm+ReLU fold changes X)
-constexpr int WG_RAW = 3, WG_XT = 2;
+constexpr int WG_XT_STAGE = 2 * WG_OP;       // dYlo | Alo
+constexpr int WG_RAW = 4, WG_XT = 3;         // 7 x 32 KB: four TMA stages in flight, three transformed stages ahead of the MMAs
 constexpr int WG_TILE = 128;
 
 // kind::tf32, fp32 accumulate, A and B MN-major, M = 128, N = 128
@@ -79,7 +80,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* raw_sm = smem;                                            // [WG_RAW][dY | X]
-  uint8_t* xt_sm = smem + WG_RAW * WG_RAW_STAGE;                     // [WG_XT][dYhi | dYlo | Ahi | Alo]
+  uint8_t* xt_sm = smem + WG_RAW * WG_RAW_STAGE;                     // [WG_XT][dYlo | Alo]
   float* s_scale = reinterpret_cast<float*>(xt_sm + WG_XT * WG_XT_STAGE);
   float* s_shift = s_scale + WG_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + WG_TILE);
@@ -138,7 +139,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, one elected lane issues (tc_common.cuh: elect_one_sync) =====
     {
-      const bool affine = a.in_scale != nullptr;
       int xs = 0; uint32_t xph = 0;
       int rs = 0;
       for (int t = 0; t < my_stages; ++t) {
@@ -146,7 +146,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         tc_fence_after();
         const uint32_t rawb = smem_u32(raw_sm + (size_t)rs * WG_RAW_STAGE);
         const uint32_t xtb = smem_u32(xt_sm + (size_t)xs * WG_XT_STAGE);
-        const uint32_t ahib = affine ? xtb + 2 * WG_OP : rawb + WG_OP;
+        const uint32_t ahib = rawb + WG_OP;           // raw X, or relu(bn(X)) written in place by the transform
         if (elect_one_sync()) {
           // the four 8-row k-steps differ in the descriptors' start-address field only (+1024 B = +64 units)
           const uint64_t dyhi = make_mnmajor_sw128_desc(rawb), dylo = make_mnmajor_sw128_desc(xtb);
@@ -182,13 +182,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const bool do_bias = !is_x && a.db != nullptr && blockIdx.z == 0;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t raw_op = is_x ? WG_OP : 0;
-    const uint32_t xt_op = is_x ? WG_OP : 0;       // lo half of this operand; Ahi sits at 2 * WG_OP
+    const uint32_t xt_op = is_x ? WG_OP : 0;       // lo half of this operand
     const uint32_t box_off = (uint32_t)(box & 3) * WG_BOX;
     int s = 0; uint32_t ph = 0;
     int xs = 0; uint32_t xph = 0;
     for (int t = 0; t < my_stages; ++t) {
       mbar_wait(&raw_full[s], ph);
-      const uint8_t* rawp = raw_sm + (size_t)s * WG_RAW_STAGE + raw_op + box_off;
+      uint8_t* rawp = raw_sm + (size_t)s * WG_RAW_STAGE + raw_op + box_off;
       float4 x[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -211,7 +211,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       }
       mbar_wait(&xt_empty[xs], xph ^ 1);
       uint8_t* lop = xt_sm + (size_t)xs * WG_XT_STAGE + xt_op + box_off;
-      uint8_t* hip = xt_sm + (size_t)xs * WG_XT_STAGE + 2 * WG_OP + box_off;   // Ahi (X boxes with an affine fold only)
+      uint8_t* hip = rawp;                           // Ahi (X boxes with an affine fold only): in place over the RAW box
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rg * 8 + i;

@@ -393,6 +393,44 @@ def test_graphed_trainer_matches_eager(monkeypatch):
     assert losses[-1] < losses[0]
 
 
+def test_pipelined_trainer_matches_eager(monkeypatch):
+    """Two-stage pipelined training step (coordinate stage of batch i+1 beside the step of batch i, two buffer slots):
+    batch by batch the loss and the gradients of the eager Trainer on the same batches in the same order (same CPU
+    generator stream for the first FPS centroids), BatchNorm buffers untouched by the capture; then it trains."""
+    from point2cyl_b200.dropin.models.pointnet_extrusion import backbone
+    from point2cyl_b200.train import PipelinedTrainer, Trainer
+    B, N, K = 4, 2048, 4
+    batches = [{k: v.to(DEV) for k, v in synthetic.s_cyl(B, N, K, seed=20 + i).items()} for i in range(5)]
+    mask = ((torch.rand(B, 128, N, generator=torch.Generator().manual_seed(1)) > 0.5).float() * 2.0).to(DEV)
+    monkeypatch.setattr(pipeline, "dropout_mask_fn", lambda x, p=0.5, **kw: mask)
+    nets = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        nets.append(backbone(output_sizes=[3, 2 * K]).to(DEV).eval())   # running-statistics BatchNorm: well conditioned
+    eager = Trainer(nets[0], lr=0.0)                       # lr 0: the weights stay equal, every batch is comparable
+    piped = PipelinedTrainer(nets[1], batches[0], lr=0.0)
+    for (k, a), (_, b) in zip(nets[0].named_buffers(), nets[1].named_buffers()):
+        assert torch.equal(a, b), k
+    torch.manual_seed(77)
+    ref = []
+    for b in batches:
+        o = eager.step(b)
+        ref.append((float(o["total"]), eager.flat_grad.clone()))
+    torch.manual_seed(77)
+    piped.prime(batches[0])
+    for i in range(len(batches)):
+        o = piped.step(batches[i + 1] if i + 1 < len(batches) else None)
+        assert abs(float(o["total"]) - ref[i][0]) <= 1e-5 * max(1.0, abs(ref[i][0])), (i, float(o["total"]), ref[i][0])
+        diff = (piped.flat_grad - ref[i][1]).double().norm() / ref[i][1].double().norm()
+        assert float(diff) <= 1e-3, (i, float(diff))
+    for net in nets:
+        net.train()
+    piped = PipelinedTrainer(nets[1], batches[0], lr=1e-3)
+    piped.prime(batches[0])
+    losses = [float(piped.step(None)["total"]) for _ in range(8)]  # step(None): the resident batches of the two slots
+    assert losses[-1] < losses[0]
+
+
 def _l2(got, ref):
     """relative L2 error: isolated ReLU / arg-max flips move single entries, not the bulk"""
     return float((got.detach().cpu().double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
