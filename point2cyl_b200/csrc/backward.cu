@@ -41,7 +41,10 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldda, const float* __
   const int RL = RED_THREADS / CL;                   // row lanes
   const int cl = threadIdx.x % CL, rl = threadIdx.x / CL;
   const int c = blockIdx.y * cb + cl * 4;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  // slabs are walked from the LAST rows to the first: dA has just been written front to back by the data-gradient
+  // kernel, so its tail is what the L2 still holds - and the applying kernel that follows starts at row 0, where this
+  // kernel ends
+  const int64_t r0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * rows_per_cta;
   const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
   float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
   if (scale) {
@@ -517,6 +520,73 @@ head_bwd_kernel(const float* __restrict__ dOut, int64_t ldo, const float* __rest
   }
 }
 
+// The same for C == 128 with the Philox mask (the training step's call): lane = four consecutive channels, so a warp
+// reads / writes whole 512-byte rows (the kernel above is thread = row: 16-byte pieces of 32 different rows per
+// instruction, half-used sectors - measured 281 us at 262,144 rows against ~62 us of HBM time).  The lane's 4 columns of
+// W stay in registers; a row's Nout upstream gradients arrive by warp-uniform 16-byte loads; the keep-bits of 32 rows
+// are drawn by the 32 lanes (one Philox call each) and handed round by shuffles.
+template <int NP>
+__global__ void __launch_bounds__(256, 2)
+head_bwd_rows_kernel(const float* __restrict__ dOut, int64_t ldo, const int64_t* __restrict__ seed,
+                     const float* __restrict__ W, int64_t M, int Nout, float* __restrict__ dA, int64_t ldda,
+                     const float* __restrict__ H, int64_t ldh, const float* __restrict__ scale,
+                     const float* __restrict__ shift, float* __restrict__ A_out, int64_t lda) {
+  constexpr int C = 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k0 = lane * 4;
+  float4 w[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j)
+    w[j] = j < Nout ? __ldg(reinterpret_cast<const float4*>(W + (size_t)j * C + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (scale) {
+    sc = __ldg(reinterpret_cast<const float4*>(scale + k0));
+    sh = __ldg(reinterpret_cast<const float4*>(shift + k0));
+  }
+  const int word = lane >> 3, bit0 = (lane & 7) * 4;       // channel c: bit (c & 31) of word (c >> 5)
+  for (int64_t m0 = ((int64_t)blockIdx.x * 8 + warp) * 32; m0 < M; m0 += (int64_t)gridDim.x * 256) {
+    P2CPhilox4 bits;
+    bits.v[0] = bits.v[1] = bits.v[2] = bits.v[3] = 0xffffffffu;
+    if (seed && m0 + lane < M) bits = p2c_dropout_bits(seed, m0 + lane, 0);
+    const int rows = (int)min((int64_t)32, M - m0);
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+      const int64_t m = m0 + r;
+      const float4* gp = reinterpret_cast<const float4*>(dOut + m * ldo);
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (A_out) h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + k0));
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j4 = 0; j4 < NP / 4; ++j4) {
+        const float4 g = __ldg(gp + j4);                    // warp-uniform address: one broadcast transaction
+        // columns >= Nout are padding of the caller's buffer (uninitialised): they must not reach the FMAs as NaN * 0
+        const float gv[4] = {g.x, j4 * 4 + 1 < Nout ? g.y : 0.f, j4 * 4 + 2 < Nout ? g.z : 0.f, j4 * 4 + 3 < Nout ? g.w : 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 ww = w[j4 * 4 + i];
+          t.x = fmaf(gv[i], ww.x, t.x); t.y = fmaf(gv[i], ww.y, t.y);
+          t.z = fmaf(gv[i], ww.z, t.z); t.w = fmaf(gv[i], ww.w, t.w);
+        }
+      }
+      const uint32_t b0 = __shfl_sync(0xffffffffu, bits.v[0], r), b1 = __shfl_sync(0xffffffffu, bits.v[1], r);
+      const uint32_t b2 = __shfl_sync(0xffffffffu, bits.v[2], r), b3 = __shfl_sync(0xffffffffu, bits.v[3], r);
+      const uint32_t bw = (word == 0 ? b0 : word == 1 ? b1 : word == 2 ? b2 : b3) >> bit0;
+      const float keep = seed ? 2.f : 1.f;
+      const float4 mq = make_float4((bw & 1u) ? keep : 0.f, (bw & 2u) ? keep : 0.f, (bw & 4u) ? keep : 0.f,
+                                    (bw & 8u) ? keep : 0.f);
+      *reinterpret_cast<float4*>(dA + m * ldda + k0) = make_float4(t.x * mq.x, t.y * mq.y, t.z * mq.z, t.w * mq.w);
+      if (A_out) {
+        float4 a = h;
+        if (scale) {
+          a.x = fmaxf(fmaf(h.x, sc.x, sh.x), 0.f); a.y = fmaxf(fmaf(h.y, sc.y, sh.y), 0.f);
+          a.z = fmaxf(fmaf(h.z, sc.z, sh.z), 0.f); a.w = fmaxf(fmaf(h.w, sc.w, sh.w), 0.f);
+        }
+        *reinterpret_cast<float4*>(A_out + m * lda + k0) = make_float4(a.x * mq.x, a.y * mq.y, a.z * mq.z, a.w * mq.w);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam defaults of train_...:189: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad)
 // over the flat parameter buffer: one launch for the whole model.
@@ -746,6 +816,20 @@ extern "C" int p2c_head_bwd(const float* dOut, int64_t ldo, const float* mask_cf
   if (C > 256 || Nout > 36) return P2C_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = (int64_t)B * N;
+  // rows-as-warps kernel: 128 channels, Philox (or no) mask, upstream rows readable as 16-byte pieces up to the padded width
+  if (C == 128 && !mask_cf && (ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(dOut) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (!scale || ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift)) & 15) == 0)) {
+    const int np = (Nout + 3) & ~3;
+    if (np <= ldo && np <= 20) {
+      const int blocks = (int)min((int64_t)148 * 16, (int64_t)p2c_ceil_div(M, 256));
+#define P2C_HBR(NPV) head_bwd_rows_kernel<NPV><<<blocks, 256, 0, st>>>(dOut, ldo, dropout_seed, W, M, Nout, dA, ldda, H, ldh, scale, shift, A_out, lda)
+      if (np <= 4) P2C_HBR(4); else if (np <= 8) P2C_HBR(8); else if (np <= 12) P2C_HBR(12);
+      else if (np <= 16) P2C_HBR(16); else P2C_HBR(20);
+#undef P2C_HBR
+      P2C_RETURN_IF_CUDA_ERROR();
+      return 0;
+    }
+  }
 #define P2C_HB(NPV)                                                                                              \
   do {                                                                                                           \
     const size_t smem = ((size_t)C * NPV + 2 * C) * sizeof(float);                                               \

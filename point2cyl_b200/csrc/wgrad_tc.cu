@@ -243,16 +243,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      // every CTA of a slab column adds into the same dW tile: 16-byte vector reductions where the row is aligned (a
+      // quarter of the L2 atomic operations), and the CTAs start at different 32-column chunks so they do not all
+      // queue on the same addresses at once
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = (cc + (int)blockIdx.x) & 3;
         uint32_t raw[32];
         tmem_ld32(tm_acc + lane_addr + (uint32_t)c * 32u, raw);
         tmem_wait_ld();
         if (n < a.N) {
           float* row = a.dW + (size_t)n * a.lddw + k0 + c * 32;
+          const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (k0 + c * 32 + j < a.K) atomicAdd(row + j, __uint_as_float(raw[j]));
+          for (int j = 0; j < 32; j += 4) {
+            if (vec && k0 + c * 32 + j + 3 < a.K) {
+              atomicAdd(reinterpret_cast<float4*>(row + j),
+                        make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]),
+                                    __uint_as_float(raw[j + 3])));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (k0 + c * 32 + j + i < a.K) atomicAdd(row + j + i, __uint_as_float(raw[j + i]));
+            }
+          }
         }
       }
     }

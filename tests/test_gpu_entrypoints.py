@@ -256,6 +256,14 @@ def test_philox_dropout_backward_regenerates_the_same_mask():
     dA2, A2 = ops.head_bwd(dOut, mask_cf, W, B, N, H, sc, sh)
     assert torch.equal(dA, dA2) and torch.equal(A, A2)
     assert rel_err(A, A_ref) <= 1e-6
+    # the training step's call: upstream rows padded to 16 bytes (the padding is uninitialised memory - NaN here) take
+    # the rows-as-warps kernel (lane = four channels); ragged row count (2000 = 62 * 32 + 16); same bits, same FMA order
+    d_buf = torch.full((B * N, 20), float("nan"), device=DEV)
+    d_buf[:, :Nout] = dOut
+    dA3, A3 = ops.head_bwd(d_buf[:, :Nout], None, W, B, N, H, sc, sh, seed=seed)
+    assert torch.equal(dA3, dA2) and torch.equal(A3, A2)
+    dA4 = ops.head_bwd(d_buf[:, :Nout], None, W, B, N)              # no mask, no re-materialised input
+    assert rel_err(dA4, dOut.double() @ W.double()) <= 1e-5
 
 
 def _small_net(K=4):
