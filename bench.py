@@ -66,14 +66,53 @@ def kernel_source_sha():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  In-process NVML (nvidia_ml_py) on a
+    polling thread: one `nvidia-smi -lms` child per rank attaches to every GPU of the box when it starts - inside the
+    timed region of an 8-rank run - and its start-up cost grows with the GPU count; the NVML handle is opened before
+    the warm-up instead.  Falls back to the nvidia-smi child when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml = self.handle = None
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = getattr(torch.cuda.get_device_properties(index), "uuid", None)
+            if uuid is not None:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}")
+            else:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = self.handle = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+        while True:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & bits[k] else "Not Active" for k in self.NAMES])
+            except Exception:
+                pass
+            if self._stop.wait(0.02):
+                return
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._sample_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -87,16 +126,19 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(self.NAMES, r[2:6]) if v == "Active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.thread is not None else "nvidia-smi"}
 
 
 def make_net(device):
@@ -673,13 +715,13 @@ def main():
         run_train(args, rank, world, dev, pd, net, host, batch, flush, timed)
         return
 
+    clocks = ClockSampler(local_rank)               # NVML handle opened here, before the warm-up and the barrier
     with torch.no_grad():
         for _ in range(args.warmup):
             step_resident()
         for _ in range(2):
             step_e2e()
     barrier()
-    clocks = ClockSampler(local_rank)
     clocks.start()
     ms = timed(step_resident, args.steps)
     ms_seq = timed(step_sequential, args.steps) if pipe is not None else ms

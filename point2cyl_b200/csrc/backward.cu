@@ -544,44 +544,65 @@ head_bwd_rows_kernel(const float* __restrict__ dOut, int64_t ldo, const int64_t*
     sh = __ldg(reinterpret_cast<const float4*>(shift + k0));
   }
   const int word = lane >> 3, bit0 = (lane & 7) * 4;       // channel c: bit (c & 31) of word (c >> 5)
+  __shared__ __align__(16) float s_g[8][32][NP];           // the warp's 32 upstream rows (columns >= Nout zeroed)
   for (int64_t m0 = ((int64_t)blockIdx.x * 8 + warp) * 32; m0 < M; m0 += (int64_t)gridDim.x * 256) {
     P2CPhilox4 bits;
     bits.v[0] = bits.v[1] = bits.v[2] = bits.v[3] = 0xffffffffu;
     if (seed && m0 + lane < M) bits = p2c_dropout_bits(seed, m0 + lane, 0);
     const int rows = (int)min((int64_t)32, M - m0);
-#pragma unroll 2
-    for (int r = 0; r < rows; ++r) {
-      const int64_t m = m0 + r;
-      const float4* gp = reinterpret_cast<const float4*>(dOut + m * ldo);
-      float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (A_out) h = __ldg(reinterpret_cast<const float4*>(H + m * ldh + k0));
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    if (lane < rows) {
+      const float4* gp = reinterpret_cast<const float4*>(dOut + (m0 + lane) * ldo);
 #pragma unroll
       for (int j4 = 0; j4 < NP / 4; ++j4) {
-        const float4 g = __ldg(gp + j4);                    // warp-uniform address: one broadcast transaction
+        float4 g = __ldg(gp + j4);
         // columns >= Nout are padding of the caller's buffer (uninitialised): they must not reach the FMAs as NaN * 0
-        const float gv[4] = {g.x, j4 * 4 + 1 < Nout ? g.y : 0.f, j4 * 4 + 2 < Nout ? g.z : 0.f, j4 * 4 + 3 < Nout ? g.w : 0.f};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 ww = w[j4 * 4 + i];
-          t.x = fmaf(gv[i], ww.x, t.x); t.y = fmaf(gv[i], ww.y, t.y);
-          t.z = fmaf(gv[i], ww.z, t.z); t.w = fmaf(gv[i], ww.w, t.w);
-        }
+        if (j4 * 4 + 1 >= Nout) g.y = 0.f;
+        if (j4 * 4 + 2 >= Nout) g.z = 0.f;
+        if (j4 * 4 + 3 >= Nout) g.w = 0.f;
+        *reinterpret_cast<float4*>(&s_g[warp][lane][j4 * 4]) = g;
       }
-      const uint32_t b0 = __shfl_sync(0xffffffffu, bits.v[0], r), b1 = __shfl_sync(0xffffffffu, bits.v[1], r);
-      const uint32_t b2 = __shfl_sync(0xffffffffu, bits.v[2], r), b3 = __shfl_sync(0xffffffffu, bits.v[3], r);
-      const uint32_t bw = (word == 0 ? b0 : word == 1 ? b1 : word == 2 ? b2 : b3) >> bit0;
-      const float keep = seed ? 2.f : 1.f;
-      const float4 mq = make_float4((bw & 1u) ? keep : 0.f, (bw & 2u) ? keep : 0.f, (bw & 4u) ? keep : 0.f,
-                                    (bw & 8u) ? keep : 0.f);
-      *reinterpret_cast<float4*>(dA + m * ldda + k0) = make_float4(t.x * mq.x, t.y * mq.y, t.z * mq.z, t.w * mq.w);
-      if (A_out) {
-        float4 a = h;
-        if (scale) {
-          a.x = fmaxf(fmaf(h.x, sc.x, sh.x), 0.f); a.y = fmaxf(fmaf(h.y, sc.y, sh.y), 0.f);
-          a.z = fmaxf(fmaf(h.z, sc.z, sh.z), 0.f); a.w = fmaxf(fmaf(h.w, sc.w, sh.w), 0.f);
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < rows; r0 += 4) {
+      float4 h[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                         // four rows of H in flight before the arithmetic starts
+        h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (A_out && r0 + u < rows) h[u] = __ldg(reinterpret_cast<const float4*>(H + (m0 + r0 + u) * ldh + k0));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u;
+        if (r >= rows) break;
+        const int64_t m = m0 + r;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j4 = 0; j4 < NP / 4; ++j4) {
+          const float4 g = *reinterpret_cast<const float4*>(&s_g[warp][r][j4 * 4]);   // broadcast read
+          const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 ww = w[j4 * 4 + i];
+            t.x = fmaf(gv[i], ww.x, t.x); t.y = fmaf(gv[i], ww.y, t.y);
+            t.z = fmaf(gv[i], ww.z, t.z); t.w = fmaf(gv[i], ww.w, t.w);
+          }
         }
-        *reinterpret_cast<float4*>(A_out + m * lda + k0) = make_float4(a.x * mq.x, a.y * mq.y, a.z * mq.z, a.w * mq.w);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, bits.v[0], r), b1 = __shfl_sync(0xffffffffu, bits.v[1], r);
+        const uint32_t b2 = __shfl_sync(0xffffffffu, bits.v[2], r), b3 = __shfl_sync(0xffffffffu, bits.v[3], r);
+        const uint32_t bw = (word == 0 ? b0 : word == 1 ? b1 : word == 2 ? b2 : b3) >> bit0;
+        const float keep = seed ? 2.f : 1.f;
+        const float4 mq = make_float4((bw & 1u) ? keep : 0.f, (bw & 2u) ? keep : 0.f, (bw & 4u) ? keep : 0.f,
+                                      (bw & 8u) ? keep : 0.f);
+        *reinterpret_cast<float4*>(dA + m * ldda + k0) = make_float4(t.x * mq.x, t.y * mq.y, t.z * mq.z, t.w * mq.w);
+        if (A_out) {
+          float4 a = h[u];
+          if (scale) {
+            a.x = fmaxf(fmaf(a.x, sc.x, sh.x), 0.f); a.y = fmaxf(fmaf(a.y, sc.y, sh.y), 0.f);
+            a.z = fmaxf(fmaf(a.z, sc.z, sh.z), 0.f); a.w = fmaxf(fmaf(a.w, sc.w, sh.w), 0.f);
+          }
+          *reinterpret_cast<float4*>(A_out + m * lda + k0) = make_float4(a.x * mq.x, a.y * mq.y, a.z * mq.z, a.w * mq.w);
+        }
       }
     }
   }
