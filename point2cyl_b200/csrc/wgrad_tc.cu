@@ -42,6 +42,9 @@ constexpr int WG_TILE = 128;
 constexpr uint32_t WG_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                               ((uint32_t)(WG_TILE >> 3) << 17) | ((uint32_t)(WG_TILE >> 4) << 24);
 
+constexpr uint32_t WG_IDESC_N64 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                  ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(WG_TILE >> 4) << 24);
+
 // MN-major SWIZZLE_128B_BASE32B descriptor: LBO = stride between 32-channel groups, SBO = stride between 4-row atoms
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -73,6 +76,12 @@ struct WgArgs {
   float* dW; int64_t lddw; float* db;
   int M, N, K;
   int stages_total, stages_per_cta;
+  // K <= 64 (the 64-channel layers of sa1: a million rows each): half of a 128-wide X operand would be zero-filled.
+  //   fold (N <= 64 too): a stage holds 64 rows - boxes 2, 3 of both operands carry channels 0..63 of the rows
+  //     m0+32.., so D[0:64, 0:64] and D[64:128, 64:128] are the products of the two 32-row halves (the off-diagonal
+  //     blocks are cross terms nobody reads): the same twelve MMAs reduce twice the rows;
+  //   narrow (N > 64): the X operand is two boxes and the MMA shape 128 x 64.
+  int fold, narrow;
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -122,15 +131,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     {
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < my_stages; ++t) {
-        const int m0 = (st0 + t) * WG_ROWS;
+        const int m0 = (st0 + t) * (a.fold ? 2 * WG_ROWS : WG_ROWS);
         mbar_wait(&raw_empty[s], ph ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&raw_full[s], WG_RAW_STAGE);
           uint8_t* dst = raw_sm + (size_t)s * WG_RAW_STAGE;
+          if (a.fold) {
+            mbar_arrive_expect_tx(&raw_full[s], WG_RAW_STAGE);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) tma_load_2d(dst + b * WG_BOX, &tmDY, &raw_full[s], n0 + b * 32, m0);
+            for (int b = 0; b < 4; ++b)
+              tma_load_2d(dst + b * WG_BOX, &tmDY, &raw_full[s], n0 + (b & 1) * 32, m0 + (b >> 1) * WG_ROWS);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) tma_load_2d(dst + WG_OP + b * WG_BOX, &tmX, &raw_full[s], k0 + b * 32, m0);
+            for (int b = 0; b < 4; ++b)
+              tma_load_2d(dst + WG_OP + b * WG_BOX, &tmX, &raw_full[s], k0 + (b & 1) * 32, m0 + (b >> 1) * WG_ROWS);
+          } else {
+            mbar_arrive_expect_tx(&raw_full[s], a.narrow ? WG_OP + 2 * WG_BOX : WG_RAW_STAGE);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tma_load_2d(dst + b * WG_BOX, &tmDY, &raw_full[s], n0 + b * 32, m0);
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (b < 2 || !a.narrow) tma_load_2d(dst + WG_OP + b * WG_BOX, &tmX, &raw_full[s], k0 + b * 32, m0);
+          }
         }
         __syncwarp();
         if (++s == WG_RAW) { s = 0; ph ^= 1; }
@@ -141,6 +161,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     {
       int xs = 0; uint32_t xph = 0;
       int rs = 0;
+      const uint32_t idesc = a.narrow ? WG_IDESC_N64 : WG_IDESC;
       for (int t = 0; t < my_stages; ++t) {
         mbar_wait(&xt_full[xs], xph);               // implies raw_full[rs]: the transform read that stage
         tc_fence_after();
@@ -154,9 +175,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t o = (uint64_t)(ks * 64);
-            umma_tf32_ss(tm_acc, dyhi + o, ahi + o, WG_IDESC, (t | ks) != 0);
-            umma_tf32_ss(tm_acc, dylo + o, ahi + o, WG_IDESC, 1u);
-            umma_tf32_ss(tm_acc, dyhi + o, alo + o, WG_IDESC, 1u);
+            umma_tf32_ss(tm_acc, dyhi + o, ahi + o, idesc, (t | ks) != 0);
+            umma_tf32_ss(tm_acc, dylo + o, ahi + o, idesc, 1u);
+            umma_tf32_ss(tm_acc, dyhi + o, alo + o, idesc, 1u);
           }
           umma_commit(&xt_empty[xs]);
           umma_commit(&raw_empty[rs]);                // the tensor core has read the RAW stage: TMA may refill it
@@ -174,10 +195,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const int cj = tt & 7, rg = (tt >> 3) & 3;
     const bool is_x = box >= 4;
     const bool has_affine = is_x && a.in_scale != nullptr;
+    const int cbox = a.fold ? (box & 1) : (box & 3);     // 32-channel group this box carries
+    const bool idle = a.narrow && box >= 6;              // narrow: X boxes 2, 3 do not exist (the warp only keeps the barriers going)
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_affine) {
-      sc = *reinterpret_cast<const float4*>(s_scale + (box - 4) * 32 + cj * 4);
-      sh = *reinterpret_cast<const float4*>(s_shift + (box - 4) * 32 + cj * 4);
+      sc = *reinterpret_cast<const float4*>(s_scale + cbox * 32 + cj * 4);
+      sh = *reinterpret_cast<const float4*>(s_shift + cbox * 32 + cj * 4);
     }
     const bool do_bias = !is_x && a.db != nullptr && blockIdx.z == 0;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -193,7 +216,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rg * 8 + i;
-        x[i] = *reinterpret_cast<const float4*>(rawp + box_off32(r, cj));
+        x[i] = idle ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(rawp + box_off32(r, cj));
       }
       if (++s == WG_RAW) { s = 0; ph ^= 1; }
       if (has_affine) {
@@ -221,6 +244,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         l.z = x[i].z - __uint_as_float(__float_as_uint(x[i].z) & 0xffffe000u);
         l.w = x[i].w - __uint_as_float(__float_as_uint(x[i].w) & 0xffffe000u);
         const uint32_t off = box_off32(r, cj);
+        if (idle) continue;
         *reinterpret_cast<float4*>(lop + off) = l;
         if (has_affine) *reinterpret_cast<float4*>(hip + off) = x[i];   // the tensor core drops the low 13 bits itself
       }
@@ -230,7 +254,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       if (++xs == WG_XT) { xs = 0; xph ^= 1; }
     }
     if (do_bias) {
-      const int n = n0 + box * 32 + cj * 4;
+      const int n = n0 + cbox * 32 + cj * 4;
       if (n + 0 < a.N) atomicAdd(a.db + n + 0, bsum.x);
       if (n + 1 < a.N) atomicAdd(a.db + n + 1, bsum.y);
       if (n + 2 < a.N) atomicAdd(a.db + n + 2, bsum.z);
@@ -239,7 +263,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     if (warp < 8) {
       // ===== epilogue: thread = row n of the dW tile; 32 accumulator columns (k) at a time =====
       const int q = warp & 3;
-      const int n = n0 + q * 32 + lane;
+      // fold: lanes 64..127 hold the second 32-row half's product of the same dW rows, in columns 64..127
+      const int n = n0 + (a.fold ? (q & 1) : q) * 32 + lane;
+      const int c_first = a.fold ? (q >> 1) * 2 : 0, c_count = (a.fold || a.narrow) ? 2 : 4;
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -247,10 +273,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       // quarter of the L2 atomic operations), and the CTAs start at different 32-column chunks so they do not all
       // queue on the same addresses at once
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = (cc + (int)blockIdx.x) & 3;
+      for (int cc = 0; cc < c_count; ++cc) {
+        const int ct = c_first + ((cc + (int)blockIdx.x) & (c_count - 1));   // accumulator chunk (32 columns)
+        const int c = a.fold ? (ct & 1) : ct;                                // its 32-column group of dW
         uint32_t raw[32];
-        tmem_ld32(tm_acc + lane_addr + (uint32_t)c * 32u, raw);
+        tmem_ld32(tm_acc + lane_addr + (uint32_t)ct * 32u, raw);
         tmem_wait_ld();
         if (n < a.N) {
           float* row = a.dW + (size_t)n * a.lddw + k0 + c * 32;
@@ -315,7 +342,9 @@ int p2c_wgrad_tc(const float* dY, int64_t lddy, const float* X, int64_t ldx, con
   }
   const int sms = p2c_sm_budget(dev < 64 ? sms_of[dev] : 148);
   const int n_tiles = (N + WG_TILE - 1) / WG_TILE, k_tiles = (K + WG_TILE - 1) / WG_TILE;
-  const int stages_total = (int)((M + WG_ROWS - 1) / WG_ROWS);
+  const int fold = (N <= 64 && K <= 64) ? 1 : 0, narrow = (!fold && K <= 64) ? 1 : 0;
+  const int stage_rows = fold ? 2 * WG_ROWS : WG_ROWS;
+  const int stages_total = (int)((M + stage_rows - 1) / stage_rows);
   int gx = sms / (n_tiles * k_tiles);
   if (gx < 1) gx = 1;
   // at least 8 stages (256 rows) per CTA so the prologue / epilogue amortise
@@ -323,7 +352,7 @@ int p2c_wgrad_tc(const float* dY, int64_t lddy, const float* X, int64_t ldx, con
   if (gx > max_gx) gx = max_gx;
   const int spc = (stages_total + gx - 1) / gx;
   gx = (stages_total + spc - 1) / spc;
-  WgArgs a{in_scale, in_shift, dW, lddw, db, (int)M, N, K, stages_total, spc};
+  WgArgs a{in_scale, in_shift, dW, lddw, db, (int)M, N, K, stages_total, spc, fold, narrow};
   dim3 grid(gx, n_tiles, k_tiles);
   wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, st>>>(tmDY, tmX, a);
   P2C_RETURN_IF_CUDA_ERROR();

@@ -297,7 +297,8 @@ def test_head_backward_vs_autograd():
 
 
 @pytest.mark.parametrize("M,N,K", [(5000, 64, 64), (3000, 128, 131), (1024, 256, 259), (700, 19, 128),
-                                   (40000, 128, 128), (33001, 64, 64), (20000, 256, 131), (4096, 512, 1024)])
+                                   (40000, 128, 128), (33001, 64, 64), (20000, 256, 131), (4096, 512, 1024),
+                                   (30001, 128, 64), (9000, 32, 64), (7003, 19, 64)])   # K <= 64: narrow / folded stages
 @pytest.mark.parametrize("tc", [False, True])
 def test_wgrad_kernel(M, N, K, tc):
     """dW = dY^T relu(bn(X)), db = column sums: fp32 SIMT kernel and the tcgen05 split-over-rows kernel (3xTF32)."""
