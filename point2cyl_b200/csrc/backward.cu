@@ -52,9 +52,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldda, const float* __
     sh = __ldg(reinterpret_cast<const float4*>(shift + c));
   }
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  for (int64_t r = r0 + rl; r < r1; r += RL) {
-    const float4 y = __ldg(reinterpret_cast<const float4*>(Y + r * ldy + c));
-    float4 g = __ldg(reinterpret_cast<const float4*>(dA + r * ldda + c));
+  auto accumulate = [&](const float4& y, float4 g) {
     if (scale) {
       if (!(fmaf(y.x, sc.x, sh.x) > 0.f)) g.x = 0.f;
       if (!(fmaf(y.y, sc.y, sh.y) > 0.f)) g.y = 0.f;
@@ -63,7 +61,21 @@ bn_bwd_reduce_kernel(const float* __restrict__ dA, int64_t ldda, const float* __
     }
     s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
     s2.x = fmaf(g.x, y.x, s2.x); s2.y = fmaf(g.y, y.y, s2.y); s2.z = fmaf(g.z, y.z, s2.z); s2.w = fmaf(g.w, y.w, s2.w);
+  };
+  // four rows (eight 16-byte loads) in flight per thread before the arithmetic starts
+  int64_t r = r0 + rl;
+  for (; r + 3 * RL < r1; r += 4 * RL) {
+    float4 y[4], g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      y[u] = __ldg(reinterpret_cast<const float4*>(Y + (r + u * RL) * ldy + c));
+      g[u] = __ldg(reinterpret_cast<const float4*>(dA + (r + u * RL) * ldda + c));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) accumulate(y[u], g[u]);
   }
+  for (; r < r1; r += RL)
+    accumulate(__ldg(reinterpret_cast<const float4*>(Y + r * ldy + c)), __ldg(reinterpret_cast<const float4*>(dA + r * ldda + c)));
   float* mine = s_red[threadIdx.x];
   mine[0] = s1.x; mine[1] = s1.y; mine[2] = s1.z; mine[3] = s1.w;
   mine[4] = s2.x; mine[5] = s2.y; mine[6] = s2.z; mine[7] = s2.w;
