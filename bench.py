@@ -801,13 +801,14 @@ def main():
         stages["p2c_linear"]["layers"] = layers
         top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
         d = per_kernel[top]
-        traffic, traffic_note = None, None
+        traffic, traffic_note, ncu_us = None, None, None
         tpath = os.path.join(ROOT, "profiles", "linear_traffic.json")   # ncu dram bytes of the same launches
         if top == "p2c_linear" and os.path.isfile(tpath):
             tj = json.load(open(tpath))
             if tj.get("kernel_source_sha") == kernel_source_sha():
                 traffic = tj.get("dram_bytes_per_step")
                 traffic_note = tj.get("source")
+                ncu_us = tj.get("ncu_duration_us_per_step")
             else:
                 traffic_note = "profiles/linear_traffic.json was measured on other kernel sources: not reported"
         ach = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["bytes"] else 0.0
@@ -819,6 +820,12 @@ def main():
                         "layer (stages.p2c_linear.layers) the binding floor is HBM for the K, N <= 128 layers on the big "
                         "row counts and the tensor pipe (3 tf32 passes) for the pooled 64->128 / 128->256 layers and the "
                         "coarse levels"}
+        if ncu_us:
+            # the same launches' gpu__time_duration under ncu (committed launch list, same kernel sources; cold cache and
+            # serialised): a CUDA-event pair around ONE launch also spans the launch gap on either side of the kernel
+            # (5-8 us per launch here, 17 launches), which ncu's per-kernel duration does not
+            roof["ncu_duration_us"] = ncu_us
+            roof["frac_by_ncu_duration"] = d["bytes"] / (ncu_us * 1e-6) / 1e9 / pk["hbm"] if d["bytes"] else None
         if d["flops"]:
             tf = d["flops"] / (d["ms"] / 1e3) / 1e12
             roof["tensor_tflops"] = tf
