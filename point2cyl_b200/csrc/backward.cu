@@ -368,38 +368,51 @@ sa_first_bwd_kernel(const float* __restrict__ dY, int64_t lddy, const float* __r
     const float* cc = new_xyz + (size_t)bsl * 3;
     const float dl0 = __ldg(pp) - __ldg(cc), dl1 = __ldg(pp + 1) - __ldg(cc + 1), dl2 = __ldg(pp + 2) - __ldg(cc + 2);
     const int nrow = (int)min((int64_t)32, rows - r0);
-#pragma unroll 4
-    for (int j = 0; j < nrow; ++j) {
-      const float d0 = __shfl_sync(P2C_FULL_MASK, dl0, j), d1 = __shfl_sync(P2C_FULL_MASK, dl1, j),
-                  d2 = __shfl_sync(P2C_FULL_MASK, dl2, j);
-      float g[CPL];
-      const float* gr = dY + (r0 + j) * lddy + c0;
-      if (CPL == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(gr));
-        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[CPL - 1] = t.w;
-      } else {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(gr));
-        g[0] = t.x; g[1] = t.y;
-      }
-      if (dQf) {
-        const unsigned sj = __shfl_sync(P2C_FULL_MASK, src, j);
-        float* q = dQf + (size_t)sj * ldq + c0;
-        // one 16-byte vector reduction instead of four scalar ones where the row allows it (L2 atomic operations are
-        // what this scatter costs)
-        if (CPL == 4 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
-          atomicAdd(reinterpret_cast<float4*>(q), make_float4(g[0], g[1], g[2], g[CPL - 1]));
-        } else if (CPL == 2 && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {
-          atomicAdd(reinterpret_cast<float2*>(q), make_float2(g[0], g[1]));
-        } else {
+    // eight rows of dY in flight before the first is consumed (ncu: 19 % of the issue slots busy, long-scoreboard
+    // stalls - the latency of these loads, not their bandwidth, was the bound: 139 us for 268 MB)
+    for (int j0 = 0; j0 < nrow; j0 += 8) {
+      float g[8][CPL];
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[i]);
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) g[u][i] = 0.f;
+        if (j0 + u < nrow) {
+          const float* gr = dY + (r0 + j0 + u) * lddy + c0;
+          if (CPL == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(gr));
+            g[u][0] = t.x; g[u][1] = t.y; g[u][2] = t.z; g[u][CPL - 1] = t.w;
+          } else {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(gr));
+            g[u][0] = t.x; g[u][1] = t.y;
+          }
         }
       }
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        gw[i][0] = fmaf(g[i], d0, gw[i][0]); gw[i][1] = fmaf(g[i], d1, gw[i][1]);
-        gw[i][2] = fmaf(g[i], d2, gw[i][2]);
-        gb[i] += g[i];
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        if (j >= nrow) break;
+        const float d0 = __shfl_sync(P2C_FULL_MASK, dl0, j), d1 = __shfl_sync(P2C_FULL_MASK, dl1, j),
+                    d2 = __shfl_sync(P2C_FULL_MASK, dl2, j);
+        if (dQf) {
+          const unsigned sj = __shfl_sync(P2C_FULL_MASK, src, j);
+          float* q = dQf + (size_t)sj * ldq + c0;
+          // one 16-byte vector reduction instead of four scalar ones where the row allows it (L2 atomic operations are
+          // what this scatter costs)
+          if (CPL == 4 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+            atomicAdd(reinterpret_cast<float4*>(q), make_float4(g[u][0], g[u][1], g[u][2], g[u][CPL - 1]));
+          } else if (CPL == 2 && (reinterpret_cast<uintptr_t>(q) & 7) == 0) {
+            atomicAdd(reinterpret_cast<float2*>(q), make_float2(g[u][0], g[u][1]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) atomicAdd(q + i, g[u][i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          gw[i][0] = fmaf(g[u][i], d0, gw[i][0]); gw[i][1] = fmaf(g[u][i], d1, gw[i][1]);
+          gw[i][2] = fmaf(g[u][i], d2, gw[i][2]);
+          gb[i] += g[u][i];
+        }
       }
     }
   }

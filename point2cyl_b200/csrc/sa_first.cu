@@ -59,34 +59,42 @@ sa_first_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz
     float t1[CPL], t2[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) { t1[i] = 0.f; t2[i] = 0.f; }
-#pragma unroll 4
-    for (int j = 0; j < nrow; ++j) {
-      const float d0 = __shfl_sync(P2C_FULL_MASK, dl0, j), d1 = __shfl_sync(P2C_FULL_MASK, dl1, j),
-                  d2 = __shfl_sync(P2C_FULL_MASK, dl2, j);
-      float y[CPL];
-      if (Qf) {
-        const unsigned sj = __shfl_sync(P2C_FULL_MASK, src, j);
-        const float* q = Qf + (size_t)sj * ldq + c0;
-        if (CPL == 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(q));
-          y[0] = t.x; y[1] = t.y; y[2] = t.z; y[CPL - 1] = t.w;
-        } else {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(q));
-          y[0] = t.x; y[1] = t.y;
+    // eight rows at a time, their feature gathers issued before any of them is consumed: the kernel is bound by the
+    // latency of those loads (ncu: issue slots 30 % busy, long-scoreboard stalls), not by their bandwidth
+    for (int j0 = 0; j0 < nrow; j0 += 8) {
+      float y[8][CPL];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) y[u][i] = 0.f;
+        if (Qf && j0 + u < nrow) {
+          const unsigned sj = __shfl_sync(P2C_FULL_MASK, src, j0 + u);
+          const float* q = Qf + (size_t)sj * ldq + c0;
+          if (CPL == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(q));
+            y[u][0] = t.x; y[u][1] = t.y; y[u][2] = t.z; y[u][CPL - 1] = t.w;
+          } else {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(q));
+            y[u][0] = t.x; y[u][1] = t.y;
+          }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) y[i] = 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        y[i] += fmaf(wx[i][2], d2, fmaf(wx[i][1], d1, wx[i][0] * d0)) + bj[i];
-        t1[i] += y[i];
-        t2[i] = fmaf(y[i], y[i], t2[i]);
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        if (j >= nrow) break;
+        const float d0 = __shfl_sync(P2C_FULL_MASK, dl0, j), d1 = __shfl_sync(P2C_FULL_MASK, dl1, j),
+                    d2 = __shfl_sync(P2C_FULL_MASK, dl2, j);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          y[u][i] += fmaf(wx[i][2], d2, fmaf(wx[i][1], d1, wx[i][0] * d0)) + bj[i];
+          t1[i] += y[u][i];
+          t2[i] = fmaf(y[u][i], y[u][i], t2[i]);
+        }
+        float* yo = Y + (size_t)(r0 + j) * ldy + c0;
+        if (CPL == 4) *reinterpret_cast<float4*>(yo) = make_float4(y[u][0], y[u][1], y[u][2], y[u][CPL - 1]);
+        else *reinterpret_cast<float2*>(yo) = make_float2(y[u][0], y[u][1]);
       }
-      float* yo = Y + (size_t)(r0 + j) * ldy + c0;
-      if (CPL == 4) *reinterpret_cast<float4*>(yo) = make_float4(y[0], y[1], y[2], y[CPL - 1]);
-      else *reinterpret_cast<float2*>(yo) = make_float2(y[0], y[1]);
     }
 #pragma unroll
     for (int i = 0; i < CPL; ++i) { s1[i] += (double)t1[i]; s2[i] += (double)t2[i]; }
