@@ -99,6 +99,49 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
   const float* f2 = feats2 + (size_t)b * S * ldf;
   const bool vec = (D % 4 == 0) && (ldf % 4 == 0) && (ldo % 4 == 0) &&
                    (((reinterpret_cast<uintptr_t>(feats2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  if (vec) {
+    // two queries per iteration, their six row loads issued before either is consumed: a warp walks its 32 queries in
+    // program order, so with one query per iteration exactly one L2 round trip was in flight per warp
+    for (int t = warp; t < QPB; t += 2 * (QPB / 32)) {
+      const int t2 = t + QPB / 32;
+      const int qa = blockIdx.x * QPB + t, qb = blockIdx.x * QPB + t2;
+      if (qa >= N) break;
+      const bool two = qb < N;
+      const int tb = two ? t2 : t;
+      const float* a0 = f2 + (size_t)s_idx[t][0] * ldf;
+      const float* a1 = f2 + (size_t)s_idx[t][1] * ldf;
+      const float* a2 = f2 + (size_t)s_idx[t][2] * ldf;
+      const float* b0 = f2 + (size_t)s_idx[tb][0] * ldf;
+      const float* b1 = f2 + (size_t)s_idx[tb][1] * ldf;
+      const float* b2 = f2 + (size_t)s_idx[tb][2] * ldf;
+      const float w0 = s_w[t][0], w1 = s_w[t][1], w2 = s_w[t][2];
+      const float x0 = s_w[tb][0], x1 = s_w[tb][1], x2 = s_w[tb][2];
+      float* oa = out + ((size_t)b * N + qa) * ldo;
+      float* ob = out + ((size_t)b * N + qb) * ldo;
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(a0 + c));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a1 + c));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a2 + c));
+        const float4 p = __ldg(reinterpret_cast<const float4*>(b0 + c));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(b1 + c));
+        const float4 r_ = __ldg(reinterpret_cast<const float4*>(b2 + c));
+        float4 r;
+        r.x = __fadd_rn(__fadd_rn(__fmul_rn(u.x, w0), __fmul_rn(v.x, w1)), __fmul_rn(w.x, w2));
+        r.y = __fadd_rn(__fadd_rn(__fmul_rn(u.y, w0), __fmul_rn(v.y, w1)), __fmul_rn(w.y, w2));
+        r.z = __fadd_rn(__fadd_rn(__fmul_rn(u.z, w0), __fmul_rn(v.z, w1)), __fmul_rn(w.z, w2));
+        r.w = __fadd_rn(__fadd_rn(__fmul_rn(u.w, w0), __fmul_rn(v.w, w1)), __fmul_rn(w.w, w2));
+        *reinterpret_cast<float4*>(oa + c) = r;
+        if (two) {
+          r.x = __fadd_rn(__fadd_rn(__fmul_rn(p.x, x0), __fmul_rn(q.x, x1)), __fmul_rn(r_.x, x2));
+          r.y = __fadd_rn(__fadd_rn(__fmul_rn(p.y, x0), __fmul_rn(q.y, x1)), __fmul_rn(r_.y, x2));
+          r.z = __fadd_rn(__fadd_rn(__fmul_rn(p.z, x0), __fmul_rn(q.z, x1)), __fmul_rn(r_.z, x2));
+          r.w = __fadd_rn(__fadd_rn(__fmul_rn(p.w, x0), __fmul_rn(q.w, x1)), __fmul_rn(r_.w, x2));
+          *reinterpret_cast<float4*>(ob + c) = r;
+        }
+      }
+    }
+    return;
+  }
   for (int t = warp; t < QPB; t += QPB / 32) {
     const int qq = blockIdx.x * QPB + t;
     if (qq >= N) break;
@@ -107,23 +150,9 @@ three_nn_interp_kernel(const float* __restrict__ xyz1, const float* __restrict__
     const float* a2 = f2 + (size_t)s_idx[t][2] * ldf;
     const float w0 = s_w[t][0], w1 = s_w[t][1], w2 = s_w[t][2];
     float* o = out + ((size_t)b * N + qq) * ldo;
-    if (vec) {
-      for (int c = lane * 4; c < D; c += 128) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(a0 + c));
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a1 + c));
-        const float4 w = __ldg(reinterpret_cast<const float4*>(a2 + c));
-        float4 r;
-        r.x = __fadd_rn(__fadd_rn(__fmul_rn(u.x, w0), __fmul_rn(v.x, w1)), __fmul_rn(w.x, w2));
-        r.y = __fadd_rn(__fadd_rn(__fmul_rn(u.y, w0), __fmul_rn(v.y, w1)), __fmul_rn(w.y, w2));
-        r.z = __fadd_rn(__fadd_rn(__fmul_rn(u.z, w0), __fmul_rn(v.z, w1)), __fmul_rn(w.z, w2));
-        r.w = __fadd_rn(__fadd_rn(__fmul_rn(u.w, w0), __fmul_rn(v.w, w1)), __fmul_rn(w.w, w2));
-        *reinterpret_cast<float4*>(o + c) = r;
-      }
-    } else {
-      for (int c = lane; c < D; c += 32)
-        o[c] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(a0 + c), w0), __fmul_rn(__ldg(a1 + c), w1)),
-                         __fmul_rn(__ldg(a2 + c), w2));
-    }
+    for (int c = lane; c < D; c += 32)
+      o[c] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(a0 + c), w0), __fmul_rn(__ldg(a1 + c), w1)),
+                       __fmul_rn(__ldg(a2 + c), w2));
   }
 }
 
