@@ -155,3 +155,25 @@ def test_reference_arm_under_torchrun_prints_one_line():
     assert d["cpu_baseline"]["cores"] >= 1 and "clouds" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("forward+loss") and d["gpu_launches"] == 0
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """bench.py's clock sampler (in-process NVML, nvidia-smi child as the fallback) must never take the bench down: on a
+    machine with neither it reports that instead of raising."""
+    spec = importlib.util.spec_from_file_location("bench_mod_clk", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.ClockSampler(0)
+    c.start()
+    out = c.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    if not torch.cuda.is_available():
+        assert out["sm_mhz"] is None or isinstance(out["sm_mhz"], float)
+
+
+def test_pipelined_trainer_surface():
+    """train.PipelinedTrainer keeps Trainer's interface (step / forward_backward / flat buffers) and adds prime / join."""
+    from point2cyl_b200 import train
+    assert issubclass(train.PipelinedTrainer, train.Trainer) and issubclass(train.GraphedTrainer, train.Trainer)
+    for name in ("prime", "step", "join", "rebuild_if_stale", "stale"):
+        assert callable(getattr(train.PipelinedTrainer, name)), name
